@@ -1,0 +1,35 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def fixtures():
+    """The reference's own golden fixtures (re-packed by tests/golden/make_golden.py)."""
+    return dict(np.load(os.path.join(GOLDEN, "fixtures.npz")))
+
+
+@pytest.fixture(scope="session")
+def live():
+    """Outputs of the live reference on small seeded inputs."""
+    return dict(np.load(os.path.join(GOLDEN, "live_cases.npz")))
+
+
+def has_cuda():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
