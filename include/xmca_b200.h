@@ -1,0 +1,146 @@
+/* xmca_b200 -- C ABI of the B200-native MCA engine (libxmca_b200.so).
+ *
+ * The reference (nicrie/xmca) has NO FFI: its hot path is numpy/LAPACK calls
+ * inside xmca/array.py and xmca/tools/rotation.py.  Each entry point below
+ * replaces one of those library-call seams; the comment above it cites the
+ * reference lines (relative to the reference repo root).  INTEGRATION.md shows
+ * the ctypes stub a maintainer of the reference would add at each seam.
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer owned by the caller (the
+ *     Python host passes torch.cuda tensor data_ptr()s); the library never
+ *     keeps a pointer after the call returns and never allocates persistent
+ *     device memory.  Scratch space is caller-supplied: ask the matching
+ *     *_workspace_bytes() function first.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it.
+ *     Calls that need a device->host decision (convergence tests) synchronise
+ *     that stream internally and say so.
+ *   - matrices are dense, real.  Complex fields are handled by the host as
+ *     planar (re, im) pairs / real embeddings.
+ *   - return value: 0 ok, 1 bad argument, 2 CUDA error, 3 not converged,
+ *     4 numerical failure.  xmca_last_error() gives the message (thread local).
+ */
+#ifndef XMCA_B200_H
+#define XMCA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { XMCA_OK = 0, XMCA_BAD_ARG = 1, XMCA_CUDA_ERROR = 2, XMCA_NOT_CONVERGED = 3, XMCA_NUMERIC = 4 };
+enum { XMCA_F32 = 0, XMCA_F64 = 1 };
+
+const char* xmca_last_error(void);
+int xmca_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+long long xmca_launch_count(void);
+
+/* ---- general dense product (SIMT FP64/FP32 cores) ------------------------
+ * D[M,N] (row-major, ldd) = alpha * opA(A) * opB(B)  (+ D if accumulate)
+ *   a_kmajor=1: A is stored M x K row-major (lda >= K);  0: K x M row-major (lda >= M)
+ *   b_kmajor=1: B is stored N x K row-major (ldb >= K);  0: K x N row-major (ldb >= N)
+ * acc_dtype selects the accumulator (XMCA_F64 for the parity-critical paths).
+ * Replaces the `@` products of array.py:556-566 (kernel), :584 (back-projection),
+ * :640 (rotated EOFs), :667-669 (PCs) and rotation.py:128-147 (Promax fit).
+ * split_k > 1 needs workspace of xmca_gemm_workspace_bytes(). */
+size_t xmca_gemm_workspace_bytes(int64_t M, int64_t N, int split_k, int acc_dtype);
+int xmca_gemm(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K, double alpha,
+              const void* d_A, int a_dtype, int64_t lda,
+              const void* d_B, int b_dtype, int64_t ldb,
+              void* d_D, int d_dtype, int64_t ldd, int accumulate,
+              int acc_dtype, int split_k, void* d_workspace, size_t workspace_bytes,
+              void* stream);
+
+/* ---- cross-covariance on the tensor cores (tcgen05 + TMA, 3xTF32) ---------
+ * Replaces the field SVDs + kernel product of array.py:552-566: forms
+ * C = A^T B * alpha directly (S1 x S2, fp32) from fp32 fields.
+ * Step 1: xmca_split_tf32 writes the (hi, lo) TF32 planes of X or X^T,
+ *         K-major, row pitch ldo (multiple of 4 floats).
+ * Step 2: xmca_tc_gemm_nt multiplies two plane pairs:
+ *         D[M,N] = alpha * sum_k A[m,k] B[n,k]  with hi*hi + hi*lo + lo*hi.
+ * frob2 (optional, device double*) accumulates sum(D^2)
+ * (= total_squared_covariance, array.py:596). */
+int xmca_split_tf32(const void* d_X, int x_dtype, int64_t rows, int64_t cols, int64_t ldx,
+                    int transpose, float* d_hi, float* d_lo, int64_t ldo, void* stream);
+int xmca_tc_gemm_nt(int64_t M, int64_t N, int64_t K, float alpha,
+                    const float* d_Ahi, const float* d_Alo, int64_t lda,
+                    const float* d_Bhi, const float* d_Blo, int64_t ldb,
+                    float* d_D, int64_t ldd, double* d_frob2, void* stream);
+
+/* ---- SVD / symmetric eigen-decomposition: blocked one-sided Jacobi --------
+ * Replaces np.linalg.svd of array.py:479 and :570 (and the p x p SVD of
+ * rotation.py:59 when called with small n).
+ * d_Kc : m x n matrix stored COLUMN-major (column j at d_Kc + j*ldk), fp64,
+ *        n_pad = xmca_jacobi_padded_cols(n) columns allocated (extra columns
+ *        must be zero).  On return column j holds u_j * sigma_j.
+ * d_Jc : optional n_pad x n_pad column-major fp64 (ldj >= n_pad), overwritten
+ *        with the accumulated right rotations (right singular vectors).
+ * d_sigma : n_pad doubles, column norms on return (NOT sorted; host sorts).
+ * Synchronises `stream` once per sweep to read the convergence measure. */
+int64_t xmca_jacobi_padded_cols(int64_t n);
+size_t xmca_jacobi_workspace_bytes(int64_t m, int64_t n);
+int xmca_jacobi_svd(int64_t m, int64_t n, double* d_Kc, int64_t ldk,
+                    double* d_Jc, int64_t ldj, double* d_sigma,
+                    int max_sweeps, double tol, int* sweeps_out, double* offnorm_out,
+                    void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ---- element-wise / layout helpers ---------------------------------------*/
+/* Y[r,c] = X[r,c] * (col_scale ? col_scale[c] : 1) * (row_scale ? row_scale[r] : 1);
+ * row-major, dtypes may differ (conversion kernel).  array.py:553, :640, :667. */
+int xmca_scale_copy(const void* d_X, int x_dtype, int64_t ldx, void* d_Y, int y_dtype, int64_t ldy,
+                    int64_t rows, int64_t cols, const double* d_col_scale, const double* d_row_scale,
+                    void* stream);
+/* Y (cols x rows, row-major) = X^T, with dtype conversion. */
+int xmca_transpose(const void* d_X, int x_dtype, int64_t rows, int64_t cols, int64_t ldx,
+                   void* d_Y, int y_dtype, int64_t ldy, void* stream);
+/* out[c] = sum_r X[r,c]^2 for r in [row0,row1)  (fp64 out); array.py:826-830. */
+int xmca_col_sumsq(const void* d_X, int x_dtype, int64_t ldx, int64_t row0, int64_t row1,
+                   int64_t cols, double* d_out, void* stream);
+/* subtract the column mean in place (array.py:199-207), mean returned in d_mean (fp64). */
+int xmca_center_columns(void* d_X, int x_dtype, int64_t rows, int64_t cols, int64_t ldx,
+                        double* d_mean, void* stream);
+/* fill X (rows x cols) with N(0,1) from Philox4x32-10, counter = element index,
+ * key = (seed, stream_id): result independent of launch geometry. array.py:1756. */
+int xmca_fill_normal(void* d_X, int x_dtype, int64_t rows, int64_t cols, int64_t ldx,
+                     uint64_t seed, uint64_t stream_id, void* stream);
+
+/* Y[i,:] = X[idx[i],:] * row_scale[i]  (mode sorting + normalisation after the Jacobi SVD;
+ * array.py:592 argsort / :584). idx: device int64. */
+int xmca_gather_rows(const void* d_X, int x_dtype, int64_t ldx, const int64_t* d_idx, int64_t n_out,
+                     int64_t cols, const double* d_row_scale, void* d_Y, int y_dtype, int64_t ldy,
+                     void* stream);
+/* out[r] = sum_c X[r,c]^2 (communalities, rotation.py:46 / :115). */
+int xmca_row_sumsq(const void* d_X, int x_dtype, int64_t ldx, int64_t rows, int64_t cols,
+                   double* d_out, void* stream);
+/* out[c] = max_r |X[r,c] * row_scale[r]|  (rotation.py:121). */
+int xmca_col_absmax(const void* d_X, int x_dtype, int64_t ldx, int64_t rows, int64_t cols,
+                    const double* d_row_scale, double* d_out, void* stream);
+/* Promax target (rotation.py:115-124): Xout = X * row_scale[r]; Pout = Xn |Xn|^(power-1),
+ * Xn = Xout / colmax[c]. */
+int xmca_promax_target(const double* d_X, int64_t ldx, int64_t rows, int64_t cols,
+                       const double* d_row_scale, const double* d_colmax, double power,
+                       double* d_Xout, double* d_Pout, int64_t ldo, void* stream);
+
+/* ---- fused Varimax / Promax rotation --------------------------------------
+ * Replaces xmca/tools/rotation.py:15-78 (varimax) driven from array.py:823.
+ * d_L : n x p loadings, row-major (ld = ldl), fp32 or fp64.  Real case.
+ * Runs the Kaiser-normalised fixed point with a persistent cooperative
+ * kernel: per iteration one streaming pass over the normalised loadings,
+ * p x p polar factor on one CTA, device-side convergence test
+ * |d - d_old| / d < tol (rotation.py:62).  All p x p state is fp64.
+ * Outputs: d_R (p x p row-major fp64), d_B (n x p row-major fp64: rotated
+ * loadings, de-normalised, rotation.py:74-77), iterations.
+ * Returns XMCA_NOT_CONVERGED after max_iter (rotation.py:66-71). */
+size_t xmca_varimax_workspace_bytes(int64_t n, int p);
+int xmca_varimax(const void* d_L, int l_dtype, int64_t n, int p, int64_t ldl,
+                 double gamma, int max_iter, double tol,
+                 double* d_B, int64_t ldb, double* d_R, int* iterations_out, double* d_out,
+                 void* d_workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XMCA_B200_H */

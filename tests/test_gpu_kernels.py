@@ -1,0 +1,151 @@
+"""GPU parity tests of the individual C-ABI kernels against numpy (fp64)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def D():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from xmca_b200 import device
+    return device
+
+
+def _rng(seed=0):
+    return np.random.default_rng(seed)
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_gemm_layouts(D, ta, tb, dt):
+    r = _rng(1)
+    M, N, K = 155, 162, 492
+    A = r.standard_normal((K, M) if ta else (M, K)).astype(dt)
+    B = r.standard_normal((N, K) if tb else (K, N)).astype(dt)
+    want = (A.T if ta else A).astype(np.float64) @ (B.T if tb else B).astype(np.float64)
+    got = D.to_host(D.matmul(D.to_device(A), D.to_device(B), trans_a=ta, trans_b=tb, alpha=0.5))
+    np.testing.assert_allclose(got, 0.5 * want, rtol=1e-12, atol=1e-12 * np.abs(want).max())
+
+
+def test_gemm_split_k_and_accumulate(D):
+    r = _rng(2)
+    A = r.standard_normal((40, 9000))
+    B = r.standard_normal((9000, 24))
+    out = D.to_device(np.ones((40, 24)))
+    got = D.to_host(D.matmul(D.to_device(A), D.to_device(B), out=out, accumulate=True))
+    np.testing.assert_allclose(got, A @ B + 1.0, rtol=1e-12, atol=1e-10)
+    got32 = D.to_host(D.matmul(D.to_device(A.astype(np.float32)), D.to_device(B.astype(np.float32)),
+                               acc="f32", out_dtype=D.f32()))
+    np.testing.assert_allclose(got32, A @ B, rtol=2e-3, atol=2e-2)
+
+
+@pytest.mark.parametrize("shape", [(128, 256, 64), (300, 200, 100), (512, 640, 1000), (96, 40, 37)])
+def test_tc_gemm_matches_fp64(D, shape):
+    """3xTF32 tcgen05 product vs fp64 numpy: error at the fp32 level."""
+    M, N, K = shape
+    r = _rng(3)
+    A = r.standard_normal((K, M)).astype(np.float32)      # time-major fields (T x S)
+    B = r.standard_normal((K, N)).astype(np.float32)
+    C, frob2 = D.cov_gemm_tc(D.to_device(A), D.to_device(B), 0.25)
+    want = 0.25 * A.astype(np.float64).T @ B.astype(np.float64)
+    got = D.to_host(C).astype(np.float64)
+    scale = np.sqrt(K) * 0.25
+    assert np.abs(got - want).max() < 2e-6 * scale * 4
+    np.testing.assert_allclose(D.to_host(frob2)[0], (got ** 2).sum(), rtol=1e-6)
+
+
+def test_tc_gemm_planted_structure(D):
+    """Catches k-slab / swizzle / descriptor mistakes: structured operands."""
+    M, N, K = 256, 512, 160
+    A = np.zeros((K, M), np.float32)
+    B = np.zeros((K, N), np.float32)
+    for k in range(K):
+        A[k, (3 * k) % M] = 1.0 + k
+        B[k, (7 * k + 1) % N] = 2.0 - 0.01 * k
+    C, _ = D.cov_gemm_tc(D.to_device(A), D.to_device(B), 1.0)
+    want = A.astype(np.float64).T @ B.astype(np.float64)
+    np.testing.assert_allclose(D.to_host(C), want, rtol=1e-6, atol=1e-4)
+
+
+@pytest.mark.parametrize("n,m", [(150, 200), (64, 64), (33, 500), (200, 200)])
+def test_jacobi_svd(D, n, m):
+    r = _rng(4)
+    X = r.standard_normal((n, m)) * np.logspace(0, -3, n)[:, None]
+    Xr, sig, Jt, sweeps = D.jacobi_svd(D.to_device(X))
+    s = D.to_host(sig)
+    order = np.argsort(-s)[:min(n, m)]
+    want = np.linalg.svd(X, compute_uv=False)
+    np.testing.assert_allclose(s[order], want[:order.size], rtol=1e-10, atol=1e-13 * want[0])
+    J = D.to_host(Jt)[:, :n]
+    np.testing.assert_allclose(J[:n] @ J[:n].T, np.eye(n), atol=1e-12)
+    # X = J Sigma U^T  with rows of Xr = sigma_j u_j^T and columns of J = rows of Jt
+    rec = J[:n].T @ D.to_host(Xr)[:n]
+    np.testing.assert_allclose(rec, X, atol=1e-12 * want[0])
+    assert sweeps <= 20
+
+
+def test_jacobi_symmetric_psd_gives_eigenpairs(D):
+    r = _rng(5)
+    Y = r.standard_normal((90, 300))
+    Y -= Y.mean(axis=0)
+    G = Y @ Y.T
+    Gr, lam, Jt, _ = D.jacobi_svd(D.to_device(G))
+    lam, J = D.to_host(lam), D.to_host(Jt)
+    order = np.argsort(-lam)[:90]
+    w = np.linalg.eigvalsh(G)[::-1]
+    np.testing.assert_allclose(lam[order], np.maximum(w, 0), atol=1e-10 * w[0])
+    U = J[order][:, :90]
+    np.testing.assert_allclose(U @ G @ U.T, np.diag(lam[order]), atol=1e-9 * w[0])
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n,p", [(317, 8), (5000, 20), (2048, 50), (100, 3)])
+def test_varimax_matches_oracle(D, dt, n, p):
+    from oracle import mca_oracle as orc
+    r = _rng(6)
+    L = (r.standard_normal((n, p)) * (1 + 5 * (r.random((n, p)) < 0.1))).astype(dt)
+    L *= np.linspace(2.0, 0.5, p)
+    try:
+        Bo, Ro, it_o = orc.varimax(L, tol=1e-8)
+    except orc.NotConverged:
+        pytest.skip("oracle did not converge on this input")
+    B, R, it = D.varimax(D.to_device(L), tol=1e-8)
+    R, B = D.to_host(R), D.to_host(B)
+    np.testing.assert_allclose(R.T @ R, np.eye(p), atol=1e-10)
+    assert abs(it - it_o) <= max(3, it_o // 20)
+    np.testing.assert_allclose(B, Bo, atol=2e-5 * np.abs(Bo).max())
+
+
+def test_elementwise_helpers(D):
+    r = _rng(7)
+    X = r.standard_normal((70, 45)).astype(np.float32) + 3.0
+    Xd = D.to_device(X.copy())
+    mean = D.to_host(D.center_columns(Xd))
+    np.testing.assert_allclose(mean, X.astype(np.float64).mean(axis=0), rtol=1e-6)
+    np.testing.assert_allclose(D.to_host(Xd), X - X.mean(axis=0), atol=1e-5)
+    np.testing.assert_allclose(D.to_host(D.transpose(D.to_device(X), out_dtype=D.f64())), X.T.astype(np.float64))
+    np.testing.assert_allclose(D.to_host(D.col_sumsq(D.to_device(X), 10, 60)),
+                               (X[10:60].astype(np.float64) ** 2).sum(axis=0), rtol=1e-12)
+    np.testing.assert_allclose(D.to_host(D.row_sumsq(D.to_device(X))),
+                               (X.astype(np.float64) ** 2).sum(axis=1), rtol=1e-12)
+    rs = r.random(70)
+    np.testing.assert_allclose(D.to_host(D.col_absmax(D.to_device(X), row_scale=D.to_device(rs))),
+                               np.abs(X * rs[:, None]).max(axis=0), rtol=1e-7)
+    idx = np.array([5, 0, 69, 5], dtype=np.int64)
+    got = D.to_host(D.gather_rows(D.to_device(X), D.to_device(idx), row_scale=D.to_device(np.array([1., 2., 3., 4.]))))
+    np.testing.assert_allclose(got, X[idx] * np.array([1, 2, 3, 4])[:, None], rtol=1e-6)
+
+
+def test_philox_normal_is_standard_and_geometry_independent(D):
+    t = D.torch()
+    X = D.fill_normal(D.empty((1000, 501), t.float64), seed=42, stream_id=3)
+    Y = D.fill_normal(D.empty((501 * 1000 // 3, 3), t.float64), seed=42, stream_id=3)
+    x, y = D.to_host(X), D.to_host(Y)
+    assert np.array_equal(x.ravel(), y.ravel())           # counter-based: same stream, any shape
+    assert abs(x.mean()) < 5e-3 and abs(x.std() - 1) < 5e-3
+    assert abs(((x - x.mean()) ** 4).mean() - 3) < 0.05
+    Z = D.to_host(D.fill_normal(D.empty((1000, 501), t.float64), seed=42, stream_id=4))
+    assert abs(np.corrcoef(x.ravel(), Z.ravel())[0, 1]) < 5e-3

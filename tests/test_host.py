@@ -1,0 +1,165 @@
+"""CPU tests: host-side class logic, C-ABI export surface, rule_n sharding over
+a 2-process gloo group.  No GPU compute is attempted here."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import mca_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ensure_built():
+    from xmca_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        sys.path.insert(0, ROOT)
+        import __graft_entry__ as g
+        g.build()
+    return _lib
+
+
+def test_library_exports_every_declared_symbol():
+    _lib = _ensure_built()
+    lib = _lib.load()
+    names = _lib.declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), n
+    assert lib.xmca_version() >= 100
+    assert lib.xmca_jacobi_padded_cols(155) == 192 and lib.xmca_jacobi_padded_cols(1) == 64
+    assert lib.xmca_gemm_workspace_bytes(10, 10, 4, 1) == 10 * 10 * 4 * 8
+    assert lib.xmca_jacobi_workspace_bytes(492, 155) > 0
+    assert lib.xmca_varimax_workspace_bytes(1000, 20) > 1000 * 20 * 8
+
+
+def test_bad_arguments_are_rejected_without_a_gpu():
+    _lib = _ensure_built()
+    lib = _lib.load()
+    rc = lib.xmca_gemm(1, 1, 0, 4, 4, 1.0, None, 0, 4, None, 0, 4, None, 0, 4, 0, 1, 1, None, 0, None)
+    assert rc == _lib.BAD_ARG
+    assert b"xmca_gemm" in lib.xmca_last_error()
+    rc = lib.xmca_varimax(None, 0, 10, 80, 80, 1.0, 10, 1e-8, None, 80, None, None, None, None, 0, None)
+    assert rc == _lib.BAD_ARG
+
+
+def test_constructor_validation_matches_reference_unit_tests():
+    from xmca_b200 import MCA
+    rng = np.random.default_rng(7)
+    A = rng.standard_normal((500, 20, 15))
+    B = rng.standard_normal((500, 15, 10))
+    MCA()
+    MCA(A)
+    m = MCA(A, B)
+    assert m._analysis["method"] == "mca" and m._analysis["is_bivariate"]
+    assert m._fields["left"].shape == (500, 300) and abs(m._fields["left"].mean(axis=0)).max() < 1e-12
+    with pytest.raises(ValueError):
+        MCA(A, B, A)
+    with pytest.raises(ValueError):
+        MCA(A[:20], B[:15])
+    with pytest.raises(TypeError):
+        MCA(list(A))
+    bad = A.copy()
+    bad[3] = np.nan
+    with pytest.raises(ValueError):
+        MCA(bad)
+    hole = A.copy()
+    hole[:, 2, 3] = np.nan                       # a NaN grid point is dropped, not an error
+    m = MCA(hole)
+    assert m._fields["left"].shape == (500, 299) and m._n_variables["left"] == 300
+    assert m.fields()["left"].shape == A.shape and np.isnan(m.fields()["left"][:, 2, 3]).all()
+    np.testing.assert_allclose(np.nan_to_num(m.fields(original_scale=True)["left"]), np.nan_to_num(hole), atol=1e-12)
+
+
+def test_getters_before_solve_raise_runtime_error():
+    from xmca_b200 import MCA
+    m = MCA(np.random.default_rng(0).standard_normal((30, 5)))
+    for call in (m.singular_values, m.eofs, m.pcs, m.norm, m.variance):
+        with pytest.raises(RuntimeError):
+            call()
+    with pytest.raises(RuntimeError):
+        MCA().solve()
+
+
+def test_mode_slice_semantics_match_oracle():
+    from xmca_b200 import MCA
+    m = MCA(np.random.default_rng(0).standard_normal((30, 5)))
+    m._analysis["rank"] = 5
+    ref = orc.solve(orc.make_model(np.random.default_rng(0).standard_normal((30, 5))))
+    for n in (None, 3, slice(2, 4), slice(None, 99), slice(1, None)):
+        assert m._get_slice(n) == orc.mode_slice(ref, n)
+    with pytest.raises(ValueError):
+        m._get_slice(1.5)
+
+
+def test_solve_fails_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from xmca_b200 import MCA
+    from xmca_b200._lib import XmcaLibraryError
+    m = MCA(np.random.default_rng(0).standard_normal((30, 5)))
+    with pytest.raises(XmcaLibraryError):
+        m.solve()
+
+
+def test_rule_n_partition_covers_all_runs():
+    from xmca_b200.rule_n import partition
+    for n, w in [(10, 1), (10, 3), (1000, 8), (3, 8)]:
+        got = [i for r in range(w) for i in partition(n, w, r)]
+        assert got == list(range(n))
+        sizes = [len(partition(n, w, r)) for r in range(w)]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _rule_n_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from xmca_b200 import MCA
+    from xmca_b200.rule_n import rule_n
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    rng = np.random.default_rng(3)
+    m = MCA(rng.standard_normal((40, 12)), rng.standard_normal((40, 9)))
+    # stand-in for a solved model: only the fields rule_n reads
+    m._analysis["rank"] = 9
+    m._norm = {"left": np.sqrt(np.linspace(9, 1, 9)), "right": np.sqrt(np.linspace(9, 1, 9))}
+    m._var_idx = np.arange(9)
+    m._singular_values = np.linspace(9, 1, 9)
+
+    def stub(T, n_vars, run, seed, cplx, rot, n_rot, power):          # deterministic in the run index
+        if run == 5:
+            return None                                               # a dropped (non-converged) run
+        r = np.random.default_rng(1000 * seed + run)
+        return np.sort(r.random(9))[::-1] + run
+
+    got = rule_n(m, 11, n_modes=4, seed=17, _surrogate_fn=stub)
+    np.save(os.path.join(out_dir, "r%d.npy" % rank), got)
+    dist.destroy_process_group()
+
+
+def test_rule_n_two_rank_gloo_matches_single_process(tmp_path):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_rule_n_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "r0.npy"), np.load(tmp_path / "r1.npy")
+    np.testing.assert_array_equal(r0, r1)
+    assert r0.shape == (4, 10)                                        # 11 runs, one dropped
+    # single-process result with the same stub
+    cols = []
+    ref_sum = np.linspace(9, 1, 9).sum()
+    for run in range(11):
+        if run == 5:
+            continue
+        s = np.sort(np.random.default_rng(1000 * 17 + run).random(9))[::-1] + run
+        cols.append(s * ref_sum / s.sum())
+    np.testing.assert_allclose(r0, np.array(cols).T[:4], rtol=1e-14)

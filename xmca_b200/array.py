@@ -1,0 +1,565 @@
+"""``MCA`` -- drop-in for ``xmca.array.MCA`` on the solve / rotate / getters /
+``rule_n`` hot path, computed by the B200 engine (``libxmca_b200.so``).
+
+Host side (this file) mirrors the reference's constructor, metadata and NaN
+handling (xmca/array.py:39-143, :145-240) and its getter semantics
+(:605-779, :898-1063); every matrix product, SVD and rotation iteration runs
+on the GPU through the C ABI.  There is no CPU fallback: without the shared
+library or a CUDA device ``solve`` raises.
+
+Out of scope for this engine: ``bootstrapping``,
+``predict``, homogeneous/heterogeneous patterns, plotting, save/load and the
+Hilbert ``extend`` options; they raise ``NotImplementedError``.
+"""
+from __future__ import annotations
+
+import cmath
+import warnings
+
+import numpy as np
+import yaml
+
+from . import __version__
+from . import _lib as L
+from . import device as D
+from . import engine as E
+
+_SIDES = ("left", "right")
+
+
+class MCA:
+    """Maximum Covariance Analysis / PCA of one or two ``numpy.ndarray`` fields
+    (time on axis 0).  Same call surface as ``xmca.array.MCA`` (array.py:30)."""
+
+    # ------------------------------------------------------------------ ctor
+    def __init__(self, *fields):
+        if len(fields) > 2:
+            raise ValueError("Too many fields. Pass 1 or 2 fields.")
+        if len(fields) == 2 and fields[0].shape[0] != fields[1].shape[0]:
+            raise ValueError("Time dimensions of given fields are different. "
+                             "Time series should have same time lengths.")
+        if not all(isinstance(f, np.ndarray) for f in fields):
+            raise TypeError("One or more fields are not `numpy.ndarray`. "
+                            "Please provide `numpy.ndarray` only.")
+        for f in fields:      # a NaN time step = a row that is NaN everywhere (tools/array.py:65-73)
+            if np.isnan(f).all(axis=tuple(range(1, f.ndim))).any():
+                raise ValueError("One or more fields contain NaN time steps. "
+                                 "Please remove these prior to analysis.")
+
+        self._keys = list(_SIDES[:max(len(fields), 1)]) if len(fields) else list(_SIDES)
+        if len(fields) == 1:
+            self._keys = ["left"]
+        self._fields = {}
+        self._shape = {}
+        self._field_names = {}
+        self._field_means = {}
+        self._field_stds = {}
+        self._fields_spatial_shape = {}
+        self._n_variables = {}
+        self._no_nan_index = {}
+        self._n_observations = {}
+        for k, f in zip(self._keys, fields):
+            self._shape[k] = f.shape
+            self._n_observations[k] = f.shape[0]
+            self._fields_spatial_shape[k] = f.shape[1:]
+            self._n_variables[k] = int(np.prod(f.shape[1:]))      # incl. NaN columns (array.py:196)
+            self._field_names[k] = k
+            flat = f.reshape(f.shape[0], self._n_variables[k])
+            keep = ~np.isnan(flat).any(axis=0)
+            self._no_nan_index[k] = keep
+            flat = flat[:, keep]
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore", category=RuntimeWarning)
+                self._field_means[k] = flat.mean(axis=0)
+                self._field_stds[k] = flat.std(axis=0)
+                self._fields[k] = flat - flat.mean(axis=0)        # dtype preserved (array.py:199-207)
+
+        self._analysis = {
+            "version": __version__,
+            "is_bivariate": len(self._fields) > 1,
+            "is_normalized": False,
+            "is_coslat_corrected": False,
+            "method": "pca",
+            "is_complex": False,
+            "extend": False,
+            "theta_period": 365,
+            "is_rotated": False,
+            "n_rot": 0,
+            "power": 0,
+            "is_truncated": False,
+            "is_truncated_at": 0,
+            "rank": 0,
+            "total_covariance": 0.0,
+            "total_squared_covariance": 0.0,
+        }
+        self._analysis["method"] = self._get_method_id()
+        self._dev = {}            # device copies of the (possibly complex-embedded) fields
+        self._dV = None           # device singular vectors
+        self._solve_info = {}
+
+    # --------------------------------------------------------------- helpers
+    def _get_method_id(self):
+        return "mca" if self._analysis["is_bivariate"] else "pca"
+
+    def set_field_names(self, left="left", right="right"):
+        self._field_names["left"] = left
+        self._field_names["right"] = right
+
+    def _get_slice(self, n):
+        """int -> modes [0, n); slice(a, b) -> 1-based inclusive (array.py:145-173)."""
+        rank = self._analysis["rank"]
+        if n is None:
+            return slice(0, rank)
+        if np.issubdtype(type(n), np.integer):
+            return slice(0, n)
+        if isinstance(n, slice):
+            lo = max(0, n.start - 1) if isinstance(n.start, (int, np.integer)) else 0
+            hi = min(n.stop, rank) if isinstance(n.stop, (int, np.integer)) else rank
+            return slice(lo, hi, n.step)
+        raise ValueError("Invalid type {:}. Must be either int or slice.".format(type(n)))
+
+    def apply_weights(self, left=None, right=None):
+        w = {"left": 1 if left is None else left, "right": 1 if right is None else right}
+        for k in self._keys:
+            self._fields[k] = self._fields[k] * w[k]
+        self._dev = {}
+
+    def normalize(self):
+        for k in self._keys:
+            self._fields[k] = self._fields[k] / self._field_stds[k]
+        self._analysis["is_normalized"] = True
+        self._analysis["is_coslat_corrected"] = False
+        self._analysis["method"] = self._get_method_id()
+        self._dev = {}
+
+    def _get_X(self, original_scale=False, real=False):
+        X = {k: f.copy() for k, f in self._fields.items()}
+        if real:
+            X = {k: x.real for k, x in X.items()}
+        if original_scale:
+            for k in X:
+                if self._analysis["is_normalized"]:
+                    X[k] *= self._field_stds[k]
+                X[k] += self._field_means[k]
+        return X
+
+    def fields(self, original_scale=False):
+        n_obs = self._n_observations["left"]
+        out = {}
+        for k, X in self._get_X(original_scale=original_scale).items():
+            full = np.zeros([n_obs, self._n_variables[k]], dtype=X.dtype) * np.nan
+            full[:, self._no_nan_index[k]] = X
+            out[k] = full.reshape((n_obs,) + self._fields_spatial_shape[k])
+        return out
+
+    # ------------------------------------------------------------ device I/O
+    def _device_fields(self):
+        """Upload (once) the centred fields; complex fields as real embeddings."""
+        if not self._dev:
+            for k in self._keys:
+                f = self._fields[k]
+                if np.iscomplexobj(f):
+                    f = E.embed_complex_field(f)
+                self._dev[k] = D.to_device(f)
+        return self._dev
+
+    @staticmethod
+    def _analytic(x):
+        """Analytic signal along time = scipy.signal.hilbert(x, axis=0) (array.py:464)."""
+        n = x.shape[0]
+        w = np.zeros(n)
+        w[0] = 1.0
+        if n % 2 == 0:
+            w[n // 2] = 1.0
+            w[1:n // 2] = 2.0
+        else:
+            w[1:(n + 1) // 2] = 2.0
+        z = np.fft.ifft(np.fft.fft(x.astype(np.float64), axis=0) * w[:, None], axis=0)
+        return z.astype(np.complex64 if x.dtype == np.float32 else np.complex128)
+
+    # ----------------------------------------------------------------- solve
+    def solve(self, complexify=False, extend=False, period=1):
+        """Solve the MCA/PCA problem on the GPU (semantics of array.py:509-603)."""
+        if len(self._fields) == 0 or any(np.isnan(f).all() for f in self._fields.values()):
+            raise RuntimeError("Fields are empty. Did you forget to load data?")
+        if extend:
+            raise NotImplementedError("Hilbert extension (extend='exp'|'theta') is outside the B200 "
+                                      "engine's scope (SURVEY.md section 2a #11).")
+        self._analysis["is_complex"] = bool(complexify)
+        self._analysis["extend"] = extend
+        self._analysis["theta_period"] = period
+
+        if complexify:          # array.py:455-464 (real part re-taken first)
+            self._fields = {k: self._analytic(np.real(f)) for k, f in self._fields.items()}
+            self._dev = {}
+        dev = self._device_fields()
+        A = dev["left"]
+        B = dev.get("right")
+        real_dtype = np.float32 if self._fields["left"].real.dtype == np.float32 else np.float64
+        try:
+            if complexify:
+                sigma, Vc, res = E.solve_complex(A, B)
+                self._dV = {k: ("complex", v) for k, v in Vc.items()}
+            else:
+                res = E.solve_real(A, B)
+                sigma = res.sigma
+                self._dV = {k: ("real", v) for k, v in res.V.items()}
+        except np.linalg.LinAlgError:
+            raise np.linalg.LinAlgError("SVD failed. NaN entries may be the problem.")
+        self._solve_info = {"route": res.route, "sweeps": res.sweeps}
+        self._Vhost = {}
+
+        sv = sigma.astype(real_dtype)                      # singular values keep the field dtype
+        self._singular_values = sv
+        self._variance = sv
+        self._var_idx = np.argsort(sv)[::-1]
+        self._norm = {k: np.sqrt(sv) for k in self._keys}
+        n = len(sv)
+        self._analysis["total_covariance"] = sv.sum()
+        self._analysis["total_squared_covariance"] = (sv ** 2).sum()
+        self._analysis["rank"] = n
+        self._analysis["is_rotated"] = False
+        self._analysis["n_rot"] = n
+        self._analysis["power"] = 0
+        self._rotation_matrix = np.eye(n)
+        self._correlation_matrix = np.eye(n)
+        self._analysis["is_truncated_at"] = n
+
+    # --------------------------------------------------------------- getters
+    def _require_solved(self, what):
+        if not hasattr(self, "_singular_values"):
+            raise RuntimeError("Cannot retrieve {}. Please call the method `solve` first.".format(what))
+
+    def _get_svals(self, n=None):
+        self._require_solved("singular values")
+        return self._singular_values[self._get_slice(n)]
+
+    def _complex_dtype(self):
+        return np.complex64 if self._singular_values.dtype == np.float32 else np.complex128
+
+    def _V_device_cols(self, k, m):
+        """First m unrotated singular vectors of field k as device tensors:
+        real -> (S x m); complex -> ((S x m) re, (S x m) im)."""
+        kind, v = self._dV[k]
+        if kind == "real":
+            return v[:, :m]
+        return (v[0][:, :m], v[1][:, :m])
+
+    def _V_host(self, k, m):
+        """Unrotated V[k][:, :m] on the host (downloaded once, cached)."""
+        cached = self._Vhost.get(k)
+        if cached is None or cached.shape[1] < m:
+            kind, v = self._dV[k]
+            if kind == "real":
+                part = D.to_host(v[:, :m].contiguous())
+            else:
+                part = (D.to_host(v[0][:, :m].contiguous())
+                        + 1j * D.to_host(v[1][:, :m].contiguous())).astype(self._complex_dtype())
+            self._Vhost[k] = cached = part
+        return cached[:, :m]
+
+    @property
+    def _V(self):
+        self._require_solved("singular vectors")
+        return {k: self._V_host(k, self._singular_values.size) for k in self._keys}
+
+    def _get_V(self, n=None, rotated=True):
+        self._require_solved("singular vectors")
+        if rotated:
+            top = self._analysis["n_rot"]
+        else:
+            top = n.stop if isinstance(n, slice) else n
+        keep = self._get_slice(n)
+        nsv = self._singular_values.size
+        top = nsv if top is None else min(top, nsv)
+        out = {}
+        for k in self._keys:
+            if rotated and self._analysis["is_rotated"]:
+                v = self._rotated_loadings_host(k)[:, self._var_idx][:, keep]   # S x n_rot, / norm, fp64
+            elif rotated:
+                # unrotated model: R = I (array.py:636-642 multiplies by eye(rank)); only the
+                # reordering and the promotion to fp64 remain -- download just the columns asked for
+                cols = self._var_idx[:top][keep]
+                need = int(cols.max()) + 1 if cols.size else 0
+                v = self._V_host(k, need)[:, cols]
+                v = v.astype(np.complex128 if np.iscomplexobj(v) else np.float64)
+            else:
+                v = self._V_host(k, top)[:, keep]
+            out[k] = v
+        return out
+
+    def _rotated_loadings_host(self, k):
+        """V sqrt(sigma) R / norm for field k (array.py:634-640), from the device
+        product L_rot computed in rotate()."""
+        return self._rot_eofs[k]
+
+    def _get_U(self, n=None, rotated=True):
+        self._require_solved("principal components")
+        if rotated:
+            top = self._analysis["n_rot"]
+        else:
+            top = n.stop if isinstance(n, slice) else n
+        nsv = self._singular_values.size
+        top = nsv if top is None else min(top, nsv)
+        keep = self._get_slice(n)
+        dev = self._device_fields()
+        root = np.sqrt(self._singular_values[:top].astype(np.float64))
+        inv_root = D.to_device(1.0 / root)
+        is_rot = rotated and self._analysis["is_rotated"]
+        Rit = self.rotation_matrix(inverse_transpose=True) if is_rot else None
+        out = {}
+        for k in self._keys:
+            kind, _ = self._dV[k]
+            X = dev[k]
+            if kind == "real":
+                Vd = self._V_device_cols(k, top)
+                Ud = D.matmul(X, Vd)                                        # T x top (array.py:667)
+                Ud = D.scale_copy(Ud, col_scale=inv_root)
+                if is_rot:
+                    Ud = D.matmul(Ud, D.to_device(np.ascontiguousarray(Rit)))
+                u = D.to_host(Ud)
+                if not rotated:
+                    u = u.astype(self._fields[k].dtype)
+            else:
+                vr, vi = self._V_device_cols(k, top)
+                t = D.torch()
+                Vst = t.cat([vr, vi], dim=0).contiguous()                   # 2S x top  ([x; y] embedding)
+                Ust = D.matmul(X, Vst)                                      # 2T x top
+                Ust = D.scale_copy(Ust, col_scale=inv_root)
+                uh = D.to_host(Ust)
+                T = uh.shape[0] // 2
+                u = uh[:T] + 1j * uh[T:]
+                if is_rot:
+                    u = u @ Rit
+                if not rotated:
+                    u = u.astype(self._fields[k].dtype)
+            if rotated:
+                u = u[:, self._var_idx]
+            out[k] = u[:, keep]
+        return out
+
+    def _get_norm(self, n=None, sorted=True):
+        self._require_solved("field norms")
+        norm = self._norm
+        if sorted:
+            norm = {k: v[self._var_idx] for k, v in norm.items()}
+        sl = self._get_slice(n)
+        return {k: v[sl] for k, v in norm.items()}
+
+    def _get_variance(self, n=None, sorted=True):
+        nrm = self._get_norm(n=n, sorted=sorted)
+        if self._analysis["is_bivariate"]:
+            return nrm["left"] * nrm["right"]
+        return nrm["left"] ** 2
+
+    @staticmethod
+    def _apply_scaling(arr, scaling, norm_k, axes):
+        if scaling == "None":
+            return arr
+        if scaling == "eigen":
+            return arr * norm_k
+        if scaling == "max":
+            return arr / np.nanmax(abs(arr.real), axis=axes)
+        if scaling == "std":
+            return arr / np.nanstd(arr.real, axis=axes)
+        raise ValueError("The scaling option {:} is not valid. Please choose one of the "
+                         "following: None, eigen, std, max".format(scaling))
+
+    def _get_eofs(self, n=None, scaling="None", phase_shift=0, rotated=True):
+        V = self._get_V(n, rotated=rotated)
+        out = {}
+        for k in self._keys:
+            nm = V[k].shape[1]
+            full = np.zeros([self._n_variables[k], nm], dtype=V[k].dtype) * np.nan
+            full[self._no_nan_index[k], :] = V[k]
+            full = full.reshape(self._fields_spatial_shape[k] + (nm,))
+            if self._analysis["is_complex"]:
+                full = full * cmath.rect(1, phase_shift)
+            norm_k = self._get_norm(V["left"].shape[1], sorted=True)[k] if scaling == "eigen" else None
+            out[k] = self._apply_scaling(full, scaling, norm_k, tuple(range(full.ndim - 1)))
+        return out
+
+    def _get_pcs(self, n=None, scaling="None", phase_shift=0, rotated=True):
+        U = self._get_U(n, rotated=rotated)
+        out = {}
+        for k in self._keys:
+            u = U[k]
+            if self._analysis["is_complex"]:
+                u = u * cmath.rect(1, phase_shift)
+            norm_k = self._get_norm(n, sorted=True)[k] if scaling == "eigen" else None
+            out[k] = self._apply_scaling(u, scaling, norm_k, 0)
+        return out
+
+    # --------------------------------------------------------------- rotate
+    def rotate(self, n_rot, power=1, tol=1e-8):
+        """Varimax / Promax rotation of the first ``n_rot`` loaded EOFs on the
+        GPU (semantics of array.py:781-844, tools/rotation.py)."""
+        if n_rot < 2:
+            raise ValueError("`n_rot` must be > 1")
+        if power < 1:
+            raise ValueError("`power` must be >=1")
+        self._require_solved("singular values")
+        if self._analysis["is_complex"]:
+            raise NotImplementedError("complex Varimax/Promax is not implemented in the B200 engine yet")
+        if n_rot > 64:
+            raise ValueError("the fused rotation kernel supports n_rot <= 64")
+        sv = self._get_svals(n_rot)
+        n_rot = sv.size
+        root = D.to_device(np.sqrt(sv.astype(np.float64)))
+        t = D.torch()
+        parts = [D.scale_copy(self._V_device_cols(k, n_rot), col_scale=root) for k in self._keys]
+        s_left = parts[0].shape[0]
+        Ld = t.cat(parts, dim=0).contiguous() if len(parts) > 1 else parts[0]     # (S1'+S2') x n_rot
+        try:
+            Lrot, R, Phi, iters = E.promax(Ld, power, max_iter=1000, tol=tol)
+        except L.NotConvergedError:
+            raise RuntimeError("Rotation process did not converge. Try decreasing the tolerance. "
+                               "Invalid NaN entries also might be a problem.")
+        n_all = Lrot.shape[0]
+        nl = np.sqrt(D.to_host(D.col_sumsq(Lrot, 0, s_left)))                      # array.py:826-830
+        nr = np.sqrt(D.to_host(D.col_sumsq(Lrot, s_left, n_all))) if self._analysis["is_bivariate"] else nl
+        self._norm = {"left": nl, "right": nr} if self._analysis["is_bivariate"] else {"left": nl}
+        self._variance = nl * nr
+        self._var_idx = np.argsort(self._variance)[::-1]
+        self._rotation_matrix = R
+        self._correlation_matrix = Phi
+        self._analysis["is_rotated"] = True
+        self._analysis["n_rot"] = n_rot
+        self._analysis["power"] = power
+        self._solve_info["varimax_iterations"] = iters
+        # rotated EOFs = L_rot / norm (array.py:640): one scaled copy per field, kept on the host
+        self._rot_eofs = {}
+        bounds = {"left": (0, s_left), "right": (s_left, n_all)}
+        for k in self._keys:
+            lo, hi = bounds[k]
+            inv = D.to_device(1.0 / self._norm[k])
+            self._rot_eofs[k] = D.to_host(D.scale_copy(Lrot[lo:hi], col_scale=inv))
+
+    def rotation_matrix(self, inverse_transpose=False):
+        try:
+            R = self._rotation_matrix
+        except AttributeError:
+            R = np.eye(len(self.singular_values()))
+        if inverse_transpose and self._analysis["power"] > 1:
+            R = np.linalg.pinv(R).conjugate().T
+        return R
+
+    def correlation_matrix(self):
+        try:
+            idx = self._var_idx
+            return self._correlation_matrix[idx, :][:, idx]
+        except AttributeError:
+            return np.eye(len(self.singular_values()))
+
+    # ----------------------------------------------------------- public API
+    def singular_values(self, n=None):
+        return self._get_svals(n)
+
+    def norm(self, n=None, sorted=True):
+        return self._get_norm(n=n, sorted=sorted)
+
+    def variance(self, n=None, sorted=True):
+        return self._get_variance(n=n, sorted=sorted)
+
+    def scf(self, n=None):
+        self._require_solved("squared covariance fraction")
+        var = self._variance[self._var_idx][:n]                  # NB: plain [:n] (array.py:982)
+        return var ** 2 / self._analysis["total_squared_covariance"] * 100
+
+    def explained_variance(self, n=None):
+        return self._get_variance(n=n, sorted=True) / self._analysis["total_covariance"] * 100
+
+    def pcs(self, n=None, scaling="None", phase_shift=0, rotated=True):
+        return self._get_pcs(n, scaling, phase_shift, rotated)
+
+    def eofs(self, n=None, scaling="None", phase_shift=0, rotated=True):
+        return self._get_eofs(n, scaling, phase_shift, rotated)
+
+    def spatial_amplitude(self, n=None, scaling="None", rotated=True):
+        e = self.eofs(n, scaling="None", rotated=rotated)
+        amp = {k: np.sqrt(v * v.conjugate()).real for k, v in e.items()}
+        if scaling == "max":
+            amp = {k: a / np.nanmax(a, axis=tuple(range(a.ndim - 1))) for k, a in amp.items()}
+        return amp
+
+    def spatial_phase(self, n=None, phase_shift=0, rotated=True):
+        e = self.eofs(n, phase_shift=phase_shift, rotated=rotated)
+        return {k: np.arctan2(v.imag, v.real).real for k, v in e.items()}
+
+    def temporal_amplitude(self, n=None, scaling="None", rotated=True):
+        p = self.pcs(n, scaling="None", rotated=rotated)
+        amp = {k: np.sqrt(v * v.conjugate()).real for k, v in p.items()}
+        if scaling == "max":
+            amp = {k: a / np.nanmax(a, axis=0) for k, a in amp.items()}
+        return amp
+
+    def temporal_phase(self, n=None, phase_shift=0, rotated=True):
+        p = self.pcs(n, phase_shift=phase_shift, rotated=rotated)
+        return {k: np.arctan2(v.imag, v.real).real for k, v in p.items()}
+
+    def truncate(self, n):
+        """array.py:1602-1627."""
+        if self._analysis["is_rotated"] and n < self._analysis["n_rot"]:
+            raise ValueError("Cannot truncte rotated solution. Please ensure `n` > `n_rot`")
+        if n < self._singular_values.size:
+            self._singular_values = self._singular_values[:n]
+            trimmed = {}
+            for k, (kind, v) in self._dV.items():
+                trimmed[k] = (kind, v[:, :n] if kind == "real" else (v[0][:, :n], v[1][:, :n]))
+            self._dV = trimmed
+            self._Vhost = {k: v[:, :n] for k, v in self._Vhost.items()}
+            self._analysis["is_truncated"] = True
+            self._analysis["is_truncated_at"] = n
+
+    def rule_north(self, n=None):
+        """array.py:1773-1811."""
+        sv = self._get_svals(n)
+        err = sv * np.sqrt(2.0 / self._n_observations["left"])
+        if self._analysis["is_complex"]:
+            err = err * np.sqrt(2)
+        return err
+
+    def summary(self):
+        """array.py:2014-2024."""
+        print(yaml.dump({k: (v.item() if hasattr(v, "item") else v) for k, v in self._analysis.items()},
+                        sort_keys=False))
+
+    # --------------------------------------------------------------- rule N
+    def rule_n(self, n_runs, n_modes=None, seed=None, group=None):
+        """Rule N (Overland & Preisendorfer 1982), semantics of array.py:1716-1771,
+        with the surrogate loop sharded over the ranks of ``group``
+        (``torch.distributed``; ``None`` = single GPU).  See ``xmca_b200.rule_n``."""
+        from . import rule_n as RN
+        return RN.rule_n(self, n_runs, n_modes=n_modes, seed=seed, group=group)
+
+    # ---------------------------------------------------------- out of scope
+    def _out_of_scope(self, name):
+        raise NotImplementedError("`{}` is outside the solve/rotate/rule_n hot path this engine "
+                                  "accelerates (SURVEY.md section 8f).".format(name))
+
+    def bootstrapping(self, *a, **k):
+        self._out_of_scope("bootstrapping")
+
+    def predict(self, *a, **k):
+        self._out_of_scope("predict")
+
+    def homogeneous_patterns(self, *a, **k):
+        self._out_of_scope("homogeneous_patterns")
+
+    def heterogeneous_patterns(self, *a, **k):
+        self._out_of_scope("heterogeneous_patterns")
+
+    def reconstructed_fields(self, *a, **k):
+        self._out_of_scope("reconstructed_fields")
+
+    def plot(self, *a, **k):
+        self._out_of_scope("plot")
+
+    def save_plot(self, *a, **k):
+        self._out_of_scope("save_plot")
+
+    def save_analysis(self, *a, **k):
+        self._out_of_scope("save_analysis")
+
+    def load_analysis(self, *a, **k):
+        self._out_of_scope("load_analysis")

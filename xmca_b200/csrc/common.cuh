@@ -1,0 +1,76 @@
+// Shared helpers for libxmca_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <atomic>
+#include "../../include/xmca_b200.h"
+
+namespace xmca {
+
+extern thread_local std::string g_last_error;
+extern std::atomic<long long> g_launches;
+
+inline int fail(int code, const char* what, const char* file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof buf, "%s (%s:%d)", what, file, line);
+  g_last_error = buf;
+  return code;
+}
+
+#define XMCA_REQUIRE(cond, msg)                                                  \
+  do {                                                                           \
+    if (!(cond)) return ::xmca::fail(XMCA_BAD_ARG, msg, __FILE__, __LINE__);     \
+  } while (0)
+
+#define XMCA_CUDA(expr)                                                          \
+  do {                                                                           \
+    cudaError_t _e = (expr);                                                     \
+    if (_e != cudaSuccess)                                                       \
+      return ::xmca::fail(XMCA_CUDA_ERROR, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+// count + check a kernel launch
+#define XMCA_LAUNCHED()                                                          \
+  do {                                                                           \
+    ::xmca::g_launches.fetch_add(1, std::memory_order_relaxed);                  \
+    XMCA_CUDA(cudaGetLastError());                                               \
+  } while (0)
+
+inline int dtype_size(int dt) { return dt == XMCA_F64 ? 8 : 4; }
+inline bool dtype_ok(int dt) { return dt == XMCA_F32 || dt == XMCA_F64; }
+
+// runtime-typed scalar access (dtype is warp-uniform, so the branch is free)
+__device__ __forceinline__ double load_as_double(const void* p, int dt, int64_t i) {
+  return dt == XMCA_F64 ? reinterpret_cast<const double*>(p)[i]
+                        : (double)reinterpret_cast<const float*>(p)[i];
+}
+__device__ __forceinline__ void store_from_double(void* p, int dt, int64_t i, double v) {
+  if (dt == XMCA_F64) reinterpret_cast<double*>(p)[i] = v;
+  else reinterpret_cast<float*>(p)[i] = (float)v;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+inline int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace xmca

@@ -1,0 +1,203 @@
+// General dense product on the FP64 / FP32 CUDA cores.
+//
+// Used wherever the reference calls `@` on operands that must keep fp64
+// accuracy (the T x T "kernel" of array.py:556-566, the back-projection of
+// array.py:584, the Promax fit of rotation.py:128-147, fp64 fields of config 5)
+// or whose shape is too skinny for the tensor-core tile (projections onto a few
+// modes, array.py:640/:667).  tcgen05 has no fp64 kind, so this is the fp64
+// path of the engine; the fp32 cross-covariance goes through gemm_tc.cu.
+//
+// Tile 128 x 128 x 16, 256 threads, 8 x 8 register micro-tile, register
+// prefetch of the next k-slab, optional split-K with a deterministic second
+// pass (no atomics -> bit-reproducible).
+#include "common.cuh"
+
+namespace xmca {
+
+constexpr int BM = 128, BN = 128, BK = 16, PAD = 1, NT = 256;
+
+template <typename T>
+__device__ __forceinline__ T ld_elem(const void* p, int dt, int64_t i) {
+  return dt == XMCA_F64 ? (T) reinterpret_cast<const double*>(p)[i]
+                        : (T) reinterpret_cast<const float*>(p)[i];
+}
+
+// Loads one BM x BK (or BN x BK) operand slab into registers.
+// KMAJOR: operand stored [mn][k] (k contiguous); else stored [k][mn].
+template <typename T, bool KMAJOR>
+__device__ __forceinline__ void load_slab(T (&r)[8], const void* p, int dt, int64_t ld,
+                                          int64_t mn0, int64_t mn_end, int64_t k0, int64_t k_end,
+                                          int tid) {
+  if (KMAJOR) {
+    const int kk = tid & 15, m = tid >> 4;       // 16 consecutive k per row: one 128B line (fp64)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int64_t mm = mn0 + m + 16 * i, k = k0 + kk;
+      r[i] = (mm < mn_end && k < k_end) ? ld_elem<T>(p, dt, mm * ld + k) : T(0);
+    }
+  } else {
+    const int m = tid & 127, kk = tid >> 7;      // 128 consecutive mn per k row
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int64_t mm = mn0 + m, k = k0 + kk + 2 * i;
+      r[i] = (mm < mn_end && k < k_end) ? ld_elem<T>(p, dt, k * ld + mm) : T(0);
+    }
+  }
+}
+
+template <typename T, bool KMAJOR>
+__device__ __forceinline__ void store_slab(const T (&r)[8], T (*s)[BM + PAD], int tid) {
+  if (KMAJOR) {
+    const int kk = tid & 15, m = tid >> 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[kk][m + 16 * i] = r[i];
+  } else {
+    const int m = tid & 127, kk = tid >> 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[kk + 2 * i][m] = r[i];
+  }
+}
+
+template <typename T, bool AK, bool BKM>
+__global__ void __launch_bounds__(NT)
+gemm_simt_kernel(int64_t M, int64_t N, int64_t K, double alpha,
+                 const void* __restrict__ A, int adt, int64_t lda,
+                 const void* __restrict__ B, int bdt, int64_t ldb,
+                 void* __restrict__ D, int ddt, int64_t ldd, int accumulate,
+                 T* __restrict__ partial, int64_t k_chunk) {
+  __shared__ T As[BK][BM + PAD];
+  __shared__ T Bs[BK][BN + PAD];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+  const int64_t kb = (int64_t)blockIdx.z * k_chunk;
+  const int64_t ke = min(K, kb + k_chunk);
+
+  T acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = T(0);
+
+  T ra[8], rb[8];
+  if (kb < ke) {
+    load_slab<T, AK>(ra, A, adt, lda, m0, M, kb, ke, tid);
+    load_slab<T, BKM>(rb, B, bdt, ldb, n0, N, kb, ke, tid);
+  }
+  for (int64_t k0 = kb; k0 < ke; k0 += BK) {
+    store_slab<T, AK>(ra, As, tid);
+    store_slab<T, BKM>(rb, Bs, tid);
+    __syncthreads();
+    if (k0 + BK < ke) {
+      load_slab<T, AK>(ra, A, adt, lda, m0, M, k0 + BK, ke, tid);
+      load_slab<T, BKM>(rb, B, bdt, ldb, n0, N, k0 + BK, ke, tid);
+    }
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      T a[8], b[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {   // interleaved micro-tile: conflict-free LDS, coalesced stores
+        a[i] = As[kk][ty + 16 * i];
+        b[i] = Bs[kk][tx + 16 * i];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t m = m0 + ty + 16 * i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int64_t n = n0 + tx + 16 * j;
+      if (n >= N) continue;
+      if (partial) {
+        partial[((int64_t)blockIdx.z * M + m) * N + n] = acc[i][j];
+      } else {
+        double v = alpha * (double)acc[i][j];
+        if (accumulate) v += load_as_double(D, ddt, m * ldd + n);
+        store_from_double(D, ddt, m * ldd + n, v);
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void splitk_reduce_kernel(int64_t M, int64_t N, int split, double alpha,
+                                     const T* __restrict__ partial,
+                                     void* __restrict__ D, int ddt, int64_t ldd, int accumulate) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * N) return;
+  double s = 0.0;
+  for (int z = 0; z < split; ++z) s += (double)partial[(int64_t)z * M * N + idx];
+  int64_t m = idx / N, n = idx % N;
+  double v = alpha * s;
+  if (accumulate) v += load_as_double(D, ddt, m * ldd + n);
+  store_from_double(D, ddt, m * ldd + n, v);
+}
+
+template <typename T>
+static int launch_gemm(int ak, int bk, int64_t M, int64_t N, int64_t K, double alpha,
+                       const void* A, int adt, int64_t lda, const void* B, int bdt, int64_t ldb,
+                       void* D, int ddt, int64_t ldd, int accumulate, int split,
+                       void* ws, cudaStream_t st) {
+  int64_t k_chunk = ((K + split - 1) / split + BK - 1) / BK * BK;
+  if (k_chunk < BK) k_chunk = BK;
+  dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)split);
+  T* partial = split > 1 ? reinterpret_cast<T*>(ws) : nullptr;
+#define GO(AKF, BKF)                                                                     \
+  gemm_simt_kernel<T, AKF, BKF><<<grid, NT, 0, st>>>(M, N, K, alpha, A, adt, lda, B, bdt, \
+                                                     ldb, D, ddt, ldd, accumulate, partial, k_chunk)
+  if (ak && bk) GO(true, true);
+  else if (ak && !bk) GO(true, false);
+  else if (!ak && bk) GO(false, true);
+  else GO(false, false);
+#undef GO
+  XMCA_LAUNCHED();
+  if (split > 1) {
+    int64_t tot = M * N;
+    splitk_reduce_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
+        M, N, split, alpha, partial, D, ddt, ldd, accumulate);
+    XMCA_LAUNCHED();
+  }
+  return XMCA_OK;
+}
+
+}  // namespace xmca
+
+using namespace xmca;
+
+extern "C" size_t xmca_gemm_workspace_bytes(int64_t M, int64_t N, int split_k, int acc_dtype) {
+  if (split_k <= 1) return 0;
+  return (size_t)M * (size_t)N * (size_t)split_k * (size_t)dtype_size(acc_dtype);
+}
+
+extern "C" int xmca_gemm(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K, double alpha,
+                         const void* d_A, int a_dtype, int64_t lda,
+                         const void* d_B, int b_dtype, int64_t ldb,
+                         void* d_D, int d_dtype, int64_t ldd, int accumulate,
+                         int acc_dtype, int split_k, void* d_workspace, size_t workspace_bytes,
+                         void* stream) {
+  XMCA_REQUIRE(M > 0 && N > 0 && K > 0, "xmca_gemm: empty problem");
+  XMCA_REQUIRE(d_A && d_B && d_D, "xmca_gemm: null operand");
+  XMCA_REQUIRE(dtype_ok(a_dtype) && dtype_ok(b_dtype) && dtype_ok(d_dtype) && dtype_ok(acc_dtype),
+               "xmca_gemm: bad dtype");
+  XMCA_REQUIRE(lda >= (a_kmajor ? K : M) && ldb >= (b_kmajor ? K : N) && ldd >= N,
+               "xmca_gemm: leading dimension too small");
+  if (split_k < 1) split_k = 1;
+  XMCA_REQUIRE(split_k <= 65535, "xmca_gemm: split_k too large");
+  XMCA_REQUIRE((M + BM - 1) / BM <= 65535, "xmca_gemm: M too large for grid.y");
+  if (split_k > 1)
+    XMCA_REQUIRE(d_workspace && workspace_bytes >= xmca_gemm_workspace_bytes(M, N, split_k, acc_dtype),
+                 "xmca_gemm: workspace too small for split_k");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (acc_dtype == XMCA_F64)
+    return launch_gemm<double>(a_kmajor, b_kmajor, M, N, K, alpha, d_A, a_dtype, lda, d_B, b_dtype,
+                               ldb, d_D, d_dtype, ldd, accumulate, split_k, d_workspace, st);
+  return launch_gemm<float>(a_kmajor, b_kmajor, M, N, K, alpha, d_A, a_dtype, lda, d_B, b_dtype, ldb,
+                            d_D, d_dtype, ldd, accumulate, split_k, d_workspace, st);
+}

@@ -1,0 +1,284 @@
+"""Thin device-level wrappers: torch.cuda tensors in, C-ABI calls out.
+
+torch is used for allocation, H2D/D2H copies and stream handles only; every
+arithmetic operation on device data goes through ``libxmca_b200.so``.
+All matrices are 2-D, row-major, unit inner stride (``stride(0)`` is the
+leading dimension).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+_SM = None
+
+
+def torch():
+    return L._torch()
+
+
+def sm_count() -> int:
+    global _SM
+    if _SM is None:
+        t = torch()
+        _SM = t.cuda.get_device_properties(t.cuda.current_device()).multi_processor_count
+    return _SM
+
+
+def dev():
+    t = torch()
+    return t.device("cuda", t.cuda.current_device())
+
+
+def empty(shape, dtype):
+    return torch().empty(shape, dtype=dtype, device=dev())
+
+
+def zeros(shape, dtype):
+    return torch().zeros(shape, dtype=dtype, device=dev())
+
+
+def f64():
+    return torch().float64
+
+
+def f32():
+    return torch().float32
+
+
+def to_device(a: np.ndarray):
+    t = torch()
+    return t.from_numpy(np.ascontiguousarray(a)).to(dev(), non_blocking=False)
+
+
+def to_host(x) -> np.ndarray:
+    return x.detach().cpu().numpy()
+
+
+def _ld(x):
+    assert x.dim() == 2 and (x.shape[1] == 1 or x.stride(1) == 1), "row-major 2-D tensor expected"
+    return x.stride(0) if x.shape[0] > 1 else max(x.shape[1], x.stride(0))
+
+
+# ---------------------------------------------------------------------- GEMM
+def matmul(A, B, trans_a=False, trans_b=False, alpha=1.0, out=None, out_dtype=None,
+           acc="f64", accumulate=False):
+    """out = alpha * op(A) @ op(B) (+ out).  fp64 accumulation by default."""
+    lib = L.load()
+    t = torch()
+    if trans_a:
+        K, M = A.shape
+    else:
+        M, K = A.shape
+    if trans_b:
+        N, Kb = B.shape
+    else:
+        Kb, N = B.shape
+    if K != Kb:
+        raise ValueError("matmul: inner dimensions differ (%d vs %d)" % (K, Kb))
+    if out is None:
+        if accumulate:
+            raise ValueError("matmul: accumulate needs `out`")
+        out = empty((M, N), out_dtype or t.float64)
+    acc_code = L.F64 if acc == "f64" else L.F32
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    split = 1
+    if tiles < sm_count() and K >= 2048:
+        split = int(min(max(1, (2 * sm_count()) // tiles), K // 512, 64))
+    ws, ws_bytes = None, 0
+    if split > 1:
+        ws_bytes = lib.xmca_gemm_workspace_bytes(M, N, split, acc_code)
+        ws = empty((ws_bytes,), t.uint8)
+    rc = lib.xmca_gemm(0 if trans_a else 1, 1 if trans_b else 0, M, N, K, float(alpha),
+                       L.ptr(A), L.dtype_code(A), _ld(A), L.ptr(B), L.dtype_code(B), _ld(B),
+                       L.ptr(out), L.dtype_code(out), _ld(out), 1 if accumulate else 0,
+                       acc_code, split, L.ptr(ws), ws_bytes, L.stream_ptr())
+    L.check(rc, "xmca_gemm")
+    return out
+
+
+# ----------------------------------------------------- tensor-core covariance
+def _pad4(n):
+    return (n + 3) // 4 * 4
+
+
+def split_tf32(X, transpose=False):
+    """(hi, lo) TF32 planes of X (or X^T), K-major, pitch padded to 4 floats."""
+    lib = L.load()
+    rows, cols = X.shape
+    orow, ocol = (cols, rows) if transpose else (rows, cols)
+    ldo = _pad4(ocol)
+    hi = zeros((orow, ldo), f32()) if ldo != ocol else empty((orow, ldo), f32())
+    lo = zeros((orow, ldo), f32()) if ldo != ocol else empty((orow, ldo), f32())
+    rc = lib.xmca_split_tf32(L.ptr(X), L.dtype_code(X), rows, cols, _ld(X), 1 if transpose else 0,
+                             L.ptr(hi), L.ptr(lo), ldo, L.stream_ptr())
+    L.check(rc, "xmca_split_tf32")
+    return hi, lo, ocol
+
+
+def tc_gemm_nt(Ahi, Alo, Bhi, Blo, K, alpha=1.0, out=None, frob2=None):
+    """out[M,N] = alpha * A[M,K] @ B[N,K]^T on tcgen05 (3xTF32); planes from split_tf32."""
+    lib = L.load()
+    M, N = Ahi.shape[0], Bhi.shape[0]
+    if out is None:
+        out = empty((M, N), f32())
+    rc = lib.xmca_tc_gemm_nt(M, N, K, float(alpha), L.ptr(Ahi), L.ptr(Alo), Ahi.stride(0),
+                             L.ptr(Bhi), L.ptr(Blo), Bhi.stride(0), L.ptr(out), _ld(out),
+                             L.ptr(frob2), L.stream_ptr())
+    L.check(rc, "xmca_tc_gemm_nt")
+    return out
+
+
+def cov_gemm_tc(A, B, alpha):
+    """C = alpha * A^T B (S1 x S2, fp32) from time-major fp32 fields, tensor-core path.
+    Returns (C, frob2 tensor)."""
+    ahi, alo, K = split_tf32(A, transpose=True)
+    if B is A:
+        bhi, blo = ahi, alo
+    else:
+        bhi, blo, _ = split_tf32(B, transpose=True)
+    frob2 = zeros((1,), f64())
+    Cm = tc_gemm_nt(ahi, alo, bhi, blo, K, alpha=alpha, frob2=frob2)
+    return Cm, frob2
+
+
+# -------------------------------------------------------------------- Jacobi
+def jacobi_svd(X, want_v=True, max_sweeps=40, tol=0.0):
+    """One-sided Jacobi on the ROWS of X (n x m, fp64, row-major == column-major m x n).
+
+    Returns (Xr, sigma, Jt, sweeps): Xr[j] = sigma_j * u_j (rows, rotated in a
+    padded copy), sigma (n_pad,), Jt (n_pad x n_pad) with Jt[j] = right singular
+    vector j (None if want_v is False).  Rows are NOT sorted."""
+    lib = L.load()
+    t = torch()
+    n, m = X.shape
+    n_pad = int(lib.xmca_jacobi_padded_cols(n))
+    Xp = zeros((n_pad, m), t.float64)
+    rc = lib.xmca_scale_copy(L.ptr(X), L.dtype_code(X), _ld(X), L.ptr(Xp), L.F64, m, n, m, None, None,
+                             L.stream_ptr())
+    L.check(rc, "xmca_scale_copy")
+    Jt = empty((n_pad, n_pad), t.float64) if want_v else None
+    sigma = empty((n_pad,), t.float64)
+    ws_bytes = lib.xmca_jacobi_workspace_bytes(m, n)
+    ws = empty((ws_bytes,), t.uint8)
+    sweeps, off = C.c_int(0), C.c_double(0.0)
+    rc = lib.xmca_jacobi_svd(m, n, L.ptr(Xp), m, L.ptr(Jt), n_pad, L.ptr(sigma), max_sweeps, float(tol),
+                             C.byref(sweeps), C.byref(off), L.ptr(ws), ws_bytes, L.stream_ptr())
+    L.check(rc, "xmca_jacobi_svd")
+    return Xp, sigma, Jt, sweeps.value
+
+
+# ------------------------------------------------------------- element-wise
+def scale_copy(X, out_dtype=None, col_scale=None, row_scale=None, out=None):
+    lib = L.load()
+    rows, cols = X.shape
+    if out is None:
+        out = empty((rows, cols), out_dtype or X.dtype)
+    rc = lib.xmca_scale_copy(L.ptr(X), L.dtype_code(X), _ld(X), L.ptr(out), L.dtype_code(out), _ld(out),
+                             rows, cols, L.ptr(col_scale), L.ptr(row_scale), L.stream_ptr())
+    L.check(rc, "xmca_scale_copy")
+    return out
+
+
+def transpose(X, out_dtype=None):
+    lib = L.load()
+    rows, cols = X.shape
+    out = empty((cols, rows), out_dtype or X.dtype)
+    rc = lib.xmca_transpose(L.ptr(X), L.dtype_code(X), rows, cols, _ld(X), L.ptr(out), L.dtype_code(out),
+                            _ld(out), L.stream_ptr())
+    L.check(rc, "xmca_transpose")
+    return out
+
+
+def col_sumsq(X, row0=0, row1=None):
+    lib = L.load()
+    rows, cols = X.shape
+    out = empty((cols,), f64())
+    rc = lib.xmca_col_sumsq(L.ptr(X), L.dtype_code(X), _ld(X), row0, rows if row1 is None else row1, cols,
+                            L.ptr(out), L.stream_ptr())
+    L.check(rc, "xmca_col_sumsq")
+    return out
+
+
+def center_columns(X):
+    lib = L.load()
+    rows, cols = X.shape
+    mean = empty((cols,), f64())
+    rc = lib.xmca_center_columns(L.ptr(X), L.dtype_code(X), rows, cols, _ld(X), L.ptr(mean), L.stream_ptr())
+    L.check(rc, "xmca_center_columns")
+    return mean
+
+
+def fill_normal(X, seed, stream_id):
+    lib = L.load()
+    rows, cols = X.shape
+    rc = lib.xmca_fill_normal(L.ptr(X), L.dtype_code(X), rows, cols, _ld(X), int(seed) & (2 ** 64 - 1),
+                              int(stream_id) & (2 ** 64 - 1), L.stream_ptr())
+    L.check(rc, "xmca_fill_normal")
+    return X
+
+
+def gather_rows(X, idx, row_scale=None, out_dtype=None, cols=None):
+    """Y[i] = X[idx[i], :cols] * row_scale[i]; idx is a device int64 tensor."""
+    lib = L.load()
+    n_out = idx.shape[0]
+    cols = X.shape[1] if cols is None else cols
+    out = empty((n_out, cols), out_dtype or X.dtype)
+    rc = lib.xmca_gather_rows(L.ptr(X), L.dtype_code(X), _ld(X), L.ptr(idx), n_out, cols, L.ptr(row_scale),
+                              L.ptr(out), L.dtype_code(out), _ld(out), L.stream_ptr())
+    L.check(rc, "xmca_gather_rows")
+    return out
+
+
+def row_sumsq(X):
+    lib = L.load()
+    rows, cols = X.shape
+    out = empty((rows,), f64())
+    rc = lib.xmca_row_sumsq(L.ptr(X), L.dtype_code(X), _ld(X), rows, cols, L.ptr(out), L.stream_ptr())
+    L.check(rc, "xmca_row_sumsq")
+    return out
+
+
+def col_absmax(X, row_scale=None):
+    lib = L.load()
+    rows, cols = X.shape
+    out = empty((cols,), f64())
+    rc = lib.xmca_col_absmax(L.ptr(X), L.dtype_code(X), _ld(X), rows, cols, L.ptr(row_scale), L.ptr(out),
+                             L.stream_ptr())
+    L.check(rc, "xmca_col_absmax")
+    return out
+
+
+def promax_target(B, row_scale, colmax, power):
+    """X = B * row_scale[:, None]; P = Xn |Xn|^(power-1), Xn = X / colmax (rotation.py:115-124)."""
+    lib = L.load()
+    rows, cols = B.shape
+    X = empty((rows, cols), f64())
+    P = empty((rows, cols), f64())
+    rc = lib.xmca_promax_target(L.ptr(B), _ld(B), rows, cols, L.ptr(row_scale), L.ptr(colmax), float(power),
+                                L.ptr(X), L.ptr(P), cols, L.stream_ptr())
+    L.check(rc, "xmca_promax_target")
+    return X, P
+
+
+# ------------------------------------------------------------------ Varimax
+def varimax(Ld, gamma=1.0, max_iter=1000, tol=1e-8):
+    """Device Varimax (rotation.py:15-78).  Ld: n x p loadings (fp32/fp64).
+    Returns (B fp64 n x p, R fp64 p x p, iterations).  Raises NotConvergedError."""
+    lib = L.load()
+    t = torch()
+    n, p = Ld.shape
+    B = empty((n, p), t.float64)
+    R = empty((p, p), t.float64)
+    out = zeros((4,), t.float64)
+    ws_bytes = lib.xmca_varimax_workspace_bytes(n, p)
+    ws = empty((ws_bytes,), t.uint8)
+    iters = C.c_int(0)
+    rc = lib.xmca_varimax(L.ptr(Ld), L.dtype_code(Ld), n, p, _ld(Ld), float(gamma), int(max_iter), float(tol),
+                          L.ptr(B), p, L.ptr(R), C.byref(iters), L.ptr(out), L.ptr(ws), ws_bytes,
+                          L.stream_ptr())
+    L.check(rc, "xmca_varimax")
+    return B, R, iters.value

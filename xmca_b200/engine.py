@@ -1,0 +1,206 @@
+"""Device pipelines behind ``MCA.solve`` / ``rotate`` / getters / ``rule_n``.
+
+Everything here runs on the GPU through the C ABI (``device.py``); the host
+only sorts the O(rank) singular values and does O(p^3) algebra for p <= 64
+(Promax fit), exactly the pieces SURVEY.md section 2b leaves on the host.
+
+Math (real fields A: T x S1, B: T x S2, centred; dof = T-1; the reference gets
+the same quantities from three LAPACK SVDs, array.py:552-584):
+
+  direct route (min(S1,S2) <= T):  C = A^T B / dof  (S1 x S2) is formed and its
+      SVD C = V_L Sigma V_R^T computed by the blocked one-sided Jacobi kernel.
+  Gram route  (T < min(S1,S2)):   G_A = A A^T = U_A L_A U_A^T, G_B likewise
+      (T x T, fp64).  With F = U sqrt(L):  K = F_A^T F_B / dof = P Sigma Q^T has the
+      singular values of C, and  V_L = A^T (F_B Q) / (Sigma dof),
+      V_R = B^T (F_A P) / (Sigma dof)  -- divisions only by Sigma itself.
+  PCA: C = A^T A / dof (direct) or  sigma = L_A / dof, V = A^T U_A / sqrt(L_A).
+
+Complex fields use the real embedding E(Z) = [[X, -Y], [Y, X]], a ring
+homomorphism (E(Z1 Z2) = E(Z1) E(Z2), E(Z^H) = E(Z)^T); every singular value of
+E(C) is doubled and each singular pair yields one complex vector.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import device as D
+
+
+class SolveResult:
+    """Device-resident result of one solve: sigma (host fp64, descending, length
+    rank) and V[k] (S'_k x rank, field dtype, device)."""
+
+    def __init__(self, sigma, V, route, sweeps, frob2=None):
+        self.sigma = sigma
+        self.V = V
+        self.route = route
+        self.sweeps = sweeps
+        self.frob2 = frob2
+
+
+def _order(sigma_dev, keep):
+    s = D.to_host(sigma_dev)
+    order = np.argsort(-s, kind="stable")[:keep]
+    return s[order], order
+
+
+def _idx(order):
+    return D.to_device(np.ascontiguousarray(order, dtype=np.int64))
+
+
+def _inv_or_zero(x, floor):
+    out = np.zeros_like(x)
+    ok = x > floor
+    out[ok] = 1.0 / x[ok]
+    return out
+
+
+def _rows_to_cols(rows, out_dtype):
+    """(r x S) row vectors -> (S x r) column vectors in the requested dtype."""
+    return D.transpose(rows, out_dtype=out_dtype)
+
+
+def solve_real(A, B, want_vectors=True, force_route=None, use_tensor_cores=None):
+    """A, B: centred device fields (T x S1, T x S2), fp32 or fp64; B may be None (PCA)."""
+    t = D.torch()
+    T, S1 = A.shape
+    dof = float(T - 1)
+    out_dtype = A.dtype
+    pca = B is None
+    S2 = S1 if pca else B.shape[1]
+    rank = min(T, S1, S2)
+    route = force_route or ("direct" if min(S1, S2) <= T else "gram")
+    sweeps = []
+
+    if route == "direct":
+        # ---- C (or C^T) with the short side as rows, fp64 accumulation -------------
+        left_short = S1 <= S2
+        frob2 = None
+        tc = use_tensor_cores if use_tensor_cores is not None else False
+        Bx = A if pca else B
+        if tc and A.dtype == t.float32:
+            X32, frob2 = D.cov_gemm_tc(A if left_short else Bx, Bx if left_short else A, 1.0 / dof)
+            X = X32
+        else:
+            X = D.matmul(A if left_short else Bx, Bx if left_short else A, trans_a=True, alpha=1.0 / dof)
+        Xr, sig, Jt, sw = D.jacobi_svd(X, want_v=want_vectors)
+        sweeps.append(sw)
+        sigma, order = _order(sig, rank)
+        if not want_vectors:
+            return SolveResult(sigma, {}, route, sweeps, frob2)
+        idx = _idx(order)
+        n_short = X.shape[0]
+        inv = D.to_device(_inv_or_zero(sigma, 0.0))
+        short_rows = D.gather_rows(Jt, idx, cols=n_short)                 # rank x S_short
+        long_rows = D.gather_rows(Xr, idx, row_scale=inv)                 # rank x S_long (unit rows)
+        Vs, Vl = _rows_to_cols(short_rows, out_dtype), _rows_to_cols(long_rows, out_dtype)
+        if pca:
+            return SolveResult(sigma, {"left": Vs}, route, sweeps, frob2)
+        V = {"left": Vs, "right": Vl} if left_short else {"left": Vl, "right": Vs}
+        return SolveResult(sigma, V, route, sweeps, frob2)
+
+    # -------------------------------- Gram route ---------------------------------
+    def gram_factor(X):
+        G = D.matmul(X, X, trans_b=True)                                  # T x T fp64
+        Gr, lam, Jt, sw = D.jacobi_svd(G, want_v=True)
+        sweeps.append(sw)
+        return lam, Jt
+
+    lamA, JtA = gram_factor(A)
+    if pca:
+        lam, order = _order(lamA, rank)
+        sigma = lam / dof
+        if not want_vectors:
+            return SolveResult(sigma, {}, route, sweeps)
+        floor = lam[0] * T * 2.3e-16 if lam.size else 0.0
+        inv_s = D.to_device(np.sqrt(_inv_or_zero(lam, floor)))
+        Ut = D.gather_rows(JtA, _idx(order), row_scale=inv_s, cols=T)     # rank x T rows u_j / s_j
+        V = D.matmul(A, Ut, trans_a=True, trans_b=True, out_dtype=out_dtype)   # S x rank
+        return SolveResult(sigma, {"left": V}, route, sweeps)
+
+    lamB, JtB = gram_factor(B)
+    npad = JtA.shape[0]
+    sA = D.to_device(np.sqrt(np.maximum(D.to_host(lamA), 0.0)))
+    sB = D.to_device(np.sqrt(np.maximum(D.to_host(lamB), 0.0)))
+    all_idx = _idx(np.arange(npad))
+    FAt = D.gather_rows(JtA, all_idx, row_scale=sA, cols=T)               # rows s_j u_j^T  (= F_A^T)
+    FBt = D.gather_rows(JtB, all_idx, row_scale=sB, cols=T)
+    K = D.matmul(FAt, FBt, trans_b=True, alpha=1.0 / dof)                 # npad x npad, = F_A^T F_B / dof
+    Kr, sig, Jt, sw = D.jacobi_svd(K, want_v=want_vectors)
+    sweeps.append(sw)
+    sigma, order = _order(sig, rank)
+    if not want_vectors:
+        return SolveResult(sigma, {}, route, sweeps)
+    # K = J Sigma U^T (rows of K orthogonalised): P = J columns, Q = unit rows of Kr
+    floor = sigma[0] * T * 2.3e-16 if sigma.size else 0.0
+    inv = _inv_or_zero(sigma, floor)
+    idx = _idx(order)
+    Pt = D.gather_rows(Jt, idx, row_scale=D.to_device(inv / dof), cols=npad)          # rank x npad : p_j / (sigma dof)
+    Qt = D.gather_rows(Kr, idx, row_scale=D.to_device(inv * inv / dof), cols=npad)    # unit q_j / (sigma dof)
+    WLt = D.matmul(Qt, FBt)                                               # rank x T : (F_B q_j)^T / (sigma dof)
+    WRt = D.matmul(Pt, FAt)
+    VL = D.matmul(A, WLt, trans_a=True, trans_b=True, out_dtype=out_dtype)            # S1 x rank
+    VR = D.matmul(B, WRt, trans_a=True, trans_b=True, out_dtype=out_dtype)
+    return SolveResult(sigma, {"left": VL, "right": VR}, route, sweeps)
+
+
+# ------------------------------------------------------------------ complex
+def embed_complex_field(Z: np.ndarray):
+    """Host helper: real embedding [[X, -Y], [Y, X]] of a complex T x S field."""
+    X, Y = np.ascontiguousarray(Z.real), np.ascontiguousarray(Z.imag)
+    return np.block([[X, -Y], [Y, X]])
+
+
+def solve_complex(Ae, Be, want_vectors=True):
+    """Ae/Be: device real embeddings (2T x 2S).  Returns sigma (rank,) and complex
+    V as (re, im) device pairs, each S x rank."""
+    T2, S12 = Ae.shape
+    T, S1 = T2 // 2, S12 // 2
+    pca = Be is None
+    S2 = S1 if pca else Be.shape[1] // 2
+    rank = min(T, S1, S2)
+    # the embedded problem has every singular value twice; dof of the ORIGINAL problem
+    res = solve_real(Ae, Be, want_vectors=want_vectors)
+    scale = (T2 - 1.0) / (T - 1.0)            # solve_real divided by (2T - 1)
+    sigma2 = res.sigma * scale
+    sigma = sigma2[0:2 * rank:2]
+    if not want_vectors:
+        return sigma, {}, res
+    V = {}
+    pick = _idx(np.arange(0, 2 * rank, 2))
+    for k, Ve in res.V.items():
+        S = Ve.shape[0] // 2
+        Vt = D.transpose(Ve)                                              # 2rank' x 2S rows
+        rows = D.gather_rows(Vt, pick)                                    # rank x 2S
+        cols = D.transpose(rows)                                          # 2S x rank
+        V[k] = (cols[:S], cols[S:])
+    return sigma, V, res
+
+
+# ------------------------------------------------------------------ rotation
+def promax(Ld, power=1, max_iter=1000, tol=1e-8):
+    """Device Promax (rotation.py:84-149), real loadings Ld (n x p).
+    Returns (B fp64 device n x p, R host p x p, Phi host p x p, iterations)."""
+    n, p = Ld.shape
+    B, Rdev, iters = D.varimax(Ld, 1.0, max_iter, tol)
+    R = D.to_host(Rdev)
+    if power == 1:
+        # the Promax step is the identity for power 1 (L = I up to rounding)
+        return B, R, np.eye(p), iters
+    h2 = D.to_host(D.row_sumsq(B))
+    h = np.sqrt(h2)
+    inv_h = D.to_device(1.0 / h)
+    colmax = D.col_absmax(B, row_scale=inv_h)
+    X, Pm = D.promax_target(B, inv_h, colmax, power)
+    XtX = D.to_host(D.matmul(X, X, trans_a=True))                         # p x p
+    XtP = D.to_host(D.matmul(X, Pm, trans_a=True))
+    Lm = np.linalg.inv(XtX) @ XtP                                         # rotation.py:128
+    try:
+        dinv = np.diag(np.linalg.inv(Lm.T @ Lm))                          # rotation.py:131-134
+    except np.linalg.LinAlgError:
+        dinv = np.diag(np.linalg.pinv(Lm.T @ Lm))
+    Lm = Lm @ np.sqrt(np.diag(dinv))                                      # rotation.py:137
+    XL = D.matmul(X, D.to_device(Lm))                                     # n x p
+    Bp = D.scale_copy(XL, row_scale=D.to_device(h))                       # rotation.py:141
+    Li = np.linalg.inv(Lm)
+    return Bp, R @ Lm, Li @ Li.T, iters

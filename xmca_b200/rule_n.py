@@ -1,0 +1,130 @@
+"""Rule N (Overland & Preisendorfer 1982) on the GPU(s).
+
+Semantics of xmca/array.py:1716-1771: ``n_runs`` times {two Gaussian fields of
+the FULL grid size (NaN columns included), always float64 -> centre -> solve
+[-> rotate] -> variance}; each spectrum is rescaled so that its sum equals the
+sum of the model's own variances; rotated runs that do not converge are dropped.
+
+B200 design: the runs are independent, so run indices are block-partitioned
+over the ranks of a ``torch.distributed`` group (one process per GPU).  The
+surrogates come from a counter-based Philox4x32-10 generator keyed by
+(seed, global run index, field) -- the result does not depend on the number of
+GPUs.  No collective is needed until the end: ONE all-gather of the
+(modes x n_local) fp64 spectra (NCCL over NVLink; gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib as L
+
+
+def partition(n_runs: int, world: int, rank: int):
+    """Contiguous block of run indices owned by ``rank`` (sizes differ by <= 1)."""
+    base, extra = divmod(n_runs, world)
+    lo = rank * base + min(rank, extra)
+    return range(lo, lo + base + (1 if rank < extra else 0))
+
+
+def device_surrogate_variance(shape_T, n_vars, run_index, seed, complexify, rotated, n_rot, power):
+    """One surrogate run on the current CUDA device.  Returns the variance
+    spectrum (fp64 numpy) or None if the rotation did not converge."""
+    from . import device as D
+    from . import engine as E
+    t = D.torch()
+    fields = []
+    for f, S in enumerate(n_vars):
+        X = D.empty((shape_T, S), t.float64)
+        D.fill_normal(X, seed, 2 * run_index + f)               # array.py:1756
+        D.center_columns(X)                                     # MCA ctor, array.py:199-207
+        fields.append(X)
+    if complexify:
+        from .array import MCA
+        hosts = [MCA._analytic(D.to_host(X)) for X in fields]
+        fields = [D.to_device(E.embed_complex_field(h)) for h in hosts]
+    A = fields[0]
+    B = fields[1] if len(fields) > 1 else None
+    if not rotated:
+        if complexify:
+            sigma, _, _ = E.solve_complex(A, B, want_vectors=False)
+            return sigma
+        return E.solve_real(A, B, want_vectors=False).sigma
+    if complexify:
+        raise NotImplementedError("rule_n on a rotated complex model is not implemented yet")
+    res = E.solve_real(A, B, want_vectors=True)
+    p = min(n_rot, res.sigma.size)
+    root = D.to_device(np.sqrt(res.sigma[:p]))
+    parts = [D.scale_copy(res.V[k][:, :p], col_scale=root) for k in res.V]
+    s_left = parts[0].shape[0]
+    Ld = t.cat(parts, dim=0).contiguous() if len(parts) > 1 else parts[0]
+    try:
+        Lrot, _, _, _ = E.promax(Ld, power, max_iter=1000, tol=1e-8)
+    except L.NotConvergedError:
+        return None                                             # array.py:1759-1763
+    nl = np.sqrt(D.to_host(D.col_sumsq(Lrot, 0, s_left)))
+    if B is None:
+        return nl ** 2
+    nr = np.sqrt(D.to_host(D.col_sumsq(Lrot, s_left, Lrot.shape[0])))
+    return nl * nr
+
+
+def gather_spectra(local: np.ndarray, valid: np.ndarray, n_runs: int, group=None):
+    """All-gather the per-rank (modes x n_local) spectra into (modes x n_runs),
+    ordered by global run index, dropping invalid columns."""
+    import torch
+    import torch.distributed as dist
+    if group is None and not (dist.is_available() and dist.is_initialized()):
+        return local[:, valid]
+    world = dist.get_world_size(group)
+    if world == 1:
+        return local[:, valid]
+    backend = dist.get_backend(group)
+    devc = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    n_max = -(-n_runs // world)
+    modes = local.shape[0]
+    buf = torch.zeros((n_max, modes), dtype=torch.float64)
+    buf[:local.shape[1]] = torch.from_numpy(np.nan_to_num(np.ascontiguousarray(local.T)))
+    mask = torch.zeros(n_max, dtype=torch.float64)               # validity flag per run slot
+    mask[:local.shape[1]] = torch.from_numpy(valid.astype(np.float64))
+    send = torch.cat([buf.reshape(-1), mask]).to(devc)
+    recv = [torch.empty_like(send) for _ in range(world)]
+    dist.all_gather(recv, send, group=group)                    # the ONE collective of rule_n
+    cols = []
+    for r, chunk in enumerate(recv):
+        chunk = chunk.cpu()
+        spec = chunk[:n_max * modes].reshape(n_max, modes).numpy()
+        ok = chunk[n_max * modes:].numpy() > 0.5
+        n_r = len(partition(n_runs, world, r))
+        cols.append(spec[:n_r][ok[:n_r]].T)
+    return np.concatenate(cols, axis=1) if cols else np.zeros((modes, 0))
+
+
+def rule_n(model, n_runs, n_modes=None, seed=None, group=None, _surrogate_fn=None):
+    """Sharded Rule N for an ``xmca_b200.MCA`` model (array.py:1716-1771)."""
+    import torch.distributed as dist
+    T = model._n_observations["left"]
+    n_vars = [model._n_variables[k] for k in model._keys]
+    complexify = model._analysis["is_complex"]
+    rotated = model._analysis["is_rotated"]
+    n_rot, power = model._analysis["n_rot"], model._analysis["power"]
+    if seed is None:
+        seed = int(np.random.randint(0, 2 ** 31 - 1))          # consume the global numpy stream once
+    if dist.is_available() and dist.is_initialized():
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+    else:
+        world, rank = 1, 0
+    fn = _surrogate_fn or device_surrogate_variance
+    ref = model._get_variance()
+    mine = partition(n_runs, world, rank)
+    modes = ref.size
+    local = np.full((modes, len(mine)), np.nan)
+    valid = np.zeros(len(mine), dtype=bool)
+    for j, i in enumerate(mine):
+        spec = fn(T, n_vars, i, seed, complexify, rotated, n_rot, power)
+        if spec is None:
+            continue
+        spec = np.asarray(spec, dtype=np.float64)
+        local[:spec.size, j] = spec * (ref.sum() / spec.sum())   # column-wise rescale, array.py:1768-1769
+        valid[j] = True
+    sv = gather_spectra(local, valid, n_runs, group)
+    return sv[model._get_slice(n_modes)]
