@@ -1,0 +1,428 @@
+#!/usr/bin/env python
+"""Benchmark of the MCA hot path (BASELINE.json metric) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl product|reference]
+                    [--workload c2|half|small] [--rule-n-runs R]
+
+One *step* = one pass of the hot path over one model: ``solve()`` +
+``rotate(n_rot=50, power=1)`` + ``singular_values(50)``/``pcs(50)``/``eofs(50)``
+on the config-2 workload (two synthetic fp32 fields T=8192, S1=S2=16384,
+low-rank + noise generator of SURVEY.md 8d).  With N > 1 ranks every rank runs
+its own model of that shape (weak scaling, independent replicas: a single
+solve/rotate does not shard) and -- the part of the path that
+does shard -- ``rule_n`` surrogates are block-partitioned over the ranks with
+one all-gather at the end.
+
+Printed JSON line (rank 0):
+  value            models/s, whole job, fields resident in HBM before the timed region
+  ms_per_step      wall milliseconds of one solve()+rotate()+getters
+  e2e              the same through ``MCA(host arrays)``: pinned host fields ->
+                   ctor -> upload -> solve -> rotate -> getters -> host results
+  solve_rotate_wall_s, cov_gemm, rule_n : the three numbers BASELINE.json names
+  roofline         dominant C-ABI call class of the step (CUDA events per call)
+  cpu_baseline     the numpy oracle port timed on this box's host cores
+``--impl reference`` times the numpy restatement of the reference path
+(oracle/, kind "port": the reference itself is pure Python that cannot travel
+to the GPU box) on a bounded sample and extrapolates to the workload size.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (T, S1, S2, n_rot, n_modes)
+    "c2": (8192, 16384, 16384, 50, 50),
+    "half": (4096, 8192, 8192, 50, 50),
+    "small": (1024, 2048, 2048, 20, 20),
+}
+
+
+def synthetic_fields(T, S1, S2, seed, k=64, dtype=np.float32):
+    """Low-rank-plus-noise fields: k shared time series with
+    geometrically decaying amplitudes + unit white noise."""
+    rng = np.random.default_rng(seed)
+    ts = rng.standard_normal((T, k), dtype=np.float32)
+    amp = (3.0 * np.sqrt(max(S1, S2)) * 0.9 ** np.arange(k) / np.sqrt(k)).astype(np.float32)
+    out = []
+    for S in (S1, S2):
+        pat = rng.standard_normal((k, S), dtype=np.float32) / np.float32(np.sqrt(S))
+        X = rng.standard_normal((T, S), dtype=np.float32)
+        X += (ts * amp) @ pat
+        out.append(X.astype(dtype, copy=False))
+    return out
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
+                "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms during the timed region (profiling recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, "/tmp/xmca_clocks_%d.csv" % os.getpid()
+
+    def start(self):
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as fh:
+            for line in fh:
+                parts = [x.strip() for x in line.split(",")]
+                if len(parts) < 7:
+                    continue
+                try:
+                    sm.append(float(parts[0])); mx.append(float(parts[1])); power.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for nm, val in zip(names, parts[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": float(max(power))}
+
+
+# ------------------------------------------------------------------ product arm
+def hot_path_step(m, n_rot, n_modes):
+    m.solve()
+    m.rotate(n_rot, 1)
+    sv = m.singular_values(n_modes)
+    pcs = m.pcs(n_modes)
+    eofs = m.eofs(n_modes)
+    return sv, pcs, eofs
+
+
+def result_bytes(res):
+    sv, pcs, eofs = res
+    return int(sv.nbytes + sum(v.nbytes for v in pcs.values()) + sum(v.nbytes for v in eofs.values()))
+
+
+def run_product(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from xmca_b200 import MCA, _lib
+    from xmca_b200 import device as D
+
+    torch.cuda.set_device(local_rank)
+    _lib.load()
+    T, S1, S2, n_rot, n_modes = WORKLOADS[args.workload]
+    peaks = load_peaks()
+
+    # pinned host fields (the e2e leg copies from these every step)
+    A0, B0 = synthetic_fields(T, S1, S2, seed=1000 + rank)
+    Ap = torch.from_numpy(A0).pin_memory()
+    Bp = torch.from_numpy(B0).pin_memory()
+    A, B = Ap.numpy(), Bp.numpy()
+    del A0, B0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = _lib.launch_count()
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = reduce_max(e0.elapsed_time(e1))
+        return ms / steps, _lib.launch_count() - n0, out
+
+    # ---- leg 1: device-resident (value) -------------------------------------------------
+    model = MCA(A, B)
+    model._device_fields()                     # upload + keep resident
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_step, launches, res = timed(lambda: hot_path_step(model, n_rot, n_modes), args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    info = dict(model._solve_info)
+
+    # ---- per-call-class device time of one more step (CUDA events on the launch stream) -
+    _lib.profile_begin()
+    hot_path_step(model, n_rot, n_modes)
+    prof = _lib.profile_end()
+    vm_iters = int(model._solve_info.get("varimax_iterations", 0))
+
+    # ---- leg 2: end to end through the public class, host buffers ----------------------
+    def e2e_step():
+        m = MCA(A, B)
+        return hot_path_step(m, n_rot, n_modes)
+    ms_e2e, _, res_e2e = timed(e2e_step, args.steps, min(args.warmup, 1))
+    h2d = int(A.nbytes + B.nbytes)
+    d2h = result_bytes(res_e2e)
+
+    # ---- cov-GEMM on the tensor cores (C = A^T B / dof, 3xTF32 tcgen05) -----------------
+    dA, dB = model._dev["left"], model._dev["right"]
+    cov = None
+    if dA.dtype == torch.float32:
+        planes = [D.split_tf32(dA, transpose=True), D.split_tf32(dB, transpose=True)]
+        Cbuf = D.empty((S1, S2), torch.float32)
+
+        def gemm_only():
+            D.tc_gemm_nt(planes[0][0], planes[0][1], planes[1][0], planes[1][1], T, alpha=1.0 / (T - 1), out=Cbuf)
+        ms_gemm, _, _ = timed(gemm_only, 5, 3)
+        ms_cov, _, _ = timed(lambda: D.cov_gemm_tc(dA, dB, 1.0 / (T - 1)), 3, 1)
+        flops = 2.0 * T * S1 * S2
+        cov = {"tflops_gemm_kernel": flops / ms_gemm / 1e9, "tflops_with_operand_split": flops / ms_cov / 1e9,
+               "ms_gemm_kernel": ms_gemm, "ms_with_operand_split": ms_cov, "flops": flops,
+               "note": "algorithmic 2*T*S1*S2 flops; the kernel issues 3 TF32 products per flop pair (3xTF32)"}
+        del planes, Cbuf
+        torch.cuda.empty_cache()
+
+    # ---- rule_n: surrogates sharded over the ranks, one all-gather ----------------------
+    rn = None
+    if args.rule_n_runs > 0:
+        model.solve()                                 # rule N of the unrotated model
+        n_runs = args.rule_n_runs * world
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        spectra = model.rule_n(n_runs, n_modes, seed=1234)
+        e1.record()
+        barrier()
+        ms_rn = reduce_max(e0.elapsed_time(e1))
+        rn = {"surrogates_per_s": n_runs / (ms_rn / 1e3), "n_runs": n_runs, "runs_per_rank": args.rule_n_runs,
+              "ms_total": ms_rn, "shape": list(spectra.shape), "dtype": "f64",
+              "collective": "1 all_gather (nccl)" if world > 1 else "none (1 rank)"}
+
+    if rank != 0:
+        return None
+
+    # ---- roofline of the dominant call class -------------------------------------------
+    total_prof = sum(v["ms"] for v in prof.values()) or 1.0
+    shares = {k: {"ms": round(v["ms"], 3), "share": round(v["ms"] / total_prof, 4), "calls": v["calls"],
+                  "launches": v["launches"]} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+    dom = next(iter(shares))
+    n_load = S1 + S2
+    e_store = 4
+    roof_list = {}
+    if "xmca_varimax" in prof:
+        v = prof["xmca_varimax"]
+        vbytes = (vm_iters + 5) * n_load * n_rot * e_store
+        roof_list["xmca_varimax"] = {"bound": "hbm", "achieved": vbytes / (v["ms"] / v["calls"]) / 1e6,
+                                     "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                     "bytes_per_launch": vbytes, "iterations": vm_iters}
+    if "xmca_jacobi_svd" in prof:
+        v = prof["xmca_jacobi_svd"]
+        sw = info.get("sweeps", [])
+        n = T
+        fl = sum(6.0 * n ** 3 for _ in sw) if sw else 0.0      # 4mn^2 (+2mn^2 vectors) per sweep
+        fl = sum(s * 6.0 * n ** 3 for s in sw)
+        roof_list["xmca_jacobi_svd"] = {"bound": "fp64-simt", "achieved": fl / v["ms"] / 1e9, "peak": 40.0,
+                                        "unit": "TFLOP/s", "sweeps": sw,
+                                        "note": "fp64 CUDA-core path; peak = nominal 40 TF fp64 (not in MEASURED_PEAKS)"}
+    if "xmca_gemm" in prof:
+        v = prof["xmca_gemm"]
+        roof_list["xmca_gemm"] = {"bound": "fp64-simt", "ms": v["ms"], "calls": v["calls"]}
+    if cov:
+        roof_list["xmca_tc_gemm_nt"] = {"bound": "tensor", "achieved": cov["tflops_gemm_kernel"] * 3,
+                                        "peak": peaks["bf16_tflops"] / 2, "unit": "TFLOP/s (TF32 issued)",
+                                        "note": "3 TF32 MMAs per algorithmic product; peak = measured bf16 / 2"}
+    for r in roof_list.values():
+        if "achieved" in r and "peak" in r:
+            r["frac"] = r["achieved"] / r["peak"]
+    roof = dict(roof_list.get(dom, {"bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                    "frac": None}))
+    roof.update({"kernel": dom, "share_of_step": shares[dom]["share"], "traffic": None,
+                 "peak_source": peaks["source"]})
+
+    out = {
+        "metric": "solve()+rotate() throughput (models/s; wall-sec in solve_rotate_wall_s, cov-GEMM TFLOP/s in "
+                  "cov_gemm, rule_n surrogates/s in rule_n)",
+        "value": world / (ms_step / 1e3), "unit": "models/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 fields; f64 accumulation/SVD/rotation", "data": "synthetic",
+        "config": {"workload": "%s: MCA T=%d S1=%d S2=%d f32, rotate(n_rot=%d, power=1), getters n=%d"
+                               % (args.workload, T, S1, S2, n_rot, n_modes),
+                   "l2": "inputs (2 x %.0f MB) larger than the 126 MB L2" % (A.nbytes / 1e6),
+                   "parallelism": "replicas x%d (solve/rotate); rule_n surrogates block-sharded" % world,
+                   "route": info.get("route"), "jacobi_sweeps": info.get("sweeps"),
+                   "varimax_iterations": vm_iters},
+        "solve_rotate_wall_s": ms_step / 1e3,
+        "e2e": {"value": world / (ms_e2e / 1e3), "unit": "models/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "cov_gemm": cov,
+        "rule_n": rn,
+        "roofline": roof,
+        "roofline_kernels": roof_list,
+        "call_shares": shares,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args.workload, steps=1, warmup=0)
+    return out
+
+
+# ------------------------------------------------------------ CPU baseline / reference arm
+def _cpu_sample(T, S1, S2, n_rot, n_modes, seed):
+    """One solve()+rotate()+getters of the numpy oracle port; returns seconds."""
+    from oracle import mca_oracle as orc
+    A, B = synthetic_fields(T, S1, S2, seed=seed)
+    t0 = time.perf_counter()
+    m = orc.solve(orc.make_model(A, B))
+    try:
+        orc.rotate(m, n_rot, 1)
+    except orc.NotConverged:
+        pass
+    orc.pcs(m, n_modes)
+    orc.eofs(m, n_modes)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(workload, steps=1, warmup=0):
+    """numpy restatement of the reference path (oracle/, kind "port") on this
+    box's host cores.  A full config-2 solve takes minutes on a CPU, so each
+    step times the SAME pipeline at 1/4 and 1/8 of T, S1, S2 and extrapolates
+    with the measured per-doubling factor f = t(1/4) / t(1/8):
+    t(full) = t(1/4) * f^2."""
+    T, S1, S2, n_rot, n_modes = WORKLOADS[workload]
+    div = 4 if workload == "c2" else (2 if workload == "half" else 1)
+    cores = os.cpu_count() or 1
+    _cpu_sample(256, 512, 512, 10, 10, 5)                       # BLAS/LAPACK warm-up
+    ts = []
+    for i in range(warmup + steps):
+        if div > 1:
+            t_hi = _cpu_sample(T // div, S1 // div, S2 // div, n_rot, n_modes, 77 + i)
+            t_lo = _cpu_sample(T // (2 * div), S1 // (2 * div), S2 // (2 * div), n_rot, n_modes, 177 + i)
+            f = max(t_hi / t_lo, 1.0)
+            full = t_hi * f ** int(np.log2(div))
+            rec = (full, t_hi, t_lo, f)
+        else:
+            t_hi = _cpu_sample(T, S1, S2, n_rot, n_modes, 77 + i)
+            rec = (t_hi, t_hi, None, None)
+        if i >= warmup:
+            ts.append(rec)
+    full = float(np.mean([r[0] for r in ts]))
+    t_hi = float(np.mean([r[1] for r in ts]))
+    sample = ("numpy oracle port: solve+rotate(%d)+pcs/eofs(%d) at T=%d,S=%d: %.2f s" %
+              (n_rot, n_modes, T // div, S1 // div, t_hi))
+    if div > 1:
+        f = float(np.mean([r[3] for r in ts]))
+        sample += ("; at T=%d,S=%d: %.2f s; per-doubling factor %.2f -> extrapolated %.1f s at the full size"
+                   % (T // (2 * div), S1 // (2 * div), float(np.mean([r[2] for r in ts])), f, full))
+    return {"value": 1.0 / full, "unit": "models/s", "cores": cores, "kind": "port", "sample": sample,
+            "seconds_per_model_extrapolated": full}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return None
+    T, S1, S2, n_rot, n_modes = WORKLOADS[args.workload]
+    t0 = time.perf_counter()
+    cb = cpu_baseline(args.workload, steps=args.steps, warmup=args.warmup)
+    wall = time.perf_counter() - t0
+    return {
+        "impl": "reference",
+        "metric": "solve()+rotate() throughput (models/s; wall-sec in solve_rotate_wall_s, cov-GEMM TFLOP/s in "
+                  "cov_gemm, rule_n surrogates/s in rule_n)",
+        "value": cb["value"], "unit": "models/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": cb["seconds_per_model_extrapolated"] * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 fields (numpy/LAPACK sgesdd), f64 rotation", "data": "synthetic",
+        "config": {"workload": "%s: MCA T=%d S1=%d S2=%d f32, rotate(n_rot=%d, power=1), getters n=%d"
+                               % (args.workload, T, S1, S2, n_rot, n_modes)},
+        "solve_rotate_wall_s": cb["seconds_per_model_extrapolated"],
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "models/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "bench_wall_s": wall,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="product", choices=["product", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--rule-n-runs", type=int, default=1, help="surrogates per rank (0 = skip rule_n)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        out = run_reference(args, rank, world)
+        if out is not None:
+            print(json.dumps(out), flush=True)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product arm has no CPU fallback")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    out = run_product(args, rank, world, local_rank)
+    if out is not None:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

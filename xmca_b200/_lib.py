@@ -84,8 +84,66 @@ def load():
         fn = getattr(lib, name)          # raises AttributeError if a declared symbol is not exported
         if fn.restype is C.c_int and name not in ("xmca_version",):
             fn.restype = i32
-    _lib = lib
-    return lib
+    _lib = _Profiled(lib)
+    return _lib
+
+
+# ------------------------------------------------------------------ profiling
+# bench.py asks for the device time of every C-ABI call class: CUDA events are
+# recorded on torch's current stream (the stream every call is enqueued on)
+# around each call while a profile is open.  Disabled -> one attribute lookup.
+_NO_TIMING = ("xmca_last_error", "xmca_version", "xmca_launch_count", "xmca_gemm_workspace_bytes",
+              "xmca_jacobi_padded_cols", "xmca_jacobi_workspace_bytes", "xmca_varimax_workspace_bytes")
+_profile = None
+
+
+class _Profiled:
+    def __init__(self, lib):
+        self._raw = lib
+        self._cache = {}
+
+    def __getattr__(self, name):
+        fn = self._cache.get(name)
+        if fn is None:
+            raw = getattr(self._raw, name)
+            if name in _NO_TIMING or not name.startswith("xmca_"):
+                fn = raw
+            else:
+                def fn(*args, _raw=raw, _name=name):
+                    if _profile is None:
+                        return _raw(*args)
+                    import torch
+                    e0 = torch.cuda.Event(enable_timing=True)
+                    e1 = torch.cuda.Event(enable_timing=True)
+                    n0 = int(self._raw.xmca_launch_count())
+                    e0.record()
+                    rc = _raw(*args)
+                    e1.record()
+                    _profile.append((_name, e0, e1, int(self._raw.xmca_launch_count()) - n0))
+                    return rc
+            self._cache[name] = fn
+        return fn
+
+
+def profile_begin():
+    """Start recording (name, start event, end event, launches) per C-ABI call."""
+    global _profile
+    _profile = []
+
+
+def profile_end():
+    """Stop recording; returns {name: {"calls", "launches", "ms"}} (synchronises)."""
+    global _profile
+    rec, _profile = _profile or [], None
+    import torch
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1, nl in rec:
+        d = out.setdefault(name, {"calls": 0, "launches": 0, "ms": 0.0})
+        d["calls"] += 1
+        d["launches"] += nl
+        d["ms"] += e0.elapsed_time(e1)
+    return out
 
 
 def launch_count() -> int:

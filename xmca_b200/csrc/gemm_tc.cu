@@ -8,15 +8,23 @@
 // covariance "kernel" (array.py:552-566): instead of SVD-ing each field and
 // multiplying the reduced factors, C = A^T B / (T-1) is formed directly.
 //
-// Structure (one 128 x BN output tile per CTA, 192 threads):
+// Structure (one 128 x BN output tile per CTA, 320 threads):
 //   warp 0      TMA producer : cp.async.bulk.tensor.2d of the 4 operand slabs
 //                              (A_hi, A_lo, B_hi, B_lo; 32 fp32 = 128 B rows,
 //                              SWIZZLE_128B) into a ring of shared-memory stages
 //   warp 1      MMA issuer   : one elected thread issues 12 tcgen05.mma per
 //                              stage (4 k-steps of 8 x 3 products), commits the
 //                              stage back to the producer with tcgen05.commit
-//   warps 2..5  epilogue     : tcgen05.ld the 128 x BN fp32 accumulator from
-//                              TMEM, scale, optional sum(D^2), store to HBM
+//   warps 2..9  accumulate + : the tensor core TRUNCATES the fp32 accumulator
+//               epilogue       on every MMA (measured: error grows linearly
+//                              with the number of chained MMAs, ~2^-24 |acc|
+//                              each), so the K loop is cut into chunks of
+//                              TC_CHUNK_KB stages.  Each chunk accumulates into
+//                              one of two TMEM buffers; these warps drain the
+//                              finished buffer with tcgen05.ld and add it into
+//                              fp32 REGISTER sums (round-to-nearest) while the
+//                              tensor core fills the other buffer.  At the end:
+//                              scale, optional sum(D^2), store to HBM.
 // Tiles are rasterised in groups of 16 tile-rows so that the ~148 concurrently
 // resident CTAs share operand slabs through the 126 MB L2.
 #include "common.cuh"
@@ -28,7 +36,9 @@ namespace xmca {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                 // fp32 elements per stage row = 128 bytes (one swizzle atom)
 constexpr int TC_UMMA_K = 8;              // tf32: 32 bytes per MMA k-step
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;           // TMA warp + MMA warp + 8 accumulate/epilogue warps
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_CHUNK_KB = 4;            // stages (of 32 k) chained in TMEM before a register flush: 48 MMAs
 constexpr int TC_GROUP_M = 16;
 
 // ------------------------------------------------------------------ PTX glue
@@ -60,6 +70,9 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -125,12 +138,14 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
                   int M, int N, int K, float alpha, float* __restrict__ D, int64_t ldd,
                   double* __restrict__ frob2, int tiles_m, int tiles_n) {
   using Cfg = TcCfg<BN>;
+  constexpr int kCols = BN / 2;             // accumulator columns per epilogue thread (two column halves)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
-  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;      // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -148,6 +163,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
   }
   const int m0 = tile_m * TC_BM, n0 = tile_n * BN;
   const int num_kb = (K + TC_BK - 1) / TC_BK;
+  const int num_chunks = (num_kb + TC_CHUNK_KB - 1) / TC_CHUNK_KB;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapAhi) : "memory");
@@ -155,12 +171,12 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBhi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBlo) : "memory");
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)BN)
+                 "r"((uint32_t)(2 * BN))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -188,59 +204,80 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
   } else if (warp == 1) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+      int kb = 0;
+      for (int c = 0; c < num_chunks; ++c) {
+        const int buf = c & 1;
+        mbar_wait(&tmem_empty_bar[buf], ((uint32_t)(c >> 1) & 1u) ^ 1u);   // drained by the epilogue warps
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-        const uint32_t a_hi = sa, a_lo = sa + Cfg::kABytes;
-        const uint32_t b_hi = sa + 2 * Cfg::kABytes, b_lo = b_hi + Cfg::kBBytes;
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+        const int kb_end = min(num_kb, kb + TC_CHUNK_KB);
+        bool first = true;
+        for (; kb < kb_end; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t a_hi = sa, a_lo = sa + Cfg::kABytes;
+          const uint32_t b_hi = sa + 2 * Cfg::kABytes, b_lo = b_hi + Cfg::kBBytes;
 #pragma unroll
-        for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
-          const uint32_t off = k * TC_UMMA_K * 4;       // 32 bytes along K inside the swizzle atom
-          const uint64_t dah = make_kmajor_sw128_desc(a_hi + off), dal = make_kmajor_sw128_desc(a_lo + off);
-          const uint64_t dbh = make_kmajor_sw128_desc(b_hi + off), dbl = make_kmajor_sw128_desc(b_lo + off);
-          umma_tf32(tmem_base, dal, dbh, Cfg::kIdesc, (kb > 0 || k > 0) ? 1u : 0u);   // small terms first
-          umma_tf32(tmem_base, dah, dbl, Cfg::kIdesc, 1u);
-          umma_tf32(tmem_base, dah, dbh, Cfg::kIdesc, 1u);
+          for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+            const uint32_t off = k * TC_UMMA_K * 4;       // 32 bytes along K inside the swizzle atom
+            const uint64_t dah = make_kmajor_sw128_desc(a_hi + off), dal = make_kmajor_sw128_desc(a_lo + off);
+            const uint64_t dbh = make_kmajor_sw128_desc(b_hi + off), dbl = make_kmajor_sw128_desc(b_lo + off);
+            umma_tf32(tmem_d, dal, dbh, Cfg::kIdesc, first ? 0u : 1u);   // small terms first
+            umma_tf32(tmem_d, dah, dbl, Cfg::kIdesc, 1u);
+            umma_tf32(tmem_d, dah, dbh, Cfg::kIdesc, 1u);
+            first = false;
+          }
+          umma_commit(&empty_bar[stage]);                  // frees the smem stage when the MMAs retire
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&empty_bar[stage]);                  // frees the smem stage when the MMAs retire
-        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        umma_commit(&tmem_full_bar[buf]);                  // this chunk's partial sum is complete
       }
-      umma_commit(tmem_full_bar);                        // accumulator complete
     }
     __syncwarp();
   } else {
-    // epilogue warps 2..5 -> TMEM lane quadrant (warp % 4)
-    const int q = warp & 3;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
+    // accumulate/epilogue warps 2..9 -> TMEM lane quadrant (warp % 4), column half (warp - 2) / 4
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    float acc[kCols];
+#pragma unroll
+    for (int j = 0; j < kCols; ++j) acc[j] = 0.f;
+    for (int c = 0; c < num_chunks; ++c) {
+      const int buf = c & 1;
+      mbar_wait(&tmem_full_bar[buf], (uint32_t)(c >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * kCols);
+#pragma unroll
+      for (int g = 0; g < kCols / 32; ++g) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)(g * 32), v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[g * 32 + j] += __uint_as_float(v[j]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+    }
     const int row = m0 + q * 32 + lane;
     double ss = 0.0;
     const bool vec_ok = ((ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(D) & 15) == 0);
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-      const int col0 = n0 + c * 32;
-      if (row < M && col0 < N) {
-        float* dst = D + (int64_t)row * ldd + col0;
-        if (vec_ok && col0 + 32 <= N) {
+    const int col0 = n0 + half * kCols;
+    if (row < M && col0 < N) {
+      float* dst = D + (int64_t)row * ldd + col0;
+      if (vec_ok && col0 + kCols <= N) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o;
-            o.x = __uint_as_float(v[j]) * alpha; o.y = __uint_as_float(v[j + 1]) * alpha;
-            o.z = __uint_as_float(v[j + 2]) * alpha; o.w = __uint_as_float(v[j + 3]) * alpha;
-            ss += (double)o.x * o.x + (double)o.y * o.y + (double)o.z * o.z + (double)o.w * o.w;
-            *reinterpret_cast<float4*>(dst + j) = o;
-          }
-        } else {
+        for (int j = 0; j < kCols; j += 4) {
+          float4 o;
+          o.x = acc[j] * alpha; o.y = acc[j + 1] * alpha; o.z = acc[j + 2] * alpha; o.w = acc[j + 3] * alpha;
+          ss += (double)o.x * o.x + (double)o.y * o.y + (double)o.z * o.z + (double)o.w * o.w;
+          *reinterpret_cast<float4*>(dst + j) = o;
+        }
+      } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (col0 + j < N) {
-              float o = __uint_as_float(v[j]) * alpha;
-              ss += (double)o * o;
-              dst[j] = o;
-            }
+        for (int j = 0; j < kCols; ++j) {
+          if (col0 + j < N) {
+            float o = acc[j] * alpha;
+            ss += (double)o * o;
+            dst[j] = o;
           }
         }
       }
@@ -254,7 +291,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN))
                  : "memory");
   }
 }

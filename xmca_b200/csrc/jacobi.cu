@@ -18,6 +18,7 @@
 #include <vector>
 #include <cstring>
 #include <math.h>
+#include <stdlib.h>
 
 namespace xmca {
 
@@ -88,6 +89,13 @@ __device__ __forceinline__ void sym_rotation(double app, double aqq, double apq,
 }
 
 // grid npairs; block 1024; dynamic smem 3 * 64*64 doubles (G ping-pong + R)
+// Two-sided cyclic Jacobi on the 64 x 64 pivot Gram.  Per step the 32 disjoint
+// rotations are computed ONCE (32 threads, fp64 div/sqrt are slow) and
+// broadcast through shared memory; all 1024 threads then apply them to their
+// 2 x 2 block of G (rows and columns) and to two rows of R.  At most
+// `max_inner` sweeps: the pivot block only has to be diagonalised as far as the
+// outer iteration can use (the off-block coupling is of the same size), and
+// close to convergence one sweep is enough (quadratic).
 __global__ void __launch_bounds__(1024)
 pair_eig_kernel(const double* __restrict__ partial, int nsplit, double* __restrict__ Rout,
                 unsigned long long* __restrict__ offmax_bits, int max_inner) {
@@ -96,8 +104,9 @@ pair_eig_kernel(const double* __restrict__ partial, int nsplit, double* __restri
   double* Gb = sm + GS;
   double* R = sm + 2 * GS;
   __shared__ double red[32];
-  __shared__ double s_stat[2];
+  __shared__ double2 s_cs[W];
   __shared__ int s_perm[P];
+  __shared__ int s_rot[2];
   const int tid = threadIdx.x, p = blockIdx.x;
   const int a = tid >> 5, b = tid & 31;
 
@@ -114,6 +123,7 @@ pair_eig_kernel(const double* __restrict__ partial, int nsplit, double* __restri
   }
   local_off = warp_max(local_off);
   if ((tid & 31) == 0) red[tid >> 5] = local_off;
+  if (tid < 2) s_rot[tid] = 0;
   __syncthreads();
   if (tid == 0) {
     double mx = 0.0;
@@ -121,7 +131,6 @@ pair_eig_kernel(const double* __restrict__ partial, int nsplit, double* __restri
     atomicMax(offmax_bits, (unsigned long long)__double_as_longlong(mx));
   }
   // symmetrise (partials are symmetric up to rounding order; enforce exactly)
-  __syncthreads();
   for (int e = tid; e < GS; e += 1024) {
     int i = e >> 6, j = e & 63;
     if (i < j) { double v = 0.5 * (Ga[i * P + j] + Ga[j * P + i]); Gb[i * P + j] = v; Gb[j * P + i] = v; }
@@ -132,31 +141,20 @@ pair_eig_kernel(const double* __restrict__ partial, int nsplit, double* __restri
   double* nxt = Ga;
 
   for (int sweep = 0; sweep < max_inner; ++sweep) {
-    // convergence: off-diagonal Frobenius mass vs diagonal
-    double off = 0.0, dg = 0.0;
-    for (int e = tid; e < GS; e += 1024) {
-      int i = e >> 6, j = e & 63;
-      double v = cur[e];
-      if (i == j) dg = fma(v, v, dg); else off = fma(v, v, off);
-    }
-    off = warp_sum(off); dg = warp_sum(dg);
-    __syncthreads();                 // red[] reuse
-    if ((tid & 31) == 0) { red[tid >> 5] = off; }
-    __syncthreads();
-    if (tid == 0) { double t = 0; for (int i = 0; i < 32; ++i) t += red[i]; s_stat[0] = t; }
-    __syncthreads();
-    if ((tid & 31) == 0) { red[tid >> 5] = dg; }
-    __syncthreads();
-    if (tid == 0) { double t = 0; for (int i = 0; i < 32; ++i) t += red[i]; s_stat[1] = t; }
-    __syncthreads();
-    if (s_stat[0] <= 1e-29 * s_stat[1] || s_stat[0] == 0.0) break;
-
+    if (tid == 0) s_rot[(sweep + 1) & 1] = 0;          // flag of the NEXT sweep (nobody reads it now)
     for (int step = 0; step < P - 1; ++step) {
       const unsigned char* tb = c_rr + step * P;
+      if (tid < W) {
+        const int pp = tb[2 * tid], qq = tb[2 * tid + 1];
+        double c, s;
+        sym_rotation(cur[pp * P + pp], cur[qq * P + qq], cur[pp * P + qq], c, s);
+        s_cs[tid] = make_double2(c, s);
+        if (s != 0.0) s_rot[sweep & 1] = 1;
+      }
+      __syncthreads();
       const int pa = tb[2 * a], qa = tb[2 * a + 1], pb = tb[2 * b], qb = tb[2 * b + 1];
-      double ca, sa, cb, sb;
-      sym_rotation(cur[pa * P + pa], cur[qa * P + qa], cur[pa * P + qa], ca, sa);
-      sym_rotation(cur[pb * P + pb], cur[qb * P + qb], cur[pb * P + qb], cb, sb);
+      const double2 ra = s_cs[a], rb = s_cs[b];
+      const double ca = ra.x, sa = ra.y, cb = rb.x, sb = rb.y;
       const double x00 = cur[pa * P + pb], x01 = cur[pa * P + qb];
       const double x10 = cur[qa * P + pb], x11 = cur[qa * P + qb];
       const double y00 = cb * x00 - sb * x01, y01 = sb * x00 + cb * x01;
@@ -177,6 +175,7 @@ pair_eig_kernel(const double* __restrict__ partial, int nsplit, double* __restri
       __syncthreads();
       double* t = cur; cur = nxt; nxt = t;
     }
+    if (s_rot[sweep & 1] == 0) break;                    // no rotation in this sweep: diagonal
   }
   __syncthreads();
   // sort eigenvalues descending (rank by counting), write permuted eigenvectors
@@ -387,6 +386,8 @@ extern "C" int xmca_jacobi_svd(int64_t m, int64_t n, double* d_Kc, int64_t ldk,
   const size_t eig_smem = 3 * GS * sizeof(double);
   const size_t app_smem = (P * (P + 1) + GS) * sizeof(double);
   const double quad_stop = 1e-2 * sqrt(tol);
+  static const int inner_sweeps = getenv("XMCA_JACOBI_INNER") ? atoi(getenv("XMCA_JACOBI_INNER")) : 1;
+  static const bool trace = getenv("XMCA_JACOBI_TRACE") != nullptr;
   int sweeps = 0;
   double measure = INFINITY;
   bool converged = false;
@@ -398,7 +399,7 @@ extern "C" int xmca_jacobi_svd(int64_t m, int64_t n, double* d_Kc, int64_t ldk,
       const int* pr = d_pairs + (size_t)r * pl.nb;
       pair_gram_kernel<<<dim3(pl.npairs, pl.nsplit), 256, 0, st>>>(d_Kc, ldk, m, pr, pl.nsplit, d_partial);
       XMCA_LAUNCHED();
-      pair_eig_kernel<<<pl.npairs, 1024, eig_smem, st>>>(d_partial, pl.nsplit, d_R, d_scal, 12);
+      pair_eig_kernel<<<pl.npairs, 1024, eig_smem, st>>>(d_partial, pl.nsplit, d_R, d_scal, inner_sweeps);
       XMCA_LAUNCHED();
       pair_apply_kernel<<<dim3(pl.npairs, (unsigned)((m + P - 1) / P)), 256, app_smem, st>>>(
           d_Kc, ldk, m, pr, d_R);
@@ -423,6 +424,7 @@ extern "C" int xmca_jacobi_svd(int64_t m, int64_t n, double* d_Kc, int64_t ldk,
                   __FILE__, __LINE__);
     }
     measure = offmax / gmax;           // state BEFORE this sweep's rotations
+    if (trace) fprintf(stderr, "[xmca jacobi] m=%lld n=%lld sweep %d: max|g_ij|/max g_kk = %.3e\n", (long long)m, (long long)n, sweeps, measure);
     if (measure <= quad_stop) { converged = true; break; }   // quadratic: this sweep finished the job
   }
   col_norm_kernel<<<(unsigned)pl.n_pad, 256, 0, st>>>(d_Kc, ldk, m, d_sigma, 1, nullptr);

@@ -100,31 +100,43 @@ def solve_real(A, B, want_vectors=True, force_route=None, use_tensor_cores=None)
         return SolveResult(sigma, V, route, sweeps, frob2)
 
     # -------------------------------- Gram route ---------------------------------
+    # G = X X^T is symmetric PSD, so one-sided Jacobi on it needs NO accumulated
+    # rotations: at convergence the rotated rows are lambda_j u_j^T, i.e. the
+    # eigenvectors are the normalised rows themselves (saves a third of the sweep cost).
+    # Directions with lambda_j below the rounding floor (the null vector that centring
+    # creates) carry no information and are zeroed instead of normalised.
+    eps = 2.220446049250313e-16
+
     def gram_factor(X):
         G = D.matmul(X, X, trans_b=True)                                  # T x T fp64
-        Gr, lam, Jt, sw = D.jacobi_svd(G, want_v=True)
+        Gr, lam, _, sw = D.jacobi_svd(G, want_v=False)
         sweeps.append(sw)
-        return lam, Jt
+        return D.to_host(lam), Gr
 
-    lamA, JtA = gram_factor(A)
+    lamA, GrA = gram_factor(A)
+    npad = GrA.shape[0]
     if pca:
-        lam, order = _order(lamA, rank)
+        order = np.argsort(-lamA, kind="stable")[:rank]
+        lam = lamA[order]
         sigma = lam / dof
         if not want_vectors:
             return SolveResult(sigma, {}, route, sweeps)
-        floor = lam[0] * T * 2.3e-16 if lam.size else 0.0
-        inv_s = D.to_device(np.sqrt(_inv_or_zero(lam, floor)))
-        Ut = D.gather_rows(JtA, _idx(order), row_scale=inv_s, cols=T)     # rank x T rows u_j / s_j
+        floor = lam[0] * T * eps * 64 if lam.size else 0.0
+        inv = _inv_or_zero(lam, floor)
+        Ut = D.gather_rows(GrA, _idx(order), row_scale=D.to_device(inv * np.sqrt(inv)), cols=T)  # u_j / s_j
         V = D.matmul(A, Ut, trans_a=True, trans_b=True, out_dtype=out_dtype)   # S x rank
         return SolveResult(sigma, {"left": V}, route, sweeps)
 
-    lamB, JtB = gram_factor(B)
-    npad = JtA.shape[0]
-    sA = D.to_device(np.sqrt(np.maximum(D.to_host(lamA), 0.0)))
-    sB = D.to_device(np.sqrt(np.maximum(D.to_host(lamB), 0.0)))
+    lamB, GrB = gram_factor(B)
     all_idx = _idx(np.arange(npad))
-    FAt = D.gather_rows(JtA, all_idx, row_scale=sA, cols=T)               # rows s_j u_j^T  (= F_A^T)
-    FBt = D.gather_rows(JtB, all_idx, row_scale=sB, cols=T)
+
+    def inv_sqrt(lam):
+        floor = lam.max() * T * eps * 64 if lam.size else 0.0
+        return D.to_device(np.sqrt(_inv_or_zero(np.maximum(lam, 0.0), floor)))
+
+    FAt = D.gather_rows(GrA, all_idx, row_scale=inv_sqrt(lamA), cols=T)   # rows sqrt(lambda_j) u_j^T (= F_A^T)
+    FBt = D.gather_rows(GrB, all_idx, row_scale=inv_sqrt(lamB), cols=T)
+    del GrA, GrB
     K = D.matmul(FAt, FBt, trans_b=True, alpha=1.0 / dof)                 # npad x npad, = F_A^T F_B / dof
     Kr, sig, Jt, sw = D.jacobi_svd(K, want_v=want_vectors)
     sweeps.append(sw)
@@ -132,7 +144,7 @@ def solve_real(A, B, want_vectors=True, force_route=None, use_tensor_cores=None)
     if not want_vectors:
         return SolveResult(sigma, {}, route, sweeps)
     # K = J Sigma U^T (rows of K orthogonalised): P = J columns, Q = unit rows of Kr
-    floor = sigma[0] * T * 2.3e-16 if sigma.size else 0.0
+    floor = sigma[0] * T * eps if sigma.size else 0.0
     inv = _inv_or_zero(sigma, floor)
     idx = _idx(order)
     Pt = D.gather_rows(Jt, idx, row_scale=D.to_device(inv / dof), cols=npad)          # rank x npad : p_j / (sigma dof)
