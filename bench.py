@@ -265,11 +265,13 @@ def run_product(args, rank, world, local_rank):
         v = prof["xmca_jacobi_svd"]
         sw = info.get("sweeps", [])
         n = T
-        fl = sum(6.0 * n ** 3 for _ in sw) if sw else 0.0      # 4mn^2 (+2mn^2 vectors) per sweep
-        fl = sum(s * 6.0 * n ** 3 for s in sw)
-        roof_list["xmca_jacobi_svd"] = {"bound": "fp64-simt", "achieved": fl / v["ms"] / 1e9, "peak": 40.0,
+        # blocked sweep: panel Gram 4 m n^2 + panel update 4 m n^2 (+ 4 n^3 when rotations are accumulated)
+        per_sweep = 8.0 * n ** 3 if info.get("route") == "cholqr" else 12.0 * n ** 3
+        fl = sum(s * per_sweep for s in sw)
+        roof_list["xmca_jacobi_svd"] = {"bound": "fp64", "achieved": fl / v["ms"] / 1e9, "peak": 37.0,
                                         "unit": "TFLOP/s", "sweeps": sw,
-                                        "note": "fp64 CUDA-core path; peak = nominal 40 TF fp64 (not in MEASURED_PEAKS)"}
+                                        "note": "fp64 CUDA-core path (tcgen05 has no fp64 kind); peak = 37 TFLOP/s DFMA "
+                                                "measured with scripts/ubench_fp64.cu (not in MEASURED_PEAKS.json)"}
     if "xmca_gemm" in prof:
         v = prof["xmca_gemm"]
         roof_list["xmca_gemm"] = {"bound": "fp64-simt", "ms": v["ms"], "calls": v["calls"]}

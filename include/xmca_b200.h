@@ -87,6 +87,26 @@ int xmca_jacobi_svd(int64_t m, int64_t n, double* d_Kc, int64_t ldk,
                     int max_sweeps, double tol, int* sweeps_out, double* offnorm_out,
                     void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* ---- Cholesky factorisation + triangular solve (fp64) ---------------------
+ * The "Cholesky-QR" route of the engine for T < S: with G_X = X X^T = L_X L_X^T
+ * the singular values of C = A^T B are those of the T x T matrix L_A^T L_B, so
+ * ONE Jacobi SVD replaces the three LAPACK SVDs of array.py:479 (x2) and :570,
+ * and V_X = X^T (L_X^{-T} P) replaces the back-projection of array.py:584.
+ * xmca_cholesky: d_A (n x n row-major, lda) is overwritten by its lower Cholesky
+ *   factor (strict upper part zeroed); d_invdiag receives the inverses of the
+ *   64 x 64 diagonal blocks (xmca_cholesky_invdiag_bytes).  Returns XMCA_NUMERIC
+ *   (info_out = 1 + failing column) if a pivot is not above min_pivot (>= 0): the
+ *   matrix is not numerically positive definite.
+ *   Synchronises `stream` once at the end to read that flag.
+ * xmca_trsm_lt: solves L^T W = R in place (R: n x nrhs row-major, ldr). */
+size_t xmca_cholesky_workspace_bytes(int64_t n);
+size_t xmca_cholesky_invdiag_bytes(int64_t n);
+int xmca_cholesky(int64_t n, double* d_A, int64_t lda, double* d_invdiag, double min_pivot,
+                  int* info_out, void* d_workspace, size_t workspace_bytes, void* stream);
+size_t xmca_trsm_workspace_bytes(int64_t n, int64_t nrhs);
+int xmca_trsm_lt(int64_t n, int64_t nrhs, const double* d_L, int64_t ldl, const double* d_invdiag,
+                 double* d_R, int64_t ldr, void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* ---- element-wise / layout helpers ---------------------------------------*/
 /* Y[r,c] = X[r,c] * (col_scale ? col_scale[c] : 1) * (row_scale ? row_scale[r] : 1);
  * row-major, dtypes may differ (conversion kernel).  array.py:553, :640, :667. */

@@ -149,3 +149,26 @@ def test_philox_normal_is_standard_and_geometry_independent(D):
     assert abs(((x - x.mean()) ** 4).mean() - 3) < 0.05
     Z = D.to_host(D.fill_normal(D.empty((1000, 501), t.float64), seed=42, stream_id=4))
     assert abs(np.corrcoef(x.ravel(), Z.ravel())[0, 1]) < 5e-3
+
+
+@pytest.mark.parametrize("n,nrhs", [(64, 5), (200, 37), (515, 515), (1000, 64)])
+def test_cholesky_and_triangular_solve(D, n, nrhs):
+    """Blocked fp64 Cholesky + L^T W = R against numpy."""
+    r = _rng(11)
+    X = r.standard_normal((n, 2 * n))
+    G = X @ X.T
+    Ld, inv = D.cholesky(D.to_device(G.copy()))
+    Lh = D.to_host(Ld)
+    want = np.linalg.cholesky(G)
+    np.testing.assert_allclose(Lh, want, rtol=0, atol=1e-11 * np.abs(want).max())
+    assert np.all(np.triu(Lh, 1) == 0.0)
+    R = r.standard_normal((n, nrhs))
+    W = D.to_host(D.trsm_lt(Ld, inv, D.to_device(R.copy())))
+    np.testing.assert_allclose(want.T @ W, R, atol=1e-9 * np.abs(R).max() * n)
+
+
+def test_cholesky_rejects_indefinite(D):
+    G = np.eye(130)
+    G[77, 77] = -1.0
+    with pytest.raises(np.linalg.LinAlgError):
+        D.cholesky(D.to_device(G))

@@ -114,7 +114,7 @@ def test_live_case_A_direct_route_fp32(MCA, live):
 def test_live_case_B_gram_route_fp64_promax4(MCA, live):
     m = MCA(live["B/left"].copy(), live["B/right"].copy())
     m.solve()
-    assert m._solve_info["route"] == "gram" and m._analysis["rank"] == 40
+    assert m._solve_info["route"] == "cholqr" and m._analysis["rank"] == 40
     assert m.singular_values().dtype == np.float64
     _check_state(m, live, "B", 8)
     assert m.singular_values()[39] < 1e-10 * m.singular_values()[0]     # centring's null mode
@@ -217,3 +217,41 @@ def test_rule_n_distribution_matches_oracle(MCA):
     np.testing.assert_allclose(np.median(got, axis=1), np.median(want, axis=1), rtol=0.15)
     again = m.rule_n(24, 8, seed=7)
     np.testing.assert_array_equal(got, again)              # counter-based RNG: reproducible
+
+
+@pytest.mark.parametrize("route", ["cholqr", "gram_eig"])
+@pytest.mark.parametrize("pca", [False, True])
+def test_gram_routes_agree_with_oracle(route, pca):
+    """Both T < S routes (Cholesky-QR: one Jacobi SVD; eigen route: the rank-deficiency
+    fallback) against the numpy oracle: all singular values and the leading vectors."""
+    from xmca_b200 import device as D, engine as E
+    A, B = orc.synthetic_fields(96, 260, 180, seed=21, k=6, dtype=np.float64)
+    ref = orc.solve(orc.make_model(A.copy()) if pca else orc.make_model(A.copy(), B.copy()))
+    dA = D.to_device(ref.fields["left"])
+    dB = None if pca else D.to_device(ref.fields["right"])
+    res = E.solve_real(dA, dB, force_route=route)
+    assert res.route == route
+    np.testing.assert_allclose(res.sigma[:90], ref.sigma[:90], rtol=1e-10)
+    np.testing.assert_allclose(res.sigma, ref.sigma, atol=1e-10 * ref.sigma[0])
+    VL = D.to_host(res.V["left"])
+    assert VL.shape == ref.V["left"].shape
+    got = [VL[:, :12]] + ([] if pca else [D.to_host(res.V["right"])[:, :12]])
+    al = orc.align_modes(ref.V["left"][:, :12], *got)
+    np.testing.assert_allclose(al[0], ref.V["left"][:, :12], atol=1e-8)
+    if not pca:
+        np.testing.assert_allclose(al[1], ref.V["right"][:, :12], atol=1e-8)
+    # orthonormality of every genuine mode (array.py test_orthogonality)
+    gram = VL[:, :94].T @ VL[:, :94]
+    np.testing.assert_allclose(gram, np.eye(94), atol=1e-8)
+
+
+def test_cholqr_falls_back_when_gram_is_singular():
+    """Duplicated time steps make X X^T rank deficient beyond the centring null vector:
+    the Cholesky route must hand over to the eigen route, not fail."""
+    from xmca_b200 import device as D, engine as E
+    A, B = orc.synthetic_fields(40, 100, 90, seed=2, k=3, dtype=np.float64)
+    A[7] = A[3]
+    ref = orc.solve(orc.make_model(A.copy(), B.copy()))
+    res = E.solve_real(D.to_device(ref.fields["left"]), D.to_device(ref.fields["right"]))
+    assert res.route == "gram_eig"
+    np.testing.assert_allclose(res.sigma[:30], ref.sigma[:30], rtol=1e-9)

@@ -67,6 +67,14 @@ def load():
     lib.xmca_jacobi_workspace_bytes.argtypes = [i64, i64]
     lib.xmca_jacobi_svd.argtypes = [i64, i64, vp, i64, vp, i64, vp, i32, dbl, C.POINTER(i32),
                                     C.POINTER(dbl), vp, sz, vp]
+    lib.xmca_cholesky_workspace_bytes.restype = sz
+    lib.xmca_cholesky_workspace_bytes.argtypes = [i64]
+    lib.xmca_cholesky_invdiag_bytes.restype = sz
+    lib.xmca_cholesky_invdiag_bytes.argtypes = [i64]
+    lib.xmca_cholesky.argtypes = [i64, vp, i64, vp, dbl, C.POINTER(i32), vp, sz, vp]
+    lib.xmca_trsm_workspace_bytes.restype = sz
+    lib.xmca_trsm_workspace_bytes.argtypes = [i64, i64]
+    lib.xmca_trsm_lt.argtypes = [i64, i64, vp, i64, vp, vp, i64, vp, sz, vp]
     lib.xmca_scale_copy.argtypes = [vp, i32, i64, vp, i32, i64, i64, i64, vp, vp, vp]
     lib.xmca_transpose.argtypes = [vp, i32, i64, i64, i64, vp, i32, i64, vp]
     lib.xmca_col_sumsq.argtypes = [vp, i32, i64, i64, i64, i64, vp, vp]
@@ -93,7 +101,8 @@ def load():
 # recorded on torch's current stream (the stream every call is enqueued on)
 # around each call while a profile is open.  Disabled -> one attribute lookup.
 _NO_TIMING = ("xmca_last_error", "xmca_version", "xmca_launch_count", "xmca_gemm_workspace_bytes",
-              "xmca_jacobi_padded_cols", "xmca_jacobi_workspace_bytes", "xmca_varimax_workspace_bytes")
+              "xmca_jacobi_padded_cols", "xmca_jacobi_workspace_bytes", "xmca_varimax_workspace_bytes",
+              "xmca_cholesky_workspace_bytes", "xmca_cholesky_invdiag_bytes", "xmca_trsm_workspace_bytes")
 _profile = None
 
 

@@ -1,0 +1,212 @@
+// Blocked Cholesky factorisation and triangular solve in fp64 -- the
+// orthogonalisation step of the engine's "Cholesky-QR" route for T < S:
+//
+//   G_A = A A^T = L_A L_A^T,  G_B = B B^T = L_B L_B^T        (T x T)
+//   C = A^T B = Q_A (L_A^T L_B) Q_B^T,  Q_X = X^T L_X^{-T} orthonormal,
+//
+// so the singular values of the S1 x S2 cross-covariance are those of the
+// T x T matrix M = L_A^T L_B and ONE Jacobi SVD replaces the three the
+// reference takes (array.py:479 twice, :570).  V = X^T (L_X^{-T} P) needs the
+// triangular solve below.
+//
+// Right-looking, block size 64:  the 64 x 64 diagonal block is factorised and
+// inverted by one CTA in shared memory; the panel solve and the trailing
+// update are products on the general fp64 kernel (xmca_gemm), which is where
+// all the n^3/3 work is.
+#include "common.cuh"
+#include <math.h>
+
+namespace xmca {
+
+constexpr int CB = 64;
+
+// One CTA, 256 threads.  A: n x n row-major (lda), block starting at (k0, k0) of
+// size nb (<= 64).  Writes L_kk in place (strict upper part of the block zeroed)
+// and inv(L_kk) (lower triangular, padded to 64 x 64 with an identity tail) to inv.
+// flag[0] is set to 1 + (failing column) when a pivot is not above min_pivot / finite.
+__global__ void __launch_bounds__(256)
+chol_diag_kernel(double* __restrict__ A, int64_t lda, int64_t k0, int nb, double* __restrict__ inv,
+                 int* __restrict__ flag, double min_pivot) {
+  extern __shared__ double chol_sm[];
+  double (*Ls)[CB + 1] = reinterpret_cast<double (*)[CB + 1]>(chol_sm);
+  double (*Is)[CB + 1] = reinterpret_cast<double (*)[CB + 1]>(chol_sm + CB * (CB + 1));
+  __shared__ int s_bad;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_bad = 0;
+  for (int e = tid; e < CB * CB; e += 256) {
+    int i = e >> 6, j = e & 63;
+    Ls[i][j] = (i < nb && j < nb && j <= i) ? A[(k0 + i) * lda + k0 + j] : ((i == j) ? 1.0 : 0.0);
+  }
+  __syncthreads();
+  for (int j = 0; j < nb; ++j) {
+    const double d = Ls[j][j];
+    if (!(d > min_pivot) || !isfinite(d)) {      // uniform: every thread reads the same value
+      if (tid == 0) s_bad = j + 1;
+      break;
+    }
+    const double r = sqrt(d);
+    __syncthreads();
+    for (int i = j + tid; i < nb; i += 256) Ls[i][j] = (i == j) ? r : Ls[i][j] / r;
+    __syncthreads();
+    // trailing update of the lower triangle: L[i][c] -= L[i][j] * L[c][j], j < c <= i
+    const int rem = nb - j - 1;
+    for (int e = tid; e < rem * rem; e += 256) {
+      int i = j + 1 + e / rem, c = j + 1 + e % rem;
+      if (c <= i) Ls[i][c] -= Ls[i][j] * Ls[c][j];
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (s_bad) {
+    if (tid == 0) atomicCAS(flag, 0, (int)(k0 + s_bad));
+    return;
+  }
+  // inverse of the lower-triangular block: column c of inv solves L x = e_c (forward substitution)
+  if (tid < CB) {
+    const int c = tid;
+    for (int i = 0; i < CB; ++i) {
+      double s = (i == c) ? 1.0 : 0.0;
+      for (int k = c; k < i; ++k) s -= Ls[i][k] * Is[k][c];
+      Is[i][c] = (i >= c) ? s / Ls[i][i] : 0.0;
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < CB * CB; e += 256) {
+    int i = e >> 6, j = e & 63;
+    inv[e] = Is[i][j];
+    if (i < nb && j < nb) A[(k0 + i) * lda + k0 + j] = (j <= i) ? Ls[i][j] : 0.0;
+  }
+}
+
+// zero the strict upper triangle of an n x n row-major matrix
+__global__ void zero_upper_kernel(double* __restrict__ A, int64_t lda, int64_t n) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  for (int64_t r = blockIdx.y; r < n; r += gridDim.y)
+    if (c > r) A[r * lda + c] = 0.0;
+}
+
+// Y (rows x cols, ldy) = X (ldx)
+__global__ void copy_block_kernel(const double* __restrict__ X, int64_t ldx, double* __restrict__ Y,
+                                  int64_t ldy, int64_t rows, int64_t cols) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) Y[r * ldy + c] = X[r * ldx + c];
+}
+
+static inline unsigned yblocks(int64_t rows) {
+  int64_t want = 8LL * sm_count();
+  int64_t g = rows < want ? rows : want;
+  return (unsigned)(g < 1 ? 1 : (g > 65535 ? 65535 : g));
+}
+
+static int copy_block(const double* X, int64_t ldx, double* Y, int64_t ldy, int64_t rows, int64_t cols,
+                      cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return XMCA_OK;
+  dim3 grid((unsigned)((cols + 127) / 128), yblocks(rows));
+  copy_block_kernel<<<grid, 128, 0, st>>>(X, ldx, Y, ldy, rows, cols);
+  XMCA_LAUNCHED();
+  return XMCA_OK;
+}
+
+struct CholPlan { int64_t nblk; size_t off_inv, off_panel, off_flag, total; };
+
+static CholPlan chol_plan(int64_t n, int64_t nrhs) {
+  CholPlan p;
+  p.nblk = (n + CB - 1) / CB;
+  size_t o = 0;
+  p.off_inv = o;   o += (size_t)p.nblk * CB * CB * sizeof(double);
+  int64_t w = nrhs > CB ? nrhs : CB;
+  p.off_panel = o; o += ((size_t)n * CB + (size_t)CB * w) * sizeof(double);
+  p.off_flag = o;  o += 256;
+  p.total = o;
+  return p;
+}
+
+}  // namespace xmca
+
+using namespace xmca;
+
+extern "C" size_t xmca_cholesky_workspace_bytes(int64_t n) { return chol_plan(n, CB).total; }
+extern "C" size_t xmca_cholesky_invdiag_bytes(int64_t n) {
+  return (size_t)((n + CB - 1) / CB) * CB * CB * sizeof(double);
+}
+
+extern "C" int xmca_cholesky(int64_t n, double* d_A, int64_t lda, double* d_invdiag, double min_pivot,
+                             int* info_out, void* d_workspace, size_t workspace_bytes, void* stream) {
+  XMCA_REQUIRE(n > 0 && d_A && d_invdiag && d_workspace, "xmca_cholesky: bad argument");
+  XMCA_REQUIRE(lda >= n, "xmca_cholesky: lda < n");
+  CholPlan pl = chol_plan(n, CB);
+  XMCA_REQUIRE(workspace_bytes >= pl.total, "xmca_cholesky: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = reinterpret_cast<char*>(d_workspace);
+  double* panel = reinterpret_cast<double*>(ws + pl.off_panel);
+  int* flag = reinterpret_cast<int*>(ws + pl.off_flag);
+  XMCA_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  const size_t diag_smem = 2 * CB * (CB + 1) * sizeof(double);
+  XMCA_CUDA(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)diag_smem));
+  for (int64_t b = 0; b < pl.nblk; ++b) {
+    const int64_t k0 = b * CB;
+    const int nb = (int)((n - k0) < CB ? (n - k0) : CB);
+    double* inv = d_invdiag + (size_t)b * CB * CB;
+    chol_diag_kernel<<<1, 256, diag_smem, st>>>(d_A, lda, k0, nb, inv, flag, min_pivot > 0.0 ? min_pivot : 0.0);
+    XMCA_LAUNCHED();
+    const int64_t rem = n - k0 - nb;
+    if (rem <= 0) break;
+    // panel: L_ik = A_ik inv(L_kk)^T   (rem x nb) -> workspace, then back in place
+    double* Aik = d_A + (k0 + nb) * lda + k0;
+    int rc = xmca_gemm(1, 1, rem, nb, nb, 1.0, Aik, XMCA_F64, lda, inv, XMCA_F64, CB, panel, XMCA_F64, CB, 0,
+                       XMCA_F64, 1, nullptr, 0, stream);
+    if (rc != XMCA_OK) return rc;
+    if ((rc = copy_block(panel, CB, Aik, lda, rem, nb, st)) != XMCA_OK) return rc;
+    // trailing update: A_ij -= L_ik L_jk^T (full square; only the lower half is used later)
+    double* Att = d_A + (k0 + nb) * lda + (k0 + nb);
+    rc = xmca_gemm(1, 1, rem, rem, nb, -1.0, panel, XMCA_F64, CB, panel, XMCA_F64, CB, Att, XMCA_F64, lda, 1,
+                   XMCA_F64, 1, nullptr, 0, stream);
+    if (rc != XMCA_OK) return rc;
+  }
+  {
+    dim3 grid((unsigned)((n + 127) / 128), yblocks(n));
+    zero_upper_kernel<<<grid, 128, 0, st>>>(d_A, lda, n);
+    XMCA_LAUNCHED();
+  }
+  int h_flag = 0;
+  XMCA_CUDA(cudaMemcpyAsync(&h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  XMCA_CUDA(cudaStreamSynchronize(st));
+  if (info_out) *info_out = h_flag;
+  if (h_flag != 0)
+    return fail(XMCA_NUMERIC, "xmca_cholesky: matrix is not (numerically) positive definite", __FILE__, __LINE__);
+  return XMCA_OK;
+}
+
+extern "C" size_t xmca_trsm_workspace_bytes(int64_t n, int64_t nrhs) { return chol_plan(n, nrhs).total; }
+
+// Solve L^T W = R in place (R: n x nrhs row-major, ldr), L lower triangular from
+// xmca_cholesky with its inverted diagonal blocks.
+extern "C" int xmca_trsm_lt(int64_t n, int64_t nrhs, const double* d_L, int64_t ldl,
+                            const double* d_invdiag, double* d_R, int64_t ldr,
+                            void* d_workspace, size_t workspace_bytes, void* stream) {
+  XMCA_REQUIRE(n > 0 && nrhs > 0 && d_L && d_invdiag && d_R && d_workspace, "xmca_trsm_lt: bad argument");
+  XMCA_REQUIRE(ldl >= n && ldr >= nrhs, "xmca_trsm_lt: leading dimension too small");
+  CholPlan pl = chol_plan(n, nrhs);
+  XMCA_REQUIRE(workspace_bytes >= pl.total, "xmca_trsm_lt: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* tmp = reinterpret_cast<double*>(reinterpret_cast<char*>(d_workspace) + pl.off_panel);  // 64 x nrhs
+  for (int64_t b = pl.nblk - 1; b >= 0; --b) {
+    const int64_t k0 = b * CB;
+    const int nb = (int)((n - k0) < CB ? (n - k0) : CB);
+    const double* inv = d_invdiag + (size_t)b * CB * CB;
+    double* Rk = d_R + k0 * ldr;
+    // W_k = inv(L_kk)^T R_k : A[m][kk] = inv[kk][m] (stored K x M)
+    int rc = xmca_gemm(0, 0, nb, nrhs, nb, 1.0, inv, XMCA_F64, CB, Rk, XMCA_F64, ldr, tmp, XMCA_F64, nrhs, 0,
+                       XMCA_F64, 1, nullptr, 0, stream);
+    if (rc != XMCA_OK) return rc;
+    if ((rc = copy_block(tmp, nrhs, Rk, ldr, nb, nrhs, st)) != XMCA_OK) return rc;
+    if (k0 == 0) break;
+    // R_i -= L_ki^T W_k for all i < k :  A[m][kk] = L[k0 + kk][m]  (stored K x M, lda = ldl)
+    rc = xmca_gemm(0, 0, k0, nrhs, nb, -1.0, d_L + k0 * ldl, XMCA_F64, ldl, tmp, XMCA_F64, nrhs, d_R, XMCA_F64,
+                   ldr, 1, XMCA_F64, 1, nullptr, 0, stream);
+    if (rc != XMCA_OK) return rc;
+  }
+  return XMCA_OK;
+}

@@ -171,6 +171,39 @@ def jacobi_svd(X, want_v=True, max_sweeps=40, tol=0.0):
     return Xp, sigma, Jt, sweeps.value
 
 
+# ------------------------------------------------------------------ Cholesky
+def cholesky(G, min_pivot=0.0):
+    """In-place lower Cholesky factor of the fp64 SPD matrix G (n x n).
+    Returns (L (= G, overwritten), invdiag).  Raises LinAlgError if a pivot is not
+    above ``min_pivot`` (G not numerically SPD)."""
+    lib = L.load()
+    t = torch()
+    n = G.shape[0]
+    assert G.dtype == t.float64 and G.shape[1] == n
+    invdiag = empty((lib.xmca_cholesky_invdiag_bytes(n) // 8,), t.float64)
+    ws_bytes = lib.xmca_cholesky_workspace_bytes(n)
+    ws = empty((ws_bytes,), t.uint8)
+    info = C.c_int(0)
+    rc = lib.xmca_cholesky(n, L.ptr(G), _ld(G), L.ptr(invdiag), float(min_pivot), C.byref(info), L.ptr(ws),
+                           ws_bytes, L.stream_ptr())
+    L.check(rc, "xmca_cholesky")
+    return G, invdiag
+
+
+def trsm_lt(Lmat, invdiag, R):
+    """Solve Lmat^T W = R in place (R: n x nrhs fp64, row-major); returns R."""
+    lib = L.load()
+    t = torch()
+    n, nrhs = R.shape
+    assert R.dtype == t.float64 and Lmat.shape[0] == n
+    ws_bytes = lib.xmca_trsm_workspace_bytes(n, nrhs)
+    ws = empty((ws_bytes,), t.uint8)
+    rc = lib.xmca_trsm_lt(n, nrhs, L.ptr(Lmat), _ld(Lmat), L.ptr(invdiag), L.ptr(R), _ld(R), L.ptr(ws), ws_bytes,
+                          L.stream_ptr())
+    L.check(rc, "xmca_trsm_lt")
+    return R
+
+
 # ------------------------------------------------------------- element-wise
 def scale_copy(X, out_dtype=None, col_scale=None, row_scale=None, out=None):
     lib = L.load()

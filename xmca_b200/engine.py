@@ -60,7 +60,7 @@ def _rows_to_cols(rows, out_dtype):
     return D.transpose(rows, out_dtype=out_dtype)
 
 
-def solve_real(A, B, want_vectors=True, force_route=None, use_tensor_cores=None):
+def solve_real(A, B, want_vectors=True, force_route=None, use_tensor_cores=None, null_basis=None):
     """A, B: centred device fields (T x S1, T x S2), fp32 or fp64; B may be None (PCA)."""
     t = D.torch()
     T, S1 = A.shape
@@ -71,6 +71,13 @@ def solve_real(A, B, want_vectors=True, force_route=None, use_tensor_cores=None)
     rank = min(T, S1, S2)
     route = force_route or ("direct" if min(S1, S2) <= T else "gram")
     sweeps = []
+    if route in ("gram", "cholqr"):
+        try:
+            return _solve_cholqr(A, B, want_vectors, null_basis)
+        except np.linalg.LinAlgError:
+            if route == "cholqr":
+                raise
+            route = "gram_eig"      # Gram matrix not numerically SPD: eigen route copes with rank deficiency
 
     if route == "direct":
         # ---- C (or C^T) with the short side as rows, fp64 accumulation -------------
@@ -156,6 +163,82 @@ def solve_real(A, B, want_vectors=True, force_route=None, use_tensor_cores=None)
     return SolveResult(sigma, {"left": VL, "right": VR}, route, sweeps)
 
 
+# ---------------------------------------------------------------- Cholesky-QR
+def _solve_cholqr(A, B, want_vectors, null_basis=None):
+    """T < min(S1, S2): ONE T x T Jacobi SVD instead of three decompositions.
+
+    Centring makes n = 1/sqrt(T) an exact null vector of X X^T (for the real
+    embedding of a complex field there are two, ``null_basis``).  With
+    X~ = [X, sqrt(mu) n] (one column appended per null vector; it lifts the zero
+    eigenvalue to mu = 4 trace(X X^T), above every genuine one) and the Cholesky
+    factor X~ X~^T = L L^T:   X~^T = Q L^T with Q = X~^T L^-T orthonormal, hence
+        C~ = A~^T B~ / dof = Q_A (L_A^T L_B / dof) Q_B^T = (Q_A P) Sigma (Q_B Q)^T.
+    C~ = diag(C, sqrt(mu_A mu_B) / dof): the appended directions do not couple with
+    the data (X^T n = 0) and show up as extra singular values, the largest by
+    construction, which are dropped.  V_X = X^T (L_X^-T P).
+    PCA: C = A^T A / dof = Q_A (L_A^T L_A / dof) Q_A^T -> SVD of L_A itself."""
+    T, S1 = A.shape
+    dof = float(T - 1)
+    pca = B is None
+    out_dtype = A.dtype
+    Nb = null_basis if null_basis is not None else D.to_device(np.full((T, 1), 1.0 / np.sqrt(T)))
+    k = Nb.shape[1]
+
+    def factor(X):
+        G = D.matmul(X, X, trans_b=True)                                  # T x T fp64 Gram
+        tr = float(D.to_host(D.col_sumsq(X)).sum())                        # trace(G) = ||X||_F^2
+        if not np.isfinite(tr) or tr <= 0.0:
+            raise np.linalg.LinAlgError("empty or non-finite field")
+        mu = 4.0 * tr
+        D.matmul(Nb, Nb, trans_b=True, alpha=mu, out=G, accumulate=True)   # + mu N N^T
+        # pivots below ~1e-11 of the mean diagonal: rank deficient beyond the centring null
+        # vector (e.g. repeated time steps) -> LinAlgError -> eigen route
+        Lm, inv = D.cholesky(G, min_pivot=1e-11 * tr / T)
+        return Lm, inv, mu
+
+    LA, invA, muA = factor(A)
+    if pca:
+        M = LA
+        extra = muA / dof                        # eigenvalue of the appended directions, / dof
+    else:
+        LB, invB, muB = factor(B)
+        M = D.matmul(LA, LB, trans_a=True, alpha=1.0 / dof)               # T x T
+        extra = np.sqrt(muA * muB) / dof
+    Mr, sig, _, sw = D.jacobi_svd(M, want_v=False)      # rows of Mr: sigma_j q_j^T (right singular vectors of M)
+    s = D.to_host(sig)
+    order = np.argsort(-s, kind="stable")[:T]
+    sv = s[order]
+    sigma_all = sv * sv / dof if pca else sv
+    if np.abs(sigma_all[:k] - extra).max() > 1e-6 * extra or (T > k and sigma_all[k] > 0.5 * extra):
+        raise np.linalg.LinAlgError("appended directions not isolated (fields not centred?)")
+    sigma = np.concatenate([sigma_all[k:], np.zeros(k)])  # rank = T modes, the last k are the centring null modes
+    if not want_vectors:
+        return SolveResult(sigma, {}, "cholqr", [sw])
+    real = order[k:]
+    nreal = real.size
+    floor = sv[k] * T * 2.3e-16 if nreal else 0.0
+    inv_s = _inv_or_zero(sv[k:], floor)
+    Qt = D.gather_rows(Mr, _idx(real), row_scale=D.to_device(inv_s), cols=T)      # nreal x T, unit rows q_j^T
+
+    def back_project(X, Lm, inv, Wt):
+        """V = X^T (L^-T W), W = Wt^T (T x nreal)."""
+        W = D.transpose(Wt)                                                # T x nreal
+        D.trsm_lt(Lm, inv, W)
+        V = D.zeros((X.shape[1], T), out_dtype)
+        D.matmul(X, W, trans_a=True, out=V[:, :nreal])
+        return V
+
+    if pca:
+        return SolveResult(sigma, {"left": back_project(A, LA, invA, Qt)}, "cholqr", [sw])
+    # P = M Q Sigma^-1  ->  Pt = Sigma^-1 Q^T M^T
+    Pt = D.matmul(Qt, M, trans_b=True)
+    Pt = D.scale_copy(Pt, row_scale=D.to_device(inv_s))
+    VL = back_project(A, LA, invA, Pt)
+    del LA, invA, Pt
+    VR = back_project(B, LB, invB, Qt)
+    return SolveResult(sigma, {"left": VL, "right": VR}, "cholqr", [sw])
+
+
 # ------------------------------------------------------------------ complex
 def embed_complex_field(Z: np.ndarray):
     """Host helper: real embedding [[X, -Y], [Y, X]] of a complex T x S field."""
@@ -171,8 +254,11 @@ def solve_complex(Ae, Be, want_vectors=True):
     pca = Be is None
     S2 = S1 if pca else Be.shape[1] // 2
     rank = min(T, S1, S2)
-    # the embedded problem has every singular value twice; dof of the ORIGINAL problem
-    res = solve_real(Ae, Be, want_vectors=want_vectors)
+    # the embedded problem has every singular value twice; dof of the ORIGINAL problem.
+    # Null vectors of the centred embedding: [1; 0] and [0; 1] (real and imaginary time means).
+    nb = np.zeros((T2, 2))
+    nb[:T, 0] = nb[T:, 1] = 1.0 / np.sqrt(T)
+    res = solve_real(Ae, Be, want_vectors=want_vectors, null_basis=D.to_device(nb))
     scale = (T2 - 1.0) / (T - 1.0)            # solve_real divided by (2T - 1)
     sigma2 = res.sigma * scale
     sigma = sigma2[0:2 * rank:2]
