@@ -79,6 +79,8 @@ int xmca_tc_gemm_nt(int64_t M, int64_t N, int64_t K, float alpha,
  * d_Jc : optional n_pad x n_pad column-major fp64 (ldj >= n_pad), overwritten
  *        with the accumulated right rotations (right singular vectors).
  * d_sigma : n_pad doubles, column norms on return (NOT sorted; host sorts).
+ * tol : sweeps stop once the largest cosine |x_i.x_j| / (|x_i||x_j|) seen BEFORE a sweep
+ *       is <= tol (<= 0: 1e-11).  Columns below 1e-11 of the largest norm count as zero.
  * Synchronises `stream` once per sweep to read the convergence measure. */
 int64_t xmca_jacobi_padded_cols(int64_t n);
 size_t xmca_jacobi_workspace_bytes(int64_t m, int64_t n);
@@ -122,6 +124,15 @@ int xmca_col_sumsq(const void* d_X, int x_dtype, int64_t ldx, int64_t row0, int6
 /* subtract the column mean in place (array.py:199-207), mean returned in d_mean (fp64). */
 int xmca_center_columns(void* d_X, int x_dtype, int64_t rows, int64_t cols, int64_t ldx,
                         double* d_mean, void* stream);
+/* Constructor pre-processing on the device (array.py:191-240, tools/array.py:26-73):
+ * per column mean / std (ddof 0) / "contains a NaN" flag, per row "has a valid value" flag. */
+int xmca_field_stats(const void* d_X, int x_dtype, int64_t rows, int64_t cols, int64_t ldx,
+                     double* d_mean, double* d_std, int* d_col_nan, int* d_row_valid, void* stream);
+/* Y[r, j] = X[r, idx[j]] - mean[idx[j]]: drop the NaN columns and centre (array.py:199-228),
+ * subtraction in the precision of X like the reference. */
+int xmca_compact_center(const void* d_X, int x_dtype, int64_t rows, int64_t ldx,
+                        const int64_t* d_idx, int64_t n_keep, const double* d_mean,
+                        void* d_Y, int y_dtype, int64_t ldy, void* stream);
 /* fill X (rows x cols) with N(0,1) from Philox4x32-10, counter = element index,
  * key = (seed, stream_id): result independent of launch geometry. array.py:1756. */
 int xmca_fill_normal(void* d_X, int x_dtype, int64_t rows, int64_t cols, int64_t ldx,

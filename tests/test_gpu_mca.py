@@ -255,3 +255,37 @@ def test_cholqr_falls_back_when_gram_is_singular():
     res = E.solve_real(D.to_device(ref.fields["left"]), D.to_device(ref.fields["right"]))
     assert res.route == "gram_eig"
     np.testing.assert_allclose(res.sigma[:30], ref.sigma[:30], rtol=1e-9)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_device_ingest_matches_reference_constructor(MCA, dtype):
+    """Constructor pre-processing on the GPU (NaN scan, NaN-column drop, mean/std, centring)
+    against numpy: array.py:191-240 semantics, incl. the reference's unit-test cases."""
+    rng = np.random.default_rng(7)
+    A = (rng.standard_normal((500, 20, 15)) * 3 + 280).astype(dtype)
+    B = rng.standard_normal((500, 15, 10)).astype(dtype)
+    hole = A.copy()
+    hole[:, 2, 3] = np.nan
+    hole[17, 5, 5] = np.nan                      # a single NaN also removes its column
+    m = MCA(hole, B)
+    flat = hole.reshape(500, 300)
+    keep = ~np.isnan(flat).any(axis=0)
+    assert keep.sum() == 298 and np.array_equal(m._no_nan_index["left"], keep)
+    assert m._n_variables["left"] == 300 and "left" not in m._host          # nothing downloaded yet
+    want = flat[:, keep] - flat[:, keep].mean(axis=0)
+    tol = 1e-4 if dtype == np.float32 else 1e-11     # |x| ~ 280: one fp32 ulp of the mean is 3e-5
+    assert m._fields["left"].dtype == dtype and m._fields["left"].shape == (500, 298)
+    np.testing.assert_allclose(m._fields["left"], want, atol=tol)
+    np.testing.assert_allclose(m._field_means["left"], flat[:, keep].mean(axis=0), rtol=1e-6)
+    np.testing.assert_allclose(m._field_stds["left"], flat[:, keep].std(axis=0), rtol=1e-5)
+    assert m._field_means["left"].dtype == dtype
+    f = m.fields(original_scale=True)["left"]
+    assert f.shape == A.shape and np.isnan(f[:, 2, 3]).all()
+    np.testing.assert_allclose(np.nan_to_num(f), np.nan_to_num(np.where(np.isnan(f), np.nan, hole)), atol=tol * 10)
+    bad = A.copy()
+    bad[3] = np.nan
+    with pytest.raises(ValueError):
+        MCA(bad)
+    m.solve()                                     # the ingested device fields feed solve() directly
+    ref = orc.solve(orc.make_model(hole.copy(), B.copy()))
+    np.testing.assert_allclose(m.singular_values(10), ref.sigma[:10], rtol=2e-5 if dtype == np.float32 else 1e-10)

@@ -79,6 +79,8 @@ def load():
     lib.xmca_transpose.argtypes = [vp, i32, i64, i64, i64, vp, i32, i64, vp]
     lib.xmca_col_sumsq.argtypes = [vp, i32, i64, i64, i64, i64, vp, vp]
     lib.xmca_center_columns.argtypes = [vp, i32, i64, i64, i64, vp, vp]
+    lib.xmca_field_stats.argtypes = [vp, i32, i64, i64, i64, vp, vp, vp, vp, vp]
+    lib.xmca_compact_center.argtypes = [vp, i32, i64, i64, vp, i64, vp, vp, i32, i64, vp]
     lib.xmca_fill_normal.argtypes = [vp, i32, i64, i64, i64, C.c_uint64, C.c_uint64, vp]
     lib.xmca_gather_rows.argtypes = [vp, i32, i64, vp, i64, i64, vp, vp, i32, i64, vp]
     lib.xmca_row_sumsq.argtypes = [vp, i32, i64, i64, i64, vp, vp]
@@ -153,6 +155,14 @@ def profile_end():
         d["launches"] += nl
         d["ms"] += e0.elapsed_time(e1)
     return out
+
+
+def cuda_available() -> bool:
+    try:
+        import torch
+        return bool(torch.cuda.is_available())
+    except Exception:
+        return False
 
 
 def launch_count() -> int:

@@ -41,15 +41,9 @@ class MCA:
         if not all(isinstance(f, np.ndarray) for f in fields):
             raise TypeError("One or more fields are not `numpy.ndarray`. "
                             "Please provide `numpy.ndarray` only.")
-        for f in fields:      # a NaN time step = a row that is NaN everywhere (tools/array.py:65-73)
-            if np.isnan(f).all(axis=tuple(range(1, f.ndim))).any():
-                raise ValueError("One or more fields contain NaN time steps. "
-                                 "Please remove these prior to analysis.")
-
-        self._keys = list(_SIDES[:max(len(fields), 1)]) if len(fields) else list(_SIDES)
-        if len(fields) == 1:
-            self._keys = ["left"]
-        self._fields = {}
+        self._keys = list(_SIDES[:len(fields)])
+        self._host = {}           # host mirror of the centred fields (filled lazily, see `_fields`)
+        self._dev = {}            # device copies of the centred (possibly complex-embedded) fields
         self._shape = {}
         self._field_names = {}
         self._field_means = {}
@@ -58,6 +52,7 @@ class MCA:
         self._n_variables = {}
         self._no_nan_index = {}
         self._n_observations = {}
+        on_device = L.cuda_available()
         for k, f in zip(self._keys, fields):
             self._shape[k] = f.shape
             self._n_observations[k] = f.shape[0]
@@ -65,18 +60,16 @@ class MCA:
             self._n_variables[k] = int(np.prod(f.shape[1:]))      # incl. NaN columns (array.py:196)
             self._field_names[k] = k
             flat = f.reshape(f.shape[0], self._n_variables[k])
-            keep = ~np.isnan(flat).any(axis=0)
-            self._no_nan_index[k] = keep
-            flat = flat[:, keep]
-            with warnings.catch_warnings():
-                warnings.simplefilter("ignore", category=RuntimeWarning)
-                self._field_means[k] = flat.mean(axis=0)
-                self._field_stds[k] = flat.std(axis=0)
-                self._fields[k] = flat - flat.mean(axis=0)        # dtype preserved (array.py:199-207)
+            if not np.issubdtype(flat.dtype, np.floating) or flat.dtype.itemsize < 4:
+                flat = flat.astype(np.float64)
+            if on_device:
+                self._ingest_device(k, flat)
+            else:
+                self._ingest_host(k, flat)
 
         self._analysis = {
             "version": __version__,
-            "is_bivariate": len(self._fields) > 1,
+            "is_bivariate": len(self._keys) > 1,
             "is_normalized": False,
             "is_coslat_corrected": False,
             "method": "pca",
@@ -93,9 +86,65 @@ class MCA:
             "total_squared_covariance": 0.0,
         }
         self._analysis["method"] = self._get_method_id()
-        self._dev = {}            # device copies of the (possibly complex-embedded) fields
         self._dV = None           # device singular vectors
         self._solve_info = {}
+
+    # ---------------------------------------------------------------- ingest
+    _NAN_STEP_MSG = ("One or more fields contain NaN time steps. "
+                     "Please remove these prior to analysis.")
+
+    def _ingest_device(self, k, flat):
+        """Constructor pre-processing of array.py:191-240 on the GPU: upload the raw field
+        once, NaN scan + column mean/std in one kernel, then drop the NaN columns and centre
+        in a second one.  Only the O(S) statistics come back to the host."""
+        raw = D.to_device(flat)
+        mean, std, col_nan, row_ok = D.field_stats(raw)
+        if not row_ok.all():      # a NaN time step = a row that is NaN everywhere (tools/array.py:65-73)
+            raise ValueError(self._NAN_STEP_MSG)
+        keep = ~col_nan
+        self._no_nan_index[k] = keep
+        self._field_means[k] = mean[keep].astype(flat.dtype)
+        self._field_stds[k] = std[keep].astype(flat.dtype)
+        self._dev[k] = D.compact_center(raw, np.flatnonzero(keep), mean)
+
+    def _ingest_host(self, k, flat):
+        """The same bookkeeping in numpy, used only on a machine WITHOUT a CUDA device so that
+        the class (validation, metadata, mode slicing) can still be constructed there; every
+        numerical method (`solve`, `rotate`, getters, `rule_n`) raises without the GPU."""
+        if np.isnan(flat).all(axis=1).any():
+            raise ValueError(self._NAN_STEP_MSG)
+        keep = ~np.isnan(flat).any(axis=0)
+        self._no_nan_index[k] = keep
+        flat = flat[:, keep]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", category=RuntimeWarning)
+            self._field_means[k] = flat.mean(axis=0)
+            self._field_stds[k] = flat.std(axis=0)
+            self._host[k] = flat - flat.mean(axis=0)          # dtype preserved (array.py:199-207)
+
+    @property
+    def _fields(self):
+        """Centred fields on the host, keyed 'left'/'right' (array.py `_fields`).  The device
+        copy is the primary one; the host mirror is downloaded on first use."""
+        for k in self._keys:
+            if k not in self._host:
+                self._host[k] = D.to_host(self._dev[k])
+        return {k: self._host[k] for k in self._keys}
+
+    @_fields.setter
+    def _fields(self, value):
+        self._host = dict(value)
+        self._dev = {}
+
+    def _n_kept(self, k):
+        return int(self._no_nan_index[k].sum())
+
+    def _field_dtype(self, k):
+        """dtype of `_fields[k]` without materialising the host mirror."""
+        real = self._field_means[k].dtype
+        if self._analysis["is_complex"]:
+            return np.dtype(np.complex64 if real == np.float32 else np.complex128)
+        return real
 
     # --------------------------------------------------------------- helpers
     def _get_method_id(self):
@@ -120,17 +169,13 @@ class MCA:
 
     def apply_weights(self, left=None, right=None):
         w = {"left": 1 if left is None else left, "right": 1 if right is None else right}
-        for k in self._keys:
-            self._fields[k] = self._fields[k] * w[k]
-        self._dev = {}
+        self._fields = {k: f * w[k] for k, f in self._fields.items()}
 
     def normalize(self):
-        for k in self._keys:
-            self._fields[k] = self._fields[k] / self._field_stds[k]
+        self._fields = {k: f / self._field_stds[k] for k, f in self._fields.items()}
         self._analysis["is_normalized"] = True
         self._analysis["is_coslat_corrected"] = False
         self._analysis["method"] = self._get_method_id()
-        self._dev = {}
 
     def _get_X(self, original_scale=False, real=False):
         X = {k: f.copy() for k, f in self._fields.items()}
@@ -155,9 +200,9 @@ class MCA:
     # ------------------------------------------------------------ device I/O
     def _device_fields(self):
         """Upload (once) the centred fields; complex fields as real embeddings."""
-        if not self._dev:
-            for k in self._keys:
-                f = self._fields[k]
+        for k in self._keys:
+            if k not in self._dev:
+                f = self._host[k]
                 if np.iscomplexobj(f):
                     f = E.embed_complex_field(f)
                 self._dev[k] = D.to_device(f)
@@ -180,8 +225,9 @@ class MCA:
     # ----------------------------------------------------------------- solve
     def solve(self, complexify=False, extend=False, period=1):
         """Solve the MCA/PCA problem on the GPU (semantics of array.py:509-603)."""
-        if len(self._fields) == 0 or any(np.isnan(f).all() for f in self._fields.values()):
+        if len(self._keys) == 0 or any(self._n_kept(k) == 0 for k in self._keys):
             raise RuntimeError("Fields are empty. Did you forget to load data?")
+        L._torch()                # no CUDA device -> XmcaLibraryError: there is no CPU fallback
         if extend:
             raise NotImplementedError("Hilbert extension (extend='exp'|'theta') is outside the B200 "
                                       "engine's scope (SURVEY.md section 2a #11).")
@@ -195,7 +241,7 @@ class MCA:
         dev = self._device_fields()
         A = dev["left"]
         B = dev.get("right")
-        real_dtype = np.float32 if self._fields["left"].real.dtype == np.float32 else np.float64
+        real_dtype = self._field_means["left"].dtype.type
         try:
             if complexify:
                 sigma, Vc, res = E.solve_complex(A, B)
@@ -319,7 +365,7 @@ class MCA:
                     Ud = D.matmul(Ud, D.to_device(np.ascontiguousarray(Rit)))
                 u = D.to_host(Ud)
                 if not rotated:
-                    u = u.astype(self._fields[k].dtype)
+                    u = u.astype(self._field_dtype(k))
             else:
                 vr, vi = self._V_device_cols(k, top)
                 t = D.torch()
@@ -332,7 +378,7 @@ class MCA:
                 if is_rot:
                     u = u @ Rit
                 if not rotated:
-                    u = u.astype(self._fields[k].dtype)
+                    u = u.astype(self._field_dtype(k))
             if rotated:
                 u = u[:, self._var_idx]
             out[k] = u[:, keep]

@@ -234,6 +234,88 @@ __global__ void promax_target_kernel(const double* __restrict__ X, int64_t ldx, 
   }
 }
 
+// ------------------------------------------------------------ field ingest
+// Constructor pre-processing on the device (array.py:191-240): per column the
+// NaN flag, mean and standard deviation (ddof = 0, two-pass like numpy);
+// one block = a strip of 32 columns x all rows, 8 row lanes per column.
+__global__ void field_col_stats_kernel(const void* __restrict__ X, int xdt, int64_t rows, int64_t cols,
+                                       int64_t ldx, double* __restrict__ mean, double* __restrict__ stdv,
+                                       int* __restrict__ col_nan) {
+  __shared__ double red[8][33];
+  __shared__ int flag[8][33];
+  const int64_t c = (int64_t)blockIdx.x * 32 + threadIdx.x;
+  double s = 0.0;
+  int bad = 0;
+  if (c < cols)
+    for (int64_t r = threadIdx.y; r < rows; r += 8) {
+      double v = load_as_double(X, xdt, r * ldx + c);
+      bad |= (v != v);
+      s += v;
+    }
+  red[threadIdx.y][threadIdx.x] = s;
+  flag[threadIdx.y][threadIdx.x] = bad;
+  __syncthreads();
+  double mu = 0.0;
+  int anybad = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { mu += red[i][threadIdx.x]; anybad |= flag[i][threadIdx.x]; }
+  mu /= (double)rows;
+  __syncthreads();
+  double q = 0.0;
+  if (c < cols && !anybad)
+    for (int64_t r = threadIdx.y; r < rows; r += 8) {
+      double d = load_as_double(X, xdt, r * ldx + c) - mu;
+      q = fma(d, d, q);
+    }
+  red[threadIdx.y][threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    mean[c] = mu;
+    stdv[c] = sqrt(t / (double)rows);
+    col_nan[c] = anybad;
+  }
+}
+
+// row_valid[r] = 1 if the row holds at least one non-NaN value (tools/array.py:65-73); one warp per row
+__global__ void field_row_valid_kernel(const void* __restrict__ X, int xdt, int64_t rows, int64_t cols,
+                                       int64_t ldx, int* __restrict__ row_valid) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
+    int ok = 0;
+    for (int64_t c = lane; c < cols && !ok; c += 32) {
+      double v = load_as_double(X, xdt, r * ldx + c);
+      ok |= (v == v);
+    }
+    ok = __any_sync(0xffffffffu, ok);
+    if (lane == 0) row_valid[r] = ok;
+  }
+}
+
+// Y[r, j] = X[r, idx[j]] - mean[idx[j]], subtraction in the field's own precision (array.py:199-207)
+__global__ void compact_center_kernel(const void* __restrict__ X, int xdt, int64_t rows, int64_t ldx,
+                                      const int64_t* __restrict__ idx, int64_t n_keep,
+                                      const double* __restrict__ mean, void* __restrict__ Y, int ydt,
+                                      int64_t ldy) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_keep) return;
+  const int64_t c = idx[j];
+  const double mu = mean[c];
+  if (xdt == XMCA_F32) {
+    const float muf = (float)mu;
+    const float* x = reinterpret_cast<const float*>(X);
+    for (int64_t r = blockIdx.y; r < rows; r += gridDim.y)
+      store_from_double(Y, ydt, r * ldy + j, (double)(x[r * ldx + c] - muf));
+  } else {
+    const double* x = reinterpret_cast<const double*>(X);
+    for (int64_t r = blockIdx.y; r < rows; r += gridDim.y)
+      store_from_double(Y, ydt, r * ldy + j, x[r * ldx + c] - mu);
+  }
+}
+
 static inline unsigned row_blocks(int64_t rows) {
   int64_t want = 8LL * sm_count();
   int64_t g = rows < want ? rows : want;
@@ -310,6 +392,36 @@ extern "C" int xmca_center_columns(void* d_X, int x_dtype, int64_t rows, int64_t
   XMCA_REQUIRE(dtype_ok(x_dtype) && ldx >= cols, "xmca_center_columns: bad dtype / ld");
   center_columns_kernel<<<(unsigned)((cols + 31) / 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(
       d_X, x_dtype, rows, cols, ldx, d_mean);
+  XMCA_LAUNCHED();
+  return XMCA_OK;
+}
+
+extern "C" int xmca_field_stats(const void* d_X, int x_dtype, int64_t rows, int64_t cols, int64_t ldx,
+                                double* d_mean, double* d_std, int* d_col_nan, int* d_row_valid,
+                                void* stream) {
+  XMCA_REQUIRE(d_X && d_mean && d_std && d_col_nan && d_row_valid && rows > 0 && cols > 0,
+               "xmca_field_stats: bad argument");
+  XMCA_REQUIRE(dtype_ok(x_dtype) && ldx >= cols, "xmca_field_stats: bad dtype / ld");
+  field_col_stats_kernel<<<(unsigned)((cols + 31) / 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+      d_X, x_dtype, rows, cols, ldx, d_mean, d_std, d_col_nan);
+  XMCA_LAUNCHED();
+  int64_t blocks = (rows + 7) / 8;
+  int64_t cap = 16LL * sm_count();
+  if (blocks > cap) blocks = cap;
+  field_row_valid_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_X, x_dtype, rows, cols, ldx,
+                                                                             d_row_valid);
+  XMCA_LAUNCHED();
+  return XMCA_OK;
+}
+
+extern "C" int xmca_compact_center(const void* d_X, int x_dtype, int64_t rows, int64_t ldx,
+                                   const int64_t* d_idx, int64_t n_keep, const double* d_mean,
+                                   void* d_Y, int y_dtype, int64_t ldy, void* stream) {
+  XMCA_REQUIRE(d_X && d_idx && d_mean && d_Y && rows > 0 && n_keep > 0, "xmca_compact_center: bad argument");
+  XMCA_REQUIRE(dtype_ok(x_dtype) && dtype_ok(y_dtype) && ldy >= n_keep, "xmca_compact_center: bad dtype / ld");
+  dim3 grid((unsigned)((n_keep + 255) / 256), row_blocks(rows));
+  compact_center_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_X, x_dtype, rows, ldx, d_idx, n_keep, d_mean,
+                                                                d_Y, y_dtype, ldy);
   XMCA_LAUNCHED();
   return XMCA_OK;
 }

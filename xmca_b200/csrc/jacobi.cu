@@ -11,9 +11,12 @@
 //   pair_apply  X_p <- X_p R_p, J_p <- J_p R_p   (streaming, in place)
 //
 // Per sweep the HBM traffic is 3 n^2 m e / W (+ the same for J); the fp64 flop
-// count 4 m n^2 (+2 m n^2 for J) does not depend on W.  Convergence measure:
-// max |g_ij| / max_k g_kk over all panels of a sweep (absolute criterion, the
-// accuracy class of LAPACK gesdd which the reference uses).
+// count 8 m n^2 (+4 m n^2 for J) does not depend on W.  Convergence measure:
+// the largest cosine |g_ij| / sqrt(g_ii g_jj) seen over all panels of a sweep
+// (scaled criterion: clustered small singular values are resolved as well as
+// the leading ones); columns whose norm is below 1e-11 of the largest count as
+// zero.  Panels whose largest cosine is already below tol / 10 are skipped
+// (no eigen-solve, no update), which makes the final, confirming sweep cheap.
 #include "common.cuh"
 #include <vector>
 #include <cstring>
@@ -98,7 +101,8 @@ __device__ __forceinline__ void sym_rotation(double app, double aqq, double apq,
 // close to convergence one sweep is enough (quadratic).
 __global__ void __launch_bounds__(1024)
 pair_eig_kernel(const double* __restrict__ partial, int nsplit, double* __restrict__ Rout,
-                unsigned long long* __restrict__ offmax_bits, int max_inner) {
+                unsigned long long* __restrict__ offmax_bits, int max_inner,
+                const unsigned long long* __restrict__ gmax_bits, double skip_tol, int* __restrict__ skip) {
   extern __shared__ double sm[];
   double* Ga = sm;
   double* Gb = sm + GS;
@@ -110,8 +114,7 @@ pair_eig_kernel(const double* __restrict__ partial, int nsplit, double* __restri
   const int tid = threadIdx.x, p = blockIdx.x;
   const int a = tid >> 5, b = tid & 31;
 
-  // load + reduce partial Grams, init R = I, pre-rotation off-diagonal max
-  double local_off = 0.0;
+  // load + reduce partial Grams, init R = I
   for (int e = tid; e < GS; e += 1024) {
     double g = 0.0;
     const double* src = partial + (int64_t)p * nsplit * GS + e;
@@ -119,17 +122,29 @@ pair_eig_kernel(const double* __restrict__ partial, int nsplit, double* __restri
     int i = e >> 6, j = e & 63;
     Ga[e] = g;
     R[e] = (i == j) ? 1.0 : 0.0;
-    if (i != j) local_off = fmax(local_off, fabs(g));
+  }
+  if (tid < 2) s_rot[tid] = 0;
+  __syncthreads();
+  // pre-rotation measure: largest cosine between two non-negligible columns of the panel
+  const double zero2 = 1e-22 * __longlong_as_double((long long)*gmax_bits);
+  double local_off = 0.0;
+  for (int e = tid; e < GS; e += 1024) {
+    int i = e >> 6, j = e & 63;
+    if (i != j) {
+      const double gi = Ga[i * P + i], gj = Ga[j * P + j];
+      if (gi > zero2 && gj > zero2) local_off = fmax(local_off, fabs(Ga[e]) * rsqrt(gi * gj));
+    }
   }
   local_off = warp_max(local_off);
   if ((tid & 31) == 0) red[tid >> 5] = local_off;
-  if (tid < 2) s_rot[tid] = 0;
   __syncthreads();
+  double pair_cos = 0.0;
+  for (int i = 0; i < 32; ++i) pair_cos = fmax(pair_cos, red[i]);
   if (tid == 0) {
-    double mx = 0.0;
-    for (int i = 0; i < 32; ++i) mx = fmax(mx, red[i]);
-    atomicMax(offmax_bits, (unsigned long long)__double_as_longlong(mx));
+    atomicMax(offmax_bits, (unsigned long long)__double_as_longlong(pair_cos));
+    skip[p] = pair_cos <= skip_tol;
   }
+  if (pair_cos <= skip_tol) return;          // uniform: panel already orthogonal to working accuracy
   // symmetrise (partials are symmetric up to rounding order; enforce exactly)
   for (int e = tid; e < GS; e += 1024) {
     int i = e >> 6, j = e & 63;
@@ -200,7 +215,8 @@ pair_eig_kernel(const double* __restrict__ partial, int nsplit, double* __restri
 // X[:, panel] <- X[:, panel] * R_p on a 64-row tile.  grid (npairs, row tiles); block 256.
 __global__ void __launch_bounds__(256)
 pair_apply_kernel(double* __restrict__ Xc, int64_t ld, int64_t rows, const int* __restrict__ pairs,
-                  const double* __restrict__ Rall) {
+                  const double* __restrict__ Rall, const int* __restrict__ skip) {
+  if (skip[blockIdx.x]) return;
   extern __shared__ double sm[];
   double* Xs = sm;                 // [col k][row]  stride 65
   double* Rs = sm + P * (P + 1);   // [k][c]        stride 64
@@ -317,7 +333,7 @@ static int upload_inner_table() {
 
 struct JacobiPlan {
   int64_t n_pad; int nb, npairs, nsplit;
-  size_t off_pairs, off_partial, off_R, off_scalars, total;
+  size_t off_pairs, off_partial, off_R, off_scalars, off_skip, total;
 };
 
 static JacobiPlan make_plan(int64_t m, int64_t n) {
@@ -337,6 +353,7 @@ static JacobiPlan make_plan(int64_t m, int64_t n) {
   pl.off_partial = o; o += (size_t)pl.npairs * pl.nsplit * GS * sizeof(double);
   pl.off_R = o;       o += (size_t)pl.npairs * GS * sizeof(double);
   pl.off_scalars = o; o += 256;
+  pl.off_skip = o;    o += ((size_t)pl.npairs * sizeof(int) + 255) / 256 * 256;
   pl.total = o;
   return pl;
 }
@@ -360,7 +377,7 @@ extern "C" int xmca_jacobi_svd(int64_t m, int64_t n, double* d_Kc, int64_t ldk,
   XMCA_REQUIRE(!d_Jc || ldj >= pl.n_pad, "xmca_jacobi_svd: ldj < padded n");
   XMCA_REQUIRE((m + P - 1) / P <= 65535 && (pl.n_pad + P - 1) / P <= 65535, "xmca_jacobi_svd: too large");
   if (max_sweeps <= 0) max_sweeps = 40;
-  if (tol <= 0.0) tol = 4.0 * sqrt((double)m) * 2.220446049250313e-16;
+  if (tol <= 0.0) tol = 1e-11;
   cudaStream_t st = (cudaStream_t)stream;
   int rc = upload_inner_table();
   if (rc != XMCA_OK) return rc;
@@ -370,6 +387,7 @@ extern "C" int xmca_jacobi_svd(int64_t m, int64_t n, double* d_Kc, int64_t ldk,
   double* d_partial = reinterpret_cast<double*>(ws + pl.off_partial);
   double* d_R = reinterpret_cast<double*>(ws + pl.off_R);
   unsigned long long* d_scal = reinterpret_cast<unsigned long long*>(ws + pl.off_scalars);
+  int* d_skip = reinterpret_cast<int*>(ws + pl.off_skip);
 
   std::vector<int> table;
   build_round_robin(pl.nb, table);
@@ -385,7 +403,7 @@ extern "C" int xmca_jacobi_svd(int64_t m, int64_t n, double* d_Kc, int64_t ldk,
   }
   const size_t eig_smem = 3 * GS * sizeof(double);
   const size_t app_smem = (P * (P + 1) + GS) * sizeof(double);
-  const double quad_stop = 1e-2 * sqrt(tol);
+  const double skip_tol = 0.1 * tol;
   static const int inner_sweeps = getenv("XMCA_JACOBI_INNER") ? atoi(getenv("XMCA_JACOBI_INNER")) : 1;
   static const bool trace = getenv("XMCA_JACOBI_TRACE") != nullptr;
   int sweeps = 0;
@@ -399,14 +417,15 @@ extern "C" int xmca_jacobi_svd(int64_t m, int64_t n, double* d_Kc, int64_t ldk,
       const int* pr = d_pairs + (size_t)r * pl.nb;
       pair_gram_kernel<<<dim3(pl.npairs, pl.nsplit), 256, 0, st>>>(d_Kc, ldk, m, pr, pl.nsplit, d_partial);
       XMCA_LAUNCHED();
-      pair_eig_kernel<<<pl.npairs, 1024, eig_smem, st>>>(d_partial, pl.nsplit, d_R, d_scal, inner_sweeps);
+      pair_eig_kernel<<<pl.npairs, 1024, eig_smem, st>>>(d_partial, pl.nsplit, d_R, d_scal, inner_sweeps, d_scal + 1,
+                                                         skip_tol, d_skip);
       XMCA_LAUNCHED();
       pair_apply_kernel<<<dim3(pl.npairs, (unsigned)((m + P - 1) / P)), 256, app_smem, st>>>(
-          d_Kc, ldk, m, pr, d_R);
+          d_Kc, ldk, m, pr, d_R, d_skip);
       XMCA_LAUNCHED();
       if (d_Jc) {
         pair_apply_kernel<<<dim3(pl.npairs, (unsigned)((pl.n_pad + P - 1) / P)), 256, app_smem, st>>>(
-            d_Jc, ldj, pl.n_pad, pr, d_R);
+            d_Jc, ldj, pl.n_pad, pr, d_R, d_skip);
         XMCA_LAUNCHED();
       }
     }
@@ -423,9 +442,9 @@ extern "C" int xmca_jacobi_svd(int64_t m, int64_t n, double* d_Kc, int64_t ldk,
       return fail(XMCA_NUMERIC, "xmca_jacobi_svd: non-finite entries (SVD failed. NaN entries may be the problem.)",
                   __FILE__, __LINE__);
     }
-    measure = offmax / gmax;           // state BEFORE this sweep's rotations
-    if (trace) fprintf(stderr, "[xmca jacobi] m=%lld n=%lld sweep %d: max|g_ij|/max g_kk = %.3e\n", (long long)m, (long long)n, sweeps, measure);
-    if (measure <= quad_stop) { converged = true; break; }   // quadratic: this sweep finished the job
+    measure = offmax;                  // largest cosine BEFORE this sweep's rotations
+    if (trace) fprintf(stderr, "[xmca jacobi] m=%lld n=%lld sweep %d: max cosine = %.3e\n", (long long)m, (long long)n, sweeps, measure);
+    if (measure <= tol) { converged = true; break; }
   }
   col_norm_kernel<<<(unsigned)pl.n_pad, 256, 0, st>>>(d_Kc, ldk, m, d_sigma, 1, nullptr);
   XMCA_LAUNCHED();

@@ -146,7 +146,7 @@ def cov_gemm_tc(A, B, alpha):
 
 
 # -------------------------------------------------------------------- Jacobi
-def jacobi_svd(X, want_v=True, max_sweeps=40, tol=0.0):
+def jacobi_svd(X, want_v=True, max_sweeps=60, tol=0.0):
     """One-sided Jacobi on the ROWS of X (n x m, fp64, row-major == column-major m x n).
 
     Returns (Xr, sigma, Jt, sweeps): Xr[j] = sigma_j * u_j (rows, rotated in a
@@ -243,6 +243,35 @@ def center_columns(X):
     rc = lib.xmca_center_columns(L.ptr(X), L.dtype_code(X), rows, cols, _ld(X), L.ptr(mean), L.stream_ptr())
     L.check(rc, "xmca_center_columns")
     return mean
+
+
+def field_stats(X):
+    """Column mean / std / NaN flag and row validity of a raw field (host numpy results)."""
+    lib = L.load()
+    t = torch()
+    rows, cols = X.shape
+    mean, std = empty((cols,), f64()), empty((cols,), f64())
+    col_nan, row_ok = empty((cols,), t.int32), empty((rows,), t.int32)
+    rc = lib.xmca_field_stats(L.ptr(X), L.dtype_code(X), rows, cols, _ld(X), L.ptr(mean), L.ptr(std),
+                              L.ptr(col_nan), L.ptr(row_ok), L.stream_ptr())
+    L.check(rc, "xmca_field_stats")
+    return to_host(mean), to_host(std), to_host(col_nan) != 0, to_host(row_ok) != 0
+
+
+def compact_center(X, keep_idx, mean):
+    """Device field without its NaN columns, centred: Y[:, j] = X[:, idx[j]] - mean[idx[j]]."""
+    lib = L.load()
+    rows = X.shape[0]
+    n_keep = int(keep_idx.size)
+    Y = empty((rows, n_keep), X.dtype)
+    if n_keep == 0:
+        return Y
+    idx = to_device(np.ascontiguousarray(keep_idx, dtype=np.int64))
+    mu = to_device(np.ascontiguousarray(mean, dtype=np.float64))
+    rc = lib.xmca_compact_center(L.ptr(X), L.dtype_code(X), rows, _ld(X), L.ptr(idx), n_keep, L.ptr(mu),
+                                 L.ptr(Y), L.dtype_code(Y), _ld(Y), L.stream_ptr())
+    L.check(rc, "xmca_compact_center")
+    return Y
 
 
 def fill_normal(X, seed, stream_id):

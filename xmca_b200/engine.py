@@ -38,6 +38,13 @@ class SolveResult:
         self.frob2 = frob2
 
 
+def _jacobi_tol(field):
+    """Largest admissible cosine between two rotated columns when the Jacobi sweeps stop:
+    1e-6 for fp32 fields (singular values then carry ~1e-12 / relative gap, far below the
+    fp32 noise of the data), the library default (1e-11) for fp64 fields."""
+    return 1e-6 if field.dtype == D.f32() else 0.0
+
+
 def _order(sigma_dev, keep):
     s = D.to_host(sigma_dev)
     order = np.argsort(-s, kind="stable")[:keep]
@@ -90,7 +97,7 @@ def solve_real(A, B, want_vectors=True, force_route=None, use_tensor_cores=None,
             X = X32
         else:
             X = D.matmul(A if left_short else Bx, Bx if left_short else A, trans_a=True, alpha=1.0 / dof)
-        Xr, sig, Jt, sw = D.jacobi_svd(X, want_v=want_vectors)
+        Xr, sig, Jt, sw = D.jacobi_svd(X, want_v=want_vectors, tol=_jacobi_tol(A))
         sweeps.append(sw)
         sigma, order = _order(sig, rank)
         if not want_vectors:
@@ -116,7 +123,7 @@ def solve_real(A, B, want_vectors=True, force_route=None, use_tensor_cores=None,
 
     def gram_factor(X):
         G = D.matmul(X, X, trans_b=True)                                  # T x T fp64
-        Gr, lam, _, sw = D.jacobi_svd(G, want_v=False)
+        Gr, lam, _, sw = D.jacobi_svd(G, want_v=False, tol=_jacobi_tol(A))
         sweeps.append(sw)
         return D.to_host(lam), Gr
 
@@ -145,7 +152,7 @@ def solve_real(A, B, want_vectors=True, force_route=None, use_tensor_cores=None,
     FBt = D.gather_rows(GrB, all_idx, row_scale=inv_sqrt(lamB), cols=T)
     del GrA, GrB
     K = D.matmul(FAt, FBt, trans_b=True, alpha=1.0 / dof)                 # npad x npad, = F_A^T F_B / dof
-    Kr, sig, Jt, sw = D.jacobi_svd(K, want_v=want_vectors)
+    Kr, sig, Jt, sw = D.jacobi_svd(K, want_v=want_vectors, tol=_jacobi_tol(A))
     sweeps.append(sw)
     sigma, order = _order(sig, rank)
     if not want_vectors:
@@ -204,7 +211,7 @@ def _solve_cholqr(A, B, want_vectors, null_basis=None):
         LB, invB, muB = factor(B)
         M = D.matmul(LA, LB, trans_a=True, alpha=1.0 / dof)               # T x T
         extra = np.sqrt(muA * muB) / dof
-    Mr, sig, _, sw = D.jacobi_svd(M, want_v=False)      # rows of Mr: sigma_j q_j^T (right singular vectors of M)
+    Mr, sig, _, sw = D.jacobi_svd(M, want_v=False, tol=_jacobi_tol(A))      # rows of Mr: sigma_j q_j^T (right singular vectors of M)
     s = D.to_host(sig)
     order = np.argsort(-s, kind="stable")[:T]
     sv = s[order]
