@@ -109,6 +109,38 @@ size_t xmca_trsm_workspace_bytes(int64_t n, int64_t nrhs);
 int xmca_trsm_lt(int64_t n, int64_t nrhs, const double* d_L, int64_t ldl, const double* d_invdiag,
                  double* d_R, int64_t ldr, void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* ---- symmetric eigen-solver by Householder tridiagonalisation (fp64) ------
+ * The engine's full-spectrum route for large problems: sigma(C)^2 are the
+ * eigenvalues of ONE T x T symmetric matrix S (engine.py), so the three LAPACK
+ * SVDs of array.py:479 (x2) and :570 become  S = Q T Q^T  (4/3 n^3 flops, one
+ * streaming pass over the trailing matrix per column), bisection for all
+ * eigenvalues, and inverse iteration + back-transformation for the vectors
+ * that are actually asked for (array.py:584 computes all of them).
+ * xmca_sytrd: d_A (n x n, row-major, symmetric, BOTH triangles stored) is
+ *   destroyed; on return d_d (n) / d_e (n-1) hold the tridiagonal, row c of d_A
+ *   (columns c+1..n-1) holds Householder vector c (leading 1 stored) and d_tau
+ *   (n) its scalar:  Q = H(0) H(1) ... H(n-2),  H(c) = I - tau_c v_c v_c^T.
+ * xmca_stebz: all n eigenvalues, DESCENDING, into d_w (d_scratch: 8 doubles).
+ *   Synchronises `stream` once (Gershgorin bounds come back to the host).
+ * xmca_stein: eigenvectors of the tridiagonal for the k eigenvalues d_lambda
+ *   (descending), written as ROWS of d_Z (k x n, ldz).  d_cluster_start
+ *   (n_clusters + 1 ints, device): members of a cluster are orthogonalised
+ *   against each other (modified Gram-Schmidt), clusters run in parallel.
+ *   tnorm = max |eigenvalue| (scale of the pivot perturbation).
+ * xmca_ormtr: rows of d_Z <- Q * row  (eigenvectors of the original matrix). */
+int64_t xmca_sytrd_max_n(void);
+size_t xmca_sytrd_workspace_bytes(int64_t n);
+int xmca_sytrd(int64_t n, double* d_A, int64_t lda, double* d_d, double* d_e, double* d_tau,
+               void* d_workspace, size_t workspace_bytes, void* stream);
+int xmca_stebz(int64_t n, const double* d_d, const double* d_e, double* d_w, double* d_scratch,
+               void* stream);
+size_t xmca_stein_workspace_bytes(int64_t n, int64_t n_clusters);
+int xmca_stein(int64_t n, const double* d_d, const double* d_e, int64_t k, const double* d_lambda,
+               const int* d_cluster_start, int64_t n_clusters, double tnorm, int iterations,
+               double* d_Z, int64_t ldz, void* d_workspace, size_t workspace_bytes, void* stream);
+int xmca_ormtr(int64_t n, const double* d_A, int64_t lda, const double* d_tau, int64_t k,
+               double* d_Z, int64_t ldz, void* stream);
+
 /* ---- element-wise / layout helpers ---------------------------------------*/
 /* Y[r,c] = X[r,c] * (col_scale ? col_scale[c] : 1) * (row_scale ? row_scale[r] : 1);
  * row-major, dtypes may differ (conversion kernel).  array.py:553, :640, :667. */

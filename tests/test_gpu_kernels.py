@@ -172,3 +172,35 @@ def test_cholesky_rejects_indefinite(D):
     G[77, 77] = -1.0
     with pytest.raises(np.linalg.LinAlgError):
         D.cholesky(D.to_device(G))
+
+
+@pytest.mark.parametrize("n", [5, 64, 200, 777, 1500])
+def test_tridiagonal_eigensolver(D, n):
+    """sytrd + stebz give all eigenvalues; stein + ormtr the leading eigenvectors (also inside
+    exactly degenerate clusters)."""
+    r = _rng(n)
+    Q, _ = np.linalg.qr(r.standard_normal((n, n)))
+    lam = np.sort(r.uniform(0.5, 2.0, n) * np.logspace(0, -3, n))[::-1].copy()
+    if n >= 64:
+        lam[3] = lam[2]                      # an exactly double eigenvalue
+        lam[10:14] = lam[10]                 # and a fourfold one
+    S = (Q * lam) @ Q.T
+    S = 0.5 * (S + S.T)
+    Sd = D.to_device(S)
+    d, e, tau = D.sytrd(Sd)
+    w = D.to_host(D.stebz(d, e))
+    ref = np.linalg.eigvalsh(S)[::-1]
+    np.testing.assert_allclose(w, ref, atol=5e-14 * n * ref[0])
+    # tridiagonal really is similar to S: compare with numpy on (d, e)
+    dh, eh = D.to_host(d), D.to_host(e)[:n - 1]
+    Tm = np.diag(dh) + np.diag(eh, 1) + np.diag(eh, -1)
+    np.testing.assert_allclose(np.linalg.eigvalsh(Tm)[::-1], ref, atol=5e-14 * n * ref[0])
+    m = min(n, 40)
+    gap = 1e-6 * w[0]
+    starts = [0] + [i for i in range(1, m) if w[i - 1] - w[i] > gap] + [m]
+    Z = D.stein(d, e, w[:m], np.asarray(starts), w[0])
+    Th = Tm @ D.to_host(Z).T
+    np.testing.assert_allclose(Th, D.to_host(Z).T * w[:m], atol=1e-11 * ref[0])      # T z = lambda z
+    X = D.to_host(D.ormtr(Sd, tau, Z)).T                                             # n x m
+    np.testing.assert_allclose(X.T @ X, np.eye(m), atol=1e-9)
+    np.testing.assert_allclose(S @ X, X * w[:m], atol=1e-10 * ref[0])

@@ -245,6 +245,70 @@ def test_gram_routes_agree_with_oracle(route, pca):
     np.testing.assert_allclose(gram, np.eye(94), atol=1e-8)
 
 
+@pytest.mark.parametrize("shape", [(96, 260, 180), (300, 90, 120), (400, 150, 700)])
+@pytest.mark.parametrize("pca", [False, True])
+def test_tridiagonal_route_agrees_with_oracle(shape, pca):
+    """Householder-tridiagonalisation route (the default for large problems), forced at small
+    sizes on both its Gram side (T < S) and its direct side: every singular value, the leading
+    vectors on demand, and the full set through the Jacobi fallback."""
+    from xmca_b200 import device as D, engine as E
+    T, S1, S2 = shape
+    A, B = orc.synthetic_fields(T, S1, S2, seed=33, k=6, dtype=np.float64)
+    ref = orc.solve(orc.make_model(A.copy()) if pca else orc.make_model(A.copy(), B.copy()))
+    dA = D.to_device(ref.fields["left"])
+    dB = None if pca else D.to_device(ref.fields["right"])
+    res = E.solve_real(dA, dB, force_route="tridiag")
+    assert res.route == "tridiag"
+    rank = ref.sigma.size
+    assert res.sigma.shape == (rank,)
+    lead = ref.sigma > 1e-3 * ref.sigma[0]
+    np.testing.assert_allclose(res.sigma[lead], ref.sigma[lead], rtol=1e-9)
+    np.testing.assert_allclose(res.sigma, ref.sigma, atol=1e-7 * ref.sigma[0])
+    V = {k: D.to_host(v) for k, v in res.vectors(12).items()}
+    assert V["left"].shape == (ref.V["left"].shape[0], 12)
+    got = [V["left"]] + ([] if pca else [V["right"]])
+    al = orc.align_modes(ref.V["left"][:, :12], *got)
+    np.testing.assert_allclose(al[0], ref.V["left"][:, :12], atol=1e-7)
+    if not pca:
+        np.testing.assert_allclose(al[1], ref.V["right"][:, :12], atol=1e-7)
+    np.testing.assert_allclose(V["left"].T @ V["left"], np.eye(12), atol=1e-8)
+    full = D.to_host(res.V["left"])
+    assert full.shape == ref.V["left"].shape
+
+
+def test_tridiagonal_route_through_the_class_complex_and_rotated(MCA):
+    """MCA class on the tridiagonal route (threshold lowered): complex solve, rotate, getters."""
+    from xmca_b200 import engine as E
+    A, B = orc.synthetic_fields(120, 300, 260, seed=44, k=6, dtype=np.float32)
+    old = E.TRIDIAG_MIN_N
+    E.TRIDIAG_MIN_N = 64
+    try:
+        m = MCA(A.copy(), B.copy())
+        m.solve()
+        assert m._solve_info["route"] == "tridiag"
+        ref = orc.solve(orc.make_model(A.copy(), B.copy()))
+        np.testing.assert_allclose(m.singular_values(20), ref.sigma[:20], rtol=1e-5)
+        np.testing.assert_allclose(m.singular_values(), ref.sigma, atol=1e-5 * ref.sigma[0])
+        m.rotate(6, 1)
+        orc.rotate(ref, 6, 1)
+        np.testing.assert_allclose(m.variance(6), orc.get_variance(ref, 6), rtol=1e-4)
+        rp, p = orc.pcs(ref, 6), m.pcs(6)
+        al, ar = orc.align_modes(rp["left"], p["left"], p["right"])
+        assert max(np.abs(al - rp["left"]).max(), np.abs(ar - rp["right"]).max()) < 1e-3
+        u = m.pcs(4, rotated=False)
+        assert u["left"].shape == (120, 4) and u["left"].dtype == np.float32
+        mc = MCA(A.copy(), B.copy())
+        mc.solve(complexify=True)
+        refc = orc.solve(orc.make_model(A.copy(), B.copy()), complexify=True)
+        np.testing.assert_allclose(mc.singular_values(20), refc.sigma[:20], rtol=2e-5)
+        e = mc.eofs(5)
+        er = orc.eofs(refc, 5)
+        al, ar = orc.align_modes(er["left"].reshape(-1, 5), e["left"].reshape(-1, 5), e["right"].reshape(-1, 5))
+        assert np.abs(al - er["left"].reshape(-1, 5)).max() < 5e-4
+    finally:
+        E.TRIDIAG_MIN_N = old
+
+
 def test_cholqr_falls_back_when_gram_is_singular():
     """Duplicated time steps make X X^T rank deficient beyond the centring null vector:
     the Cholesky route must hand over to the eigen route, not fail."""

@@ -75,6 +75,16 @@ def load():
     lib.xmca_trsm_workspace_bytes.restype = sz
     lib.xmca_trsm_workspace_bytes.argtypes = [i64, i64]
     lib.xmca_trsm_lt.argtypes = [i64, i64, vp, i64, vp, vp, i64, vp, sz, vp]
+    lib.xmca_sytrd_max_n.restype = i64
+    lib.xmca_sytrd_max_n.argtypes = []
+    lib.xmca_sytrd_workspace_bytes.restype = sz
+    lib.xmca_sytrd_workspace_bytes.argtypes = [i64]
+    lib.xmca_sytrd.argtypes = [i64, vp, i64, vp, vp, vp, vp, sz, vp]
+    lib.xmca_stebz.argtypes = [i64, vp, vp, vp, vp, vp]
+    lib.xmca_stein_workspace_bytes.restype = sz
+    lib.xmca_stein_workspace_bytes.argtypes = [i64, i64]
+    lib.xmca_stein.argtypes = [i64, vp, vp, i64, vp, vp, i64, dbl, i32, vp, i64, vp, sz, vp]
+    lib.xmca_ormtr.argtypes = [i64, vp, i64, vp, i64, vp, i64, vp]
     lib.xmca_scale_copy.argtypes = [vp, i32, i64, vp, i32, i64, i64, i64, vp, vp, vp]
     lib.xmca_transpose.argtypes = [vp, i32, i64, i64, i64, vp, i32, i64, vp]
     lib.xmca_col_sumsq.argtypes = [vp, i32, i64, i64, i64, i64, vp, vp]
@@ -104,7 +114,8 @@ def load():
 # around each call while a profile is open.  Disabled -> one attribute lookup.
 _NO_TIMING = ("xmca_last_error", "xmca_version", "xmca_launch_count", "xmca_gemm_workspace_bytes",
               "xmca_jacobi_padded_cols", "xmca_jacobi_workspace_bytes", "xmca_varimax_workspace_bytes",
-              "xmca_cholesky_workspace_bytes", "xmca_cholesky_invdiag_bytes", "xmca_trsm_workspace_bytes")
+              "xmca_cholesky_workspace_bytes", "xmca_cholesky_invdiag_bytes", "xmca_trsm_workspace_bytes",
+              "xmca_sytrd_max_n", "xmca_sytrd_workspace_bytes", "xmca_stein_workspace_bytes")
 _profile = None
 
 

@@ -244,12 +244,12 @@ class MCA:
         real_dtype = self._field_means["left"].dtype.type
         try:
             if complexify:
-                sigma, Vc, res = E.solve_complex(A, B)
-                self._dV = {k: ("complex", v) for k, v in Vc.items()}
+                sigma, vec, res = E.solve_complex(A, B)
+                self._dV = ("complex", vec)
             else:
                 res = E.solve_real(A, B)
                 sigma = res.sigma
-                self._dV = {k: ("real", v) for k, v in res.V.items()}
+                self._dV = ("real", res)
         except np.linalg.LinAlgError:
             raise np.linalg.LinAlgError("SVD failed. NaN entries may be the problem.")
         self._solve_info = {"route": res.route, "sweeps": res.sweeps}
@@ -286,21 +286,21 @@ class MCA:
     def _V_device_cols(self, k, m):
         """First m unrotated singular vectors of field k as device tensors:
         real -> (S x m); complex -> ((S x m) re, (S x m) im)."""
-        kind, v = self._dV[k]
-        if kind == "real":
-            return v[:, :m]
-        return (v[0][:, :m], v[1][:, :m])
+        _, provider = self._dV
+        m = min(int(m), self._singular_values.size)
+        return provider.vectors(m)[k]       # singular vectors are computed on demand (engine.TridiagResult)
 
     def _V_host(self, k, m):
         """Unrotated V[k][:, :m] on the host (downloaded once, cached)."""
         cached = self._Vhost.get(k)
         if cached is None or cached.shape[1] < m:
-            kind, v = self._dV[k]
+            kind, _ = self._dV
+            v = self._V_device_cols(k, m)
             if kind == "real":
-                part = D.to_host(v[:, :m].contiguous())
+                part = D.to_host(v.contiguous())
             else:
-                part = (D.to_host(v[0][:, :m].contiguous())
-                        + 1j * D.to_host(v[1][:, :m].contiguous())).astype(self._complex_dtype())
+                part = (D.to_host(v[0].contiguous())
+                        + 1j * D.to_host(v[1].contiguous())).astype(self._complex_dtype())
             self._Vhost[k] = cached = part
         return cached[:, :m]
 
@@ -348,40 +348,52 @@ class MCA:
         nsv = self._singular_values.size
         top = nsv if top is None else min(top, nsv)
         keep = self._get_slice(n)
-        dev = self._device_fields()
-        root = np.sqrt(self._singular_values[:top].astype(np.float64))
-        inv_root = D.to_device(1.0 / root)
         is_rot = rotated and self._analysis["is_rotated"]
+        if is_rot:
+            cols, need = None, top
+        else:
+            # unrotated: R = I (array.py:668-669 multiplies by eye(rank)); project only onto the
+            # modes that are returned instead of onto all `rank` of them
+            order = self._var_idx[:top] if rotated else np.arange(top)
+            cols = order[keep]
+            need = int(cols.max()) + 1 if cols.size else 0
+        dev = self._device_fields()
+        root = np.sqrt(self._singular_values[:need].astype(np.float64))
+        inv_root = D.to_device(1.0 / root) if need else None
         Rit = self.rotation_matrix(inverse_transpose=True) if is_rot else None
+        kind, _ = self._dV
         out = {}
         for k in self._keys:
-            kind, _ = self._dV[k]
             X = dev[k]
+            if need == 0:
+                T = self._n_observations[k]
+                out[k] = np.zeros((T, 0), dtype=np.float64 if rotated else self._field_dtype(k))
+                continue
             if kind == "real":
-                Vd = self._V_device_cols(k, top)
-                Ud = D.matmul(X, Vd)                                        # T x top (array.py:667)
+                Vd = self._V_device_cols(k, need)
+                Ud = D.matmul(X, Vd)                                        # T x need (array.py:667)
                 Ud = D.scale_copy(Ud, col_scale=inv_root)
                 if is_rot:
                     Ud = D.matmul(Ud, D.to_device(np.ascontiguousarray(Rit)))
                 u = D.to_host(Ud)
-                if not rotated:
-                    u = u.astype(self._field_dtype(k))
             else:
-                vr, vi = self._V_device_cols(k, top)
+                vr, vi = self._V_device_cols(k, need)
                 t = D.torch()
-                Vst = t.cat([vr, vi], dim=0).contiguous()                   # 2S x top  ([x; y] embedding)
-                Ust = D.matmul(X, Vst)                                      # 2T x top
+                Vst = t.cat([vr, vi], dim=0).contiguous()                   # 2S x need  ([x; y] embedding)
+                Ust = D.matmul(X, Vst)                                      # 2T x need
                 Ust = D.scale_copy(Ust, col_scale=inv_root)
                 uh = D.to_host(Ust)
                 T = uh.shape[0] // 2
                 u = uh[:T] + 1j * uh[T:]
                 if is_rot:
                     u = u @ Rit
+            if is_rot:
+                u = u[:, self._var_idx][:, keep]
+            else:
+                u = u[:, cols]
                 if not rotated:
                     u = u.astype(self._field_dtype(k))
-            if rotated:
-                u = u[:, self._var_idx]
-            out[k] = u[:, keep]
+            out[k] = u
         return out
 
     def _get_norm(self, n=None, sorted=True):
@@ -548,11 +560,7 @@ class MCA:
         if self._analysis["is_rotated"] and n < self._analysis["n_rot"]:
             raise ValueError("Cannot truncte rotated solution. Please ensure `n` > `n_rot`")
         if n < self._singular_values.size:
-            self._singular_values = self._singular_values[:n]
-            trimmed = {}
-            for k, (kind, v) in self._dV.items():
-                trimmed[k] = (kind, v[:, :n] if kind == "real" else (v[0][:, :n], v[1][:, :n]))
-            self._dV = trimmed
+            self._singular_values = self._singular_values[:n]     # also caps every vector request
             self._Vhost = {k: v[:, :n] for k, v in self._Vhost.items()}
             self._analysis["is_truncated"] = True
             self._analysis["is_truncated_at"] = n

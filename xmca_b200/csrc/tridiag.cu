@@ -1,0 +1,565 @@
+// Symmetric eigen-solver by Householder tridiagonalisation (fp64):
+//   xmca_sytrd : S = Q T Q^T, blocked (LAPACK dsytrd/dlatrd scheme), one persistent
+//                cooperative kernel per panel of 64 columns + one rank-128 update
+//   xmca_stebz : all eigenvalues of T by bisection on the Sturm count
+//   xmca_stein : selected eigenvectors of T by inverse iteration (pivoted LU of
+//                T - lambda I), modified Gram-Schmidt inside eigenvalue clusters
+//   xmca_ormtr : back-transformation  x = Q z
+//
+// This is the engine's full-spectrum route for large problems: it replaces the
+// np.linalg.svd calls of array.py:479 (x2) and :570 by the eigen-decomposition
+// of ONE T x T symmetric matrix (see engine.py), at 4/3 n^3 flops instead of the
+// ~150 n^3 of a converged Jacobi SVD.  The dominant cost is one streaming pass
+// over the trailing matrix per column (y = A v): n^3 * 8 / 3 bytes in total,
+// HBM-bound -- that pass is the roofline kernel of solve().
+#include "common.cuh"
+#include <cooperative_groups.h>
+#include <math.h>
+
+namespace cg = cooperative_groups;
+
+namespace xmca {
+
+constexpr int TD_NB = 64;                 // panel width
+constexpr int TD_THREADS = 1024;          // one CTA per SM
+constexpr int TD_WARPS = TD_THREADS / 32;
+constexpr int TD_K2 = 2 * TD_NB;          // row length of the [V | W] panel buffers
+constexpr int TD_PART = TD_K2 + 8;        // per-CTA reduction slots: [0] ssq, [1..128] p, [130] w.v
+constexpr int TD_MAXF = 16;               // max column split of one row in the symv
+
+struct SytrdParams {
+  double* A; int64_t lda; int n;
+  int j0, nb;
+  double* VW;          // n x 128 row-major: [V | W]
+  double* WV;          // n x 128 row-major: [W | V]
+  double* u;           // n
+  double* wraw;        // TD_MAXF x n
+  double* wpre;        // n
+  double* part;        // grid x TD_PART
+  double* d; double* e; double* tau;
+};
+
+__device__ __forceinline__ double block_sum_1024(double v, double* red) {
+  // all threads get the sum; red: 32 doubles of shared memory
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = red[threadIdx.x & 31];
+  t = warp_sum(t);
+  return t;
+}
+
+// sum over CTAs of part[g * TD_PART + slot]; every thread gets the result
+__device__ __forceinline__ double grid_slot_sum(const double* part, int slot, int G, double* red) {
+  double s = 0.0;
+  for (int g = threadIdx.x; g < G; g += TD_THREADS) s += part[(int64_t)g * TD_PART + slot];
+  return block_sum_1024(s, red);
+}
+
+__global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams P) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ double vs[];                 // current Householder vector (n doubles)
+  __shared__ double red[32];
+  __shared__ double Vc[TD_NB], Wc[TD_NB];        // row c of V and W
+  __shared__ double pv[TD_K2];                   // p1 = V^T v (first 64), p2 = W^T v (last 64)
+  __shared__ double psum[8][TD_K2];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = gridDim.x;
+  const int NW = G * TD_WARPS, gw = blockIdx.x * TD_WARPS + warp;
+  const int n = P.n;
+  const int64_t lda = P.lda;
+  double alpha2_prev = 0.0;
+
+  for (int i = 0; i < P.nb; ++i) {
+    const int c = P.j0 + i;
+    const int n1 = n - c - 1;
+    // ------------------------------------------------------------ phase A: column c
+    if (tid < i) {
+      if (tid == i - 1) { Vc[tid] = 1.0; Wc[tid] = P.wpre[c] + alpha2_prev; }
+      else { Vc[tid] = P.VW[(int64_t)c * TD_K2 + tid]; Wc[tid] = P.VW[(int64_t)c * TD_K2 + TD_NB + tid]; }
+    }
+    __syncthreads();
+    double ssq = 0.0;
+    {
+      int r = c + ((gw - c % NW) + NW) % NW;      // first row >= c with r % NW == gw
+      for (; r < n; r += NW) {
+        double acc = 0.0;
+        const double* vw = P.VW + (int64_t)r * TD_K2;
+        for (int t = lane; t < i; t += 32) acc = fma(vw[t], Wc[t], fma(vw[TD_NB + t], Vc[t], acc));
+        acc = warp_sum(acc);
+        if (lane == 0) {
+          const double ur = P.A[(int64_t)c * lda + r] - acc;
+          P.u[r] = ur;
+          if (r == c) P.d[c] = ur;
+          if (r >= c + 2) ssq = fma(ur, ur, ssq);
+        }
+      }
+    }
+    if (n1 == 0) break;                           // last column: only its diagonal entry
+    ssq = block_sum_1024(ssq, red);
+    if (tid == 0) P.part[(int64_t)blockIdx.x * TD_PART] = ssq;
+    __threadfence();
+    grid.sync();                                  // #1
+
+    // ------------------------------------------------------------ phase B: reflector, A v
+    const double xnorm2 = grid_slot_sum(P.part, 0, G, red);
+    const double alpha = P.u[c + 1];
+    double beta, tau, scale;
+    if (xnorm2 == 0.0) { beta = alpha; tau = 0.0; scale = 0.0; }
+    else {
+      beta = -copysign(sqrt(fma(alpha, alpha, xnorm2)), alpha);
+      tau = (beta - alpha) / beta;
+      scale = 1.0 / (alpha - beta);
+    }
+    for (int j = tid; j < n1; j += TD_THREADS) vs[j] = (j == 0) ? 1.0 : P.u[c + 1 + j] * scale;
+    for (int j = blockIdx.x * TD_THREADS + tid; j < n1; j += G * TD_THREADS)
+      P.A[(int64_t)c * lda + c + 1 + j] = (j == 0) ? 1.0 : P.u[c + 1 + j] * scale;     // reflector storage
+    if (blockIdx.x == 0 && tid == 0) { P.e[c] = beta; P.tau[c] = tau; }
+    __syncthreads();
+
+    // column split so that every warp of the grid gets >= ~4 row pieces of >= 256 elements
+    int F = 1;
+    while (F < TD_MAXF && (int64_t)n1 * F < 4LL * NW && n1 / (2 * F) >= 256) F *= 2;
+    const int len = ((n1 + F - 1) / F + 31) & ~31;
+    {
+      const int64_t items = (int64_t)n1 * F;
+      for (int64_t item = gw; item < items; item += NW) {
+        const int rr = (int)(item / F), q = (int)(item - (int64_t)rr * F);
+        const int s0 = q * len, s1 = min(n1, s0 + len);
+        const double* row = P.A + (int64_t)(c + 1 + rr) * lda + (c + 1);
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0, a5 = 0.0, a6 = 0.0, a7 = 0.0;
+        int s = s0 + lane;
+        for (; s + 224 < s1; s += 256) {
+          const double x0 = row[s], x1 = row[s + 32], x2 = row[s + 64], x3 = row[s + 96];
+          const double x4 = row[s + 128], x5 = row[s + 160], x6 = row[s + 192], x7 = row[s + 224];
+          a0 = fma(x0, vs[s], a0);       a1 = fma(x1, vs[s + 32], a1);
+          a2 = fma(x2, vs[s + 64], a2);  a3 = fma(x3, vs[s + 96], a3);
+          a4 = fma(x4, vs[s + 128], a4); a5 = fma(x5, vs[s + 160], a5);
+          a6 = fma(x6, vs[s + 192], a6); a7 = fma(x7, vs[s + 224], a7);
+        }
+        for (; s < s1; s += 32) a0 = fma(row[s], vs[s], a0);
+        double sum = warp_sum(((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7)));
+        if (lane == 0) P.wraw[(int64_t)q * n + c + 1 + rr] = sum;
+      }
+    }
+    if (i > 0) {
+      double pa[4] = {0.0, 0.0, 0.0, 0.0};
+      int r = c + 1 + ((gw - (c + 1) % NW) + NW) % NW;
+      for (; r < n; r += NW) {
+        const double vr = vs[r - c - 1];
+        const double* vw = P.VW + (int64_t)r * TD_K2;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int idx = lane + 32 * k;
+          if ((idx & (TD_NB - 1)) < i) pa[k] = fma(vw[idx], vr, pa[k]);
+        }
+      }
+      // CTA reduction of the 32 per-warp partial vectors, 8 warps at a time
+      for (int pass = 0; pass < 4; ++pass) {
+        __syncthreads();
+        if ((warp >> 3) == pass) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) psum[warp & 7][lane + 32 * k] = pa[k];
+        }
+        __syncthreads();
+        if (tid < TD_K2) {
+          double s = 0.0;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) s += psum[w][tid];
+          pv[tid] = (pass == 0 ? 0.0 : pv[tid]) + s;
+        }
+      }
+      __syncthreads();
+      if (tid < TD_K2) P.part[(int64_t)blockIdx.x * TD_PART + 1 + tid] = pv[tid];
+    }
+    __threadfence();
+    grid.sync();                                  // #2
+
+    // ------------------------------------------------------------ phase C: w (before the alpha correction)
+    if (i > 0) {
+      const int idx = tid & (TD_K2 - 1), gq = tid >> 7;        // 8 groups of CTAs
+      double s = 0.0;
+      for (int g = gq; g < G; g += 8) s += P.part[(int64_t)g * TD_PART + 1 + idx];
+      psum[gq][idx] = s;
+      __syncthreads();
+      if (tid < TD_K2) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += psum[w][tid];
+        pv[tid] = t;
+      }
+      __syncthreads();
+    }
+    double dotacc = 0.0;
+    {
+      int r = c + 1 + ((gw - (c + 1) % NW) + NW) % NW;
+      for (; r < n; r += NW) {
+        double acc = 0.0;
+        const double* vw = P.VW + (int64_t)r * TD_K2;
+        for (int t = lane; t < i; t += 32) acc = fma(vw[t], pv[TD_NB + t], fma(vw[TD_NB + t], pv[t], acc));
+        double wr = (lane < F) ? P.wraw[(int64_t)lane * n + r] : 0.0;
+        const double tot = warp_sum(wr - acc);
+        if (lane == 0) {
+          const double wp = tau * tot;
+          P.wpre[r] = wp;
+          dotacc = fma(wp, vs[r - c - 1], dotacc);
+        }
+      }
+    }
+    dotacc = block_sum_1024(dotacc, red);
+    if (tid == 0) P.part[(int64_t)blockIdx.x * TD_PART + 130] = dotacc;
+    __threadfence();
+    grid.sync();                                  // #3
+
+    // ------------------------------------------------------------ phase D: finish w, store panel column i
+    const double dot = grid_slot_sum(P.part, 130, G, red);
+    const double alpha2 = -0.5 * tau * dot;
+    {
+      int r = c + 1 + ((gw - (c + 1) % NW) + NW) % NW;
+      for (; r < n; r += NW) {
+        if (lane == 0) {
+          const double v = vs[r - c - 1];
+          const double w = fma(alpha2, v, P.wpre[r]);
+          P.VW[(int64_t)r * TD_K2 + i] = v;          P.VW[(int64_t)r * TD_K2 + TD_NB + i] = w;
+          P.WV[(int64_t)r * TD_K2 + i] = w;          P.WV[(int64_t)r * TD_K2 + TD_NB + i] = v;
+        }
+      }
+    }
+    alpha2_prev = alpha2;
+    __syncwarp();
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ bisection
+// One thread per eigenvalue index k (0 = LARGEST, descending output).
+__global__ void stebz_kernel(int n, const double* __restrict__ d, const double* __restrict__ e,
+                             double gl, double gu, double pivmin, double* __restrict__ w) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int want = n - 1 - k;              // index in ascending order
+  double lo = gl, hi = gu;
+  for (int it = 0; it < 200; ++it) {
+    const double mid = 0.5 * (lo + hi);
+    if (mid <= lo || mid >= hi) break;
+    // Sturm count: number of eigenvalues < mid
+    int cnt = 0;
+    double q = d[0] - mid;
+    cnt += (q < 0.0);
+    for (int j = 1; j < n; ++j) {
+      if (fabs(q) < pivmin) q = -pivmin;
+      const double ej = e[j - 1];
+      q = d[j] - mid - ej * ej / q;
+      cnt += (q < 0.0);
+    }
+    if (cnt > want) hi = mid; else lo = mid;
+  }
+  w[k] = 0.5 * (lo + hi);
+}
+
+__global__ void tridiag_bounds_kernel(int n, const double* __restrict__ d, const double* __restrict__ e,
+                                      double* __restrict__ out) {
+  // out[0] = Gershgorin lower, out[1] = upper, out[2] = max e^2   (single CTA)
+  __shared__ double red[3][32];
+  double lo = INFINITY, hi = -INFINITY, e2 = 0.0;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const double a = (j > 0) ? fabs(e[j - 1]) : 0.0, b = (j < n - 1) ? fabs(e[j]) : 0.0;
+    lo = fmin(lo, d[j] - a - b);
+    hi = fmax(hi, d[j] + a + b);
+    e2 = fmax(e2, b * b);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    e2 = fmax(e2, __shfl_xor_sync(0xffffffffu, e2, o));
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = lo; red[1][threadIdx.x >> 5] = hi; red[2][threadIdx.x >> 5] = e2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) {
+      lo = fmin(lo, red[0][i]); hi = fmax(hi, red[1][i]); e2 = fmax(e2, red[2][i]);
+    }
+    out[0] = lo; out[1] = hi; out[2] = e2;
+  }
+}
+
+// ---------------------------------------------------------- inverse iteration
+// One CTA per cluster of eigenvalues (clusters processed member after member, MGS
+// against the earlier members).  Thread 0 runs the serial tridiagonal LU / solves.
+constexpr int ST_THREADS = 256;
+
+__device__ __forceinline__ double block_sum_256(double v, double* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = (threadIdx.x & 31) < (ST_THREADS / 32) ? red[threadIdx.x & 31] : 0.0;
+  return warp_sum(t);
+}
+
+__device__ __forceinline__ double hash_unit(uint32_t a, uint32_t b) {
+  uint32_t x = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u) * 0x85EBCA77u;
+  x ^= x >> 15; x *= 0x2C1B3C6Du; x ^= x >> 12; x *= 0x297A2D39u; x ^= x >> 15;
+  return ((double)x + 0.5) * (1.0 / 4294967296.0) - 0.5;
+}
+
+__global__ void __launch_bounds__(ST_THREADS)
+stein_kernel(int n, const double* __restrict__ d, const double* __restrict__ e,
+             const double* __restrict__ lam, const int* __restrict__ cluster_start, int n_clusters,
+             double tnorm, int iters, double* __restrict__ Z, int64_t ldz, double* __restrict__ work) {
+  __shared__ double red[32];
+  const int cl = blockIdx.x;
+  if (cl >= n_clusters) return;
+  const int k0 = cluster_start[cl], k1 = cluster_start[cl + 1];
+  const int tid = threadIdx.x;
+  double* u0 = work + (int64_t)cl * 5 * n;
+  double* u1 = u0 + n;
+  double* u2 = u1 + n;
+  double* lm = u2 + n;          // multiplier; sign bit of sw folded in a separate array below
+  double* sw = lm + n;          // 0 / 1 swap flags (stored as doubles)
+  const double tiny = 2.220446049250313e-16 * tnorm + 1e-300;
+
+  double prev_used = 0.0;
+  for (int k = k0; k < k1; ++k) {
+    // separate numerically identical eigenvalues a little (dstein), keeps the solves distinct;
+    // eigenvalues are descending inside a cluster
+    double lk = lam[k];
+    if (k > k0) {
+      const double pert = 10.0 * 2.220446049250313e-16 * fabs(lk) + tiny;
+      if (prev_used - lk < pert) lk = prev_used - pert;
+    }
+    prev_used = lk;
+    double* x = Z + (int64_t)k * ldz;
+    if (tid == 0) {
+      // ---- pivoted LU of T - lk I
+      double ca = d[0] - lk, cb = (n > 1) ? e[0] : 0.0;
+      for (int j = 0; j < n - 1; ++j) {
+        const double cj = e[j], an = d[j + 1] - lk, bn = (j + 2 < n) ? e[j + 1] : 0.0;
+        if (fabs(ca) >= fabs(cj)) {
+          double piv = ca;
+          if (fabs(piv) < tiny) piv = copysign(tiny, piv);
+          const double m = cj / piv;
+          u0[j] = piv; u1[j] = cb; u2[j] = 0.0; lm[j] = m; sw[j] = 0.0;
+          ca = an - m * cb; cb = bn;
+        } else {
+          const double m = ca / cj;
+          u0[j] = cj; u1[j] = an; u2[j] = bn; lm[j] = m; sw[j] = 1.0;
+          ca = cb - m * an; cb = -m * bn;
+        }
+      }
+      if (fabs(ca) < tiny) ca = copysign(tiny, ca);
+      u0[n - 1] = ca; u1[n - 1] = 0.0; u2[n - 1] = 0.0;
+    }
+    for (int j = tid; j < n; j += ST_THREADS) x[j] = hash_unit((uint32_t)j, (uint32_t)k);
+    __threadfence_block();
+    __syncthreads();
+    for (int it = 0; it < iters; ++it) {
+      if (tid == 0) {
+        if (it > 0) {             // first pass: the random vector stands for L^-1 P b (dstein)
+          for (int j = 0; j < n - 1; ++j) {
+            double yj = x[j], yn = x[j + 1];
+            if (sw[j] != 0.0) { const double t = yj; yj = yn; yn = t; x[j] = yj; }
+            x[j + 1] = yn - lm[j] * yj;
+          }
+        }
+        double xp1 = 0.0, xp2 = 0.0;
+        for (int j = n - 1; j >= 0; --j) {
+          const double v = (x[j] - u1[j] * xp1 - u2[j] * xp2) / u0[j];
+          x[j] = v; xp2 = xp1; xp1 = v;
+        }
+      }
+      __threadfence_block();
+      __syncthreads();
+      // scale down first (the solve amplifies by up to 1/eps), then MGS inside the cluster
+      double mx = 0.0;
+      for (int j = tid; j < n; j += ST_THREADS) mx = fmax(mx, fabs(x[j]));
+      mx = warp_max(mx);
+      __syncthreads();
+      if ((tid & 31) == 0) red[tid >> 5] = mx;
+      __syncthreads();
+      mx = 0.0;
+      for (int w = 0; w < ST_THREADS / 32; ++w) mx = fmax(mx, red[w]);
+      const double inv = mx > 0.0 ? 1.0 / mx : 1.0;
+      for (int j = tid; j < n; j += ST_THREADS) x[j] *= inv;
+      __syncthreads();
+      for (int p = k0; p < k; ++p) {
+        const double* z = Z + (int64_t)p * ldz;
+        double dt = 0.0;
+        for (int j = tid; j < n; j += ST_THREADS) dt = fma(z[j], x[j], dt);
+        dt = block_sum_256(dt, red);
+        for (int j = tid; j < n; j += ST_THREADS) x[j] = fma(-dt, z[j], x[j]);
+        __syncthreads();
+      }
+      double ss = 0.0;
+      for (int j = tid; j < n; j += ST_THREADS) ss = fma(x[j], x[j], ss);
+      ss = block_sum_256(ss, red);
+      const double rn = ss > 0.0 ? rsqrt(ss) : 0.0;
+      for (int j = tid; j < n; j += ST_THREADS) x[j] *= rn;
+      __threadfence_block();
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------- back-transformation
+// Z[k, :] <- Q Z[k, :],  Q = H(0) H(1) ... H(n-2), reflector c stored in A[c, c+1:n].
+// One CTA per vector, vector kept in shared memory.
+constexpr int OR_THREADS = 512;
+
+__global__ void __launch_bounds__(OR_THREADS)
+ormtr_kernel(int n, const double* __restrict__ A, int64_t lda, const double* __restrict__ tau,
+             double* __restrict__ Z, int64_t ldz) {
+  extern __shared__ double zs[];
+  __shared__ double red[2][OR_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* z = Z + (int64_t)blockIdx.x * ldz;
+  for (int j = tid; j < n; j += OR_THREADS) zs[j] = z[j];
+  __syncthreads();
+  int par = 0;
+  for (int c = n - 2; c >= 0; --c) {
+    const double tc = tau[c];
+    if (tc == 0.0) continue;                 // uniform
+    const double* v = A + (int64_t)c * lda + (c + 1);
+    const int n1 = n - c - 1;
+    double dt = 0.0;
+    for (int j = tid; j < n1; j += OR_THREADS) dt = fma(v[j], zs[c + 1 + j], dt);
+    dt = warp_sum(dt);
+    if (lane == 0) red[par][warp] = dt;
+    __syncthreads();
+    double tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < OR_THREADS / 32; ++w) tot += red[par][w];
+    const double f = -tc * tot;
+    for (int j = tid; j < n1; j += OR_THREADS) zs[c + 1 + j] = fma(f, v[j], zs[c + 1 + j]);
+    par ^= 1;
+    __syncthreads();
+  }
+  for (int j = tid; j < n; j += OR_THREADS) z[j] = zs[j];
+}
+
+static int sytrd_grid(size_t smem, int* grid_out) {
+  int occ = 0;
+  XMCA_CUDA(cudaFuncSetAttribute(sytrd_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  XMCA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sytrd_panel_kernel, TD_THREADS, smem));
+  if (occ < 1) return fail(XMCA_CUDA_ERROR, "sytrd panel kernel does not fit on an SM", __FILE__, __LINE__);
+  *grid_out = sm_count();
+  return XMCA_OK;
+}
+
+static size_t al256(size_t b) { return (b + 255) / 256 * 256; }
+
+}  // namespace xmca
+
+using namespace xmca;
+
+extern "C" int64_t xmca_sytrd_max_n(void) { return 26000; }
+
+extern "C" size_t xmca_sytrd_workspace_bytes(int64_t n) {
+  size_t b = 0;
+  b += 2 * al256((size_t)n * TD_K2 * 8);          // VW, WV
+  b += al256((size_t)n * 8) * 2;                  // u, wpre
+  b += al256((size_t)n * TD_MAXF * 8);            // wraw
+  b += al256((size_t)(148 * 2) * TD_PART * 8);    // partials
+  return b;
+}
+
+extern "C" int xmca_sytrd(int64_t n, double* d_A, int64_t lda, double* d_d, double* d_e, double* d_tau,
+                          void* d_workspace, size_t workspace_bytes, void* stream) {
+  XMCA_REQUIRE(n >= 1 && d_A && d_d && d_e && d_tau && d_workspace, "xmca_sytrd: bad argument");
+  XMCA_REQUIRE(lda >= n, "xmca_sytrd: lda < n");
+  XMCA_REQUIRE(n <= xmca_sytrd_max_n(), "xmca_sytrd: n too large for the shared-memory Householder vector");
+  XMCA_REQUIRE(workspace_bytes >= xmca_sytrd_workspace_bytes(n), "xmca_sytrd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (size_t)n * 8;
+  int grid = 0;
+  int rc = sytrd_grid(smem, &grid);
+  if (rc != XMCA_OK) return rc;
+  XMCA_REQUIRE(grid <= 148 * 2, "xmca_sytrd: grid larger than the workspace plan");
+
+  char* ws = reinterpret_cast<char*>(d_workspace);
+  SytrdParams P;
+  P.A = d_A; P.lda = lda; P.n = (int)n;
+  size_t o = 0;
+  P.VW = reinterpret_cast<double*>(ws + o); o += al256((size_t)n * TD_K2 * 8);
+  P.WV = reinterpret_cast<double*>(ws + o); o += al256((size_t)n * TD_K2 * 8);
+  P.u = reinterpret_cast<double*>(ws + o); o += al256((size_t)n * 8);
+  P.wpre = reinterpret_cast<double*>(ws + o); o += al256((size_t)n * 8);
+  P.wraw = reinterpret_cast<double*>(ws + o); o += al256((size_t)n * TD_MAXF * 8);
+  P.part = reinterpret_cast<double*>(ws + o);
+  P.d = d_d; P.e = d_e; P.tau = d_tau;
+  XMCA_CUDA(cudaMemsetAsync(d_tau, 0, (size_t)n * 8, st));
+
+  for (int64_t j0 = 0; j0 < n; j0 += TD_NB) {
+    const int nb = (int)((n - j0 < TD_NB) ? (n - j0) : TD_NB);
+    P.j0 = (int)j0; P.nb = nb;
+    // (only the last panel can be short, and it has no trailing block to update)
+    void* args[] = {&P};
+    XMCA_CUDA(cudaLaunchCooperativeKernel((void*)sytrd_panel_kernel, dim3(grid), dim3(TD_THREADS), args, smem, st));
+    XMCA_LAUNCHED();
+    const int64_t r0 = j0 + nb;
+    if (r0 < n) {
+      // trailing update  A22 -= V W^T + W V^T  =  [V | W] [W | V]^T   (dsyr2k, full square kept)
+      const int64_t m = n - r0;
+      rc = xmca_gemm(1, 1, m, m, TD_K2, -1.0, P.VW + r0 * TD_K2, XMCA_F64, TD_K2, P.WV + r0 * TD_K2, XMCA_F64,
+                     TD_K2, d_A + r0 * lda + r0, XMCA_F64, lda, 1, XMCA_F64, 1, nullptr, 0, stream);
+      if (rc != XMCA_OK) return rc;
+    }
+  }
+  return XMCA_OK;
+}
+
+extern "C" int xmca_stebz(int64_t n, const double* d_d, const double* d_e, double* d_w, double* d_scratch,
+                          void* stream) {
+  XMCA_REQUIRE(n >= 1 && d_d && d_e && d_w && d_scratch, "xmca_stebz: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  tridiag_bounds_kernel<<<1, 1024, 0, st>>>((int)n, d_d, d_e, d_scratch);
+  XMCA_LAUNCHED();
+  double h[3];
+  XMCA_CUDA(cudaMemcpyAsync(h, d_scratch, sizeof h, cudaMemcpyDeviceToHost, st));
+  XMCA_CUDA(cudaStreamSynchronize(st));
+  if (!isfinite(h[0]) || !isfinite(h[1]))
+    return fail(XMCA_NUMERIC, "xmca_stebz: non-finite tridiagonal (SVD failed. NaN entries may be the problem.)",
+                __FILE__, __LINE__);
+  const double tn = fmax(fabs(h[0]), fabs(h[1]));
+  const double gl = h[0] - 2.0 * 2.220446049250313e-16 * tn * (double)n - 1e-300;
+  const double gu = h[1] + 2.0 * 2.220446049250313e-16 * tn * (double)n + 1e-300;
+  const double pivmin = 2.2250738585072014e-308 * fmax(1.0, h[2]);
+  stebz_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>((int)n, d_d, d_e, gl, gu, pivmin, d_w);
+  XMCA_LAUNCHED();
+  return XMCA_OK;
+}
+
+extern "C" size_t xmca_stein_workspace_bytes(int64_t n, int64_t n_clusters) {
+  return (size_t)n_clusters * 5 * (size_t)n * 8;
+}
+
+extern "C" int xmca_stein(int64_t n, const double* d_d, const double* d_e, int64_t k, const double* d_lambda,
+                          const int* d_cluster_start, int64_t n_clusters, double tnorm, int iterations,
+                          double* d_Z, int64_t ldz, void* d_workspace, size_t workspace_bytes, void* stream) {
+  XMCA_REQUIRE(n >= 1 && k >= 1 && d_d && d_e && d_lambda && d_cluster_start && d_Z && d_workspace,
+               "xmca_stein: bad argument");
+  XMCA_REQUIRE(n_clusters >= 1 && n_clusters <= k && ldz >= n, "xmca_stein: bad cluster table / ldz");
+  XMCA_REQUIRE(workspace_bytes >= xmca_stein_workspace_bytes(n, n_clusters), "xmca_stein: workspace too small");
+  if (iterations <= 0) iterations = 3;
+  stein_kernel<<<(unsigned)n_clusters, ST_THREADS, 0, (cudaStream_t)stream>>>(
+      (int)n, d_d, d_e, d_lambda, d_cluster_start, (int)n_clusters, tnorm, iterations, d_Z, ldz,
+      reinterpret_cast<double*>(d_workspace));
+  XMCA_LAUNCHED();
+  return XMCA_OK;
+}
+
+extern "C" int xmca_ormtr(int64_t n, const double* d_A, int64_t lda, const double* d_tau, int64_t k,
+                          double* d_Z, int64_t ldz, void* stream) {
+  XMCA_REQUIRE(n >= 1 && k >= 1 && d_A && d_tau && d_Z && lda >= n && ldz >= n, "xmca_ormtr: bad argument");
+  XMCA_REQUIRE(n <= xmca_sytrd_max_n(), "xmca_ormtr: n too large");
+  static bool attr = false;
+  if (!attr) {
+    XMCA_CUDA(cudaFuncSetAttribute(ormtr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 26000 * 8));
+    attr = true;
+  }
+  ormtr_kernel<<<(unsigned)k, OR_THREADS, (size_t)n * 8, (cudaStream_t)stream>>>((int)n, d_A, lda, d_tau, d_Z, ldz);
+  XMCA_LAUNCHED();
+  return XMCA_OK;
+}

@@ -204,6 +204,65 @@ def trsm_lt(Lmat, invdiag, R):
     return R
 
 
+# ------------------------------------------------- tridiagonal eigen-solver
+def sytrd_max_n():
+    return int(L.load().xmca_sytrd_max_n())
+
+
+def sytrd(S):
+    """Householder tridiagonalisation of the symmetric fp64 matrix S (n x n, both triangles,
+    DESTROYED: its rows then hold the reflectors).  Returns (d, e, tau) device vectors."""
+    lib = L.load()
+    t = torch()
+    n = S.shape[0]
+    assert S.dtype == t.float64 and S.shape[1] == n
+    d, e, tau = empty((n,), t.float64), zeros((max(n - 1, 1),), t.float64), empty((n,), t.float64)
+    ws_bytes = lib.xmca_sytrd_workspace_bytes(n)
+    ws = empty((ws_bytes,), t.uint8)
+    rc = lib.xmca_sytrd(n, L.ptr(S), _ld(S), L.ptr(d), L.ptr(e), L.ptr(tau), L.ptr(ws), ws_bytes, L.stream_ptr())
+    L.check(rc, "xmca_sytrd")
+    return d, e, tau
+
+
+def stebz(d, e):
+    """All eigenvalues of the symmetric tridiagonal (d, e), descending (device fp64)."""
+    lib = L.load()
+    n = d.shape[0]
+    w = empty((n,), f64())
+    scratch = empty((8,), f64())
+    rc = lib.xmca_stebz(n, L.ptr(d), L.ptr(e), L.ptr(w), L.ptr(scratch), L.stream_ptr())
+    L.check(rc, "xmca_stebz")
+    return w
+
+
+def stein(d, e, lam_host, cluster_start, tnorm, iterations=3):
+    """Eigenvectors (rows of the returned k x n tensor) of the tridiagonal for the eigenvalues
+    `lam_host` (descending numpy array); `cluster_start`: numpy int array of cluster boundaries."""
+    lib = L.load()
+    t = torch()
+    n, k = d.shape[0], int(lam_host.size)
+    ncl = int(len(cluster_start) - 1)
+    lam = to_device(np.ascontiguousarray(lam_host, dtype=np.float64))
+    cs = to_device(np.ascontiguousarray(cluster_start, dtype=np.int32))
+    Z = empty((k, n), t.float64)
+    ws_bytes = lib.xmca_stein_workspace_bytes(n, ncl)
+    ws = empty((ws_bytes,), t.uint8)
+    rc = lib.xmca_stein(n, L.ptr(d), L.ptr(e), k, L.ptr(lam), L.ptr(cs), ncl, float(tnorm), int(iterations),
+                        L.ptr(Z), n, L.ptr(ws), ws_bytes, L.stream_ptr())
+    L.check(rc, "xmca_stein")
+    return Z
+
+
+def ormtr(S_reflectors, tau, Z):
+    """Rows of Z <- Q row (in place), Q from `sytrd`."""
+    lib = L.load()
+    n = S_reflectors.shape[0]
+    rc = lib.xmca_ormtr(n, L.ptr(S_reflectors), _ld(S_reflectors), L.ptr(tau), Z.shape[0], L.ptr(Z), _ld(Z),
+                        L.stream_ptr())
+    L.check(rc, "xmca_ormtr")
+    return Z
+
+
 # ------------------------------------------------------------- element-wise
 def scale_copy(X, out_dtype=None, col_scale=None, row_scale=None, out=None):
     lib = L.load()

@@ -26,6 +26,14 @@ import numpy as np
 from . import device as D
 
 
+# The tridiagonal route is used when the symmetric eigenproblem has at least this many rows
+# (below it the Jacobi routes finish in milliseconds and deliver every vector at once) ...
+TRIDIAG_MIN_N = 768
+# ... and it computes singular vectors on demand for requests of up to this many leading modes;
+# larger requests (e.g. the full `_V` of the reference) fall back to the Jacobi routes.
+TRIDIAG_MAX_VECTORS = 512
+
+
 class SolveResult:
     """Device-resident result of one solve: sigma (host fp64, descending, length
     rank) and V[k] (S'_k x rank, field dtype, device)."""
@@ -36,6 +44,10 @@ class SolveResult:
         self.route = route
         self.sweeps = sweeps
         self.frob2 = frob2
+
+    def vectors(self, m):
+        """First m singular vectors per field (device, S'_k x m)."""
+        return {k: v[:, :m] for k, v in self.V.items()}
 
 
 def _jacobi_tol(field):
@@ -77,6 +89,13 @@ def solve_real(A, B, want_vectors=True, force_route=None, use_tensor_cores=None,
     S2 = S1 if pca else B.shape[1]
     rank = min(T, S1, S2)
     route = force_route or ("direct" if min(S1, S2) <= T else "gram")
+    if force_route is None and TRIDIAG_MIN_N <= rank <= D.sytrd_max_n():
+        route = "tridiag"
+    if route == "tridiag":
+        try:
+            return TridiagResult(A, B, null_basis)
+        except np.linalg.LinAlgError:
+            route = "gram_eig" if min(S1, S2) > T else "direct"
     sweeps = []
     if route in ("gram", "cholqr"):
         try:
@@ -168,6 +187,142 @@ def solve_real(A, B, want_vectors=True, force_route=None, use_tensor_cores=None,
     VL = D.matmul(A, WLt, trans_a=True, trans_b=True, out_dtype=out_dtype)            # S1 x rank
     VR = D.matmul(B, WRt, trans_a=True, trans_b=True, out_dtype=out_dtype)
     return SolveResult(sigma, {"left": VL, "right": VR}, route, sweeps)
+
+
+# ------------------------------------------------------- tridiagonal route
+class TridiagResult:
+    """Full spectrum by Householder tridiagonalisation + bisection, vectors on demand.
+
+    sigma(C)^2 (MCA) / sigma(C) (PCA) are the eigenvalues of ONE symmetric matrix S:
+      Gram side  (T < min(S1, S2)), with G_X = X X^T (T x T, fp64):
+         MCA:  S = L_B^T G_A L_B / dof^2,   G_B + mu N N^T = L_B L_B^T  (N: the exact null
+               vectors that centring gives G_B, lifted by mu = mean eigenvalue so that the
+               Cholesky factor exists; A^T N = 0, so the lift never reaches C)
+               V_R = B^T (L_B^-T q),   V_L = A^T (L_B q) / (sigma dof)
+         PCA:  S = G_A / dof,   V = A^T q / sqrt(lambda dof)
+      direct side (S_short <= T):  MCA: S = C_s C_s^T with C_s = X_s^T X_l / dof,
+               V_short = q, V_long = C_s^T q / sigma;   PCA: S = A^T A / dof, V = q.
+    S = Q T Q^T (xmca_sytrd), all eigenvalues by bisection (xmca_stebz); the first m
+    eigenvectors q by inverse iteration on T (xmca_stein) and x = Q z (xmca_ormtr) when
+    `vectors(m)` is called.  The reference computes all `rank` vectors in solve()
+    (array.py:584); here requests beyond TRIDIAG_MAX_VECTORS run the Jacobi route once."""
+
+    route = "tridiag"
+
+    def __init__(self, A, B, null_basis=None):
+        T, S1 = A.shape
+        self.A, self.B = A, B
+        self.pca = B is None
+        S2 = S1 if self.pca else B.shape[1]
+        self.dof = float(T - 1)
+        self.out_dtype = A.dtype
+        self.null_basis = null_basis
+        self.gram_side = T < min(S1, S2)
+        self.sweeps = []
+        self.frob2 = None
+        self._cache = (0, None)
+        self._full = None
+        dof = self.dof
+        self.n_null = 0
+        if self.gram_side:
+            Nb = null_basis if null_basis is not None else D.to_device(np.full((T, 1), 1.0 / np.sqrt(T)))
+            self.n_null = Nb.shape[1]
+            if self.pca:
+                S = D.matmul(A, A, trans_b=True, alpha=1.0 / dof)
+            else:
+                GA = D.matmul(A, A, trans_b=True)
+                GB = D.matmul(B, B, trans_b=True)
+                tr = float(D.to_host(D.col_sumsq(B)).sum())
+                if not np.isfinite(tr) or tr <= 0.0:
+                    raise np.linalg.LinAlgError("empty or non-finite field")
+                D.matmul(Nb, Nb, trans_b=True, alpha=tr / T, out=GB, accumulate=True)
+                self.LB, self.invB = D.cholesky(GB, min_pivot=1e-11 * tr / T)
+                W = D.matmul(GA, self.LB)
+                del GA
+                S = D.matmul(self.LB, W, trans_a=True, alpha=1.0 / dof ** 2)
+                del W
+        else:
+            self.left_short = S1 <= S2
+            if self.pca:
+                S = D.matmul(A, A, trans_a=True, alpha=1.0 / dof)
+            else:
+                Xs, Xl = (A, B) if self.left_short else (B, A)
+                self.C = D.matmul(Xs, Xl, trans_a=True, alpha=1.0 / dof)          # S_short x S_long
+                S = D.matmul(self.C, self.C, trans_b=True)
+        self.n = S.shape[0]
+        self.d, self.e, self.tau = D.sytrd(S)
+        self.Q = S                                                            # rows now hold the reflectors
+        lam = D.to_host(D.stebz(self.d, self.e))
+        if not np.isfinite(lam).all():
+            raise np.linalg.LinAlgError("non-finite spectrum")
+        lam = np.maximum(lam, 0.0)
+        if self.n_null:
+            lam[self.n - self.n_null:] = 0.0           # the centring null directions: structurally zero
+        self.lam = lam
+        self.sigma = lam.copy() if self.pca else np.sqrt(lam)
+
+    # -- eigenvectors of S for the leading m eigenvalues, as ROWS (m x n, fp64)
+    def _eigvec_rows(self, m):
+        lam = self.lam[:m]
+        tnorm = float(self.lam[0]) if self.lam.size else 0.0
+        gap = 1e-6 * tnorm
+        starts = [0] + [i for i in range(1, m) if lam[i - 1] - lam[i] > gap] + [m]
+        Z = D.stein(self.d, self.e, lam, np.asarray(starts), tnorm, iterations=3)
+        return D.ormtr(self.Q, self.tau, Z)
+
+    def vectors(self, m):
+        m = int(min(max(m, 0), self.sigma.size))
+        have, V = self._cache
+        if V is not None and have >= m:
+            return {k: v[:, :m] for k, v in V.items()}
+        if m > TRIDIAG_MAX_VECTORS:
+            return {k: v[:, :m] for k, v in self.V.items()}
+        want = int(min(max(m, 64), self.sigma.size, TRIDIAG_MAX_VECTORS))
+        Z = self._eigvec_rows(want)
+        A, B, dof, od = self.A, self.B, self.dof, self.out_dtype
+        sig = self.sigma[:want]
+        if self.gram_side:
+            if self.pca:
+                floor = self.lam[0] * self.n * 2.3e-16 * 64 if self.lam.size else 0.0
+                inv = np.sqrt(_inv_or_zero(self.lam[:want] * dof, floor * dof))
+                Zs = D.scale_copy(Z, row_scale=D.to_device(inv))
+                V = {"left": D.matmul(A, Zs, trans_a=True, trans_b=True, out_dtype=od)}
+            else:
+                inv = _inv_or_zero(sig, 1e-7 * sig[0] if sig.size else 0.0)
+                Wr = D.transpose(Z)                                           # T x m
+                D.trsm_lt(self.LB, self.invB, Wr)                             # L_B^-T q
+                nz = D.to_device((inv > 0).astype(np.float64))
+                Wr = D.scale_copy(Wr, col_scale=nz)                           # null modes -> zero vectors
+                VR = D.matmul(B, Wr, trans_a=True, out_dtype=od)
+                Zs = D.scale_copy(Z, row_scale=D.to_device(inv / dof))
+                Yt = D.matmul(Zs, self.LB, trans_b=True)                      # rows (L_B q)^T / (sigma dof)
+                VL = D.matmul(A, Yt, trans_a=True, trans_b=True, out_dtype=od)
+                V = {"left": VL, "right": VR}
+        else:
+            Vs = D.transpose(Z, out_dtype=od)                                 # S_short x m
+            if self.pca:
+                V = {"left": Vs}
+            else:
+                inv = _inv_or_zero(sig, 1e-7 * sig[0] if sig.size else 0.0)
+                Zs = D.scale_copy(Z, row_scale=D.to_device(inv))
+                Vl = D.matmul(self.C, Zs, trans_a=True, trans_b=True, out_dtype=od)
+                V = {"left": Vs, "right": Vl} if self.left_short else {"left": Vl, "right": Vs}
+        self._cache = (want, V)
+        return {k: v[:, :m] for k, v in V.items()}
+
+    @property
+    def V(self):
+        """All `rank` singular vectors (the reference's `_V`): one Jacobi solve, cached."""
+        if self.sigma.size <= TRIDIAG_MAX_VECTORS:
+            return self.vectors(self.sigma.size)
+        if self._full is None:
+            T, S1 = self.A.shape
+            S2 = S1 if self.pca else self.B.shape[1]
+            route = "gram" if T < min(S1, S2) else "direct"
+            res = solve_real(self.A, self.B, want_vectors=True, force_route=route, null_basis=self.null_basis)
+            self.sweeps = res.sweeps
+            self._full = res.V
+        return self._full
 
 
 # ---------------------------------------------------------------- Cholesky-QR
@@ -269,17 +424,34 @@ def solve_complex(Ae, Be, want_vectors=True):
     scale = (T2 - 1.0) / (T - 1.0)            # solve_real divided by (2T - 1)
     sigma2 = res.sigma * scale
     sigma = sigma2[0:2 * rank:2]
-    if not want_vectors:
-        return sigma, {}, res
-    V = {}
-    pick = _idx(np.arange(0, 2 * rank, 2))
-    for k, Ve in res.V.items():
-        S = Ve.shape[0] // 2
-        Vt = D.transpose(Ve)                                              # 2rank' x 2S rows
-        rows = D.gather_rows(Vt, pick)                                    # rank x 2S
-        cols = D.transpose(rows)                                          # 2S x rank
-        V[k] = (cols[:S], cols[S:])
-    return sigma, V, res
+    return sigma, ComplexVectors(res, rank), res
+
+
+class ComplexVectors:
+    """Complex singular vectors out of the real-embedded solve: every singular value of the
+    embedding is double and each pair {x, Jx} spans one complex vector, so the even-numbered
+    embedded vectors are taken; `vectors(m)` -> {field: (re, im)} device pairs, each S x m."""
+
+    def __init__(self, res, rank):
+        self.res, self.rank = res, rank
+        self._cache = (0, None)
+
+    def vectors(self, m):
+        m = int(min(max(m, 0), self.rank))
+        have, V = self._cache
+        if V is None or have < m:
+            Ve_all = self.res.vectors(2 * m)
+            pick = _idx(np.arange(0, 2 * m, 2))
+            V = {}
+            for k, Ve in Ve_all.items():
+                S = Ve.shape[0] // 2
+                Vt = D.transpose(Ve)                                          # 2m x 2S rows
+                rows = D.gather_rows(Vt, pick)                                # m x 2S
+                cols = D.transpose(rows)                                      # 2S x m
+                V[k] = (cols[:S], cols[S:])
+            self._cache = (m, V)
+            have = m
+        return {k: (v[0][:, :m], v[1][:, :m]) for k, v in V.items()}
 
 
 # ------------------------------------------------------------------ rotation

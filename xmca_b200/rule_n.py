@@ -54,7 +54,8 @@ def device_surrogate_variance(shape_T, n_vars, run_index, seed, complexify, rota
     res = E.solve_real(A, B, want_vectors=True)
     p = min(n_rot, res.sigma.size)
     root = D.to_device(np.sqrt(res.sigma[:p]))
-    parts = [D.scale_copy(res.V[k][:, :p], col_scale=root) for k in res.V]
+    Vp = res.vectors(p)
+    parts = [D.scale_copy(Vp[k], col_scale=root) for k in Vp]
     s_left = parts[0].shape[0]
     Ld = t.cat(parts, dim=0).contiguous() if len(parts) > 1 else parts[0]
     try:
