@@ -24,6 +24,7 @@ constexpr int VP = 64;          // padded number of rotated modes (p <= 64)
 constexpr int VT = 32;          // rows per tile
 constexpr int VTHREADS = 512;
 constexpr int VSLOT = VP * VP + VP;   // doubles per partial: T1 (64x64) + c (64)
+constexpr int VPP = VP + 1;           // padded stride of the column-major p x p work matrices (bank-conflict free)
 
 struct VarimaxParams {
   const void* L; int ldt; int64_t n; int p; int64_t ldl;
@@ -35,72 +36,163 @@ struct VarimaxParams {
   double* B; int64_t ldb; double* R; double* out;   // out: [0]=iterations [1]=converged [2]=d [3]=svd sweeps total
 };
 
-__device__ __forceinline__ void block_matmul_64(const double* X, const double* Y, double* Z, int p,
-                                                bool y_transposed) {
-  // Z[i][j] = sum_k X[i][k] * (y_transposed ? Y[j][k] : Y[k][j]),  i,j,k < p; padded entries -> 0
-  for (int e = threadIdx.x; e < VP * VP; e += blockDim.x) {
-    int i = e >> 6, j = e & 63;
-    double s = 0.0;
-    if (i < p && j < p) {
-      if (y_transposed) for (int k = 0; k < p; ++k) s = fma(X[i * VP + k], Y[j * VP + k], s);
-      else              for (int k = 0; k < p; ++k) s = fma(X[i * VP + k], Y[k * VP + j], s);
+// fp64 reciprocal / reciprocal square root from the hardware approximations (~20 bits) and two
+// Newton steps: relative error ~1e-15, a fraction of the latency of the IEEE division / sqrt.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  y = y * fma(-hx * y, y, 1.5);
+  y = y * fma(-hx * y, y, 1.5);
+  y = y * fma(-hx * y, y, 1.5);
+  return y;
+}
+
+// Z[i][j] = sum_k X(i,k) Y(k,j) for i, j, k < p (padded entries -> 0), 64 x 64 output by the whole
+// CTA: thread -> column j and 8 rows (8 independent accumulators hide the DFMA latency).
+// Element access: X(i,k) = X[i * xs_i + k * xs_k], Y(k,j) = Y[k * ys_k + j * ys_j] (so transposed
+// / padded operands are expressed through strides); Z is written at Z[i * zs_i + j * zs_j].
+__device__ __forceinline__ void small_matmul(const double* X, int xs_i, int xs_k, const double* Y, int ys_k, int ys_j,
+                                             double* Z, int zs_i, int zs_j, int p) {
+  const int j = threadIdx.x & 63, ig = threadIdx.x >> 6;     // VTHREADS / 64 = 8 row groups
+  double acc[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+  if (j < p) {
+    for (int k = 0; k < p; ++k) {
+      const double y = Y[k * ys_k + j * ys_j];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] = fma(X[(ig + 8 * q) * xs_i + k * xs_k], y, acc[q]);
     }
-    Z[e] = s;
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int i = ig + 8 * q;
+    Z[i * zs_i + j * zs_j] = (i < p && j < p) ? acc[q] : 0.0;
   }
 }
 
-// One-sided Jacobi on the columns of X (p x p, stride VP), accumulating V.
+// One-sided Jacobi on the columns of X (p x p), accumulating V.  Both are held COLUMN-major
+// with stride VPP (X[c * VPP + r]) so that a warp reads a column without bank conflicts.
 // pe = p rounded up to even (column p is a zero column when p is odd).
-// rr: round-robin table [(pe-1)][pe].  Returns number of sweeps used.
-__device__ int polar_jacobi(double* X, double* V, int pe, const unsigned char* rr, int* s_flag) {
+// rr: round-robin table [(pe-1)][pe].  Every warp rotates TWO column pairs per step with
+// interleaved instruction streams (the step is latency bound: three 64-bit shuffle
+// reductions, a division and two square roots), so one step serves all pe/2 <= 32 pairs of
+// the round.  A sweep whose largest cosine (before rotating) is <= 1e-6 leaves cosines of
+// ~1e-12: no confirming sweep is run.  Returns the number of sweeps used.
+__device__ int polar_jacobi(double* X, double* V, int pe, const unsigned char* rr, double* s_max) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int npairs = pe >> 1;
   int sweeps = 0;
-  for (; sweeps < 40; ++sweeps) {
-    if (threadIdx.x == 0) *s_flag = 0;
-    __syncthreads();
+  while (sweeps < 40) {
+    double cmax2 = 0.0;
     for (int step = 0; step < pe - 1; ++step) {
-      for (int pr = warp; pr < pe / 2; pr += nwarps) {
-        const int cp = rr[step * pe + 2 * pr], cq = rr[step * pe + 2 * pr + 1];
-        double xp0 = X[lane * VP + cp], xp1 = X[(lane + 32) * VP + cp];
-        double xq0 = X[lane * VP + cq], xq1 = X[(lane + 32) * VP + cq];
-        double al = warp_sum(xp0 * xp0 + xp1 * xp1);
-        double be = warp_sum(xq0 * xq0 + xq1 * xq1);
-        double ga = warp_sum(xp0 * xq0 + xp1 * xq1);
-        if (fabs(ga) > 1e-14 * sqrt(al * be) && fabs(ga) > 1e-300) {
-          double zeta = (be - al) / (2.0 * ga);
-          double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          double c = rsqrt(1.0 + t * t), s = c * t;
-          X[lane * VP + cp] = c * xp0 - s * xq0;        X[lane * VP + cq] = s * xp0 + c * xq0;
-          X[(lane + 32) * VP + cp] = c * xp1 - s * xq1; X[(lane + 32) * VP + cq] = s * xp1 + c * xq1;
-          double vp0 = V[lane * VP + cp], vp1 = V[(lane + 32) * VP + cp];
-          double vq0 = V[lane * VP + cq], vq1 = V[(lane + 32) * VP + cq];
-          V[lane * VP + cp] = c * vp0 - s * vq0;        V[lane * VP + cq] = s * vp0 + c * vq0;
-          V[(lane + 32) * VP + cp] = c * vp1 - s * vq1; V[(lane + 32) * VP + cq] = s * vp1 + c * vq1;
-          if (lane == 0) *s_flag = 1;
+      int cp[2], cq[2];
+      bool on[2];
+      double xp0[2], xp1[2], xq0[2], xq1[2], al[2], be[2], ga[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int pr = warp + u * nwarps;
+        on[u] = pr < npairs;
+        cp[u] = on[u] ? rr[step * pe + 2 * pr] : 0;
+        cq[u] = on[u] ? rr[step * pe + 2 * pr + 1] : 1;
+        xp0[u] = X[cp[u] * VPP + lane]; xp1[u] = X[cp[u] * VPP + lane + 32];
+        xq0[u] = X[cq[u] * VPP + lane]; xq1[u] = X[cq[u] * VPP + lane + 32];
+        al[u] = xp0[u] * xp0[u] + xp1[u] * xp1[u];
+        be[u] = xq0[u] * xq0[u] + xq1[u] * xq1[u];
+        ga[u] = xp0[u] * xq0[u] + xp1[u] * xq1[u];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          al[u] += __shfl_xor_sync(0xffffffffu, al[u], o);
+          be[u] += __shfl_xor_sync(0xffffffffu, be[u], o);
+          ga[u] += __shfl_xor_sync(0xffffffffu, ga[u], o);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (!on[u]) continue;
+        // |cos| = |ga| / sqrt(al be), compared and recorded through its square (no sqrt / division)
+        const double ab = al[u] * be[u], g2 = ga[u] * ga[u];
+        if (g2 > 1e-30 * ab && fabs(ga[u]) > 1e-300) {
+          cmax2 = fmax(cmax2, g2 * fast_rcp(ab));
+          // The rotation angle only steers convergence: zeta and t in fp32 (hardware MUFU ops);
+          // c = 1/sqrt(1 + t^2), s = c t in fp64, so the rotation is orthogonal to rounding.
+          const float zf = (float)((be[u] - al[u]) * fast_rcp(2.0 * ga[u]));
+          const float tf = copysignf(1.0f, zf) / (fabsf(zf) + sqrtf(fmaf(zf, zf, 1.0f)));
+          const double t = (double)tf;
+          const double c = fast_rsqrt(fma(t, t, 1.0)), sn = c * t;
+          X[cp[u] * VPP + lane] = c * xp0[u] - sn * xq0[u];        X[cq[u] * VPP + lane] = sn * xp0[u] + c * xq0[u];
+          X[cp[u] * VPP + lane + 32] = c * xp1[u] - sn * xq1[u]; X[cq[u] * VPP + lane + 32] = sn * xp1[u] + c * xq1[u];
+          const double vp0 = V[cp[u] * VPP + lane], vp1 = V[cp[u] * VPP + lane + 32];
+          const double vq0 = V[cq[u] * VPP + lane], vq1 = V[cq[u] * VPP + lane + 32];
+          V[cp[u] * VPP + lane] = c * vp0 - sn * vq0;        V[cq[u] * VPP + lane] = sn * vp0 + c * vq0;
+          V[cp[u] * VPP + lane + 32] = c * vp1 - sn * vq1; V[cq[u] * VPP + lane + 32] = sn * vp1 + c * vq1;
         }
       }
       __syncthreads();
     }
-    if (*s_flag == 0) { ++sweeps; break; }
+    ++sweeps;
+    if (lane == 0) s_max[warp] = cmax2;
     __syncthreads();
+    double m = 0.0;
+    for (int w = 0; w < nwarps; ++w) m = fmax(m, s_max[w]);
+    __syncthreads();
+    if (m <= 1e-12) break;              // largest squared cosine of the sweep
   }
   return sweeps;
+}
+
+// Two-stage deterministic reduction of the per-CTA partials: every CTA owns a slice of the
+// VSLOT entries; 16 lanes share one entry (strided over the CTAs) and combine by shuffles.
+__device__ __forceinline__ void reduce_partials(const double* partial, double* reduced, int nslots) {
+  const int per_cta = (VSLOT + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int sub = threadIdx.x & 15, loc = threadIdx.x >> 4;          // VTHREADS / 16 = 32 entries per pass
+  for (int base = 0; base < per_cta; base += VTHREADS / 16) {
+    const int e = blockIdx.x * per_cta + base + loc;
+    const bool ok = (base + loc) < per_cta && e < VSLOT;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (ok) {
+      int k = sub;
+      for (; k + 48 < nslots; k += 64) {
+        s0 += partial[(int64_t)k * VSLOT + e];
+        s1 += partial[(int64_t)(k + 16) * VSLOT + e];
+        s2 += partial[(int64_t)(k + 32) * VSLOT + e];
+        s3 += partial[(int64_t)(k + 48) * VSLOT + e];
+      }
+      for (; k < nslots; k += 16) s0 += partial[(int64_t)k * VSLOT + e];
+    }
+    double s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (ok && sub == 0) reduced[e] = s;
+  }
 }
 
 template <typename TS>
 __global__ void __launch_bounds__(VTHREADS, 1) varimax_kernel(VarimaxParams P) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ double sm[];
-  double* Rs = sm;                    // rotation (64x64)
-  double* Vs = Rs + VP * VP;          // right singular vectors, warm start
-  double* Gs = Vs + VP * VP;          // A^T A
-  double* Xs = Gs + VP * VP;          // SVD work matrix
-  double* Ws = Xs + VP * VP;          // scratch (G R, U)
-  double* As = Ws + VP * VP;          // tile [32][64]
+  double* Rs = sm;                    // rotation (64x64, row-major)
+  double* Gs = Rs + VP * VP;          // A^T A
+  double* Ws = Gs + VP * VP;          // scratch (G R)
+  double* Vs = Ws + VP * VP;          // right singular vectors, warm start   (column-major, stride VPP)
+  double* Xs = Vs + VP * VPP;         // SVD work matrix, then U              (column-major, stride VPP)
+  double* As = Xs + VP * VPP;         // tile [32][64]
   double* Bs = As + VT * VP;          // tile [32][64]
-  double* cs = Bs + VT * VP;          // [64] column sums / sigma
+  double* Ts = As;                    // T^T (stride VPP), aliases the tiles between the streaming passes
+  double* cs = As + VP * VPP;         // [64] column sums / sigma
   unsigned char* rr = reinterpret_cast<unsigned char*>(cs + VP);   // [(pe-1)*pe]
-  __shared__ int s_flag;
+  __shared__ double s_max[VTHREADS / 32];
 
   const int tid = threadIdx.x, p = P.p, pe = (p + 1) & ~1;
   const int64_t n = P.n;
@@ -122,7 +214,7 @@ __global__ void __launch_bounds__(VTHREADS, 1) varimax_kernel(VarimaxParams P) {
   for (int e = tid; e < VP * VP; e += VTHREADS) {
     int i = e >> 6, j = e & 63;
     double id = (i == j && i < p) ? 1.0 : 0.0;
-    Rs[e] = id; Vs[e] = (i == j) ? 1.0 : 0.0;
+    Rs[e] = id; Vs[i * VPP + j] = (i == j) ? 1.0 : 0.0;
   }
 
   // T1-phase thread mapping: 4x4 register block of the 64x64 accumulator, two row-halves
@@ -188,11 +280,7 @@ __global__ void __launch_bounds__(VTHREADS, 1) varimax_kernel(VarimaxParams P) {
   }
   __threadfence();
   grid.sync();
-  for (int64_t e = (int64_t)blockIdx.x * VTHREADS + tid; e < VSLOT; e += (int64_t)gridDim.x * VTHREADS) {
-    double s = 0.0;
-    for (int k = 0; k < 2 * (int)gridDim.x; ++k) s += P.partial[(int64_t)k * VSLOT + e];
-    P.reduced[e] = s;
-  }
+  reduce_partials(P.partial, P.reduced, 2 * (int)gridDim.x);
   __threadfence();
   grid.sync();
   for (int e = tid; e < VP * VP; e += VTHREADS) Gs[e] = P.reduced[e];
@@ -201,8 +289,10 @@ __global__ void __launch_bounds__(VTHREADS, 1) varimax_kernel(VarimaxParams P) {
   // ---------------- fixed-point iteration ----------------
   double d = 0.0;
   int it = 0, converged = 0, svd_sweeps = 0;
+  long long tk[6] = {0, 0, 0, 0, 0, 0};   // per-phase clock64 totals (block 0), returned in out[4..9]
   for (it = 1; it <= P.max_iter; ++it) {
     const double d_old = d;
+    long long c0 = clock64();
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -261,48 +351,50 @@ __global__ void __launch_bounds__(VTHREADS, 1) varimax_kernel(VarimaxParams P) {
       }
     }
     __threadfence();
+    { long long c1 = clock64(); tk[0] += c1 - c0; c0 = c1; }
     grid.sync();
-    for (int64_t e = (int64_t)blockIdx.x * VTHREADS + tid; e < VSLOT; e += (int64_t)gridDim.x * VTHREADS) {
-      double s = 0.0;
-      for (int k = 0; k < 2 * (int)gridDim.x; ++k) s += P.partial[(int64_t)k * VSLOT + e];
-      P.reduced[e] = s;
-    }
+    { long long c1 = clock64(); tk[1] += c1 - c0; c0 = c1; }
+    reduce_partials(P.partial, P.reduced, 2 * (int)gridDim.x);
     __threadfence();
     grid.sync();
+    { long long c1 = clock64(); tk[2] += c1 - c0; c0 = c1; }
 
     // ---- phase 2 (redundant on every CTA): T, polar factor, convergence ----
     if (tid < VP) cs[tid] = P.reduced[VP * VP + tid];
-    block_matmul_64(Gs, Rs, Ws, p, false);               // Ws = G R
+    small_matmul(Gs, VP, 1, Rs, VP, 1, Ws, VP, 1, p);      // Ws = G R
     __syncthreads();
     const double gn = P.gamma / (double)n;
     for (int e = tid; e < VP * VP; e += VTHREADS) {
-      int i = e >> 6, j = e & 63;
-      Rs[e] = (i < p && j < p) ? P.reduced[e] - gn * Ws[e] * cs[j] : 0.0;    // Rs now holds T
+      int i = e >> 6, k = e & 63;                        // T^T[k][i] = T[i][k]
+      Ts[k * VPP + i] = (i < p && k < p) ? P.reduced[e] - gn * Ws[e] * cs[k] : 0.0;
     }
     __syncthreads();
-    block_matmul_64(Rs, Vs, Xs, p, false);               // X = T V   (warm start)
+    // X = T V (warm start): X(i,j) = sum_k T(i,k) V(k,j); T(i,k) = Ts[k*VPP+i], V(k,j) = Vs[j*VPP+k]; lanes <-> i
+    small_matmul(Vs, VPP, 1, Ts, VPP, 1, Xs, VPP, 1, p);   // computed as X^T = V^T T^T: Z(j,i) = sum_k V^T(j,k) T^T(k,i)
     __syncthreads();
-    svd_sweeps += polar_jacobi(Xs, Vs, pe, rr, &s_flag);
+    { long long c1 = clock64(); tk[3] += c1 - c0; c0 = c1; }
+    svd_sweeps += polar_jacobi(Xs, Vs, pe, rr, s_max);
+    { long long c1 = clock64(); tk[4] += c1 - c0; c0 = c1; }
     __syncthreads();
-    // sigma_j = ||x_j||, d = sum sigma, U = X / sigma
+    // sigma_j = ||x_j||, U = X / sigma (in place)
     {
       const int warp = tid >> 5, lane = tid & 31;
       for (int j = warp; j < VP; j += VTHREADS / 32) {
-        double x0 = Xs[lane * VP + j], x1 = Xs[(lane + 32) * VP + j];
-        double nn = sqrt(warp_sum(x0 * x0 + x1 * x1));
+        const double x0 = Xs[j * VPP + lane], x1 = Xs[j * VPP + lane + 32];
+        const double nn = sqrt(warp_sum(x0 * x0 + x1 * x1));
+        const bool live = (j < p) && nn > 0.0;
         if (lane == 0) cs[j] = (j < p) ? nn : 0.0;
+        Xs[j * VPP + lane] = live ? x0 / nn : 0.0;
+        Xs[j * VPP + lane + 32] = live ? x1 / nn : 0.0;
       }
     }
     __syncthreads();
-    for (int e = tid; e < VP * VP; e += VTHREADS) {
-      int j = e & 63;
-      Ws[e] = (j < p && cs[j] > 0.0) ? Xs[e] / cs[j] : 0.0;                // U
-    }
-    __syncthreads();
-    block_matmul_64(Ws, Vs, Rs, p, true);                 // R = U V^T
+    // R = U V^T : R(i,l) = sum_j U(i,j) V(l,j); U(i,j) = Xs[j*VPP+i], V(l,j) = Vs[j*VPP+l]
+    small_matmul(Xs, 1, VPP, Vs, VPP, 1, Rs, VP, 1, p);
     d = 0.0;
     for (int j = 0; j < p; ++j) d += cs[j];
     __syncthreads();
+    { long long c1 = clock64(); tk[5] += c1 - c0; c0 = c1; }
     if (fabs(d - d_old) / d < P.tol) { converged = 1; break; }
   }
   if (it > P.max_iter) it = P.max_iter;
@@ -334,12 +426,13 @@ __global__ void __launch_bounds__(VTHREADS, 1) varimax_kernel(VarimaxParams P) {
   }
   if (blockIdx.x == 0) {
     for (int e = tid; e < p * p; e += VTHREADS) P.R[e] = Rs[(e / p) * VP + (e % p)];
-    if (tid == 0) { P.out[0] = (double)it; P.out[1] = (double)converged; P.out[2] = d; P.out[3] = (double)svd_sweeps; }
+    if (tid == 0) { P.out[0] = (double)it; P.out[1] = (double)converged; P.out[2] = d; P.out[3] = (double)svd_sweeps;
+      for (int q = 0; q < 6; ++q) P.out[4 + q] = (double)tk[q]; }
   }
 }
 
 static size_t varimax_smem_bytes() {
-  return (size_t)(5 * VP * VP + 2 * VT * VP + VP) * sizeof(double) + (size_t)VP * VP;
+  return (size_t)(3 * VP * VP + 3 * VP * VPP + VP) * sizeof(double) + (size_t)VP * VP;
 }
 
 template <typename TS>

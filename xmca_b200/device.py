@@ -14,6 +14,7 @@ import numpy as np
 from . import _lib as L
 
 _SM = None
+last_varimax_stats = None      # device tensor: [iterations, converged, d, svd sweeps, 6 x phase clocks]
 
 
 def torch():
@@ -394,12 +395,14 @@ def varimax(Ld, gamma=1.0, max_iter=1000, tol=1e-8):
     n, p = Ld.shape
     B = empty((n, p), t.float64)
     R = empty((p, p), t.float64)
-    out = zeros((4,), t.float64)
+    out = zeros((16,), t.float64)
     ws_bytes = lib.xmca_varimax_workspace_bytes(n, p)
     ws = empty((ws_bytes,), t.uint8)
     iters = C.c_int(0)
     rc = lib.xmca_varimax(L.ptr(Ld), L.dtype_code(Ld), n, p, _ld(Ld), float(gamma), int(max_iter), float(tol),
                           L.ptr(B), p, L.ptr(R), C.byref(iters), L.ptr(out), L.ptr(ws), ws_bytes,
                           L.stream_ptr())
+    global last_varimax_stats
+    last_varimax_stats = out
     L.check(rc, "xmca_varimax")
     return B, R, iters.value
