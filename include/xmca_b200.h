@@ -120,7 +120,7 @@ int xmca_trsm_lt(int64_t n, int64_t nrhs, const double* d_L, int64_t ldl, const 
  *   destroyed; on return d_d (n) / d_e (n-1) hold the tridiagonal, row c of d_A
  *   (columns c+1..n-1) holds Householder vector c (leading 1 stored) and d_tau
  *   (n) its scalar:  Q = H(0) H(1) ... H(n-2),  H(c) = I - tau_c v_c v_c^T.
- * xmca_stebz: all n eigenvalues, DESCENDING, into d_w (d_scratch: 8 doubles).
+ * xmca_stebz: all n eigenvalues, DESCENDING, into d_w (d_scratch: n + 8 doubles).
  *   Synchronises `stream` once (Gershgorin bounds come back to the host).
  * xmca_stein: eigenvectors of the tridiagonal for the k eigenvalues d_lambda
  *   (descending), written as ROWS of d_Z (k x n, ldz).  d_cluster_start

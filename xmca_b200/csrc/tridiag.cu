@@ -234,29 +234,61 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
 }
 
 // ------------------------------------------------------------------ bisection
-// One thread per eigenvalue index k (0 = LARGEST, descending output).
-__global__ void stebz_kernel(int n, const double* __restrict__ d, const double* __restrict__ e,
-                             double gl, double gu, double pivmin, double* __restrict__ w) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  const int want = n - 1 - k;              // index in ascending order
+// fp64 reciprocal from the hardware approximation + two Newton steps (rel. error ~1e-15):
+// the Sturm recurrence is one long dependent chain, its latency is what is being paid for.
+__device__ __forceinline__ double td_fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+}
+
+// Eight lanes per eigenvalue index k (0 = LARGEST, descending output): every level evaluates the
+// Sturm count at 8 interior points of the current bracket (9-section, ~3.2 bits per level), so
+// the dependent chain is ~17 levels * n steps instead of ~55 * n for plain bisection.
+constexpr int SB_LANES = 8;
+
+__global__ void __launch_bounds__(128)
+stebz_kernel(int n, const double* __restrict__ d, const double* __restrict__ e2,
+             double gl, double gu, double pivmin, double abstol, double* __restrict__ w) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = gid / SB_LANES, sub = gid % SB_LANES;
+  const bool live = k < n;
+  const int want = n - 1 - (live ? k : n - 1);          // index in ascending order
+  const unsigned lane = threadIdx.x & 31, grp = lane & ~(SB_LANES - 1);
   double lo = gl, hi = gu;
-  for (int it = 0; it < 200; ++it) {
-    const double mid = 0.5 * (lo + hi);
-    if (mid <= lo || mid >= hi) break;
-    // Sturm count: number of eigenvalues < mid
+  for (int it = 0; it < 80; ++it) {
+    const double h = (hi - lo) * (1.0 / (SB_LANES + 1));
+    const double x = lo + h * (double)(sub + 1);
+    // Sturm count: number of eigenvalues < x
     int cnt = 0;
-    double q = d[0] - mid;
+    double q = d[0] - x;
     cnt += (q < 0.0);
     for (int j = 1; j < n; ++j) {
       if (fabs(q) < pivmin) q = -pivmin;
-      const double ej = e[j - 1];
-      q = d[j] - mid - ej * ej / q;
+      q = d[j] - x - e2[j - 1] * td_fast_rcp(q);
       cnt += (q < 0.0);
     }
-    if (cnt > want) hi = mid; else lo = mid;
+    // first sub-point whose count exceeds `want` bounds the eigenvalue from above
+    const unsigned above = __ballot_sync(0xffffffffu, cnt > want);
+    const unsigned mine = (above >> grp) & ((1u << SB_LANES) - 1u);
+    const int first = mine ? (__ffs(mine) - 1) : SB_LANES;       // SB_LANES: above every sub-point
+    const double nlo = (first == 0) ? lo : lo + h * (double)first;
+    const double nhi = (first == SB_LANES) ? hi : lo + h * (double)(first + 1);
+    const bool stalled = !(nlo > lo || nhi < hi) || !(nhi - nlo > 0.0);
+    lo = nlo; hi = nhi;
+    // converged when the bracket no longer shrinks in floating point (uniform per group: all
+    // lanes of a group hold the same lo / hi); other groups of the warp may continue
+    const bool done = stalled || (hi - lo) <= fmax(abstol, 2.220446049250313e-16 * fmax(fabs(lo), fabs(hi)));
+    if (__all_sync(0xffffffffu, done)) break;
   }
-  w[k] = 0.5 * (lo + hi);
+  if (live && sub == 0) w[k] = 0.5 * (lo + hi);
+}
+
+__global__ void square_kernel(int n, const double* __restrict__ e, double* __restrict__ e2) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) e2[j] = e[j] * e[j];
 }
 
 __global__ void tridiag_bounds_kernel(int n, const double* __restrict__ d, const double* __restrict__ e,
@@ -305,21 +337,28 @@ __device__ __forceinline__ double hash_unit(uint32_t a, uint32_t b) {
   return ((double)x + 0.5) * (1.0 / 4294967296.0) - 0.5;
 }
 
+constexpr int ST_CH = 512;                 // chunk of the tridiagonal staged in shared memory
+
+// The LU factorisation and the two triangular solves are first-order recurrences: thread 0 runs
+// them on chunks that all threads stage through shared memory (coalesced global traffic, no
+// global-memory latency inside the dependent chain, pivots stored as reciprocals).
 __global__ void __launch_bounds__(ST_THREADS)
 stein_kernel(int n, const double* __restrict__ d, const double* __restrict__ e,
              const double* __restrict__ lam, const int* __restrict__ cluster_start, int n_clusters,
              double tnorm, int iters, double* __restrict__ Z, int64_t ldz, double* __restrict__ work) {
   __shared__ double red[32];
+  __shared__ double buf[6][ST_CH + 2];
   const int cl = blockIdx.x;
   if (cl >= n_clusters) return;
   const int k0 = cluster_start[cl], k1 = cluster_start[cl + 1];
   const int tid = threadIdx.x;
-  double* u0 = work + (int64_t)cl * 5 * n;
-  double* u1 = u0 + n;
+  double* u0i = work + (int64_t)cl * 5 * n;   // reciprocal pivots
+  double* u1 = u0i + n;
   double* u2 = u1 + n;
-  double* lm = u2 + n;          // multiplier; sign bit of sw folded in a separate array below
-  double* sw = lm + n;          // 0 / 1 swap flags (stored as doubles)
+  double* lm = u2 + n;                        // multipliers
+  double* sw = lm + n;                        // 0 / 1 row-swap flags
   const double tiny = 2.220446049250313e-16 * tnorm + 1e-300;
+  const int n_it = (k1 - k0 > 1) ? iters + 1 : iters;
 
   double prev_used = 0.0;
   for (int k = k0; k < k1; ++k) {
@@ -332,42 +371,101 @@ stein_kernel(int n, const double* __restrict__ d, const double* __restrict__ e,
     }
     prev_used = lk;
     double* x = Z + (int64_t)k * ldz;
-    if (tid == 0) {
-      // ---- pivoted LU of T - lk I
-      double ca = d[0] - lk, cb = (n > 1) ? e[0] : 0.0;
-      for (int j = 0; j < n - 1; ++j) {
-        const double cj = e[j], an = d[j + 1] - lk, bn = (j + 2 < n) ? e[j + 1] : 0.0;
-        if (fabs(ca) >= fabs(cj)) {
-          double piv = ca;
-          if (fabs(piv) < tiny) piv = copysign(tiny, piv);
-          const double m = cj / piv;
-          u0[j] = piv; u1[j] = cb; u2[j] = 0.0; lm[j] = m; sw[j] = 0.0;
-          ca = an - m * cb; cb = bn;
-        } else {
-          const double m = ca / cj;
-          u0[j] = cj; u1[j] = an; u2[j] = bn; lm[j] = m; sw[j] = 1.0;
-          ca = cb - m * an; cb = -m * bn;
+
+    // ---- pivoted LU of T - lk I (rows j = 0 .. n-2 eliminate; row n-1 closes)
+    double ca = d[0] - lk, cb = (n > 1) ? e[0] : 0.0;          // carried by thread 0
+    for (int base = 0; base < n - 1; base += ST_CH) {
+      const int len = min(ST_CH, n - 1 - base);
+      for (int t = tid; t <= len; t += ST_THREADS) {
+        const int j = base + t;
+        buf[0][t] = (j + 1 < n) ? d[j + 1] - lk : 0.0;         // next diagonal
+        const double ej = (j < n - 1) ? e[j] : 0.0;
+        buf[1][t] = ej;                                        // e[j]   (t + 1 -> e[j + 1])
+        buf[2][t] = (ej != 0.0) ? 1.0 / ej : 0.0;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        for (int t = 0; t < len; ++t) {
+          const double cj = buf[1][t], an = buf[0][t], bn = buf[1][t + 1];
+          if (fabs(ca) >= fabs(cj)) {
+            double piv = ca;
+            if (fabs(piv) < tiny) piv = copysign(tiny, piv);
+            const double ip = td_fast_rcp(piv);
+            const double m = cj * ip;
+            buf[3][t] = m; buf[4][t] = 0.0;                    // lm, sw
+            buf[0][t] = ip; buf[5][t] = cb;                    // u0i, u1   (u2 = 0)
+            buf[2][t] = 0.0;
+            ca = fma(-m, cb, an); cb = bn;
+          } else {
+            const double m = ca * buf[2][t];
+            buf[3][t] = m; buf[4][t] = 1.0;
+            buf[0][t] = buf[2][t]; buf[5][t] = an;
+            buf[2][t] = bn;                                    // u2
+            ca = fma(-m, an, cb); cb = -m * bn;
+          }
         }
       }
+      __syncthreads();
+      for (int t = tid; t < len; t += ST_THREADS) {
+        const int j = base + t;
+        u0i[j] = buf[0][t]; u1[j] = buf[5][t]; u2[j] = buf[2][t]; lm[j] = buf[3][t]; sw[j] = buf[4][t];
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
       if (fabs(ca) < tiny) ca = copysign(tiny, ca);
-      u0[n - 1] = ca; u1[n - 1] = 0.0; u2[n - 1] = 0.0;
+      u0i[n - 1] = 1.0 / ca; u1[n - 1] = 0.0; u2[n - 1] = 0.0;
     }
     for (int j = tid; j < n; j += ST_THREADS) x[j] = hash_unit((uint32_t)j, (uint32_t)k);
     __threadfence_block();
     __syncthreads();
-    for (int it = 0; it < iters; ++it) {
-      if (tid == 0) {
-        if (it > 0) {             // first pass: the random vector stands for L^-1 P b (dstein)
-          for (int j = 0; j < n - 1; ++j) {
-            double yj = x[j], yn = x[j + 1];
-            if (sw[j] != 0.0) { const double t = yj; yj = yn; yn = t; x[j] = yj; }
-            x[j + 1] = yn - lm[j] * yj;
+
+    for (int it = 0; it < n_it; ++it) {
+      if (it > 0) {               // first pass: the random vector stands for L^-1 P b (dstein)
+        double cur = x[0];
+        for (int base = 0; base < n - 1; base += ST_CH) {
+          const int len = min(ST_CH, n - 1 - base);
+          for (int t = tid; t < len; t += ST_THREADS) {
+            buf[0][t] = x[base + t + 1]; buf[1][t] = lm[base + t]; buf[2][t] = sw[base + t];
           }
+          __syncthreads();
+          if (tid == 0) {
+            for (int t = 0; t < len; ++t) {
+              double yj = cur, yn = buf[0][t];
+              if (buf[2][t] != 0.0) { const double tmp = yj; yj = yn; yn = tmp; }
+              buf[3][t] = yj;
+              cur = fma(-buf[1][t], yj, yn);
+            }
+            buf[4][0] = cur;
+          }
+          __syncthreads();
+          cur = buf[4][0];
+          for (int t = tid; t < len; t += ST_THREADS) x[base + t] = buf[3][t];
+          __syncthreads();
         }
+        if (tid == 0) x[n - 1] = cur;
+        __threadfence_block();
+        __syncthreads();
+      }
+      {
         double xp1 = 0.0, xp2 = 0.0;
-        for (int j = n - 1; j >= 0; --j) {
-          const double v = (x[j] - u1[j] * xp1 - u2[j] * xp2) / u0[j];
-          x[j] = v; xp2 = xp1; xp1 = v;
+        for (int top = n; top > 0; top -= ST_CH) {
+          const int base = max(0, top - ST_CH), len = top - base;
+          for (int t = tid; t < len; t += ST_THREADS) {
+            buf[0][t] = x[base + t]; buf[1][t] = u0i[base + t]; buf[2][t] = u1[base + t]; buf[3][t] = u2[base + t];
+          }
+          __syncthreads();
+          if (tid == 0) {
+            for (int t = len - 1; t >= 0; --t) {
+              const double v = fma(-buf[3][t], xp2, fma(-buf[2][t], xp1, buf[0][t])) * buf[1][t];
+              buf[0][t] = v; xp2 = xp1; xp1 = v;
+            }
+            buf[4][0] = xp1; buf[4][1] = xp2;
+          }
+          __syncthreads();
+          xp1 = buf[4][0]; xp2 = buf[4][1];
+          for (int t = tid; t < len; t += ST_THREADS) x[base + t] = buf[0][t];
+          __syncthreads();
         }
       }
       __threadfence_block();
@@ -512,7 +610,7 @@ extern "C" int xmca_sytrd(int64_t n, double* d_A, int64_t lda, double* d_d, doub
 
 extern "C" int xmca_stebz(int64_t n, const double* d_d, const double* d_e, double* d_w, double* d_scratch,
                           void* stream) {
-  XMCA_REQUIRE(n >= 1 && d_d && d_e && d_w && d_scratch, "xmca_stebz: bad argument");
+  XMCA_REQUIRE(n >= 1 && d_d && d_e && d_w && d_scratch, "xmca_stebz: bad argument");   // d_scratch: n + 8 doubles
   cudaStream_t st = (cudaStream_t)stream;
   tridiag_bounds_kernel<<<1, 1024, 0, st>>>((int)n, d_d, d_e, d_scratch);
   XMCA_LAUNCHED();
@@ -526,7 +624,11 @@ extern "C" int xmca_stebz(int64_t n, const double* d_d, const double* d_e, doubl
   const double gl = h[0] - 2.0 * 2.220446049250313e-16 * tn * (double)n - 1e-300;
   const double gu = h[1] + 2.0 * 2.220446049250313e-16 * tn * (double)n + 1e-300;
   const double pivmin = 2.2250738585072014e-308 * fmax(1.0, h[2]);
-  stebz_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>((int)n, d_d, d_e, gl, gu, pivmin, d_w);
+  double* d_e2 = d_scratch + 8;
+  square_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((int)n - 1, d_e, d_e2);
+  XMCA_LAUNCHED();
+  const int64_t threads = n * SB_LANES;
+  stebz_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>((int)n, d_d, d_e2, gl, gu, pivmin, 1e-18 * tn, d_w);
   XMCA_LAUNCHED();
   return XMCA_OK;
 }
@@ -542,7 +644,7 @@ extern "C" int xmca_stein(int64_t n, const double* d_d, const double* d_e, int64
                "xmca_stein: bad argument");
   XMCA_REQUIRE(n_clusters >= 1 && n_clusters <= k && ldz >= n, "xmca_stein: bad cluster table / ldz");
   XMCA_REQUIRE(workspace_bytes >= xmca_stein_workspace_bytes(n, n_clusters), "xmca_stein: workspace too small");
-  if (iterations <= 0) iterations = 3;
+  if (iterations <= 0) iterations = 2;   // singletons; clusters run one more
   stein_kernel<<<(unsigned)n_clusters, ST_THREADS, 0, (cudaStream_t)stream>>>(
       (int)n, d_d, d_e, d_lambda, d_cluster_start, (int)n_clusters, tnorm, iterations, d_Z, ldz,
       reinterpret_cast<double*>(d_workspace));

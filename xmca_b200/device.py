@@ -230,13 +230,13 @@ def stebz(d, e):
     lib = L.load()
     n = d.shape[0]
     w = empty((n,), f64())
-    scratch = empty((8,), f64())
+    scratch = empty((n + 8,), f64())
     rc = lib.xmca_stebz(n, L.ptr(d), L.ptr(e), L.ptr(w), L.ptr(scratch), L.stream_ptr())
     L.check(rc, "xmca_stebz")
     return w
 
 
-def stein(d, e, lam_host, cluster_start, tnorm, iterations=3):
+def stein(d, e, lam_host, cluster_start, tnorm, iterations=2):
     """Eigenvectors (rows of the returned k x n tensor) of the tridiagonal for the eigenvalues
     `lam_host` (descending numpy array); `cluster_start`: numpy int array of cluster boundaries."""
     lib = L.load()

@@ -265,9 +265,12 @@ class TridiagResult:
     def _eigvec_rows(self, m):
         lam = self.lam[:m]
         tnorm = float(self.lam[0]) if self.lam.size else 0.0
-        gap = 1e-6 * tnorm
+        # eigenvalues closer than `gap` share a cluster (mutual re-orthogonalisation, run
+        # sequentially); vectors of different clusters are computed independently and are then
+        # orthogonal to ~eps * tnorm / gap: 1e-7 for fp32 fields, 1e-10 for fp64 fields
+        gap = 2.2e-16 * tnorm / (1e-7 if self.out_dtype == D.f32() else 1e-10)
         starts = [0] + [i for i in range(1, m) if lam[i - 1] - lam[i] > gap] + [m]
-        Z = D.stein(self.d, self.e, lam, np.asarray(starts), tnorm, iterations=3)
+        Z = D.stein(self.d, self.e, lam, np.asarray(starts), tnorm, iterations=2)
         return D.ormtr(self.Q, self.tau, Z)
 
     def vectors(self, m):
@@ -277,7 +280,7 @@ class TridiagResult:
             return {k: v[:, :m] for k, v in V.items()}
         if m > TRIDIAG_MAX_VECTORS:
             return {k: v[:, :m] for k, v in self.V.items()}
-        want = int(min(max(m, 64), self.sigma.size, TRIDIAG_MAX_VECTORS))
+        want = int(min(max(m, 16), self.sigma.size, TRIDIAG_MAX_VECTORS))
         Z = self._eigvec_rows(want)
         A, B, dof, od = self.A, self.B, self.dof, self.out_dtype
         sig = self.sigma[:want]
