@@ -272,9 +272,19 @@ def run_product(args, rank, world, local_rank):
                                         "unit": "TFLOP/s", "sweeps": sw,
                                         "note": "fp64 CUDA-core path (tcgen05 has no fp64 kind); peak = 37 TFLOP/s DFMA "
                                                 "measured with scripts/ubench_fp64.cu (not in MEASURED_PEAKS.json)"}
-    if "xmca_gemm" in prof:
-        v = prof["xmca_gemm"]
-        roof_list["xmca_gemm"] = {"bound": "fp64-simt", "ms": v["ms"], "calls": v["calls"]}
+    if "xmca_sytrd" in prof:
+        v = prof["xmca_sytrd"]
+        n_eig = min(T, S1, S2)
+        sbytes = n_eig ** 3 * 8.0 / 3.0          # one streaming pass over the trailing matrix per column (y = A v)
+        roof_list["xmca_sytrd"] = {"bound": "hbm", "achieved": sbytes * v["calls"] / v["ms"] / 1e6,
+                                   "peak": peaks["hbm_gbs"], "unit": "GB/s", "bytes_per_call": sbytes, "n": n_eig,
+                                   "kernel": "sytrd_panel_kernel (+ rank-128 trailing update)",
+                                   "note": "algorithmic bytes n^3*8/3 = the y = A v pass of every Householder column; "
+                                           "the time is the whole xmca_sytrd call (panel kernels + trailing updates)"}
+    for name in ("xmca_gemm_ex", "xmca_gemm"):
+        if name in prof:
+            v = prof[name]
+            roof_list[name] = {"bound": "fp64-simt", "ms": v["ms"], "calls": v["calls"]}
     if cov:
         roof_list["xmca_tc_gemm_nt"] = {"bound": "tensor", "achieved": cov["tflops_gemm_kernel"] * 3,
                                         "peak": peaks["bf16_tflops"] / 2, "unit": "TFLOP/s (TF32 issued)",

@@ -54,6 +54,20 @@ int xmca_gemm(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K, doubl
               int acc_dtype, int split_k, void* d_workspace, size_t workspace_bytes,
               void* stream);
 
+/* The same product when the operands / the result have structure (M == N, split_k = 1):
+ *   XMCA_GEMM_SYMMETRIC : the result is symmetric (X X^T, L^T G L, V W^T + W V^T with D symmetric
+ *                         when accumulating): tiles above the diagonal are mirrored, not computed
+ *   XMCA_GEMM_A_LOWER_T : opA = L^T with L lower triangular, stored K x M (a_kmajor = 0)
+ *   XMCA_GEMM_B_LOWER   : opB = L lower triangular, stored K x N (b_kmajor = 0)
+ * Used for the T x T Gram matrices and S = L_B^T G_A L_B of the tridiagonal route. */
+enum { XMCA_GEMM_SYMMETRIC = 1, XMCA_GEMM_A_LOWER_T = 2, XMCA_GEMM_B_LOWER = 4 };
+int xmca_gemm_ex(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K, double alpha,
+                 const void* d_A, int a_dtype, int64_t lda,
+                 const void* d_B, int b_dtype, int64_t ldb,
+                 void* d_D, int d_dtype, int64_t ldd, int accumulate,
+                 int acc_dtype, int split_k, void* d_workspace, size_t workspace_bytes,
+                 int flags, void* stream);
+
 /* ---- cross-covariance on the tensor cores (tcgen05 + TMA, 3xTF32) ---------
  * Replaces the field SVDs + kernel product of array.py:552-566: forms
  * C = A^T B * alpha directly (S1 x S2, fp32) from fp32 fields.

@@ -1,0 +1,24 @@
+"""Time the tridiagonal eigen-solver kernels alone (for ncu captures and phase traces)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from xmca_b200 import device as D
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+g = torch.Generator(device="cuda").manual_seed(0)
+X = torch.randn((n, 2 * n), dtype=torch.float64, device="cuda", generator=g)
+S0 = D.matmul(X, X, trans_b=True, symmetric=True)
+for r in range(reps):
+    S = S0.clone()
+    torch.cuda.synchronize()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    d, e, tau = D.sytrd(S)
+    e1.record()
+    w = D.stebz(d, e)
+    e2.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1)
+    print("n=%d: sytrd %.1f ms (%.0f GB/s on n^3*8/3 algorithmic bytes), stebz %.1f ms" %
+          (n, t, n ** 3 * 8 / 3 / t / 1e6, e1.elapsed_time(e2)), flush=True)

@@ -204,3 +204,24 @@ def test_tridiagonal_eigensolver(D, n):
     X = D.to_host(D.ormtr(Sd, tau, Z)).T                                             # n x m
     np.testing.assert_allclose(X.T @ X, np.eye(m), atol=1e-9)
     np.testing.assert_allclose(S @ X, X * w[:m], atol=1e-10 * ref[0])
+
+
+def test_gemm_structure_flags(D):
+    """Symmetric-result and triangular-operand shortcuts give the same numbers as the plain product."""
+    r = _rng(5)
+    n, K = 300, 700
+    X = r.standard_normal((n, K))
+    G = D.to_host(D.matmul(D.to_device(X), D.to_device(X), trans_b=True, symmetric=True, alpha=0.5))
+    np.testing.assert_allclose(G, 0.5 * X @ X.T, rtol=1e-12, atol=1e-11)
+    Lm = np.tril(r.standard_normal((n, n)))
+    Gs = X @ X.T
+    W = D.to_host(D.matmul(D.to_device(Gs), D.to_device(Lm), b_lower=True))
+    np.testing.assert_allclose(W, Gs @ Lm, rtol=1e-12, atol=1e-9)
+    S = D.to_host(D.matmul(D.to_device(Lm), D.to_device(W), trans_a=True, symmetric=True, a_lower_t=True))
+    np.testing.assert_allclose(S, Lm.T @ Gs @ Lm, rtol=1e-11, atol=1e-8)
+    # accumulate into a symmetric matrix (the rank-2k update of the tridiagonalisation)
+    V, Wp = r.standard_normal((n, 128)), r.standard_normal((n, 128))
+    VW, WV = np.hstack([V, Wp]), np.hstack([Wp, V])
+    out = D.to_device(Gs.copy())
+    D.matmul(D.to_device(VW), D.to_device(WV), trans_b=True, alpha=-1.0, out=out, accumulate=True, symmetric=True)
+    np.testing.assert_allclose(D.to_host(out), Gs - VW @ WV.T, rtol=1e-11, atol=1e-8)

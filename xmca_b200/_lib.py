@@ -19,6 +19,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libxmca_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "xmca_b200.h")
 
 F32, F64 = 0, 1
+GEMM_SYMMETRIC, GEMM_A_LOWER_T, GEMM_B_LOWER = 1, 2, 4
 OK, BAD_ARG, CUDA_ERROR, NOT_CONVERGED, NUMERIC = 0, 1, 2, 3, 4
 
 
@@ -59,6 +60,8 @@ def load():
     lib.xmca_gemm_workspace_bytes.argtypes = [i64, i64, i32, i32]
     lib.xmca_gemm.argtypes = [i32, i32, i64, i64, i64, dbl, vp, i32, i64, vp, i32, i64, vp, i32, i64,
                               i32, i32, i32, vp, sz, vp]
+    lib.xmca_gemm_ex.argtypes = [i32, i32, i64, i64, i64, dbl, vp, i32, i64, vp, i32, i64, vp, i32, i64,
+                                 i32, i32, i32, vp, sz, i32, vp]
     lib.xmca_split_tf32.argtypes = [vp, i32, i64, i64, i64, i32, vp, vp, i64, vp]
     lib.xmca_tc_gemm_nt.argtypes = [i64, i64, i64, C.c_float, vp, vp, i64, vp, vp, i64, vp, i64, vp, vp]
     lib.xmca_jacobi_padded_cols.restype = i64

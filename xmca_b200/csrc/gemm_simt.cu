@@ -64,13 +64,18 @@ gemm_simt_kernel(int64_t M, int64_t N, int64_t K, double alpha,
                  const void* __restrict__ A, int adt, int64_t lda,
                  const void* __restrict__ B, int bdt, int64_t ldb,
                  void* __restrict__ D, int ddt, int64_t ldd, int accumulate,
-                 T* __restrict__ partial, int64_t k_chunk) {
+                 T* __restrict__ partial, int64_t k_chunk, int flags) {
   __shared__ T As[BK][BM + PAD];
   __shared__ T Bs[BK][BN + PAD];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
-  const int64_t kb = (int64_t)blockIdx.z * k_chunk;
+  // structure flags (M == N): symmetric result -> only tiles on or below the diagonal are
+  // computed and mirrored; lower-triangular operands -> the k range that is all zeros is skipped
+  if ((flags & XMCA_GEMM_SYMMETRIC) && n0 > m0) return;
+  int64_t kb = (int64_t)blockIdx.z * k_chunk;
   const int64_t ke = min(K, kb + k_chunk);
+  if (flags & XMCA_GEMM_A_LOWER_T) kb = max(kb, m0 / BK * BK);      // opA = L^T: L[k][m] = 0 for k < m
+  if (flags & XMCA_GEMM_B_LOWER) kb = max(kb, n0 / BK * BK);        // opB = L  : L[k][n] = 0 for k < n
 
   T acc[8][8];
 #pragma unroll
@@ -121,6 +126,7 @@ gemm_simt_kernel(int64_t M, int64_t N, int64_t K, double alpha,
         double v = alpha * (double)acc[i][j];
         if (accumulate) v += load_as_double(D, ddt, m * ldd + n);
         store_from_double(D, ddt, m * ldd + n, v);
+        if ((flags & XMCA_GEMM_SYMMETRIC) && n0 < m0) store_from_double(D, ddt, n * ldd + m, v);
       }
     }
   }
@@ -144,14 +150,14 @@ template <typename T>
 static int launch_gemm(int ak, int bk, int64_t M, int64_t N, int64_t K, double alpha,
                        const void* A, int adt, int64_t lda, const void* B, int bdt, int64_t ldb,
                        void* D, int ddt, int64_t ldd, int accumulate, int split,
-                       void* ws, cudaStream_t st) {
+                       void* ws, int flags, cudaStream_t st) {
   int64_t k_chunk = ((K + split - 1) / split + BK - 1) / BK * BK;
   if (k_chunk < BK) k_chunk = BK;
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)split);
   T* partial = split > 1 ? reinterpret_cast<T*>(ws) : nullptr;
 #define GO(AKF, BKF)                                                                     \
   gemm_simt_kernel<T, AKF, BKF><<<grid, NT, 0, st>>>(M, N, K, alpha, A, adt, lda, B, bdt, \
-                                                     ldb, D, ddt, ldd, accumulate, partial, k_chunk)
+                                                     ldb, D, ddt, ldd, accumulate, partial, k_chunk, flags)
   if (ak && bk) GO(true, true);
   else if (ak && !bk) GO(true, false);
   else if (!ak && bk) GO(false, true);
@@ -182,6 +188,22 @@ extern "C" int xmca_gemm(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64
                          void* d_D, int d_dtype, int64_t ldd, int accumulate,
                          int acc_dtype, int split_k, void* d_workspace, size_t workspace_bytes,
                          void* stream) {
+  return xmca_gemm_ex(a_kmajor, b_kmajor, M, N, K, alpha, d_A, a_dtype, lda, d_B, b_dtype, ldb, d_D, d_dtype, ldd,
+                      accumulate, acc_dtype, split_k, d_workspace, workspace_bytes, 0, stream);
+}
+
+extern "C" int xmca_gemm_ex(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K, double alpha,
+                            const void* d_A, int a_dtype, int64_t lda,
+                            const void* d_B, int b_dtype, int64_t ldb,
+                            void* d_D, int d_dtype, int64_t ldd, int accumulate,
+                            int acc_dtype, int split_k, void* d_workspace, size_t workspace_bytes,
+                            int flags, void* stream) {
+  if (flags) {
+    XMCA_REQUIRE(M == N, "xmca_gemm_ex: structure flags need a square result");
+    XMCA_REQUIRE(split_k <= 1, "xmca_gemm_ex: structure flags cannot be combined with split_k");
+    XMCA_REQUIRE(!(flags & XMCA_GEMM_A_LOWER_T) || (!a_kmajor && K == M), "xmca_gemm_ex: A_LOWER_T needs opA = L^T (K x M storage)");
+    XMCA_REQUIRE(!(flags & XMCA_GEMM_B_LOWER) || (!b_kmajor && K == N), "xmca_gemm_ex: B_LOWER needs opB = L (K x N storage)");
+  }
   XMCA_REQUIRE(M > 0 && N > 0 && K > 0, "xmca_gemm: empty problem");
   XMCA_REQUIRE(d_A && d_B && d_D, "xmca_gemm: null operand");
   XMCA_REQUIRE(dtype_ok(a_dtype) && dtype_ok(b_dtype) && dtype_ok(d_dtype) && dtype_ok(acc_dtype),
@@ -197,7 +219,7 @@ extern "C" int xmca_gemm(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (acc_dtype == XMCA_F64)
     return launch_gemm<double>(a_kmajor, b_kmajor, M, N, K, alpha, d_A, a_dtype, lda, d_B, b_dtype,
-                               ldb, d_D, d_dtype, ldd, accumulate, split_k, d_workspace, st);
+                               ldb, d_D, d_dtype, ldd, accumulate, split_k, d_workspace, flags, st);
   return launch_gemm<float>(a_kmajor, b_kmajor, M, N, K, alpha, d_A, a_dtype, lda, d_B, b_dtype, ldb,
-                            d_D, d_dtype, ldd, accumulate, split_k, d_workspace, st);
+                            d_D, d_dtype, ldd, accumulate, split_k, d_workspace, flags, st);
 }

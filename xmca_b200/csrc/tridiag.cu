@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace cg = cooperative_groups;
 
@@ -37,6 +38,7 @@ struct SytrdParams {
   double* wpre;        // n
   double* part;        // grid x TD_PART
   double* d; double* e; double* tau;
+  unsigned long long* clk;   // [8] per-phase clock totals of CTA 0 (XMCA_SYTRD_TRACE)
 };
 
 __device__ __forceinline__ double block_sum_1024(double v, double* red) {
@@ -71,8 +73,10 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
   const int n = P.n;
   const int64_t lda = P.lda;
   double alpha2_prev = 0.0;
+  long long tk[5] = {0, 0, 0, 0, 0};
 
   for (int i = 0; i < P.nb; ++i) {
+    long long c0 = clock64();
     const int c = P.j0 + i;
     const int n1 = n - c - 1;
     // ------------------------------------------------------------ phase A: column c
@@ -101,7 +105,9 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
     ssq = block_sum_1024(ssq, red);
     if (tid == 0) P.part[(int64_t)blockIdx.x * TD_PART] = ssq;
     __threadfence();
+    { long long c1 = clock64(); tk[0] += c1 - c0; c0 = c1; }
     grid.sync();                                  // #1
+    { long long c1 = clock64(); tk[1] += c1 - c0; c0 = c1; }
 
     // ------------------------------------------------------------ phase B: reflector, A v
     const double xnorm2 = grid_slot_sum(P.part, 0, G, red);
@@ -175,7 +181,9 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
       if (tid < TD_K2) P.part[(int64_t)blockIdx.x * TD_PART + 1 + tid] = pv[tid];
     }
     __threadfence();
+    { long long c1 = clock64(); tk[2] += c1 - c0; c0 = c1; }
     grid.sync();                                  // #2
+    { long long c1 = clock64(); tk[1] += c1 - c0; c0 = c1; }
 
     // ------------------------------------------------------------ phase C: w (before the alpha correction)
     if (i > 0) {
@@ -211,7 +219,9 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
     dotacc = block_sum_1024(dotacc, red);
     if (tid == 0) P.part[(int64_t)blockIdx.x * TD_PART + 130] = dotacc;
     __threadfence();
+    { long long c1 = clock64(); tk[3] += c1 - c0; c0 = c1; }
     grid.sync();                                  // #3
+    { long long c1 = clock64(); tk[1] += c1 - c0; c0 = c1; }
 
     // ------------------------------------------------------------ phase D: finish w, store panel column i
     const double dot = grid_slot_sum(P.part, 130, G, red);
@@ -230,7 +240,10 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
     alpha2_prev = alpha2;
     __syncwarp();
     __syncthreads();
+    { long long c1 = clock64(); tk[4] += c1 - c0; c0 = c1; }
   }
+  if (blockIdx.x == 0 && tid == 0 && P.clk)
+    for (int q = 0; q < 5; ++q) P.clk[q] += (unsigned long long)tk[q];
 }
 
 // ------------------------------------------------------------------ bisection
@@ -560,6 +573,7 @@ extern "C" size_t xmca_sytrd_workspace_bytes(int64_t n) {
   b += al256((size_t)n * 8) * 2;                  // u, wpre
   b += al256((size_t)n * TD_MAXF * 8);            // wraw
   b += al256((size_t)(148 * 2) * TD_PART * 8);    // partials
+  b += 256;                                       // phase clocks
   return b;
 }
 
@@ -585,7 +599,9 @@ extern "C" int xmca_sytrd(int64_t n, double* d_A, int64_t lda, double* d_d, doub
   P.u = reinterpret_cast<double*>(ws + o); o += al256((size_t)n * 8);
   P.wpre = reinterpret_cast<double*>(ws + o); o += al256((size_t)n * 8);
   P.wraw = reinterpret_cast<double*>(ws + o); o += al256((size_t)n * TD_MAXF * 8);
-  P.part = reinterpret_cast<double*>(ws + o);
+  P.part = reinterpret_cast<double*>(ws + o); o += al256((size_t)(148 * 2) * TD_PART * 8);
+  P.clk = reinterpret_cast<unsigned long long*>(ws + o);
+  XMCA_CUDA(cudaMemsetAsync(P.clk, 0, 64, st));
   P.d = d_d; P.e = d_e; P.tau = d_tau;
   XMCA_CUDA(cudaMemsetAsync(d_tau, 0, (size_t)n * 8, st));
 
@@ -600,10 +616,18 @@ extern "C" int xmca_sytrd(int64_t n, double* d_A, int64_t lda, double* d_d, doub
     if (r0 < n) {
       // trailing update  A22 -= V W^T + W V^T  =  [V | W] [W | V]^T   (dsyr2k, full square kept)
       const int64_t m = n - r0;
-      rc = xmca_gemm(1, 1, m, m, TD_K2, -1.0, P.VW + r0 * TD_K2, XMCA_F64, TD_K2, P.WV + r0 * TD_K2, XMCA_F64,
-                     TD_K2, d_A + r0 * lda + r0, XMCA_F64, lda, 1, XMCA_F64, 1, nullptr, 0, stream);
+      rc = xmca_gemm_ex(1, 1, m, m, TD_K2, -1.0, P.VW + r0 * TD_K2, XMCA_F64, TD_K2, P.WV + r0 * TD_K2, XMCA_F64,
+                        TD_K2, d_A + r0 * lda + r0, XMCA_F64, lda, 1, XMCA_F64, 1, nullptr, 0, XMCA_GEMM_SYMMETRIC,
+                        stream);
       if (rc != XMCA_OK) return rc;
     }
+  }
+  if (getenv("XMCA_SYTRD_TRACE")) {
+    unsigned long long h[5];
+    XMCA_CUDA(cudaMemcpyAsync(h, P.clk, sizeof h, cudaMemcpyDeviceToHost, st));
+    XMCA_CUDA(cudaStreamSynchronize(st));
+    fprintf(stderr, "[xmca sytrd] n=%lld clocks (CTA 0): column update %.3e | grid syncs %.3e | reflector+symv+p %.3e | w %.3e | store %.3e\n",
+            (long long)n, (double)h[0], (double)h[1], (double)h[2], (double)h[3], (double)h[4]);
   }
   return XMCA_OK;
 }

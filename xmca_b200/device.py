@@ -66,8 +66,11 @@ def _ld(x):
 
 # ---------------------------------------------------------------------- GEMM
 def matmul(A, B, trans_a=False, trans_b=False, alpha=1.0, out=None, out_dtype=None,
-           acc="f64", accumulate=False):
-    """out = alpha * op(A) @ op(B) (+ out).  fp64 accumulation by default."""
+           acc="f64", accumulate=False, symmetric=False, a_lower_t=False, b_lower=False):
+    """out = alpha * op(A) @ op(B) (+ out).  fp64 accumulation by default.
+    symmetric: the result is symmetric (only the lower tiles are computed, then mirrored);
+    a_lower_t: op(A) = L^T with L lower triangular (needs trans_a); b_lower: op(B) = L lower
+    triangular (no trans_b): the all-zero part of the k range is skipped."""
     lib = L.load()
     t = torch()
     if trans_a:
@@ -87,16 +90,20 @@ def matmul(A, B, trans_a=False, trans_b=False, alpha=1.0, out=None, out_dtype=No
     acc_code = L.F64 if acc == "f64" else L.F32
     tiles = ((M + 127) // 128) * ((N + 127) // 128)
     split = 1
-    if tiles < sm_count() and K >= 2048:
+    flags = (L.GEMM_SYMMETRIC if symmetric else 0) | (L.GEMM_A_LOWER_T if a_lower_t else 0) | \
+            (L.GEMM_B_LOWER if b_lower else 0)
+    if flags and (M != N or (a_lower_t and not trans_a) or (b_lower and trans_b)):
+        raise ValueError("matmul: structure flags need a square result and L^T @ . / . @ L operands")
+    if not flags and tiles < sm_count() and K >= 2048:
         split = int(min(max(1, (2 * sm_count()) // tiles), K // 512, 64))
     ws, ws_bytes = None, 0
     if split > 1:
         ws_bytes = lib.xmca_gemm_workspace_bytes(M, N, split, acc_code)
         ws = empty((ws_bytes,), t.uint8)
-    rc = lib.xmca_gemm(0 if trans_a else 1, 1 if trans_b else 0, M, N, K, float(alpha),
-                       L.ptr(A), L.dtype_code(A), _ld(A), L.ptr(B), L.dtype_code(B), _ld(B),
-                       L.ptr(out), L.dtype_code(out), _ld(out), 1 if accumulate else 0,
-                       acc_code, split, L.ptr(ws), ws_bytes, L.stream_ptr())
+    rc = lib.xmca_gemm_ex(0 if trans_a else 1, 1 if trans_b else 0, M, N, K, float(alpha),
+                          L.ptr(A), L.dtype_code(A), _ld(A), L.ptr(B), L.dtype_code(B), _ld(B),
+                          L.ptr(out), L.dtype_code(out), _ld(out), 1 if accumulate else 0,
+                          acc_code, split, L.ptr(ws), ws_bytes, flags, L.stream_ptr())
     L.check(rc, "xmca_gemm")
     return out
 

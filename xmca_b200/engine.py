@@ -228,27 +228,27 @@ class TridiagResult:
             Nb = null_basis if null_basis is not None else D.to_device(np.full((T, 1), 1.0 / np.sqrt(T)))
             self.n_null = Nb.shape[1]
             if self.pca:
-                S = D.matmul(A, A, trans_b=True, alpha=1.0 / dof)
+                S = D.matmul(A, A, trans_b=True, alpha=1.0 / dof, symmetric=True)
             else:
-                GA = D.matmul(A, A, trans_b=True)
-                GB = D.matmul(B, B, trans_b=True)
+                GA = D.matmul(A, A, trans_b=True, symmetric=True)
+                GB = D.matmul(B, B, trans_b=True, symmetric=True)
                 tr = float(D.to_host(D.col_sumsq(B)).sum())
                 if not np.isfinite(tr) or tr <= 0.0:
                     raise np.linalg.LinAlgError("empty or non-finite field")
                 D.matmul(Nb, Nb, trans_b=True, alpha=tr / T, out=GB, accumulate=True)
                 self.LB, self.invB = D.cholesky(GB, min_pivot=1e-11 * tr / T)
-                W = D.matmul(GA, self.LB)
+                W = D.matmul(GA, self.LB, b_lower=True)
                 del GA
-                S = D.matmul(self.LB, W, trans_a=True, alpha=1.0 / dof ** 2)
+                S = D.matmul(self.LB, W, trans_a=True, alpha=1.0 / dof ** 2, symmetric=True, a_lower_t=True)
                 del W
         else:
             self.left_short = S1 <= S2
             if self.pca:
-                S = D.matmul(A, A, trans_a=True, alpha=1.0 / dof)
+                S = D.matmul(A, A, trans_a=True, alpha=1.0 / dof, symmetric=True)
             else:
                 Xs, Xl = (A, B) if self.left_short else (B, A)
                 self.C = D.matmul(Xs, Xl, trans_a=True, alpha=1.0 / dof)          # S_short x S_long
-                S = D.matmul(self.C, self.C, trans_b=True)
+                S = D.matmul(self.C, self.C, trans_b=True, symmetric=True)
         self.n = S.shape[0]
         self.d, self.e, self.tau = D.sytrd(S)
         self.Q = S                                                            # rows now hold the reflectors
