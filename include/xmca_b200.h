@@ -155,6 +155,20 @@ int xmca_stein(int64_t n, const double* d_d, const double* d_e, int64_t k, const
 int xmca_ormtr(int64_t n, const double* d_A, int64_t lda, const double* d_tau, int64_t k,
                double* d_Z, int64_t ldz, void* stream);
 
+/* ---- analytic signal (Hilbert transform along time) ----------------------
+ * Replaces scipy.signal.hilbert(field, axis=0) of array.py:464 by two linear operators that
+ * are applied to the T x S field as GEMMs (xmca_tc_gemm_nt for fp32 fields, xmca_gemm for fp64):
+ * xmca_hilbert_matrix: H (T x T, circulant) with  imag(analytic signal) = H x;  d_taps: T doubles.
+ * xmca_dft_matrix: F (xmca_dft_rows(T) = 2 floor(T/2) rows x T): stacked [Re; Im] rows of
+ *   diag(w) DFT / sqrt(T) for the positive frequencies f = 1..floor(T/2) (w = 2, Nyquist 1): the
+ *   one-sided spectrum Z^ = F x satisfies  Z_A^H Z_B = Z^_A^H Z^_B, so solve() runs on Z^.
+ * xmca_embed_complex: real embedding [[Zr, -Zi], [Zi, Zr]] of the stacked [Zr; Zi] (2 rows_half x cols). */
+int xmca_hilbert_matrix(int64_t T, void* d_H, int h_dtype, int64_t ldh, double* d_taps, void* stream);
+int64_t xmca_dft_rows(int64_t T);
+int xmca_dft_matrix(int64_t T, void* d_F, int f_dtype, int64_t ldf, void* stream);
+int xmca_embed_complex(const void* d_Z, int z_dtype, int64_t ldz, int64_t rows_half, int64_t cols,
+                       void* d_E, int e_dtype, int64_t lde, void* stream);
+
 /* ---- element-wise / layout helpers ---------------------------------------*/
 /* Y[r,c] = X[r,c] * (col_scale ? col_scale[c] : 1) * (row_scale ? row_scale[r] : 1);
  * row-major, dtypes may differ (conversion kernel).  array.py:553, :640, :667. */

@@ -225,3 +225,29 @@ def test_gemm_structure_flags(D):
     out = D.to_device(Gs.copy())
     D.matmul(D.to_device(VW), D.to_device(WV), trans_b=True, alpha=-1.0, out=out, accumulate=True, symmetric=True)
     np.testing.assert_allclose(D.to_host(out), Gs - VW @ WV.T, rtol=1e-11, atol=1e-8)
+
+
+@pytest.mark.parametrize("T,dt", [(64, np.float64), (77, np.float64), (492, np.float32), (250, np.float32)])
+def test_hilbert_operators_match_analytic_signal(D, T, dt):
+    """Device analytic signal (circulant Hilbert operator) and one-sided spectrum operator against the
+    FFT definition of scipy.signal.hilbert (oracle.analytic_signal), even and odd lengths."""
+    from oracle import mca_oracle as orc
+    r = _rng(T)
+    X = r.standard_normal((T, 37)).astype(dt)
+    X -= X.mean(axis=0)
+    Z = orc.analytic_signal(X)
+    Xd = D.to_device(X)
+    Y, _ = D.apply_time_operator(D.hilbert_matrix(T, Xd.dtype), Xd)
+    tol = 2e-5 if dt == np.float32 else 1e-11
+    np.testing.assert_allclose(D.to_host(Y), Z.imag, atol=tol * np.abs(Z).max())
+    # spectrum operator: Z_A^H Z_B is preserved, with half the rows
+    ZZ, _ = D.apply_time_operator(D.dft_matrix(T, Xd.dtype), Xd)
+    zz = D.to_host(ZZ).astype(np.float64)
+    Tp = T // 2
+    assert zz.shape == (2 * Tp, 37)
+    Zh = zz[:Tp] + 1j * zz[Tp:]
+    Zc = Z.astype(np.complex128)
+    np.testing.assert_allclose(Zh.conj().T @ Zh, Zc.conj().T @ Zc, atol=(5e-5 if dt == np.float32 else 1e-10) * T)
+    E = D.to_host(D.embed_complex(ZZ))
+    np.testing.assert_array_equal(E[:Tp, 37:], -E[Tp:, :37])
+    np.testing.assert_array_equal(E[:Tp, :37], E[Tp:, 37:])

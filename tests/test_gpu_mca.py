@@ -299,12 +299,19 @@ def test_tridiagonal_route_through_the_class_complex_and_rotated(MCA):
         assert u["left"].shape == (120, 4) and u["left"].dtype == np.float32
         mc = MCA(A.copy(), B.copy())
         mc.solve(complexify=True)
+        assert mc._solve_info["route"] == "tridiag"
         refc = orc.solve(orc.make_model(A.copy(), B.copy()), complexify=True)
         np.testing.assert_allclose(mc.singular_values(20), refc.sigma[:20], rtol=2e-5)
         e = mc.eofs(5)
         er = orc.eofs(refc, 5)
         al, ar = orc.align_modes(er["left"].reshape(-1, 5), e["left"].reshape(-1, 5), e["right"].reshape(-1, 5))
         assert np.abs(al - er["left"].reshape(-1, 5)).max() < 5e-4
+        # complex PCs through the device Hilbert transform, and the lazily mirrored analytic fields
+        pr, pc = orc.pcs(refc, 5), mc.pcs(5)
+        al, ar = orc.align_modes(pr["left"], pc["left"], pc["right"])
+        assert max(np.abs(al - pr["left"]).max(), np.abs(ar - pr["right"]).max()) < 2e-3 * np.abs(pr["left"]).max()
+        assert mc._fields["left"].dtype == np.complex64
+        np.testing.assert_allclose(mc._fields["left"], refc.fields["left"], atol=2e-4 * np.abs(refc.fields["left"]).max())
     finally:
         E.TRIDIAG_MIN_N = old
 

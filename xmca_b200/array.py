@@ -43,7 +43,8 @@ class MCA:
                             "Please provide `numpy.ndarray` only.")
         self._keys = list(_SIDES[:len(fields)])
         self._host = {}           # host mirror of the centred fields (filled lazily, see `_fields`)
-        self._dev = {}            # device copies of the centred (possibly complex-embedded) fields
+        self._dev = {}            # device copies of the centred REAL fields (always real, see `solve`)
+        self._devY = {}           # their Hilbert transforms (complex models, filled lazily)
         self._shape = {}
         self._field_names = {}
         self._field_means = {}
@@ -128,13 +129,26 @@ class MCA:
         copy is the primary one; the host mirror is downloaded on first use."""
         for k in self._keys:
             if k not in self._host:
-                self._host[k] = D.to_host(self._dev[k])
+                x = D.to_host(self._dev[k])
+                if self._analysis["is_complex"]:          # analytic field x + i H x (array.py:464)
+                    x = (x + 1j * D.to_host(self._hilbert_dev(k))).astype(self._field_dtype(k))
+                self._host[k] = x
         return {k: self._host[k] for k in self._keys}
 
     @_fields.setter
     def _fields(self, value):
         self._host = dict(value)
         self._dev = {}
+        self._devY = {}
+
+    def _hilbert_dev(self, k):
+        """Device Hilbert transform H x of the centred real field k (imaginary part of the
+        analytic signal, array.py:464): one GEMM with the circulant operator, cached."""
+        if k not in self._devY:
+            X = self._device_fields()[k]
+            H = D.hilbert_matrix(X.shape[0], X.dtype)
+            self._devY[k], _ = D.apply_time_operator(H, X)
+        return self._devY[k]
 
     def _n_kept(self, k):
         return int(self._no_nan_index[k].sum())
@@ -199,28 +213,13 @@ class MCA:
 
     # ------------------------------------------------------------ device I/O
     def _device_fields(self):
-        """Upload (once) the centred fields; complex fields as real embeddings."""
+        """Centred REAL fields on the device (uploaded once).  A complex model keeps the real
+        field here; its imaginary part is `_hilbert_dev` (the reference re-takes `.real` before
+        every Hilbert transform as well, array.py:456)."""
         for k in self._keys:
             if k not in self._dev:
-                f = self._host[k]
-                if np.iscomplexobj(f):
-                    f = E.embed_complex_field(f)
-                self._dev[k] = D.to_device(f)
+                self._dev[k] = D.to_device(np.ascontiguousarray(np.real(self._host[k])))
         return self._dev
-
-    @staticmethod
-    def _analytic(x):
-        """Analytic signal along time = scipy.signal.hilbert(x, axis=0) (array.py:464)."""
-        n = x.shape[0]
-        w = np.zeros(n)
-        w[0] = 1.0
-        if n % 2 == 0:
-            w[n // 2] = 1.0
-            w[1:n // 2] = 2.0
-        else:
-            w[1:(n + 1) // 2] = 2.0
-        z = np.fft.ifft(np.fft.fft(x.astype(np.float64), axis=0) * w[:, None], axis=0)
-        return z.astype(np.complex64 if x.dtype == np.float32 else np.complex128)
 
     # ----------------------------------------------------------------- solve
     def solve(self, complexify=False, extend=False, period=1):
@@ -235,10 +234,9 @@ class MCA:
         self._analysis["extend"] = extend
         self._analysis["theta_period"] = period
 
-        if complexify:          # array.py:455-464 (real part re-taken first)
-            self._fields = {k: self._analytic(np.real(f)) for k, f in self._fields.items()}
-            self._dev = {}
         dev = self._device_fields()
+        if self._host and any(np.iscomplexobj(f) for f in self._host.values()) != bool(complexify):
+            self._host = {}       # host mirror no longer matches the model (rebuilt lazily from the device)
         A = dev["left"]
         B = dev.get("right")
         real_dtype = self._field_means["left"].dtype.type
@@ -377,14 +375,14 @@ class MCA:
                     Ud = D.matmul(Ud, D.to_device(np.ascontiguousarray(Rit)))
                 u = D.to_host(Ud)
             else:
+                # Z V = (X + iY)(Vr + iVi): two skinny products over the real field and its Hilbert transform
                 vr, vi = self._V_device_cols(k, need)
                 t = D.torch()
-                Vst = t.cat([vr, vi], dim=0).contiguous()                   # 2S x need  ([x; y] embedding)
-                Ust = D.matmul(X, Vst)                                      # 2T x need
-                Ust = D.scale_copy(Ust, col_scale=inv_root)
-                uh = D.to_host(Ust)
-                T = uh.shape[0] // 2
-                u = uh[:T] + 1j * uh[T:]
+                Vri = t.cat([vr, vi], dim=1).contiguous()                   # S x 2 need
+                sc2 = t.cat([inv_root, inv_root])
+                P1 = D.to_host(D.scale_copy(D.matmul(X, Vri), col_scale=sc2))
+                P2 = D.to_host(D.scale_copy(D.matmul(self._hilbert_dev(k), Vri), col_scale=sc2))
+                u = (P1[:, :need] - P2[:, need:]) + 1j * (P1[:, need:] + P2[:, :need])
                 if is_rot:
                     u = u @ Rit
             if is_rot:

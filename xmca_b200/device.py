@@ -271,6 +271,52 @@ def ormtr(S_reflectors, tau, Z):
     return Z
 
 
+# ----------------------------------------------------------- analytic signal
+def hilbert_matrix(T, dtype):
+    """Circulant H (T x T) with imag(scipy.signal.hilbert(x, axis=0)) = H @ x (array.py:464)."""
+    lib = L.load()
+    H = empty((T, T), dtype)
+    taps = empty((T,), f64())
+    rc = lib.xmca_hilbert_matrix(T, L.ptr(H), L.dtype_code(H), T, L.ptr(taps), L.stream_ptr())
+    L.check(rc, "xmca_hilbert_matrix")
+    return H
+
+
+def dft_matrix(T, dtype):
+    """Stacked [Re; Im] one-sided, weighted, orthonormally scaled DFT operator (2 floor(T/2) x T)."""
+    lib = L.load()
+    F = empty((int(lib.xmca_dft_rows(T)), T), dtype)
+    rc = lib.xmca_dft_matrix(T, L.ptr(F), L.dtype_code(F), T, L.stream_ptr())
+    L.check(rc, "xmca_dft_matrix")
+    return F
+
+
+def embed_complex(Z):
+    """[[Zr, -Zi], [Zi, Zr]] from the stacked Z = [Zr; Zi] (2 Tp x S)."""
+    lib = L.load()
+    rows2, S = Z.shape
+    Tp = rows2 // 2
+    E = empty((rows2, 2 * S), Z.dtype)
+    rc = lib.xmca_embed_complex(L.ptr(Z), L.dtype_code(Z), _ld(Z), Tp, S, L.ptr(E), L.dtype_code(E), 2 * S,
+                                L.stream_ptr())
+    L.check(rc, "xmca_embed_complex")
+    return E
+
+
+def apply_time_operator(Op, X, x_planes=None):
+    """Op (M x T) @ X (T x S) in the dtype of X: 3xTF32 tcgen05 GEMM for fp32 fields (Op and X^T are
+    split into TF32 planes; pass `x_planes` to reuse the split of X), fp64 CUDA cores otherwise.
+    Returns (result, x_planes)."""
+    t = torch()
+    if X.dtype == t.float32:
+        if x_planes is None:
+            x_planes = split_tf32(X, transpose=True)          # S x T, K-major
+        ohi, olo, K = split_tf32(Op)
+        out = tc_gemm_nt(ohi, olo, x_planes[0], x_planes[1], K)
+        return out, x_planes
+    return matmul(Op, X, out_dtype=X.dtype), None
+
+
 # ------------------------------------------------------------- element-wise
 def scale_copy(X, out_dtype=None, col_scale=None, row_scale=None, out=None):
     lib = L.load()

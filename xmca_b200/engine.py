@@ -79,11 +79,13 @@ def _rows_to_cols(rows, out_dtype):
     return D.transpose(rows, out_dtype=out_dtype)
 
 
-def solve_real(A, B, want_vectors=True, force_route=None, use_tensor_cores=None, null_basis=None):
-    """A, B: centred device fields (T x S1, T x S2), fp32 or fp64; B may be None (PCA)."""
+def solve_real(A, B, want_vectors=True, force_route=None, use_tensor_cores=None, null_basis=None, dof=None):
+    """A, B: centred device fields (T x S1, T x S2), fp32 or fp64; B may be None (PCA).
+    null_basis: T x k device matrix of exact null vectors of X X^T (default: the constant
+    vector that centring creates; 0: none).  dof: degrees of freedom (default T - 1)."""
     t = D.torch()
     T, S1 = A.shape
-    dof = float(T - 1)
+    dof = float(T - 1) if dof is None else float(dof)
     out_dtype = A.dtype
     pca = B is None
     S2 = S1 if pca else B.shape[1]
@@ -93,13 +95,13 @@ def solve_real(A, B, want_vectors=True, force_route=None, use_tensor_cores=None,
         route = "tridiag"
     if route == "tridiag":
         try:
-            return TridiagResult(A, B, null_basis)
+            return TridiagResult(A, B, null_basis, dof)
         except np.linalg.LinAlgError:
             route = "gram_eig" if min(S1, S2) > T else "direct"
     sweeps = []
     if route in ("gram", "cholqr"):
         try:
-            return _solve_cholqr(A, B, want_vectors, null_basis)
+            return _solve_cholqr(A, B, want_vectors, null_basis, dof)
         except np.linalg.LinAlgError:
             if route == "cholqr":
                 raise
@@ -209,12 +211,12 @@ class TridiagResult:
 
     route = "tridiag"
 
-    def __init__(self, A, B, null_basis=None):
+    def __init__(self, A, B, null_basis=None, dof=None):
         T, S1 = A.shape
         self.A, self.B = A, B
         self.pca = B is None
         S2 = S1 if self.pca else B.shape[1]
-        self.dof = float(T - 1)
+        self.dof = float(T - 1) if dof is None else float(dof)
         self.out_dtype = A.dtype
         self.null_basis = null_basis
         self.gram_side = T < min(S1, S2)
@@ -225,8 +227,11 @@ class TridiagResult:
         dof = self.dof
         self.n_null = 0
         if self.gram_side:
-            Nb = null_basis if null_basis is not None else D.to_device(np.full((T, 1), 1.0 / np.sqrt(T)))
-            self.n_null = Nb.shape[1]
+            if isinstance(null_basis, int):          # 0: the Gram matrices have no structural null vector
+                Nb = None
+            else:
+                Nb = null_basis if null_basis is not None else D.to_device(np.full((T, 1), 1.0 / np.sqrt(T)))
+                self.n_null = Nb.shape[1]
             if self.pca:
                 S = D.matmul(A, A, trans_b=True, alpha=1.0 / dof, symmetric=True)
             else:
@@ -235,7 +240,8 @@ class TridiagResult:
                 tr = float(D.to_host(D.col_sumsq(B)).sum())
                 if not np.isfinite(tr) or tr <= 0.0:
                     raise np.linalg.LinAlgError("empty or non-finite field")
-                D.matmul(Nb, Nb, trans_b=True, alpha=tr / T, out=GB, accumulate=True)
+                if Nb is not None:
+                    D.matmul(Nb, Nb, trans_b=True, alpha=tr / T, out=GB, accumulate=True)
                 self.LB, self.invB = D.cholesky(GB, min_pivot=1e-11 * tr / T)
                 W = D.matmul(GA, self.LB, b_lower=True)
                 del GA
@@ -322,14 +328,15 @@ class TridiagResult:
             T, S1 = self.A.shape
             S2 = S1 if self.pca else self.B.shape[1]
             route = "gram" if T < min(S1, S2) else "direct"
-            res = solve_real(self.A, self.B, want_vectors=True, force_route=route, null_basis=self.null_basis)
+            res = solve_real(self.A, self.B, want_vectors=True, force_route=route, null_basis=self.null_basis,
+                             dof=self.dof)
             self.sweeps = res.sweeps
             self._full = res.V
         return self._full
 
 
 # ---------------------------------------------------------------- Cholesky-QR
-def _solve_cholqr(A, B, want_vectors, null_basis=None):
+def _solve_cholqr(A, B, want_vectors, null_basis=None, dof=None):
     """T < min(S1, S2): ONE T x T Jacobi SVD instead of three decompositions.
 
     Centring makes n = 1/sqrt(T) an exact null vector of X X^T (for the real
@@ -343,11 +350,14 @@ def _solve_cholqr(A, B, want_vectors, null_basis=None):
     construction, which are dropped.  V_X = X^T (L_X^-T P).
     PCA: C = A^T A / dof = Q_A (L_A^T L_A / dof) Q_A^T -> SVD of L_A itself."""
     T, S1 = A.shape
-    dof = float(T - 1)
+    dof = float(T - 1) if dof is None else float(dof)
     pca = B is None
     out_dtype = A.dtype
-    Nb = null_basis if null_basis is not None else D.to_device(np.full((T, 1), 1.0 / np.sqrt(T)))
-    k = Nb.shape[1]
+    if isinstance(null_basis, int):              # 0: no structural null vector, nothing to lift
+        Nb, k = None, 0
+    else:
+        Nb = null_basis if null_basis is not None else D.to_device(np.full((T, 1), 1.0 / np.sqrt(T)))
+        k = Nb.shape[1]
 
     def factor(X):
         G = D.matmul(X, X, trans_b=True)                                  # T x T fp64 Gram
@@ -355,7 +365,8 @@ def _solve_cholqr(A, B, want_vectors, null_basis=None):
         if not np.isfinite(tr) or tr <= 0.0:
             raise np.linalg.LinAlgError("empty or non-finite field")
         mu = 4.0 * tr
-        D.matmul(Nb, Nb, trans_b=True, alpha=mu, out=G, accumulate=True)   # + mu N N^T
+        if Nb is not None:
+            D.matmul(Nb, Nb, trans_b=True, alpha=mu, out=G, accumulate=True)   # + mu N N^T
         # pivots below ~1e-11 of the mean diagonal: rank deficient beyond the centring null
         # vector (e.g. repeated time steps) -> LinAlgError -> eigen route
         Lm, inv = D.cholesky(G, min_pivot=1e-11 * tr / T)
@@ -374,7 +385,7 @@ def _solve_cholqr(A, B, want_vectors, null_basis=None):
     order = np.argsort(-s, kind="stable")[:T]
     sv = s[order]
     sigma_all = sv * sv / dof if pca else sv
-    if np.abs(sigma_all[:k] - extra).max() > 1e-6 * extra or (T > k and sigma_all[k] > 0.5 * extra):
+    if k and (np.abs(sigma_all[:k] - extra).max() > 1e-6 * extra or (T > k and sigma_all[k] > 0.5 * extra)):
         raise np.linalg.LinAlgError("appended directions not isolated (fields not centred?)")
     sigma = np.concatenate([sigma_all[k:], np.zeros(k)])  # rank = T modes, the last k are the centring null modes
     if not want_vectors:
@@ -406,54 +417,70 @@ def _solve_cholqr(A, B, want_vectors, null_basis=None):
 
 # ------------------------------------------------------------------ complex
 def embed_complex_field(Z: np.ndarray):
-    """Host helper: real embedding [[X, -Y], [Y, X]] of a complex T x S field."""
+    """Host helper (tests): real embedding [[X, -Y], [Y, X]] of a complex T x S field."""
     X, Y = np.ascontiguousarray(Z.real), np.ascontiguousarray(Z.imag)
     return np.block([[X, -Y], [Y, X]])
 
 
-def solve_complex(Ae, Be, want_vectors=True):
-    """Ae/Be: device real embeddings (2T x 2S).  Returns sigma (rank,) and complex
-    V as (re, im) device pairs, each S x rank."""
-    T2, S12 = Ae.shape
-    T, S1 = T2 // 2, S12 // 2
-    pca = Be is None
-    S2 = S1 if pca else Be.shape[1] // 2
+def spectrum_embedding(X, F=None):
+    """Real embedding (2 Tp x 2 S) of the one-sided spectrum Z^ = F X of a centred real field
+    (array.py:429-472 `_complexify` in the frequency domain, see csrc/hilbert.cu)."""
+    if F is None:
+        F = D.dft_matrix(X.shape[0], X.dtype)
+    ZZ, _ = D.apply_time_operator(F, X)
+    return D.embed_complex(ZZ)
+
+
+def solve_complex(XA, XB, want_vectors=True):
+    """Complex MCA/PCA (solve(complexify=True), array.py:546-547) of the CENTRED REAL device fields
+    XA, XB (T x S1, T x S2; XB may be None).  The analytic fields Z = X + i H X satisfy
+    Z_A^H Z_B = Z^_A^H Z^_B with the one-sided spectra Z^ (T/2 rows, full row rank), so the real
+    solver runs on the embeddings of Z^; every singular value of the embedding is double.
+    Returns (sigma (rank,), ComplexVectors, embedded result)."""
+    T, S1 = XA.shape
+    pca = XB is None
+    S2 = S1 if pca else XB.shape[1]
     rank = min(T, S1, S2)
-    # the embedded problem has every singular value twice; dof of the ORIGINAL problem.
-    # Null vectors of the centred embedding: [1; 0] and [0; 1] (real and imaginary time means).
-    nb = np.zeros((T2, 2))
-    nb[:T, 0] = nb[T:, 1] = 1.0 / np.sqrt(T)
-    res = solve_real(Ae, Be, want_vectors=want_vectors, null_basis=D.to_device(nb))
-    scale = (T2 - 1.0) / (T - 1.0)            # solve_real divided by (2T - 1)
-    sigma2 = res.sigma * scale
-    sigma = sigma2[0:2 * rank:2]
-    return sigma, ComplexVectors(res, rank), res
+    F = D.dft_matrix(T, XA.dtype)
+    Ae = spectrum_embedding(XA, F)
+    Be = None if pca else spectrum_embedding(XB, F)
+    del F
+    res = solve_real(Ae, Be, want_vectors=want_vectors, null_basis=0, dof=T - 1)
+    s = res.sigma[0::2]
+    sigma = np.zeros(rank)
+    n = min(rank, s.size)
+    sigma[:n] = s[:n]               # modes beyond the T/2 positive frequencies are exactly zero
+    return sigma, ComplexVectors(res, n, rank), res
 
 
 class ComplexVectors:
-    """Complex singular vectors out of the real-embedded solve: every singular value of the
-    embedding is double and each pair {x, Jx} spans one complex vector, so the even-numbered
-    embedded vectors are taken; `vectors(m)` -> {field: (re, im)} device pairs, each S x m."""
+    """Complex singular vectors out of the real-embedded solve: each pair of equal singular
+    values {x, Jx} spans one complex vector, so the even-numbered embedded vectors are taken;
+    `vectors(m)` -> {field: (re, im)} device pairs, each S x m (zero columns for null modes)."""
 
-    def __init__(self, res, rank):
-        self.res, self.rank = res, rank
+    def __init__(self, res, n_live, rank):
+        self.res, self.n_live, self.rank = res, n_live, rank
         self._cache = (0, None)
 
     def vectors(self, m):
         m = int(min(max(m, 0), self.rank))
         have, V = self._cache
         if V is None or have < m:
-            Ve_all = self.res.vectors(2 * m)
-            pick = _idx(np.arange(0, 2 * m, 2))
+            live = min(m, self.n_live)
+            Ve_all = self.res.vectors(2 * live)
+            pick = _idx(np.arange(0, 2 * live, 2))
             V = {}
             for k, Ve in Ve_all.items():
                 S = Ve.shape[0] // 2
-                Vt = D.transpose(Ve)                                          # 2m x 2S rows
-                rows = D.gather_rows(Vt, pick)                                # m x 2S
-                cols = D.transpose(rows)                                      # 2S x m
+                Vt = D.transpose(Ve)                                          # 2 live x 2S rows
+                rows = D.gather_rows(Vt, pick)                                # live x 2S
+                cols = D.transpose(rows)                                      # 2S x live
+                if live < m:
+                    full = D.zeros((2 * S, m), cols.dtype)
+                    full[:, :live].copy_(cols)
+                    cols = full
                 V[k] = (cols[:S], cols[S:])
             self._cache = (m, V)
-            have = m
         return {k: (v[0][:, :m], v[1][:, :m]) for k, v in V.items()}
 
 

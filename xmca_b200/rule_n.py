@@ -38,10 +38,6 @@ def device_surrogate_variance(shape_T, n_vars, run_index, seed, complexify, rota
         D.fill_normal(X, seed, 2 * run_index + f)               # array.py:1756
         D.center_columns(X)                                     # MCA ctor, array.py:199-207
         fields.append(X)
-    if complexify:
-        from .array import MCA
-        hosts = [MCA._analytic(D.to_host(X)) for X in fields]
-        fields = [D.to_device(E.embed_complex_field(h)) for h in hosts]
     A = fields[0]
     B = fields[1] if len(fields) > 1 else None
     if not rotated:
