@@ -231,6 +231,17 @@ int xmca_varimax(const void* d_L, int l_dtype, int64_t n, int p, int64_t ldl,
                  double* d_B, int64_t ldb, double* d_R, int* iterations_out, double* d_out,
                  void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* Complex loadings (complex MCA): planar (re, im) n x p inputs in storage precision, p <= 32;
+ * outputs planar fp64 B (rotated loadings) and R (p x p unitary rotation).  Same fixed point
+ * evaluated with complex arithmetic (rotation.py:46-62 with complex dtype: |b|^2 b, A^H, polar
+ * factor of a complex p x p matrix). */
+size_t xmca_varimax_complex_workspace_bytes(int64_t n, int p);
+int xmca_varimax_complex(const void* d_Lr, const void* d_Li, int l_dtype, int64_t n, int p, int64_t ldl,
+                         double gamma, int max_iter, double tol,
+                         double* d_Br, double* d_Bi, int64_t ldb, double* d_Rr, double* d_Ri,
+                         int* iterations_out, double* d_out,
+                         void* d_workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -360,3 +360,64 @@ def test_device_ingest_matches_reference_constructor(MCA, dtype):
     m.solve()                                     # the ingested device fields feed solve() directly
     ref = orc.solve(orc.make_model(hole.copy(), B.copy()))
     np.testing.assert_allclose(m.singular_values(10), ref.sigma[:10], rtol=2e-5 if dtype == np.float32 else 1e-10)
+
+
+def test_xmca_facade_wraps_engine_results():
+    """xMCA (xarray facade, xmca/xarray.py:270-514, :1447-1488): coordinates and attrs on the way out,
+    numbers identical to the ndarray class."""
+    import xr_stub as stub
+    from xmca_b200 import MCA, xarray as X
+    X.set_backend(stub)
+    rng = np.random.default_rng(12)
+    t, lat, lon = np.arange(80), np.linspace(-40, 40, 6), np.linspace(0, 100, 7)
+    a = rng.standard_normal((80, 6, 7)).astype(np.float32)
+    b = rng.standard_normal((80, 6, 7)).astype(np.float32)
+    a[:, 1, 2] = np.nan
+    mk = lambda v, nm: stub.DataArray(v, dims=("time", "lat", "lon"), coords={"time": t, "lat": lat, "lon": lon}, name=nm)
+    xm = X.xMCA(mk(a, "a"), mk(b, "b"))
+    xm.set_field_names("sst", "prcp")
+    xm.solve()
+    m = MCA(a.copy(), b.copy())
+    m.solve()
+    sv = xm.singular_values(5)
+    assert sv.dims == ("mode",) and list(sv.coords["mode"]) == [1, 2, 3, 4, 5] and sv.attrs["rank"] == str(41)
+    np.testing.assert_array_equal(sv.values, m.singular_values(5))
+    e = xm.eofs(slice(2, 4))
+    assert e["left"].dims == ("lat", "lon", "mode") and list(e["left"].coords["mode"]) == [2, 3, 4]
+    assert e["left"].name == "sst eofs" and np.isnan(e["left"].values[1, 2]).all()
+    np.testing.assert_array_equal(np.nan_to_num(e["right"].values), np.nan_to_num(m.eofs(slice(2, 4))["right"]))
+    p = xm.pcs(3)
+    assert p["right"].dims == ("time", "mode") and p["right"].shape == (80, 3) and p["right"].name == "prcp pcs"
+    xm.rotate(4, 1)
+    assert xm.explained_variance(4).name == "covariance fraction"
+    r = xm.rule_n(3, 4, seed=1)
+    assert r.dims == ("mode", "run") and r.shape == (4, 3) and list(r.coords["run"]) == [1, 2, 3]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_complex_varimax_matches_oracle(MCA, dtype):
+    """Complex MCA + Varimax (config 3 in miniature): the fused complex kernel against the numpy
+    restatement of rotation.py:15-78 evaluated with complex dtype."""
+    A, B = orc.synthetic_fields(150, 200, 170, seed=55, k=6, dtype=dtype)
+    m = MCA(A.copy(), B.copy())
+    m.solve(complexify=True)
+    m.rotate(5, 1)
+    ref = orc.rotate(orc.solve(orc.make_model(A.copy(), B.copy()), complexify=True), 5, 1)
+    np.testing.assert_allclose(m.variance(5), orc.get_variance(ref, 5), rtol=2e-4)
+    for k in ("left", "right"):
+        np.testing.assert_allclose(m.norm(5)[k], orc.get_norm(ref, 5)[k], rtol=2e-4)
+    R = m.rotation_matrix()
+    assert np.iscomplexobj(R) and R.shape == (5, 5)
+    np.testing.assert_allclose(R.conj().T @ R, np.eye(5), atol=1e-10)
+    e, er = m.eofs(5), orc.eofs(ref, 5)
+    assert e["left"].dtype == np.complex128
+    al, ar = orc.align_modes(er["left"].reshape(-1, 5), e["left"].reshape(-1, 5), e["right"].reshape(-1, 5))
+    assert np.abs(al - er["left"].reshape(-1, 5)).max() < 2e-3 * np.abs(er["left"]).max()
+    p, pr = m.pcs(5), orc.pcs(ref, 5)
+    al, ar = orc.align_modes(pr["left"], p["left"], p["right"])
+    scale = np.abs(pr["left"]).max()
+    assert max(np.abs(al - pr["left"]).max(), np.abs(ar - pr["right"]).max()) < 5e-3 * scale
+    with pytest.raises(NotImplementedError):
+        m.rotate(5, 2)
+    sv = m.rule_n(4, 3, seed=3)
+    assert sv.shape == (3, 4) and np.isfinite(sv).all()

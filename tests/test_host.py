@@ -163,3 +163,30 @@ def test_rule_n_two_rank_gloo_matches_single_process(tmp_path):
         s = np.sort(np.random.default_rng(1000 * 17 + run).random(9))[::-1] + run
         cols.append(s * ref_sum / s.sum())
     np.testing.assert_allclose(r0, np.array(cols).T[:4], rtol=1e-14)
+
+
+def test_xmca_facade_constructor_and_metadata():
+    """xmca/xarray.py:31-85 and tests/unit/test_xarray.py:30-38: DataArrays only, <= 2 fields,
+    dims/coords kept; works with a duck-typed backend because xarray is absent from the image."""
+    import xr_stub as stub
+    from xmca_b200 import xarray as X
+    X.set_backend(stub)
+    rng = np.random.default_rng(3)
+    t, lat, lon = np.arange(30), np.linspace(-60, 60, 5), np.linspace(0, 300, 6)
+    da = stub.DataArray(rng.standard_normal((30, 5, 6)), dims=("time", "lat", "lon"),
+                        coords={"time": t, "lat": lat, "lon": lon}, name="sst")
+    m = X.xMCA(da, da)
+    assert m._field_dims["left"] == ("time", "lat", "lon") and m._n_variables["right"] == 30
+    f = m.fields()
+    assert isinstance(f["left"], stub.DataArray) and f["left"].dims == ("time", "lat", "lon")
+    with pytest.raises(TypeError):
+        X.xMCA(np.zeros((30, 5, 6)))
+    with pytest.raises(ValueError):
+        X.xMCA(da, da, da)
+    with pytest.raises(RuntimeError):
+        m.singular_values()
+    m.apply_coslat()
+    assert m._analysis["is_coslat_corrected"]
+    w = np.sqrt(np.cos(np.deg2rad(lat)) + 1e-6)
+    want = (da.values - da.values.mean(axis=0)) * w[None, :, None]
+    np.testing.assert_allclose(m.fields()["left"].values, want, atol=1e-12)

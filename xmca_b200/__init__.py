@@ -4,5 +4,6 @@ path of Maximum Covariance Analysis, behind the ``xmca.array.MCA`` /
 __version__ = "0.1.0"
 
 from .array import MCA  # noqa: E402,F401
+from .xarray import xMCA  # noqa: E402,F401  (xarray itself is imported lazily)
 
-__all__ = ["MCA", "__version__"]
+__all__ = ["MCA", "xMCA", "__version__"]

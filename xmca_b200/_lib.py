@@ -108,6 +108,10 @@ def load():
     lib.xmca_varimax_workspace_bytes.argtypes = [i64, i32]
     lib.xmca_varimax.argtypes = [vp, i32, i64, i32, i64, dbl, i32, dbl, vp, i64, vp, C.POINTER(i32), vp,
                                  vp, sz, vp]
+    lib.xmca_varimax_complex_workspace_bytes.restype = sz
+    lib.xmca_varimax_complex_workspace_bytes.argtypes = [i64, i32]
+    lib.xmca_varimax_complex.argtypes = [vp, vp, i32, i64, i32, i64, dbl, i32, dbl, vp, vp, i64, vp, vp,
+                                         C.POINTER(i32), vp, vp, sz, vp]
     for name in declared_symbols():
         fn = getattr(lib, name)          # raises AttributeError if a declared symbol is not exported
         if fn.restype is C.c_int and name not in ("xmca_version",):
@@ -123,7 +127,8 @@ def load():
 _NO_TIMING = ("xmca_last_error", "xmca_version", "xmca_launch_count", "xmca_gemm_workspace_bytes",
               "xmca_jacobi_padded_cols", "xmca_jacobi_workspace_bytes", "xmca_varimax_workspace_bytes",
               "xmca_cholesky_workspace_bytes", "xmca_cholesky_invdiag_bytes", "xmca_trsm_workspace_bytes",
-              "xmca_sytrd_max_n", "xmca_sytrd_workspace_bytes", "xmca_stein_workspace_bytes", "xmca_dft_rows")
+              "xmca_sytrd_max_n", "xmca_sytrd_workspace_bytes", "xmca_stein_workspace_bytes", "xmca_dft_rows",
+              "xmca_varimax_complex_workspace_bytes")
 _profile = None
 
 

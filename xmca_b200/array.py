@@ -455,12 +455,12 @@ class MCA:
         if power < 1:
             raise ValueError("`power` must be >=1")
         self._require_solved("singular values")
-        if self._analysis["is_complex"]:
-            raise NotImplementedError("complex Varimax/Promax is not implemented in the B200 engine yet")
-        if n_rot > 64:
-            raise ValueError("the fused rotation kernel supports n_rot <= 64")
+        if n_rot > (32 if self._analysis["is_complex"] else 64):
+            raise ValueError("the fused rotation kernel supports n_rot <= 64 (<= 32 for complex models)")
         sv = self._get_svals(n_rot)
         n_rot = sv.size
+        if self._analysis["is_complex"]:
+            return self._rotate_complex(sv, n_rot, power, tol)
         root = D.to_device(np.sqrt(sv.astype(np.float64)))
         t = D.torch()
         parts = [D.scale_copy(self._V_device_cols(k, n_rot), col_scale=root) for k in self._keys]
@@ -490,6 +490,33 @@ class MCA:
             lo, hi = bounds[k]
             inv = D.to_device(1.0 / self._norm[k])
             self._rot_eofs[k] = D.to_host(D.scale_copy(Lrot[lo:hi], col_scale=inv))
+
+    def _rotate_complex(self, sv, n_rot, power, tol):
+        """Complex model: fused complex Varimax kernel on the planar loadings."""
+        _, provider = self._dV
+        V = provider.vectors(n_rot)
+        try:
+            Br, Bi, s_left, R, iters = E.rotate_complex(V, sv.astype(np.float64), self._keys, n_rot, power, tol=tol)
+        except L.NotConvergedError:
+            raise RuntimeError("Rotation process did not converge. Try decreasing the tolerance. "
+                               "Invalid NaN entries also might be a problem.")
+        n_all = Br.shape[0]
+        nl = E.complex_col_norms(Br, Bi, 0, s_left)
+        nr = E.complex_col_norms(Br, Bi, s_left, n_all) if self._analysis["is_bivariate"] else nl
+        self._norm = {"left": nl, "right": nr} if self._analysis["is_bivariate"] else {"left": nl}
+        self._variance = nl * nr
+        self._var_idx = np.argsort(self._variance)[::-1]
+        self._rotation_matrix = R
+        self._correlation_matrix = np.eye(n_rot)
+        self._analysis["is_rotated"] = True
+        self._analysis["n_rot"] = n_rot
+        self._analysis["power"] = power
+        self._solve_info["varimax_iterations"] = iters
+        self._rot_eofs = {}
+        bounds = {"left": (0, s_left), "right": (s_left, n_all)}
+        for k in self._keys:
+            lo, hi = bounds[k]
+            self._rot_eofs[k] = (D.to_host(Br[lo:hi]) + 1j * D.to_host(Bi[lo:hi])) / self._norm[k]
 
     def rotation_matrix(self, inverse_transpose=False):
         try:

@@ -247,16 +247,7 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
 }
 
 // ------------------------------------------------------------------ bisection
-// fp64 reciprocal from the hardware approximation + two Newton steps (rel. error ~1e-15):
-// the Sturm recurrence is one long dependent chain, its latency is what is being paid for.
-__device__ __forceinline__ double td_fast_rcp(double x) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  r = fma(r, fma(-x, r, 1.0), r);
-  r = fma(r, fma(-x, r, 1.0), r);
-  return r;
-}
-
+// (fast_rcp: the Sturm recurrence is one long dependent chain, its latency is what is being paid for)
 // Eight lanes per eigenvalue index k (0 = LARGEST, descending output): every level evaluates the
 // Sturm count at 8 interior points of the current bracket (9-section, ~3.2 bits per level), so
 // the dependent chain is ~17 levels * n steps instead of ~55 * n for plain bisection.
@@ -280,7 +271,7 @@ stebz_kernel(int n, const double* __restrict__ d, const double* __restrict__ e2,
     cnt += (q < 0.0);
     for (int j = 1; j < n; ++j) {
       if (fabs(q) < pivmin) q = -pivmin;
-      q = d[j] - x - e2[j - 1] * td_fast_rcp(q);
+      q = d[j] - x - e2[j - 1] * fast_rcp(q);
       cnt += (q < 0.0);
     }
     // first sub-point whose count exceeds `want` bounds the eigenvalue from above
@@ -403,7 +394,7 @@ stein_kernel(int n, const double* __restrict__ d, const double* __restrict__ e,
           if (fabs(ca) >= fabs(cj)) {
             double piv = ca;
             if (fabs(piv) < tiny) piv = copysign(tiny, piv);
-            const double ip = td_fast_rcp(piv);
+            const double ip = fast_rcp(piv);
             const double m = cj * ip;
             buf[3][t] = m; buf[4][t] = 0.0;                    // lm, sw
             buf[0][t] = ip; buf[5][t] = cb;                    // u0i, u1   (u2 = 0)

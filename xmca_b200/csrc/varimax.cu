@@ -36,25 +36,6 @@ struct VarimaxParams {
   double* B; int64_t ldb; double* R; double* out;   // out: [0]=iterations [1]=converged [2]=d [3]=svd sweeps total
 };
 
-// fp64 reciprocal / reciprocal square root from the hardware approximations (~20 bits) and two
-// Newton steps: relative error ~1e-15, a fraction of the latency of the IEEE division / sqrt.
-__device__ __forceinline__ double fast_rcp(double x) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  r = fma(r, fma(-x, r, 1.0), r);
-  r = fma(r, fma(-x, r, 1.0), r);
-  return r;
-}
-__device__ __forceinline__ double fast_rsqrt(double x) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  const double hx = 0.5 * x;
-  y = y * fma(-hx * y, y, 1.5);
-  y = y * fma(-hx * y, y, 1.5);
-  y = y * fma(-hx * y, y, 1.5);
-  return y;
-}
-
 // Z[i][j] = sum_k X(i,k) Y(k,j) for i, j, k < p (padded entries -> 0), 64 x 64 output by the whole
 // CTA: thread -> column j and 8 rows (8 independent accumulators hide the DFMA latency).
 // Element access: X(i,k) = X[i * xs_i + k * xs_k], Y(k,j) = Y[k * ys_k + j * ys_j] (so transposed

@@ -459,3 +459,25 @@ def varimax(Ld, gamma=1.0, max_iter=1000, tol=1e-8):
     last_varimax_stats = out
     L.check(rc, "xmca_varimax")
     return B, R, iters.value
+
+
+def varimax_complex(Lr, Li, gamma=1.0, max_iter=1000, tol=1e-8):
+    """Device Varimax for complex loadings given as planar (re, im) n x p tensors (p <= 32).
+    Returns (Br, Bi fp64 n x p, R complex128 host p x p, iterations).  Raises NotConvergedError."""
+    lib = L.load()
+    t = torch()
+    n, p = Lr.shape
+    assert Li.shape == Lr.shape and Li.dtype == Lr.dtype and _ld(Li) == _ld(Lr)
+    Br, Bi = empty((n, p), t.float64), empty((n, p), t.float64)
+    Rr, Ri = empty((p, p), t.float64), empty((p, p), t.float64)
+    out = zeros((16,), t.float64)
+    ws_bytes = lib.xmca_varimax_complex_workspace_bytes(n, p)
+    ws = empty((ws_bytes,), t.uint8)
+    iters = C.c_int(0)
+    rc = lib.xmca_varimax_complex(L.ptr(Lr), L.ptr(Li), L.dtype_code(Lr), n, p, _ld(Lr), float(gamma), int(max_iter),
+                                  float(tol), L.ptr(Br), L.ptr(Bi), p, L.ptr(Rr), L.ptr(Ri), C.byref(iters),
+                                  L.ptr(out), L.ptr(ws), ws_bytes, L.stream_ptr())
+    global last_varimax_stats
+    last_varimax_stats = out
+    L.check(rc, "xmca_varimax_complex")
+    return Br, Bi, to_host(Rr) + 1j * to_host(Ri), iters.value

@@ -511,3 +511,25 @@ def promax(Ld, power=1, max_iter=1000, tol=1e-8):
     Bp = D.scale_copy(XL, row_scale=D.to_device(h))                       # rotation.py:141
     Li = np.linalg.inv(Lm)
     return Bp, R @ Lm, Li @ Li.T, iters
+
+
+def rotate_complex(V, sigma, keys, n_rot, power=1, max_iter=1000, tol=1e-8):
+    """Varimax rotation of complex loadings L = [V_L; V_R] sqrt(sigma) (array.py:815-833 with complex
+    dtype).  V: {field: (re, im)} device pairs (S x >= n_rot).  Returns (Br, Bi, s_left, R, iterations);
+    norms follow from the column sums of |B|^2 over each field's rows."""
+    if power != 1:
+        raise NotImplementedError("Promax (power > 1) of a complex model is not implemented in the B200 engine yet")
+    t = D.torch()
+    root = D.to_device(np.sqrt(np.asarray(sigma[:n_rot], dtype=np.float64)))
+    re = [D.scale_copy(V[k][0][:, :n_rot], col_scale=root) for k in keys]
+    im = [D.scale_copy(V[k][1][:, :n_rot], col_scale=root) for k in keys]
+    s_left = re[0].shape[0]
+    Lr = t.cat(re, dim=0).contiguous() if len(re) > 1 else re[0]
+    Li = t.cat(im, dim=0).contiguous() if len(im) > 1 else im[0]
+    Br, Bi, R, iters = D.varimax_complex(Lr, Li, 1.0, max_iter, tol)
+    return Br, Bi, s_left, R, iters
+
+
+def complex_col_norms(Br, Bi, row0, row1):
+    """sqrt(sum_rows |B|^2) per column over rows [row0, row1) (array.py:826-830)."""
+    return np.sqrt(D.to_host(D.col_sumsq(Br, row0, row1)) + D.to_host(D.col_sumsq(Bi, row0, row1)))

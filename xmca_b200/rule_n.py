@@ -46,7 +46,17 @@ def device_surrogate_variance(shape_T, n_vars, run_index, seed, complexify, rota
             return sigma
         return E.solve_real(A, B, want_vectors=False).sigma
     if complexify:
-        raise NotImplementedError("rule_n on a rotated complex model is not implemented yet")
+        sigma, vec, _ = E.solve_complex(A, B)
+        p = min(n_rot, sigma.size)
+        keys = ["left", "right"][:len(fields)]
+        try:
+            Br, Bi, s_left, _, _ = E.rotate_complex(vec.vectors(p), sigma, keys, p, power)
+        except L.NotConvergedError:
+            return None
+        nl = E.complex_col_norms(Br, Bi, 0, s_left)
+        if B is None:
+            return nl ** 2
+        return nl * E.complex_col_norms(Br, Bi, s_left, Br.shape[0])
     res = E.solve_real(A, B, want_vectors=True)
     p = min(n_rot, res.sigma.size)
     root = D.to_device(np.sqrt(res.sigma[:p]))
