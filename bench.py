@@ -41,11 +41,25 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (T, S1, S2, n_rot, n_modes)
+    # name: (T, S1, S2, n_rot, n_modes)   -- extra settings in WORKLOAD_OPTS
     "c2": (8192, 16384, 16384, 50, 50),
     "half": (4096, 8192, 8192, 50, 50),
     "small": (1024, 2048, 2048, 20, 20),
+    "c3": (8192, 32768, 32768, 20, 20),        # complex MCA (Hilbert) + Varimax n_rot = 20
+    "c3half": (4096, 16384, 16384, 20, 20),
+    "c5": (16384, 65536, 32768, 50, 50),       # fp64, Promax power 4
+    "c5half": (8192, 32768, 16384, 50, 50),
 }
+WORKLOAD_OPTS = {
+    "c3": {"complexify": True}, "c3half": {"complexify": True},
+    "c5": {"dtype": np.float64, "power": 4}, "c5half": {"dtype": np.float64, "power": 4},
+}
+
+
+def opts(workload):
+    o = {"complexify": False, "dtype": np.float32, "power": 1}
+    o.update(WORKLOAD_OPTS.get(workload, {}))
+    return o
 
 
 def synthetic_fields(T, S1, S2, seed, k=64, dtype=np.float32):
@@ -128,9 +142,9 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ product arm
-def hot_path_step(m, n_rot, n_modes):
-    m.solve()
-    m.rotate(n_rot, 1)
+def hot_path_step(m, n_rot, n_modes, complexify=False, power=1):
+    m.solve(complexify=complexify)
+    m.rotate(n_rot, power)
     sv = m.singular_values(n_modes)
     pcs = m.pcs(n_modes)
     eofs = m.eofs(n_modes)
@@ -151,10 +165,11 @@ def run_product(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     _lib.load()
     T, S1, S2, n_rot, n_modes = WORKLOADS[args.workload]
+    wo = opts(args.workload)
     peaks = load_peaks()
 
     # pinned host fields (the e2e leg copies from these every step)
-    A0, B0 = synthetic_fields(T, S1, S2, seed=1000 + rank)
+    A0, B0 = synthetic_fields(T, S1, S2, seed=1000 + rank, dtype=wo["dtype"])
     Ap = torch.from_numpy(A0).pin_memory()
     Bp = torch.from_numpy(B0).pin_memory()
     A, B = Ap.numpy(), Bp.numpy()
@@ -192,20 +207,21 @@ def run_product(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_step, launches, res = timed(lambda: hot_path_step(model, n_rot, n_modes), args.steps, args.warmup)
+    step = lambda mm: hot_path_step(mm, n_rot, n_modes, wo["complexify"], wo["power"])
+    ms_step, launches, res = timed(lambda: step(model), args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
     info = dict(model._solve_info)
 
     # ---- per-call-class device time of one more step (CUDA events on the launch stream) -
     _lib.profile_begin()
-    hot_path_step(model, n_rot, n_modes)
+    step(model)
     prof = _lib.profile_end()
     vm_iters = int(model._solve_info.get("varimax_iterations", 0))
 
     # ---- leg 2: end to end through the public class, host buffers ----------------------
     def e2e_step():
         m = MCA(A, B)
-        return hot_path_step(m, n_rot, n_modes)
+        return step(m)
     ms_e2e, _, res_e2e = timed(e2e_step, args.steps, min(args.warmup, 1))
     h2d = int(A.nbytes + B.nbytes)
     d2h = result_bytes(res_e2e)
@@ -213,7 +229,7 @@ def run_product(args, rank, world, local_rank):
     # ---- cov-GEMM on the tensor cores (C = A^T B / dof, 3xTF32 tcgen05) -----------------
     dA, dB = model._dev["left"], model._dev["right"]
     cov = None
-    if dA.dtype == torch.float32:
+    if dA.dtype == torch.float32 and not wo["complexify"]:
         planes = [D.split_tf32(dA, transpose=True), D.split_tf32(dB, transpose=True)]
         Cbuf = D.empty((S1, S2), torch.float32)
 
@@ -231,18 +247,25 @@ def run_product(args, rank, world, local_rank):
     # ---- rule_n: surrogates sharded over the ranks, one all-gather ----------------------
     rn = None
     if args.rule_n_runs > 0:
-        model.solve()                                 # rule N of the unrotated model
+        model.solve(complexify=wo["complexify"])      # rule N of the unrotated model
         n_runs = args.rule_n_runs * world
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        model.rule_n(world, n_modes, seed=99)          # warm-up (allocator, kernel attributes)
+        barrier()
         e0.record()
         spectra = model.rule_n(n_runs, n_modes, seed=1234)
         e1.record()
         barrier()
         ms_rn = reduce_max(e0.elapsed_time(e1))
+        _lib.profile_begin()
+        model.rule_n(world, n_modes, seed=4321)
+        rn_prof = _lib.profile_end()
         rn = {"surrogates_per_s": n_runs / (ms_rn / 1e3), "n_runs": n_runs, "runs_per_rank": args.rule_n_runs,
               "ms_total": ms_rn, "shape": list(spectra.shape), "dtype": "f64",
-              "collective": "1 all_gather (nccl)" if world > 1 else "none (1 rank)"}
+              "collective": "1 all_gather (nccl)" if world > 1 else "none (1 rank)",
+              "call_ms_one_surrogate": {k: round(v["ms"], 2) for k, v in
+                                        sorted(rn_prof.items(), key=lambda kv: -kv[1]["ms"])}}
 
     if rank != 0:
         return None
@@ -253,7 +276,7 @@ def run_product(args, rank, world, local_rank):
                   "launches": v["launches"]} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
     dom = next(iter(shares))
     n_load = S1 + S2
-    e_store = 4
+    e_store = np.dtype(wo["dtype"]).itemsize * (2 if wo["complexify"] else 1)
     roof_list = {}
     if "xmca_varimax" in prof:
         v = prof["xmca_varimax"]
@@ -302,9 +325,10 @@ def run_product(args, rank, world, local_rank):
                   "cov_gemm, rule_n surrogates/s in rule_n)",
         "value": world / (ms_step / 1e3), "unit": "models/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32 fields; f64 accumulation/SVD/rotation", "data": "synthetic",
-        "config": {"workload": "%s: MCA T=%d S1=%d S2=%d f32, rotate(n_rot=%d, power=1), getters n=%d"
-                               % (args.workload, T, S1, S2, n_rot, n_modes),
+        "vs_baseline": None, "dtype": "%s fields; f64 accumulation/eigen-solver/rotation" % np.dtype(wo["dtype"]).name, "data": "synthetic",
+        "config": {"workload": "%s: %sMCA T=%d S1=%d S2=%d %s, rotate(n_rot=%d, power=%d), getters n=%d"
+                               % (args.workload, "complex " if wo["complexify"] else "", T, S1, S2,
+                                  np.dtype(wo["dtype"]).name, n_rot, wo["power"], n_modes),
                    "l2": "inputs (2 x %.0f MB) larger than the 126 MB L2" % (A.nbytes / 1e6),
                    "parallelism": "replicas x%d (solve/rotate); rule_n surrogates block-sharded" % world,
                    "route": info.get("route"), "jacobi_sweeps": info.get("sweeps"),
@@ -320,7 +344,7 @@ def run_product(args, rank, world, local_rank):
         "roofline_kernels": roof_list,
         "call_shares": shares,
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.workload in ("c2", "half", "small"):
         out["cpu_baseline"] = cpu_baseline(args.workload, steps=1, warmup=0)
     return out
 

@@ -59,8 +59,10 @@ int xmca_gemm(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K, doubl
  *                         when accumulating): tiles above the diagonal are mirrored, not computed
  *   XMCA_GEMM_A_LOWER_T : opA = L^T with L lower triangular, stored K x M (a_kmajor = 0)
  *   XMCA_GEMM_B_LOWER   : opB = L lower triangular, stored K x N (b_kmajor = 0)
+ *   XMCA_GEMM_LOWER_ONLY: only the 128 x 128 tiles on or below the diagonal are computed / written
+ *                         (trailing update of the Cholesky factorisation)
  * Used for the T x T Gram matrices and S = L_B^T G_A L_B of the tridiagonal route. */
-enum { XMCA_GEMM_SYMMETRIC = 1, XMCA_GEMM_A_LOWER_T = 2, XMCA_GEMM_B_LOWER = 4 };
+enum { XMCA_GEMM_SYMMETRIC = 1, XMCA_GEMM_A_LOWER_T = 2, XMCA_GEMM_B_LOWER = 4, XMCA_GEMM_LOWER_ONLY = 8 };
 int xmca_gemm_ex(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K, double alpha,
                  const void* d_A, int a_dtype, int64_t lda,
                  const void* d_B, int b_dtype, int64_t ldb,

@@ -265,8 +265,10 @@ class MCA:
         self._analysis["is_rotated"] = False
         self._analysis["n_rot"] = n
         self._analysis["power"] = 0
-        self._rotation_matrix = np.eye(n)
-        self._correlation_matrix = np.eye(n)
+        # array.py:601-602 store eye(rank) twice (2 x 512 MB at rank 8192); kept lazy here, the
+        # getters below materialise the identity on demand
+        self._rot_R = None
+        self._rot_Phi = None
         self._analysis["is_truncated_at"] = n
 
     # --------------------------------------------------------------- getters
@@ -477,8 +479,8 @@ class MCA:
         self._norm = {"left": nl, "right": nr} if self._analysis["is_bivariate"] else {"left": nl}
         self._variance = nl * nr
         self._var_idx = np.argsort(self._variance)[::-1]
-        self._rotation_matrix = R
-        self._correlation_matrix = Phi
+        self._rot_R = R
+        self._rot_Phi = Phi
         self._analysis["is_rotated"] = True
         self._analysis["n_rot"] = n_rot
         self._analysis["power"] = power
@@ -506,8 +508,8 @@ class MCA:
         self._norm = {"left": nl, "right": nr} if self._analysis["is_bivariate"] else {"left": nl}
         self._variance = nl * nr
         self._var_idx = np.argsort(self._variance)[::-1]
-        self._rotation_matrix = R
-        self._correlation_matrix = np.eye(n_rot)
+        self._rot_R = R
+        self._rot_Phi = np.eye(n_rot)
         self._analysis["is_rotated"] = True
         self._analysis["n_rot"] = n_rot
         self._analysis["power"] = power
@@ -517,6 +519,16 @@ class MCA:
         for k in self._keys:
             lo, hi = bounds[k]
             self._rot_eofs[k] = (D.to_host(Br[lo:hi]) + 1j * D.to_host(Bi[lo:hi])) / self._norm[k]
+
+    @property
+    def _rotation_matrix(self):
+        self._require_solved("rotation matrix")
+        return self._rot_R if self._rot_R is not None else np.eye(self._singular_values.size)
+
+    @property
+    def _correlation_matrix(self):
+        self._require_solved("correlation matrix")
+        return self._rot_Phi if self._rot_Phi is not None else np.eye(self._singular_values.size)
 
     def rotation_matrix(self, inverse_transpose=False):
         try:

@@ -38,25 +38,25 @@ chol_diag_kernel(double* __restrict__ A, int64_t lda, int64_t k0, int nb, double
     Ls[i][j] = (i < nb && j < nb && j <= i) ? A[(k0 + i) * lda + k0 + j] : ((i == j) ? 1.0 : 0.0);
   }
   __syncthreads();
+  // left-looking factorisation, thread i owns row i: per column one dot product of length j per
+  // thread (operands in shared memory, row j broadcast) and two barriers -- the block is on the
+  // critical path of the whole factorisation (n / 64 strictly sequential launches)
   for (int j = 0; j < nb; ++j) {
-    const double d = Ls[j][j];
-    if (!(d > min_pivot) || !isfinite(d)) {      // uniform: every thread reads the same value
-      if (tid == 0) s_bad = j + 1;
-      break;
-    }
-    const double r = sqrt(d);
-    __syncthreads();
-    for (int i = j + tid; i < nb; i += 256) Ls[i][j] = (i == j) ? r : Ls[i][j] / r;
-    __syncthreads();
-    // trailing update of the lower triangle: L[i][c] -= L[i][j] * L[c][j], j < c <= i
-    const int rem = nb - j - 1;
-    for (int e = tid; e < rem * rem; e += 256) {
-      int i = j + 1 + e / rem, c = j + 1 + e % rem;
-      if (c <= i) Ls[i][c] -= Ls[i][j] * Ls[c][j];
+    double sdot = 0.0;
+    if (tid >= j && tid < nb) {
+      sdot = Ls[tid][j];
+      for (int k = 0; k < j; ++k) sdot = fma(-Ls[tid][k], Ls[j][k], sdot);
     }
     __syncthreads();
+    if (tid == j) {
+      if (!(sdot > min_pivot) || !isfinite(sdot)) s_bad = j + 1;
+      Ls[j][j] = sqrt(sdot);
+    }
+    __syncthreads();
+    if (s_bad) break;                              // uniform
+    if (tid > j && tid < nb) Ls[tid][j] = sdot / Ls[j][j];
+    __syncthreads();                               // row j + 1 is read by every thread next
   }
-  __syncthreads();
   if (s_bad) {
     if (tid == 0) atomicCAS(flag, 0, (int)(k0 + s_bad));
     return;
@@ -159,10 +159,10 @@ extern "C" int xmca_cholesky(int64_t n, double* d_A, int64_t lda, double* d_invd
                        XMCA_F64, 1, nullptr, 0, stream);
     if (rc != XMCA_OK) return rc;
     if ((rc = copy_block(panel, CB, Aik, lda, rem, nb, st)) != XMCA_OK) return rc;
-    // trailing update: A_ij -= L_ik L_jk^T (full square; only the lower half is used later)
+    // trailing update: A_ij -= L_ik L_jk^T (tiles on or below the diagonal; only the lower half is used later)
     double* Att = d_A + (k0 + nb) * lda + (k0 + nb);
-    rc = xmca_gemm(1, 1, rem, rem, nb, -1.0, panel, XMCA_F64, CB, panel, XMCA_F64, CB, Att, XMCA_F64, lda, 1,
-                   XMCA_F64, 1, nullptr, 0, stream);
+    rc = xmca_gemm_ex(1, 1, rem, rem, nb, -1.0, panel, XMCA_F64, CB, panel, XMCA_F64, CB, Att, XMCA_F64, lda, 1,
+                      XMCA_F64, 1, nullptr, 0, XMCA_GEMM_LOWER_ONLY, stream);
     if (rc != XMCA_OK) return rc;
   }
   {

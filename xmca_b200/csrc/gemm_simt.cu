@@ -71,7 +71,7 @@ gemm_simt_kernel(int64_t M, int64_t N, int64_t K, double alpha,
   const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
   // structure flags (M == N): symmetric result -> only tiles on or below the diagonal are
   // computed and mirrored; lower-triangular operands -> the k range that is all zeros is skipped
-  if ((flags & XMCA_GEMM_SYMMETRIC) && n0 > m0) return;
+  if ((flags & (XMCA_GEMM_SYMMETRIC | XMCA_GEMM_LOWER_ONLY)) && n0 > m0) return;
   int64_t kb = (int64_t)blockIdx.z * k_chunk;
   const int64_t ke = min(K, kb + k_chunk);
   if (flags & XMCA_GEMM_A_LOWER_T) kb = max(kb, m0 / BK * BK);      // opA = L^T: L[k][m] = 0 for k < m
