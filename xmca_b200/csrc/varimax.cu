@@ -128,7 +128,7 @@ __device__ int polar_jacobi(double* X, double* V, int pe, const unsigned char* r
     double m = 0.0;
     for (int w = 0; w < nwarps; ++w) m = fmax(m, s_max[w]);
     __syncthreads();
-    if (m <= 1e-8) break;               // largest squared cosine BEFORE this sweep's rotations: they leave ~1e-8
+    if (m <= 1e-11) break;              // largest squared cosine BEFORE this sweep's rotations: they leave ~1e-11
   }
   return sweeps;
 }

@@ -111,7 +111,7 @@ __device__ int polar_jacobi_complex(double* Xr, double* Xi, double* Vr, double* 
     double m = 0.0;
     for (int w = 0; w < nwarps; ++w) m = fmax(m, s_max[w]);
     __syncthreads();
-    if (m <= 1e-8) break;               // largest squared cosine BEFORE this sweep's rotations: they leave ~1e-8
+    if (m <= 1e-11) break;              // largest squared cosine BEFORE this sweep's rotations: they leave ~1e-11
   }
   return sweeps;
 }
