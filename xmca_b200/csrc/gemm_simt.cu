@@ -132,6 +132,128 @@ gemm_simt_kernel(int64_t M, int64_t N, int64_t K, double alpha,
   }
 }
 
+// ------------------------------------------------------------------ fp64 on the DMMA pipe
+// Same tiling contract (128 x 128 x 16 block tile, register prefetch of the next k-slab, split-K
+// partials, structure flags) with the inner product on mma.sync.m8n8k4.f64: 16 warps, each a
+// 32 x 32 warp tile = 4 x 4 MMA tiles (32 accumulator doubles per thread); per k-step of 4 a thread
+// loads 4 + 4 fragment doubles for 16 MMAs, a quarter of the shared-memory traffic per flop of the
+// 8 x 8 scalar micro-tile above, which is what kept that kernel at ~45 % of the DFMA peak.
+// Operand slabs are stored [k][mn] with a row pitch of 132 doubles: the fragment loads (k = lane % 4,
+// mn = lane / 4) then hit 16 distinct 8-byte banks per half-warp.
+constexpr int DT = 512, DLD = BM + 4;
+
+template <bool KMAJOR>
+__device__ __forceinline__ void dload_slab(double (&r)[4], const void* p, int dt, int64_t ld,
+                                           int64_t mn0, int64_t mn_end, int64_t k0, int64_t k_end, int tid) {
+  if (KMAJOR) {
+    const int kk = tid & 15, m = tid >> 4;        // 16 consecutive k per row
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t mm = mn0 + m + 32 * i, k = k0 + kk;
+      r[i] = (mm < mn_end && k < k_end) ? ld_elem<double>(p, dt, mm * ld + k) : 0.0;
+    }
+  } else {
+    const int m = tid & 127, kk = tid >> 7;       // 128 consecutive mn per k row
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t mm = mn0 + m, k = k0 + kk + 4 * i;
+      r[i] = (mm < mn_end && k < k_end) ? ld_elem<double>(p, dt, k * ld + mm) : 0.0;
+    }
+  }
+}
+
+template <bool KMAJOR>
+__device__ __forceinline__ void dstore_slab(const double (&r)[4], double (*s)[DLD], int tid) {
+  if (KMAJOR) {
+    const int kk = tid & 15, m = tid >> 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s[kk][m + 32 * i] = r[i];
+  } else {
+    const int m = tid & 127, kk = tid >> 7;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s[kk + 4 * i][m] = r[i];
+  }
+}
+
+template <bool AK, bool BKM>
+__global__ void __launch_bounds__(DT)
+gemm_dmma_kernel(int64_t M, int64_t N, int64_t K, double alpha,
+                 const void* __restrict__ A, int adt, int64_t lda,
+                 const void* __restrict__ B, int bdt, int64_t ldb,
+                 void* __restrict__ D, int ddt, int64_t ldd, int accumulate,
+                 double* __restrict__ partial, int64_t k_chunk, int flags) {
+  __shared__ double As[BK][DLD];
+  __shared__ double Bs[BK][DLD];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
+  const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+  if ((flags & (XMCA_GEMM_SYMMETRIC | XMCA_GEMM_LOWER_ONLY)) && n0 > m0) return;
+  int64_t kb = (int64_t)blockIdx.z * k_chunk;
+  const int64_t ke = min(K, kb + k_chunk);
+  if (flags & XMCA_GEMM_A_LOWER_T) kb = max(kb, m0 / BK * BK);
+  if (flags & XMCA_GEMM_B_LOWER) kb = max(kb, n0 / BK * BK);
+
+  double c[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { c[i][j][0] = 0.0; c[i][j][1] = 0.0; }
+
+  double ra[4], rb[4];
+  if (kb < ke) {
+    dload_slab<AK>(ra, A, adt, lda, m0, M, kb, ke, tid);
+    dload_slab<BKM>(rb, B, bdt, ldb, n0, N, kb, ke, tid);
+  }
+  for (int64_t k0 = kb; k0 < ke; k0 += BK) {
+    dstore_slab<AK>(ra, As, tid);
+    dstore_slab<BKM>(rb, Bs, tid);
+    __syncthreads();
+    if (k0 + BK < ke) {
+      dload_slab<AK>(ra, A, adt, lda, m0, M, k0 + BK, ke, tid);
+      dload_slab<BKM>(rb, B, bdt, ldb, n0, N, k0 + BK, ke, tid);
+    }
+#pragma unroll
+    for (int ks = 0; ks < BK; ks += 4) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        a[i] = As[ks + tig][wm + 8 * i + gid];
+        b[i] = Bs[ks + tig][wn + 8 * i + gid];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(c[i][j][0]), "+d"(c[i][j][1]) : "d"(a[i]), "d"(b[j]));
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + wm + 8 * i + gid;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int64_t n = n0 + wn + 8 * j + 2 * tig + e;
+        if (n >= N) continue;
+        if (partial) {
+          partial[((int64_t)blockIdx.z * M + m) * N + n] = c[i][j][e];
+        } else {
+          double v = alpha * c[i][j][e];
+          if (accumulate) v += load_as_double(D, ddt, m * ldd + n);
+          store_from_double(D, ddt, m * ldd + n, v);
+          if ((flags & XMCA_GEMM_SYMMETRIC) && n0 < m0) store_from_double(D, ddt, n * ldd + m, v);
+        }
+      }
+    }
+  }
+}
+
 template <typename T>
 __global__ void splitk_reduce_kernel(int64_t M, int64_t N, int split, double alpha,
                                      const T* __restrict__ partial,
@@ -155,6 +277,25 @@ static int launch_gemm(int ak, int bk, int64_t M, int64_t N, int64_t K, double a
   if (k_chunk < BK) k_chunk = BK;
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)split);
   T* partial = split > 1 ? reinterpret_cast<T*>(ws) : nullptr;
+  if (sizeof(T) == 8) {                 // fp64 accumulation: DMMA kernel
+    double* dpart = reinterpret_cast<double*>(partial);
+#define GOD(AKF, BKF)                                                                    \
+  gemm_dmma_kernel<AKF, BKF><<<grid, DT, 0, st>>>(M, N, K, alpha, A, adt, lda, B, bdt, ldb, \
+                                                  D, ddt, ldd, accumulate, dpart, k_chunk, flags)
+    if (ak && bk) GOD(true, true);
+    else if (ak && !bk) GOD(true, false);
+    else if (!ak && bk) GOD(false, true);
+    else GOD(false, false);
+#undef GOD
+    XMCA_LAUNCHED();
+    if (split > 1) {
+      int64_t tot = M * N;
+      splitk_reduce_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
+          M, N, split, alpha, partial, D, ddt, ldd, accumulate);
+      XMCA_LAUNCHED();
+    }
+    return XMCA_OK;
+  }
 #define GO(AKF, BKF)                                                                     \
   gemm_simt_kernel<T, AKF, BKF><<<grid, NT, 0, st>>>(M, N, K, alpha, A, adt, lda, B, bdt, \
                                                      ldb, D, ddt, ldd, accumulate, partial, k_chunk, flags)
