@@ -332,7 +332,8 @@ def run_product(args, rank, world, local_rank):
                    "l2": "inputs (2 x %.0f MB) larger than the 126 MB L2" % (A.nbytes / 1e6),
                    "parallelism": "replicas x%d (solve/rotate); rule_n surrogates block-sharded" % world,
                    "route": info.get("route"), "jacobi_sweeps": info.get("sweeps"),
-                   "varimax_iterations": vm_iters},
+                   "varimax_iterations": vm_iters,
+                   "varimax_polar_jacobi_sweeps": info.get("varimax_svd_sweeps")},
         "solve_rotate_wall_s": ms_step / 1e3,
         "e2e": {"value": world / (ms_e2e / 1e3), "unit": "models/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

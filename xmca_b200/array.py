@@ -485,6 +485,9 @@ class MCA:
         self._analysis["n_rot"] = n_rot
         self._analysis["power"] = power
         self._solve_info["varimax_iterations"] = iters
+        st = D.to_host(D.last_varimax_stats)
+        self._solve_info["varimax_svd_sweeps"] = int(st[3])
+        self._solve_info["varimax_phase_clocks"] = [float(x) for x in st[4:10]]
         # rotated EOFs = L_rot / norm (array.py:640): one scaled copy per field, kept on the host
         self._rot_eofs = {}
         bounds = {"left": (0, s_left), "right": (s_left, n_all)}

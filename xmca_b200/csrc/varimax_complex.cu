@@ -63,7 +63,7 @@ __device__ __forceinline__ void cmatmul(const double* Xr, const double* Xi, int 
 // One-sided complex Jacobi on the columns of X (p x p, column-major stride CPP, planar), accumulating V.
 // One pair per warp (pe / 2 <= 16 warps), lane <-> row.
 __device__ int polar_jacobi_complex(double* Xr, double* Xi, double* Vr, double* Vi, int pe,
-                                    const unsigned char* rr, double* s_max) {
+                                    const unsigned char* rr, double* s_max, double stop2) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int npairs = pe >> 1;
   int sweeps = 0;
@@ -111,7 +111,7 @@ __device__ int polar_jacobi_complex(double* Xr, double* Xi, double* Vr, double* 
     double m = 0.0;
     for (int w = 0; w < nwarps; ++w) m = fmax(m, s_max[w]);
     __syncthreads();
-    if (m <= 1e-11) break;              // largest squared cosine BEFORE this sweep's rotations: they leave ~1e-11
+    if (m <= stop2) break;              // largest squared cosine seen BEFORE this sweep's rotations
   }
   return sweeps;
 }
@@ -317,23 +317,36 @@ __global__ void __launch_bounds__(CTHREADS, 1) varimax_complex_kernel(VarimaxCPa
     // X = T V, computed as X^T(j,i) = sum_k V^T(j,k) T^T(k,i)  (both factors plain, no conjugation)
     cmatmul(Vr, Vi, CPP, 1, Tr, Ti, CPP, 1, false, Xr, Xi, CPP, 1, p);
     __syncthreads();
-    svd_sweeps += polar_jacobi_complex(Xr, Xi, Vr, Vi, pe, rr, s_max);
+    // inexact polar factor inside the iteration, polished once converged (see varimax.cu)
+    svd_sweeps += polar_jacobi_complex(Xr, Xi, Vr, Vi, pe, rr, s_max, 1e-6);
     __syncthreads();
-    for (int j = warp; j < CP; j += CTHREADS / 32) {                            // sigma_j, U = X / sigma
-      const double xr = Xr[j * CPP + lane], xi = Xi[j * CPP + lane];
-      const double nn = sqrt(warp_sum(xr * xr + xi * xi));
-      const bool live = (j < p) && nn > 0.0;
-      if (lane == 0) cs[j] = (j < p) ? nn : 0.0;
-      Xr[j * CPP + lane] = live ? xr / nn : 0.0;
-      Xi[j * CPP + lane] = live ? xi / nn : 0.0;
+    auto finish_polar = [&]() {
+      for (int j = warp; j < CP; j += CTHREADS / 32) {                            // sigma_j, U = X / sigma
+        const double xr = Xr[j * CPP + lane], xi = Xi[j * CPP + lane];
+        const double nn = sqrt(warp_sum(xr * xr + xi * xi));
+        const bool live = (j < p) && nn > 0.0;
+        if (lane == 0) cs[j] = (j < p) ? nn : 0.0;
+        Xr[j * CPP + lane] = live ? xr / nn : 0.0;
+        Xi[j * CPP + lane] = live ? xi / nn : 0.0;
+      }
+      __syncthreads();
+      // R = U V^H : R(i,l) = sum_j U(i,j) conj(V(l,j)); U(i,j) = X[j*CPP+i], V(l,j) = V[j*CPP+l]
+      cmatmul(Xr, Xi, 1, CPP, Vr, Vi, CPP, 1, true, Rr, Ri, CP, 1, p);
+      double dd = 0.0;
+      for (int j = 0; j < p; ++j) dd += cs[j];
+      __syncthreads();
+      return dd;
+    };
+    d = finish_polar();
+    if (fabs(d - d_old) / d < P.tol) {
+      cmatmul(Vr, Vi, CPP, 1, Tr, Ti, CPP, 1, false, Xr, Xi, CPP, 1, p);          // X = T V again
+      __syncthreads();
+      svd_sweeps += polar_jacobi_complex(Xr, Xi, Vr, Vi, pe, rr, s_max, 1e-22);
+      __syncthreads();
+      d = finish_polar();
+      converged = 1;
+      break;
     }
-    __syncthreads();
-    // R = U V^H : R(i,l) = sum_j U(i,j) conj(V(l,j)); U(i,j) = X[j*CPP+i], V(l,j) = V[j*CPP+l]
-    cmatmul(Xr, Xi, 1, CPP, Vr, Vi, CPP, 1, true, Rr, Ri, CP, 1, p);
-    d = 0.0;
-    for (int j = 0; j < p; ++j) d += cs[j];
-    __syncthreads();
-    if (fabs(d - d_old) / d < P.tol) { converged = 1; break; }
   }
   if (it > P.max_iter) it = P.max_iter;
 
