@@ -56,6 +56,16 @@ WORKLOAD_OPTS = {
 }
 
 
+def workload_string(workload):
+    T, S1, S2, n_rot, n_modes = WORKLOADS[workload]
+    o = opts(workload)
+    return "%s: %sMCA T=%d S1=%d S2=%d %s, rotate(n_rot=%d, power=%d), getters n=%d" % (
+        workload, "complex " if o["complexify"] else "", T, S1, S2, np.dtype(o["dtype"]).name, n_rot, o["power"], n_modes)
+
+
+CPU_SAMPLE_DIV = {"c2": 4, "half": 2, "small": 1, "c3": 8, "c3half": 4, "c5": 16, "c5half": 8}
+
+
 def opts(workload):
     o = {"complexify": False, "dtype": np.float32, "power": 1}
     o.update(WORKLOAD_OPTS.get(workload, {}))
@@ -317,8 +327,16 @@ def run_product(args, rank, world, local_rank):
             r["frac"] = r["achieved"] / r["peak"]
     roof = dict(roof_list.get(dom, {"bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                     "frac": None}))
-    roof.update({"kernel": dom, "share_of_step": shares[dom]["share"], "traffic": None,
+    roof.update({"kernel": roof.get("kernel", dom), "call": dom, "share_of_step": shares[dom]["share"],
                  "peak_source": peaks["source"]})
+    if dom == "xmca_sytrd":
+        # one `ncu --set full` capture of sytrd_panel_kernel (profiles/r1_ncu_summary.md): launch 9 of 128 at
+        # n = 8192 read 30.34 GB + wrote 0.10 GB of DRAM for 29.9 GB of algorithmic bytes (64 columns x n'^2 x 8 B)
+        roof.update({"traffic": 30.44e9, "traffic_algorithmic_same_launch": 29.9e9,
+                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE panel launch (ncu, n=8192, "
+                                     "panel 9/128); `achieved` averages all panel launches and trailing updates of a call"})
+    else:
+        roof.setdefault("traffic", None)
 
     out = {
         "metric": "solve()+rotate() throughput (models/s; wall-sec in solve_rotate_wall_s, cov-GEMM TFLOP/s in "
@@ -326,9 +344,7 @@ def run_product(args, rank, world, local_rank):
         "value": world / (ms_step / 1e3), "unit": "models/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "%s fields; f64 accumulation/eigen-solver/rotation" % np.dtype(wo["dtype"]).name, "data": "synthetic",
-        "config": {"workload": "%s: %sMCA T=%d S1=%d S2=%d %s, rotate(n_rot=%d, power=%d), getters n=%d"
-                               % (args.workload, "complex " if wo["complexify"] else "", T, S1, S2,
-                                  np.dtype(wo["dtype"]).name, n_rot, wo["power"], n_modes),
+        "config": {"workload": workload_string(args.workload),
                    "l2": "inputs (2 x %.0f MB) larger than the 126 MB L2" % (A.nbytes / 1e6),
                    "parallelism": "replicas x%d (solve/rotate); rule_n surrogates block-sharded" % world,
                    "route": info.get("route"), "jacobi_sweeps": info.get("sweeps"),
@@ -345,20 +361,21 @@ def run_product(args, rank, world, local_rank):
         "roofline_kernels": roof_list,
         "call_shares": shares,
     }
-    if world == 1 and not args.no_cpu_baseline and args.workload in ("c2", "half", "small"):
+    if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args.workload, steps=1, warmup=0)
     return out
 
 
 # ------------------------------------------------------------ CPU baseline / reference arm
-def _cpu_sample(T, S1, S2, n_rot, n_modes, seed):
+def _cpu_sample(T, S1, S2, n_rot, n_modes, seed, wo=None):
     """One solve()+rotate()+getters of the numpy oracle port; returns seconds."""
     from oracle import mca_oracle as orc
-    A, B = synthetic_fields(T, S1, S2, seed=seed)
+    wo = wo or {"complexify": False, "dtype": np.float32, "power": 1}
+    A, B = synthetic_fields(T, S1, S2, seed=seed, dtype=wo["dtype"])
     t0 = time.perf_counter()
-    m = orc.solve(orc.make_model(A, B))
+    m = orc.solve(orc.make_model(A, B), complexify=wo["complexify"])
     try:
-        orc.rotate(m, n_rot, 1)
+        orc.rotate(m, n_rot, wo["power"])
     except orc.NotConverged:
         pass
     orc.pcs(m, n_modes)
@@ -368,34 +385,35 @@ def _cpu_sample(T, S1, S2, n_rot, n_modes, seed):
 
 def cpu_baseline(workload, steps=1, warmup=0):
     """numpy restatement of the reference path (oracle/, kind "port") on this
-    box's host cores.  A full config-2 solve takes minutes on a CPU, so each
-    step times the SAME pipeline at 1/4 and 1/8 of T, S1, S2 and extrapolates
-    with the measured per-doubling factor f = t(1/4) / t(1/8):
-    t(full) = t(1/4) * f^2."""
+    box's host cores.  A full-size solve takes minutes to hours on a CPU, so each
+    step times the SAME pipeline at 1/div and 1/(2 div) of T, S1, S2 and extrapolates
+    with the measured per-doubling factor f = t(1/div) / t(1/(2 div)):
+    t(full) = t(1/div) * f^log2(div)."""
     T, S1, S2, n_rot, n_modes = WORKLOADS[workload]
-    div = 4 if workload == "c2" else (2 if workload == "half" else 1)
+    wo = opts(workload)
+    div = CPU_SAMPLE_DIV.get(workload, 4)
     cores = os.cpu_count() or 1
     _cpu_sample(256, 512, 512, 10, 10, 5)                       # BLAS/LAPACK warm-up
     ts = []
     for i in range(warmup + steps):
         if div > 1:
-            t_hi = _cpu_sample(T // div, S1 // div, S2 // div, n_rot, n_modes, 77 + i)
-            t_lo = _cpu_sample(T // (2 * div), S1 // (2 * div), S2 // (2 * div), n_rot, n_modes, 177 + i)
+            t_hi = _cpu_sample(T // div, S1 // div, S2 // div, n_rot, n_modes, 77 + i, wo)
+            t_lo = _cpu_sample(T // (2 * div), S1 // (2 * div), S2 // (2 * div), n_rot, n_modes, 177 + i, wo)
             f = max(t_hi / t_lo, 1.0)
             full = t_hi * f ** int(np.log2(div))
             rec = (full, t_hi, t_lo, f)
         else:
-            t_hi = _cpu_sample(T, S1, S2, n_rot, n_modes, 77 + i)
+            t_hi = _cpu_sample(T, S1, S2, n_rot, n_modes, 77 + i, wo)
             rec = (t_hi, t_hi, None, None)
         if i >= warmup:
             ts.append(rec)
     full = float(np.mean([r[0] for r in ts]))
     t_hi = float(np.mean([r[1] for r in ts]))
-    sample = ("numpy oracle port: solve+rotate(%d)+pcs/eofs(%d) at T=%d,S=%d: %.2f s" %
-              (n_rot, n_modes, T // div, S1 // div, t_hi))
+    sample = ("numpy oracle port: %ssolve+rotate(%d, %d)+pcs/eofs(%d) at T=%d,S1=%d: %.2f s" %
+              ("complex " if wo["complexify"] else "", n_rot, wo["power"], n_modes, T // div, S1 // div, t_hi))
     if div > 1:
         f = float(np.mean([r[3] for r in ts]))
-        sample += ("; at T=%d,S=%d: %.2f s; per-doubling factor %.2f -> extrapolated %.1f s at the full size"
+        sample += ("; at T=%d,S1=%d: %.2f s; per-doubling factor %.2f -> extrapolated %.1f s at the full size"
                    % (T // (2 * div), S1 // (2 * div), float(np.mean([r[2] for r in ts])), f, full))
     return {"value": 1.0 / full, "unit": "models/s", "cores": cores, "kind": "port", "sample": sample,
             "seconds_per_model_extrapolated": full}
@@ -414,9 +432,9 @@ def run_reference(args, rank, world):
                   "cov_gemm, rule_n surrogates/s in rule_n)",
         "value": cb["value"], "unit": "models/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": cb["seconds_per_model_extrapolated"] * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32 fields (numpy/LAPACK sgesdd), f64 rotation", "data": "synthetic",
-        "config": {"workload": "%s: MCA T=%d S1=%d S2=%d f32, rotate(n_rot=%d, power=1), getters n=%d"
-                               % (args.workload, T, S1, S2, n_rot, n_modes)},
+        "vs_baseline": None, "dtype": "%s fields (numpy/LAPACK gesdd in the field dtype), f64 rotation"
+                                      % np.dtype(opts(args.workload)["dtype"]).name, "data": "synthetic",
+        "config": {"workload": workload_string(args.workload)},
         "solve_rotate_wall_s": cb["seconds_per_model_extrapolated"],
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "models/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
