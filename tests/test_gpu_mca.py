@@ -421,3 +421,37 @@ def test_complex_varimax_matches_oracle(MCA, dtype):
         m.rotate(5, 2)
     sv = m.rule_n(4, 3, seed=3)
     assert sv.shape == (3, 4) and np.isfinite(sv).all()
+
+
+def test_full_size_config2_invariants(MCA):
+    """BASELINE.json config 2 at FULL size (T 8192, S1 = S2 16384, fp32) through size-independent
+    properties (the oracle cannot run this size in seconds): the independent tensor-core covariance
+    C = A^T B / dof gives sum(sigma^2) = ||C||_F^2 (array.py:596) and sigma_1..k = the singular values
+    of V_L^T C V_R; V orthonormal (test_orthogonality), U_L^T U_R / dof = I (test_correlation)."""
+    import torch
+    from bench import synthetic_fields
+    from xmca_b200 import device as D
+    T, S = 8192, 16384
+    A, B = synthetic_fields(T, S, S, seed=2024)
+    m = MCA(A, B)
+    del A, B
+    m.solve()
+    assert m._solve_info["route"] == "tridiag" and m._analysis["rank"] == T
+    sv = m.singular_values().astype(np.float64)
+    assert np.all(np.diff(sv) <= 1e-6 * sv[0]) and sv[-1] <= 1e-6 * sv[0]       # sorted, centring null mode last
+    dA, dB = m._device_fields()["left"], m._device_fields()["right"]
+    C, frob2 = D.cov_gemm_tc(dA, dB, 1.0 / (T - 1))
+    np.testing.assert_allclose((sv ** 2).sum(), float(frob2.item()), rtol=2e-6)
+    k = 40
+    V = m._get_V(k, rotated=False)
+    for side in ("left", "right"):
+        np.testing.assert_allclose(V[side].T.astype(np.float64) @ V[side], np.eye(k), atol=2e-5)
+    VL, VR = torch.from_numpy(V["left"]).cuda(), torch.from_numpy(V["right"]).cuda()
+    small = D.to_host(D.matmul(D.matmul(VL, C, trans_a=True), VR))                  # k x k, = diag(sigma)
+    np.testing.assert_allclose(np.diag(small), sv[:k], rtol=2e-5)
+    off = small - np.diag(np.diag(small))
+    assert np.abs(off).max() < 2e-5 * sv[0]
+    U = m.pcs(k, rotated=False)
+    np.testing.assert_allclose(U["left"].T.astype(np.float64) @ U["right"] / (T - 1), np.eye(k), atol=5e-4)
+    del C
+    torch.cuda.empty_cache()
