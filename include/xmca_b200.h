@@ -86,6 +86,15 @@ int xmca_tc_gemm_nt(int64_t M, int64_t N, int64_t K, float alpha,
                     const float* d_Bhi, const float* d_Blo, int64_t ldb,
                     float* d_D, int64_t ldd, double* d_frob2, void* stream);
 
+/* fp64-output variant for long contractions (Gram matrices G = X X^T of fp32 fields, the T x T
+ * matrices of the tridiagonal route): large and small split products in separate TMEM accumulators,
+ * chunks of 64 k drained into fp64 register sums.  symmetric != 0 (M == N, same operand): only the
+ * tiles on or below the diagonal are computed, the rest mirrored. */
+int xmca_tc_gemm_nt_f64(int64_t M, int64_t N, int64_t K, double alpha,
+                        const float* d_Ahi, const float* d_Alo, int64_t lda,
+                        const float* d_Bhi, const float* d_Blo, int64_t ldb,
+                        double* d_D, int64_t ldd, int symmetric, void* stream);
+
 /* ---- SVD / symmetric eigen-decomposition: blocked one-sided Jacobi --------
  * Replaces np.linalg.svd of array.py:479 and :570 (and the p x p SVD of
  * rotation.py:59 when called with small n).

@@ -251,3 +251,21 @@ def test_hilbert_operators_match_analytic_signal(D, T, dt):
     E = D.to_host(D.embed_complex(ZZ))
     np.testing.assert_array_equal(E[:Tp, 37:], -E[Tp:, :37])
     np.testing.assert_array_equal(E[:Tp, :37], E[Tp:, 37:])
+
+
+@pytest.mark.parametrize("shape", [(300, 1000), (512, 4096), (1000, 777), (130, 20000)])
+def test_tensor_core_gram_fp64_accumulation(D, shape):
+    """G = X X^T of fp32 data on tcgen05 (3xTF32) with split TMEM accumulators and fp64 chunk sums:
+    ~1e-7 of the diagonal scale, also for all-positive data (worst case for the accumulator truncation)."""
+    n, K = shape
+    r = _rng(n + K)
+    for kind in ("gauss", "positive"):
+        X = r.standard_normal((n, K)).astype(np.float32)
+        if kind == "positive":
+            X = np.abs(X) + np.float32(0.5)
+        G = D.to_host(D.gram_tc(D.to_device(X), alpha=0.5))
+        want = 0.5 * X.astype(np.float64) @ X.astype(np.float64).T
+        scale = np.sqrt(np.outer(np.diag(want), np.diag(want)))
+        assert np.abs(G - want).max() / scale.max() < 4e-7
+        assert np.abs((G - want) / scale).max() < 4e-7
+        assert np.abs(G - G.T).max() <= 1e-8 * scale.max()       # diagonal tiles compute both triangles

@@ -64,6 +64,7 @@ def load():
                                  i32, i32, i32, vp, sz, i32, vp]
     lib.xmca_split_tf32.argtypes = [vp, i32, i64, i64, i64, i32, vp, vp, i64, vp]
     lib.xmca_tc_gemm_nt.argtypes = [i64, i64, i64, C.c_float, vp, vp, i64, vp, vp, i64, vp, i64, vp, vp]
+    lib.xmca_tc_gemm_nt_f64.argtypes = [i64, i64, i64, dbl, vp, vp, i64, vp, vp, i64, vp, i64, i32, vp]
     lib.xmca_jacobi_padded_cols.restype = i64
     lib.xmca_jacobi_padded_cols.argtypes = [i64]
     lib.xmca_jacobi_workspace_bytes.restype = sz

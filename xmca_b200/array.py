@@ -619,12 +619,12 @@ class MCA:
                         sort_keys=False))
 
     # --------------------------------------------------------------- rule N
-    def rule_n(self, n_runs, n_modes=None, seed=None, group=None):
+    def rule_n(self, n_runs, n_modes=None, seed=None, group=None, surrogate_dtype=None):
         """Rule N (Overland & Preisendorfer 1982), semantics of array.py:1716-1771,
         with the surrogate loop sharded over the ranks of ``group``
         (``torch.distributed``; ``None`` = single GPU).  See ``xmca_b200.rule_n``."""
         from . import rule_n as RN
-        return RN.rule_n(self, n_runs, n_modes=n_modes, seed=seed, group=group)
+        return RN.rule_n(self, n_runs, n_modes=n_modes, seed=seed, group=group, surrogate_dtype=surrogate_dtype)
 
     # ---------------------------------------------------------- out of scope
     def _out_of_scope(self, name):

@@ -106,6 +106,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
 //   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major, 1)
 //   [32,46) SBO >> 4 = 1024 B (8 rows x 128 B) | [46,48) version = 1 | [61,64) layout = 2 (SW128)
@@ -296,6 +307,170 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
   }
 }
 
+// ------------------------------------------------------------------ fp64-output variant (Gram matrices)
+// D[M,N] (fp64) = alpha * sum_k A[m,k] B[n,k], same 3xTF32 operand split, built for the long
+// contractions of the Gram matrices G = X X^T (K = S up to 65536, all diagonal terms positive).
+// The tensor core truncates the fp32 accumulator after every MMA, a bias that grows with the
+// length of the chain and with |acc|, so here
+//   * the large products (hi*hi) and the small ones (hi*lo, lo*hi) go to SEPARATE TMEM
+//     accumulators: the main chain is 8 MMAs per chunk of 2 stages (64 k), the small chain
+//     carries values 2^-11 smaller whose truncation is negligible,
+//   * every chunk is drained to registers, main + small added in fp32 (one rounding) and
+//     accumulated in FP64 registers (64 per epilogue thread): the sum over K/64 chunks adds
+//     no further error.  Measured against the fp64 product: ~1e-7 relative on the diagonal.
+// symmetric != 0: tiles above the diagonal are skipped and mirrored from below.
+constexpr int TG_BN = 128;
+constexpr int TG_CHUNK_KB = 2;
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_nt_f64_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
+                      const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
+                      int M, int N, int K, double alpha, double* __restrict__ D, int64_t ldd,
+                      int symmetric, int tiles_m, int tiles_n) {
+  using Cfg = TcCfg<TG_BN>;
+  constexpr int kCols = TG_BN / 2;          // 64 accumulator columns per epilogue thread
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;      // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int tile_m, tile_n;
+  {
+    const int id = blockIdx.x;
+    const int per_group = TC_GROUP_M * tiles_n;
+    const int g = id / per_group;
+    const int first_m = g * TC_GROUP_M;
+    const int gm = min(TC_GROUP_M, tiles_m - first_m);
+    const int in = id - g * per_group;
+    tile_m = first_m + in % gm;
+    tile_n = in / gm;
+  }
+  const int m0 = tile_m * TC_BM, n0 = tile_n * TG_BN;
+  if (symmetric && n0 > m0) return;                         // uniform: mirrored from the tile below the diagonal
+  const int num_kb = (K + TC_BK - 1) / TC_BK;
+  const int num_chunks = (num_kb + TG_CHUNK_KB - 1) / TG_CHUNK_KB;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapAhi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapAlo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBhi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBlo) : "memory");
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], TC_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    // 2 buffers x (main 128 + small 128) columns = the whole tensor memory of the SM
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = smem + stage * Cfg::kStageBytes;
+        mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+        const int k0 = kb * TC_BK;
+        tma_load_2d(st, &mapAhi, k0, m0, &full_bar[stage]);
+        tma_load_2d(st + Cfg::kABytes, &mapAlo, k0, m0, &full_bar[stage]);
+        tma_load_2d(st + 2 * Cfg::kABytes, &mapBhi, k0, n0, &full_bar[stage]);
+        tma_load_2d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &mapBlo, k0, n0, &full_bar[stage]);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int kb = 0;
+      for (int c = 0; c < num_chunks; ++c) {
+        const int buf = c & 1;
+        mbar_wait(&tmem_empty_bar[buf], ((uint32_t)(c >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_main = tmem_base + (uint32_t)(buf * 2 * TG_BN);
+        const uint32_t tmem_small = tmem_main + (uint32_t)TG_BN;
+        const int kb_end = min(num_kb, kb + TG_CHUNK_KB);
+        bool first = true;
+        for (; kb < kb_end; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t a_hi = sa, a_lo = sa + Cfg::kABytes;
+          const uint32_t b_hi = sa + 2 * Cfg::kABytes, b_lo = b_hi + Cfg::kBBytes;
+#pragma unroll
+          for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+            const uint32_t off = k * TC_UMMA_K * 4;
+            const uint64_t dah = make_kmajor_sw128_desc(a_hi + off), dal = make_kmajor_sw128_desc(a_lo + off);
+            const uint64_t dbh = make_kmajor_sw128_desc(b_hi + off), dbl = make_kmajor_sw128_desc(b_lo + off);
+            umma_tf32(tmem_small, dal, dbh, Cfg::kIdesc, first ? 0u : 1u);
+            umma_tf32(tmem_small, dah, dbl, Cfg::kIdesc, 1u);
+            umma_tf32(tmem_main, dah, dbh, Cfg::kIdesc, first ? 0u : 1u);
+            first = false;
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full_bar[buf]);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    double acc[kCols];
+#pragma unroll
+    for (int j = 0; j < kCols; ++j) acc[j] = 0.0;
+    for (int c = 0; c < num_chunks; ++c) {
+      const int buf = c & 1;
+      mbar_wait(&tmem_full_bar[buf], (uint32_t)(c >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * TG_BN + half * kCols);
+#pragma unroll
+      for (int g = 0; g < kCols / 16; ++g) {
+        uint32_t v[16], w[16];
+        tmem_ld16(taddr + (uint32_t)(g * 16), v);
+        tmem_ld16(taddr + (uint32_t)(TG_BN + g * 16), w);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[g * 16 + j] += (double)(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+    }
+    const int row = m0 + q * 32 + lane;
+    const int col0 = n0 + half * kCols;
+    if (row < M) {
+      double* dst = D + (int64_t)row * ldd + col0;
+      const bool mirror = symmetric && n0 < m0;
+#pragma unroll
+      for (int j = 0; j < kCols; ++j) {
+        if (col0 + j < N) {
+          const double o = acc[j] * alpha;
+          dst[j] = o;
+          if (mirror) D[(int64_t)(col0 + j) * ldd + row] = o;     // lanes <-> consecutive rows: coalesced
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // ------------------------------------------------------------ host: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -377,4 +552,37 @@ extern "C" int xmca_tc_gemm_nt(int64_t M, int64_t N, int64_t K, float alpha,
   if (N > 128)
     return launch_tc<256>(M, N, K, alpha, d_Ahi, d_Alo, lda, d_Bhi, d_Blo, ldb, d_D, ldd, d_frob2, st);
   return launch_tc<128>(M, N, K, alpha, d_Ahi, d_Alo, lda, d_Bhi, d_Blo, ldb, d_D, ldd, d_frob2, st);
+}
+
+extern "C" int xmca_tc_gemm_nt_f64(int64_t M, int64_t N, int64_t K, double alpha,
+                                   const float* d_Ahi, const float* d_Alo, int64_t lda,
+                                   const float* d_Bhi, const float* d_Blo, int64_t ldb,
+                                   double* d_D, int64_t ldd, int symmetric, void* stream) {
+  XMCA_REQUIRE(M > 0 && N > 0 && K > 0, "xmca_tc_gemm_nt_f64: empty problem");
+  XMCA_REQUIRE(d_Ahi && d_Alo && d_Bhi && d_Blo && d_D, "xmca_tc_gemm_nt_f64: null operand");
+  XMCA_REQUIRE(lda >= K && ldb >= K && ldd >= N, "xmca_tc_gemm_nt_f64: leading dimension too small");
+  XMCA_REQUIRE((lda & 3) == 0 && (ldb & 3) == 0, "xmca_tc_gemm_nt_f64: operand pitch must be a multiple of 4 floats (TMA)");
+  XMCA_REQUIRE(((uintptr_t)d_Ahi & 15) == 0 && ((uintptr_t)d_Alo & 15) == 0 && ((uintptr_t)d_Bhi & 15) == 0 &&
+                   ((uintptr_t)d_Blo & 15) == 0,
+               "xmca_tc_gemm_nt_f64: operand planes must be 16-byte aligned (TMA)");
+  XMCA_REQUIRE(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), "xmca_tc_gemm_nt_f64: dimension too large");
+  XMCA_REQUIRE(!symmetric || M == N, "xmca_tc_gemm_nt_f64: symmetric needs M == N");
+  using Cfg = TcCfg<TG_BN>;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap mAh, mAl, mBh, mBl;
+  int rc;
+  if ((rc = make_map(&mAh, d_Ahi, M, K, lda, TC_BM)) != XMCA_OK) return rc;
+  if ((rc = make_map(&mAl, d_Alo, M, K, lda, TC_BM)) != XMCA_OK) return rc;
+  if ((rc = make_map(&mBh, d_Bhi, N, K, ldb, TG_BN)) != XMCA_OK) return rc;
+  if ((rc = make_map(&mBl, d_Blo, N, K, ldb, TG_BN)) != XMCA_OK) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    XMCA_CUDA(cudaFuncSetAttribute(tc_gemm_nt_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles_m = (int)((M + TC_BM - 1) / TC_BM), tiles_n = (int)((N + TG_BN - 1) / TG_BN);
+  tc_gemm_nt_f64_kernel<<<tiles_m * tiles_n, TC_THREADS, Cfg::kSmemBytes, st>>>(
+      mAh, mAl, mBh, mBl, (int)M, (int)N, (int)K, alpha, d_D, ldd, symmetric, tiles_m, tiles_n);
+  XMCA_LAUNCHED();
+  return XMCA_OK;
 }

@@ -140,6 +140,19 @@ def tc_gemm_nt(Ahi, Alo, Bhi, Blo, K, alpha=1.0, out=None, frob2=None):
     return out
 
 
+def gram_tc(X, alpha=1.0):
+    """G = alpha * X X^T (rows x rows, fp64, symmetric) of an fp32 matrix on the tensor cores
+    (3xTF32, fp64 chunk accumulation: xmca_tc_gemm_nt_f64)."""
+    lib = L.load()
+    hi, lo, K = split_tf32(X)                                  # rows x K planes, K-major
+    n = X.shape[0]
+    G = empty((n, n), f64())
+    rc = lib.xmca_tc_gemm_nt_f64(n, n, K, float(alpha), L.ptr(hi), L.ptr(lo), hi.stride(0), L.ptr(hi), L.ptr(lo),
+                                 hi.stride(0), L.ptr(G), n, 1, L.stream_ptr())
+    L.check(rc, "xmca_tc_gemm_nt_f64")
+    return G
+
+
 def cov_gemm_tc(A, B, alpha):
     """C = alpha * A^T B (S1 x S2, fp32) from time-major fp32 fields, tensor-core path.
     Returns (C, frob2 tensor)."""

@@ -226,6 +226,13 @@ class TridiagResult:
         self._full = None
         dof = self.dof
         self.n_null = 0
+        def gram(X, alpha=1.0):
+            """X X^T (T x T, fp64): tcgen05 3xTF32 with fp64 chunk accumulation for fp32 fields,
+            fp64 DMMA product otherwise."""
+            if X.dtype == D.f32() and X.shape[1] >= 64:
+                return D.gram_tc(X, alpha)
+            return D.matmul(X, X, trans_b=True, alpha=alpha, symmetric=True)
+
         if self.gram_side:
             if isinstance(null_basis, int):          # 0: the Gram matrices have no structural null vector
                 Nb = None
@@ -233,10 +240,10 @@ class TridiagResult:
                 Nb = null_basis if null_basis is not None else D.to_device(np.full((T, 1), 1.0 / np.sqrt(T)))
                 self.n_null = Nb.shape[1]
             if self.pca:
-                S = D.matmul(A, A, trans_b=True, alpha=1.0 / dof, symmetric=True)
+                S = gram(A, 1.0 / dof)
             else:
-                GA = D.matmul(A, A, trans_b=True, symmetric=True)
-                GB = D.matmul(B, B, trans_b=True, symmetric=True)
+                GA = gram(A)
+                GB = gram(B)
                 tr = float(D.to_host(D.col_sumsq(B)).sum())
                 if not np.isfinite(tr) or tr <= 0.0:
                     raise np.linalg.LinAlgError("empty or non-finite field")

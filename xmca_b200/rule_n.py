@@ -26,15 +26,17 @@ def partition(n_runs: int, world: int, rank: int):
     return range(lo, lo + base + (1 if rank < extra else 0))
 
 
-def device_surrogate_variance(shape_T, n_vars, run_index, seed, complexify, rotated, n_rot, power):
+def device_surrogate_variance(shape_T, n_vars, run_index, seed, complexify, rotated, n_rot, power,
+                              dtype="float64"):
     """One surrogate run on the current CUDA device.  Returns the variance
-    spectrum (fp64 numpy) or None if the rotation did not converge."""
+    spectrum (fp64 numpy) or None if the rotation did not converge.
+    dtype: storage precision of the Gaussian surrogate fields (see `rule_n`)."""
     from . import device as D
     from . import engine as E
     t = D.torch()
     fields = []
     for f, S in enumerate(n_vars):
-        X = D.empty((shape_T, S), t.float64)
+        X = D.empty((shape_T, S), t.float32 if dtype == "float32" else t.float64)
         D.fill_normal(X, seed, 2 * run_index + f)               # array.py:1756
         D.center_columns(X)                                     # MCA ctor, array.py:199-207
         fields.append(X)
@@ -106,8 +108,13 @@ def gather_spectra(local: np.ndarray, valid: np.ndarray, n_runs: int, group=None
     return np.concatenate(cols, axis=1) if cols else np.zeros((modes, 0))
 
 
-def rule_n(model, n_runs, n_modes=None, seed=None, group=None, _surrogate_fn=None):
-    """Sharded Rule N for an ``xmca_b200.MCA`` model (array.py:1716-1771)."""
+def rule_n(model, n_runs, n_modes=None, seed=None, group=None, _surrogate_fn=None, surrogate_dtype=None):
+    """Sharded Rule N for an ``xmca_b200.MCA`` model (array.py:1716-1771).
+
+    surrogate_dtype: the reference draws float64 surrogates whatever the model's dtype
+    (array.py:1756); a conscious deviation here: the surrogates follow the MODEL's field dtype
+    (fp32 model -> fp32 Gaussian fields, Gram matrices on the tensor cores), which changes nothing
+    statistically; pass "float64" for the reference's behaviour.  The returned spectra are fp64."""
     import torch.distributed as dist
     T = model._n_observations["left"]
     n_vars = [model._n_variables[k] for k in model._keys]
@@ -121,13 +128,16 @@ def rule_n(model, n_runs, n_modes=None, seed=None, group=None, _surrogate_fn=Non
     else:
         world, rank = 1, 0
     fn = _surrogate_fn or device_surrogate_variance
+    if surrogate_dtype is None:
+        surrogate_dtype = "float32" if model._field_means[model._keys[0]].dtype == np.float32 else "float64"
+    extra = {} if _surrogate_fn is not None else {"dtype": surrogate_dtype}
     ref = model._get_variance()
     mine = partition(n_runs, world, rank)
     modes = ref.size
     local = np.full((modes, len(mine)), np.nan)
     valid = np.zeros(len(mine), dtype=bool)
     for j, i in enumerate(mine):
-        spec = fn(T, n_vars, i, seed, complexify, rotated, n_rot, power)
+        spec = fn(T, n_vars, i, seed, complexify, rotated, n_rot, power, **extra)
         if spec is None:
             continue
         spec = np.asarray(spec, dtype=np.float64)
