@@ -162,16 +162,19 @@ __device__ __forceinline__ void dload_slab(double (&r)[4], const void* p, int dt
   }
 }
 
+// Column index XOR-swizzled by (k / 4) & 3: the K-major store (16 lanes = 16 consecutive k of one row)
+// then hits 16 distinct 8-byte banks instead of 4, and the fragment loads see a permutation that is
+// uniform per k-step, so they stay conflict free.
 template <bool KMAJOR>
 __device__ __forceinline__ void dstore_slab(const double (&r)[4], double (*s)[DLD], int tid) {
   if (KMAJOR) {
     const int kk = tid & 15, m = tid >> 4;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) s[kk][m + 32 * i] = r[i];
+    for (int i = 0; i < 4; ++i) s[kk][(m + 32 * i) ^ ((kk >> 2) & 3)] = r[i];
   } else {
     const int m = tid & 127, kk = tid >> 7;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) s[kk + 4 * i][m] = r[i];
+    for (int i = 0; i < 4; ++i) s[kk + 4 * i][m ^ (((kk + 4 * i) >> 2) & 3)] = r[i];
   }
 }
 
@@ -218,8 +221,8 @@ gemm_dmma_kernel(int64_t M, int64_t N, int64_t K, double alpha,
       double a[4], b[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        a[i] = As[ks + tig][wm + 8 * i + gid];
-        b[i] = Bs[ks + tig][wn + 8 * i + gid];
+        a[i] = As[ks + tig][(wm + 8 * i + gid) ^ ((ks >> 2) & 3)];
+        b[i] = Bs[ks + tig][(wn + 8 * i + gid) ^ ((ks >> 2) & 3)];
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
