@@ -39,6 +39,7 @@ struct SytrdParams {
   double* part;        // grid x TD_PART
   double* d; double* e; double* tau;
   unsigned long long* clk;   // [8] per-phase clock totals of CTA 0 (XMCA_SYTRD_TRACE)
+  unsigned int* bar;         // arrival counter of this launch's grid barrier (zeroed by the host)
 };
 
 __device__ __forceinline__ double block_sum_1024(double v, double* red) {
@@ -59,6 +60,21 @@ __device__ __forceinline__ double grid_slot_sum(const double* part, int slot, in
   return block_sum_1024(s, red);
 }
 
+// Grid-wide barrier for the co-resident CTAs of a cooperative launch: one monotonically increasing
+// arrival counter per launch, release/acquire through __threadfence; about half the latency of
+// cooperative_groups' grid.sync(), which is paid three times per column.
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    epoch += gridDim.x;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while (*((volatile unsigned int*)counter) < epoch) { }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams P) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ double vs[];                 // current Householder vector (n doubles)
@@ -73,6 +89,7 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
   const int n = P.n;
   const int64_t lda = P.lda;
   double alpha2_prev = 0.0;
+  unsigned int epoch = 0;
   long long tk[5] = {0, 0, 0, 0, 0};
 
   for (int i = 0; i < P.nb; ++i) {
@@ -104,9 +121,8 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
     if (n1 == 0) break;                           // last column: only its diagonal entry
     ssq = block_sum_1024(ssq, red);
     if (tid == 0) P.part[(int64_t)blockIdx.x * TD_PART] = ssq;
-    __threadfence();
     { long long c1 = clock64(); tk[0] += c1 - c0; c0 = c1; }
-    grid.sync();                                  // #1
+    grid_barrier(P.bar, epoch);                   // #1
     { long long c1 = clock64(); tk[1] += c1 - c0; c0 = c1; }
 
     // ------------------------------------------------------------ phase B: reflector, A v
@@ -138,8 +154,10 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0, a5 = 0.0, a6 = 0.0, a7 = 0.0;
         int s = s0 + lane;
         for (; s + 224 < s1; s += 256) {
-          const double x0 = row[s], x1 = row[s + 32], x2 = row[s + 64], x3 = row[s + 96];
-          const double x4 = row[s + 128], x5 = row[s + 160], x6 = row[s + 192], x7 = row[s + 224];
+          // streaming loads (evict-first): the trailing matrix is read once per column and must not
+          // push the panel buffers / partial vectors out of the caches
+          const double x0 = __ldcs(row + s), x1 = __ldcs(row + s + 32), x2 = __ldcs(row + s + 64), x3 = __ldcs(row + s + 96);
+          const double x4 = __ldcs(row + s + 128), x5 = __ldcs(row + s + 160), x6 = __ldcs(row + s + 192), x7 = __ldcs(row + s + 224);
           a0 = fma(x0, vs[s], a0);       a1 = fma(x1, vs[s + 32], a1);
           a2 = fma(x2, vs[s + 64], a2);  a3 = fma(x3, vs[s + 96], a3);
           a4 = fma(x4, vs[s + 128], a4); a5 = fma(x5, vs[s + 160], a5);
@@ -180,9 +198,8 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
       __syncthreads();
       if (tid < TD_K2) P.part[(int64_t)blockIdx.x * TD_PART + 1 + tid] = pv[tid];
     }
-    __threadfence();
     { long long c1 = clock64(); tk[2] += c1 - c0; c0 = c1; }
-    grid.sync();                                  // #2
+    grid_barrier(P.bar, epoch);                   // #2
     { long long c1 = clock64(); tk[1] += c1 - c0; c0 = c1; }
 
     // ------------------------------------------------------------ phase C: w (before the alpha correction)
@@ -218,9 +235,8 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
     }
     dotacc = block_sum_1024(dotacc, red);
     if (tid == 0) P.part[(int64_t)blockIdx.x * TD_PART + 130] = dotacc;
-    __threadfence();
     { long long c1 = clock64(); tk[3] += c1 - c0; c0 = c1; }
-    grid.sync();                                  // #3
+    grid_barrier(P.bar, epoch);                   // #3
     { long long c1 = clock64(); tk[1] += c1 - c0; c0 = c1; }
 
     // ------------------------------------------------------------ phase D: finish w, store panel column i
@@ -565,6 +581,7 @@ extern "C" size_t xmca_sytrd_workspace_bytes(int64_t n) {
   b += al256((size_t)n * TD_MAXF * 8);            // wraw
   b += al256((size_t)(148 * 2) * TD_PART * 8);    // partials
   b += 256;                                       // phase clocks
+  b += al256((size_t)(n / TD_NB + 2) * 4);       // one barrier counter per panel launch
   return b;
 }
 
@@ -591,14 +608,17 @@ extern "C" int xmca_sytrd(int64_t n, double* d_A, int64_t lda, double* d_d, doub
   P.wpre = reinterpret_cast<double*>(ws + o); o += al256((size_t)n * 8);
   P.wraw = reinterpret_cast<double*>(ws + o); o += al256((size_t)n * TD_MAXF * 8);
   P.part = reinterpret_cast<double*>(ws + o); o += al256((size_t)(148 * 2) * TD_PART * 8);
-  P.clk = reinterpret_cast<unsigned long long*>(ws + o);
+  P.clk = reinterpret_cast<unsigned long long*>(ws + o); o += 256;
+  unsigned int* bars = reinterpret_cast<unsigned int*>(ws + o);
   XMCA_CUDA(cudaMemsetAsync(P.clk, 0, 64, st));
+  XMCA_CUDA(cudaMemsetAsync(bars, 0, (size_t)(n / TD_NB + 2) * 4, st));
   P.d = d_d; P.e = d_e; P.tau = d_tau;
   XMCA_CUDA(cudaMemsetAsync(d_tau, 0, (size_t)n * 8, st));
 
   for (int64_t j0 = 0; j0 < n; j0 += TD_NB) {
     const int nb = (int)((n - j0 < TD_NB) ? (n - j0) : TD_NB);
     P.j0 = (int)j0; P.nb = nb;
+    P.bar = bars + j0 / TD_NB;
     // (only the last panel can be short, and it has no trailing block to update)
     void* args[] = {&P};
     XMCA_CUDA(cudaLaunchCooperativeKernel((void*)sytrd_panel_kernel, dim3(grid), dim3(TD_THREADS), args, smem, st));
