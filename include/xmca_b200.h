@@ -226,6 +226,14 @@ int xmca_promax_target(const double* d_X, int64_t ldx, int64_t rows, int64_t col
                        const double* d_row_scale, const double* d_colmax, double power,
                        double* d_Xout, double* d_Pout, int64_t ldo, void* stream);
 
+/* complex (planar fp64) versions of the two Promax helpers above (rotation.py:115-124, complex dtype) */
+int xmca_col_absmax_complex(const double* d_Xr, const double* d_Xi, int64_t ldx, int64_t rows, int64_t cols,
+                            const double* d_row_scale, double* d_out, void* stream);
+int xmca_promax_target_complex(const double* d_Xr, const double* d_Xi, int64_t ldx, int64_t rows, int64_t cols,
+                               const double* d_row_scale, const double* d_colmax, double power,
+                               double* d_Xor, double* d_Xoi, double* d_Por, double* d_Poi, int64_t ldo,
+                               void* stream);
+
 /* ---- fused Varimax / Promax rotation --------------------------------------
  * Replaces xmca/tools/rotation.py:15-78 (varimax) driven from array.py:823.
  * d_L : n x p loadings, row-major (ld = ldl), fp32 or fp64.  Real case.

@@ -417,8 +417,15 @@ def test_complex_varimax_matches_oracle(MCA, dtype):
     al, ar = orc.align_modes(pr["left"], p["left"], p["right"])
     scale = np.abs(pr["left"]).max()
     assert max(np.abs(al - pr["left"]).max(), np.abs(ar - pr["right"]).max()) < 5e-3 * scale
-    with pytest.raises(NotImplementedError):
-        m.rotate(5, 2)
+    # complex Promax (rotation.py:84-149 with complex dtype)
+    m.rotate(5, 2)
+    refp = orc.rotate(orc.solve(orc.make_model(A.copy(), B.copy()), complexify=True), 5, 2)
+    np.testing.assert_allclose(m.variance(5), orc.get_variance(refp, 5), rtol=5e-4)
+    idx = refp.var_idx
+    np.testing.assert_allclose(np.abs(m.correlation_matrix()), np.abs(refp.Phi[idx, :][:, idx]), atol=1e-3)
+    pp, ppr = m.pcs(5), orc.pcs(refp, 5)
+    al, ar = orc.align_modes(ppr["left"], pp["left"], pp["right"])
+    assert max(np.abs(al - ppr["left"]).max(), np.abs(ar - ppr["right"]).max()) < 5e-3 * np.abs(ppr["left"]).max()
     sv = m.rule_n(4, 3, seed=3)
     assert sv.shape == (3, 4) and np.isfinite(sv).all()
 

@@ -105,6 +105,8 @@ def load():
     lib.xmca_row_sumsq.argtypes = [vp, i32, i64, i64, i64, vp, vp]
     lib.xmca_col_absmax.argtypes = [vp, i32, i64, i64, i64, vp, vp, vp]
     lib.xmca_promax_target.argtypes = [vp, i64, i64, i64, vp, vp, dbl, vp, vp, i64, vp]
+    lib.xmca_col_absmax_complex.argtypes = [vp, vp, i64, i64, i64, vp, vp, vp]
+    lib.xmca_promax_target_complex.argtypes = [vp, vp, i64, i64, i64, vp, vp, dbl, vp, vp, vp, vp, i64, vp]
     lib.xmca_varimax_workspace_bytes.restype = sz
     lib.xmca_varimax_workspace_bytes.argtypes = [i64, i32]
     lib.xmca_varimax.argtypes = [vp, i32, i64, i32, i64, dbl, i32, dbl, vp, i64, vp, C.POINTER(i32), vp,

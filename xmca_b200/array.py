@@ -501,7 +501,8 @@ class MCA:
         _, provider = self._dV
         V = provider.vectors(n_rot)
         try:
-            Br, Bi, s_left, R, iters = E.rotate_complex(V, sv.astype(np.float64), self._keys, n_rot, power, tol=tol)
+            Br, Bi, s_left, R, Phi, iters = E.rotate_complex(V, sv.astype(np.float64), self._keys, n_rot, power,
+                                                             tol=tol)
         except L.NotConvergedError:
             raise RuntimeError("Rotation process did not converge. Try decreasing the tolerance. "
                                "Invalid NaN entries also might be a problem.")
@@ -512,7 +513,7 @@ class MCA:
         self._variance = nl * nr
         self._var_idx = np.argsort(self._variance)[::-1]
         self._rot_R = R
-        self._rot_Phi = np.eye(n_rot)
+        self._rot_Phi = Phi
         self._analysis["is_rotated"] = True
         self._analysis["n_rot"] = n_rot
         self._analysis["power"] = power

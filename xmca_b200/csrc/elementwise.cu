@@ -234,6 +234,40 @@ __global__ void promax_target_kernel(const double* __restrict__ X, int64_t ldx, 
   }
 }
 
+// Complex counterparts (planar re / im, fp64): column maximum of |x| and the Promax target
+// P = Xn |Xn|^(power-1) with Xn = X * row_scale / colmax (rotation.py:115-124 with complex dtype).
+__global__ void col_absmax_complex_kernel(const double* __restrict__ Xr, const double* __restrict__ Xi, int64_t ldx,
+                                          int64_t rows, int64_t cols, const double* __restrict__ rs,
+                                          unsigned long long* __restrict__ out_bits) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  double m = 0.0;
+  for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
+    const double a = Xr[r * ldx + c], b = Xi[r * ldx + c];
+    double v = sqrt(a * a + b * b);
+    if (rs) v *= rs[r];
+    m = fmax(m, v);
+  }
+  atomicMax(out_bits + c, (unsigned long long)__double_as_longlong(m));
+}
+
+__global__ void promax_target_complex_kernel(const double* __restrict__ Xr, const double* __restrict__ Xi,
+                                             int64_t ldx, int64_t rows, int64_t cols,
+                                             const double* __restrict__ rs, const double* __restrict__ colmax,
+                                             double power, double* __restrict__ Xor, double* __restrict__ Xoi,
+                                             double* __restrict__ Por, double* __restrict__ Poi, int64_t ldo) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const double cm = colmax[c];
+  for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
+    const double xr = Xr[r * ldx + c] * rs[r], xi = Xi[r * ldx + c] * rs[r];
+    const double nr = xr / cm, ni = xi / cm;
+    const double f = pow(sqrt(nr * nr + ni * ni), power - 1.0);
+    Xor[r * ldo + c] = xr; Xoi[r * ldo + c] = xi;
+    Por[r * ldo + c] = nr * f; Poi[r * ldo + c] = ni * f;
+  }
+}
+
 // ------------------------------------------------------------ field ingest
 // Constructor pre-processing on the device (array.py:191-240): per column the
 // NaN flag, mean and standard deviation (ddof = 0, two-pass like numpy);
@@ -473,6 +507,31 @@ extern "C" int xmca_col_absmax(const void* d_X, int x_dtype, int64_t ldx, int64_
   dim3 grid((unsigned)((cols + 255) / 256), row_blocks(rows));
   col_absmax_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       d_X, x_dtype, ldx, rows, cols, d_row_scale, reinterpret_cast<unsigned long long*>(d_out));
+  XMCA_LAUNCHED();
+  return XMCA_OK;
+}
+
+extern "C" int xmca_col_absmax_complex(const double* d_Xr, const double* d_Xi, int64_t ldx, int64_t rows, int64_t cols,
+                                       const double* d_row_scale, double* d_out, void* stream) {
+  XMCA_REQUIRE(d_Xr && d_Xi && d_out && rows > 0 && cols > 0 && ldx >= cols, "xmca_col_absmax_complex: bad argument");
+  XMCA_CUDA(cudaMemsetAsync(d_out, 0, (size_t)cols * sizeof(double), (cudaStream_t)stream));
+  dim3 grid((unsigned)((cols + 255) / 256), row_blocks(rows));
+  col_absmax_complex_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      d_Xr, d_Xi, ldx, rows, cols, d_row_scale, reinterpret_cast<unsigned long long*>(d_out));
+  XMCA_LAUNCHED();
+  return XMCA_OK;
+}
+
+extern "C" int xmca_promax_target_complex(const double* d_Xr, const double* d_Xi, int64_t ldx, int64_t rows,
+                                          int64_t cols, const double* d_row_scale, const double* d_colmax,
+                                          double power, double* d_Xor, double* d_Xoi, double* d_Por, double* d_Poi,
+                                          int64_t ldo, void* stream) {
+  XMCA_REQUIRE(d_Xr && d_Xi && d_row_scale && d_colmax && d_Xor && d_Xoi && d_Por && d_Poi && rows > 0 && cols > 0,
+               "xmca_promax_target_complex: bad argument");
+  XMCA_REQUIRE(ldx >= cols && ldo >= cols, "xmca_promax_target_complex: leading dimension too small");
+  dim3 grid((unsigned)((cols + 255) / 256), row_blocks(rows));
+  promax_target_complex_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_Xr, d_Xi, ldx, rows, cols, d_row_scale,
+                                                                       d_colmax, power, d_Xor, d_Xoi, d_Por, d_Poi, ldo);
   XMCA_LAUNCHED();
   return XMCA_OK;
 }

@@ -494,3 +494,25 @@ def varimax_complex(Lr, Li, gamma=1.0, max_iter=1000, tol=1e-8):
     last_varimax_stats = out
     L.check(rc, "xmca_varimax_complex")
     return Br, Bi, to_host(Rr) + 1j * to_host(Ri), iters.value
+
+
+def col_absmax_complex(Xr, Xi, row_scale=None):
+    lib = L.load()
+    rows, cols = Xr.shape
+    out = empty((cols,), f64())
+    rc = lib.xmca_col_absmax_complex(L.ptr(Xr), L.ptr(Xi), _ld(Xr), rows, cols, L.ptr(row_scale), L.ptr(out),
+                                     L.stream_ptr())
+    L.check(rc, "xmca_col_absmax_complex")
+    return out
+
+
+def promax_target_complex(Br, Bi, row_scale, colmax, power):
+    """Planar complex X = B * row_scale[:, None] and P = Xn |Xn|^(power-1), Xn = X / colmax."""
+    lib = L.load()
+    rows, cols = Br.shape
+    out = [empty((rows, cols), f64()) for _ in range(4)]
+    rc = lib.xmca_promax_target_complex(L.ptr(Br), L.ptr(Bi), _ld(Br), rows, cols, L.ptr(row_scale), L.ptr(colmax),
+                                        float(power), L.ptr(out[0]), L.ptr(out[1]), L.ptr(out[2]), L.ptr(out[3]),
+                                        cols, L.stream_ptr())
+    L.check(rc, "xmca_promax_target_complex")
+    return out

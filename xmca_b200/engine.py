@@ -520,12 +520,27 @@ def promax(Ld, power=1, max_iter=1000, tol=1e-8):
     return Bp, R @ Lm, Li @ Li.T, iters
 
 
+def _cgemm_tn(Ar, Ai, Br, Bi):
+    """A^H B for planar complex n x p operands -> host complex p x p (four real products)."""
+    rr = D.to_host(D.matmul(Ar, Br, trans_a=True)) + D.to_host(D.matmul(Ai, Bi, trans_a=True))
+    ii = D.to_host(D.matmul(Ar, Bi, trans_a=True)) - D.to_host(D.matmul(Ai, Br, trans_a=True))
+    return rr + 1j * ii
+
+
+def _cgemm_right(Xr, Xi, M):
+    """X M for planar complex X (n x p, device) and a host complex p x p matrix M -> planar device."""
+    Mr, Mi = D.to_device(np.ascontiguousarray(M.real)), D.to_device(np.ascontiguousarray(M.imag))
+    Yr = D.matmul(Xr, Mr)
+    D.matmul(Xi, Mi, alpha=-1.0, out=Yr, accumulate=True)
+    Yi = D.matmul(Xr, Mi)
+    D.matmul(Xi, Mr, out=Yi, accumulate=True)
+    return Yr, Yi
+
+
 def rotate_complex(V, sigma, keys, n_rot, power=1, max_iter=1000, tol=1e-8):
-    """Varimax rotation of complex loadings L = [V_L; V_R] sqrt(sigma) (array.py:815-833 with complex
-    dtype).  V: {field: (re, im)} device pairs (S x >= n_rot).  Returns (Br, Bi, s_left, R, iterations);
-    norms follow from the column sums of |B|^2 over each field's rows."""
-    if power != 1:
-        raise NotImplementedError("Promax (power > 1) of a complex model is not implemented in the B200 engine yet")
+    """Varimax / Promax rotation of complex loadings L = [V_L; V_R] sqrt(sigma) (array.py:815-833 and
+    rotation.py:84-149 with complex dtype).  V: {field: (re, im)} device pairs (S x >= n_rot).
+    Returns (Br, Bi, s_left, R, Phi, iterations); norms follow from the column sums of |B|^2."""
     t = D.torch()
     root = D.to_device(np.sqrt(np.asarray(sigma[:n_rot], dtype=np.float64)))
     re = [D.scale_copy(V[k][0][:, :n_rot], col_scale=root) for k in keys]
@@ -534,7 +549,27 @@ def rotate_complex(V, sigma, keys, n_rot, power=1, max_iter=1000, tol=1e-8):
     Lr = t.cat(re, dim=0).contiguous() if len(re) > 1 else re[0]
     Li = t.cat(im, dim=0).contiguous() if len(im) > 1 else im[0]
     Br, Bi, R, iters = D.varimax_complex(Lr, Li, 1.0, max_iter, tol)
-    return Br, Bi, s_left, R, iters
+    p = n_rot
+    if power == 1:
+        return Br, Bi, s_left, R, np.eye(p), iters
+    # Promax step (rotation.py:115-147): streaming passes on the device, p x p algebra on the host
+    h = np.sqrt(D.to_host(D.row_sumsq(t.cat([Br, Bi], dim=1).contiguous())))
+    inv_h = D.to_device(1.0 / h)
+    colmax = D.col_absmax_complex(Br, Bi, row_scale=inv_h)
+    Xr, Xi, Pr, Pi = D.promax_target_complex(Br, Bi, inv_h, colmax, power)
+    XhX = _cgemm_tn(Xr, Xi, Xr, Xi)
+    XhP = _cgemm_tn(Xr, Xi, Pr, Pi)
+    Lm = np.linalg.inv(XhX) @ XhP                                         # rotation.py:128
+    try:
+        dinv = np.diag(np.linalg.inv(Lm.conj().T @ Lm))                   # rotation.py:131-134
+    except np.linalg.LinAlgError:
+        dinv = np.diag(np.linalg.pinv(Lm.conj().T @ Lm))
+    Lm = Lm @ np.sqrt(np.diag(dinv))                                      # rotation.py:137
+    Yr, Yi = _cgemm_right(Xr, Xi, Lm)
+    hd = D.to_device(h)
+    Br, Bi = D.scale_copy(Yr, row_scale=hd), D.scale_copy(Yi, row_scale=hd)   # rotation.py:141
+    Li_ = np.linalg.inv(Lm)
+    return Br, Bi, s_left, R @ Lm, Li_ @ Li_.conj().T, iters
 
 
 def complex_col_norms(Br, Bi, row0, row1):

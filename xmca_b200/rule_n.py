@@ -52,7 +52,7 @@ def device_surrogate_variance(shape_T, n_vars, run_index, seed, complexify, rota
         p = min(n_rot, sigma.size)
         keys = ["left", "right"][:len(fields)]
         try:
-            Br, Bi, s_left, _, _ = E.rotate_complex(vec.vectors(p), sigma, keys, p, power)
+            Br, Bi, s_left, _, _, _ = E.rotate_complex(vec.vectors(p), sigma, keys, p, power)
         except L.NotConvergedError:
             return None
         nl = E.complex_col_norms(Br, Bi, 0, s_left)
