@@ -30,6 +30,12 @@ def live():
     return dict(np.load(os.path.join(GOLDEN, "live_cases.npz")))
 
 
+@pytest.fixture(scope="session")
+def live_next():
+    """Live-reference outputs of predict / reconstructed_fields / hom-het patterns / bootstrapping."""
+    return dict(np.load(os.path.join(GOLDEN, "live_next.npz")))
+
+
 def has_cuda():
     try:
         import torch

@@ -7,9 +7,9 @@ handling (xmca/array.py:39-143, :145-240) and its getter semantics
 on the GPU through the C ABI.  There is no CPU fallback: without the shared
 library or a CUDA device ``solve`` raises.
 
-Out of scope for this engine: ``bootstrapping``,
-``predict``, homogeneous/heterogeneous patterns, plotting, save/load and the
-Hilbert ``extend`` options; they raise ``NotImplementedError``.
+The callers either side of the path (``predict``, ``reconstructed_fields``, homogeneous /
+heterogeneous patterns, ``bootstrapping``: SURVEY.md section 8f) live in ``downstream.py``.
+Out of scope: plotting, save/load and the Hilbert ``extend`` options (``NotImplementedError``).
 """
 from __future__ import annotations
 
@@ -23,6 +23,7 @@ from . import __version__
 from . import _lib as L
 from . import device as D
 from . import engine as E
+from . import downstream as DS
 
 _SIDES = ("left", "right")
 
@@ -627,25 +628,37 @@ class MCA:
         from . import rule_n as RN
         return RN.rule_n(self, n_runs, n_modes=n_modes, seed=seed, group=group, surrogate_dtype=surrogate_dtype)
 
+    # ------------------------------------------- callers downstream of the hot path
+    def _scale_X(self, data_dict):
+        return DS.scale_X(self, data_dict)
+
+    def _scale_X_inverse(self, data_dict):
+        return DS.scale_X_inverse(self, data_dict)
+
+    def predict(self, left=None, right=None, n=None, scaling="None", phase_shift=0):
+        return DS.predict(self, left, right, n, scaling, phase_shift)
+
+    def _reconstructed_X(self, mode=None, original_scale=True):
+        return DS.reconstructed_X(self, mode, original_scale)
+
+    def reconstructed_fields(self, mode=None, original_scale=True):
+        return DS.reconstructed_fields(self, mode, original_scale)
+
+    def homogeneous_patterns(self, n=None, phase_shift=0):
+        return DS.homogeneous_patterns(self, n, phase_shift)
+
+    def heterogeneous_patterns(self, n=None, phase_shift=0):
+        return DS.heterogeneous_patterns(self, n, phase_shift)
+
+    def bootstrapping(self, n_runs, n_modes=20, axis=0, on_left=True, on_right=False, block_size=1,
+                      replace=True, strategy="standard", disable_progress=False):
+        return DS.bootstrapping(self, n_runs, n_modes, axis, on_left, on_right, block_size, replace, strategy,
+                                disable_progress)
+
     # ---------------------------------------------------------- out of scope
     def _out_of_scope(self, name):
         raise NotImplementedError("`{}` is outside the solve/rotate/rule_n hot path this engine "
                                   "accelerates (SURVEY.md section 8f).".format(name))
-
-    def bootstrapping(self, *a, **k):
-        self._out_of_scope("bootstrapping")
-
-    def predict(self, *a, **k):
-        self._out_of_scope("predict")
-
-    def homogeneous_patterns(self, *a, **k):
-        self._out_of_scope("homogeneous_patterns")
-
-    def heterogeneous_patterns(self, *a, **k):
-        self._out_of_scope("heterogeneous_patterns")
-
-    def reconstructed_fields(self, *a, **k):
-        self._out_of_scope("reconstructed_fields")
 
     def plot(self, *a, **k):
         self._out_of_scope("plot")

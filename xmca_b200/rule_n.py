@@ -26,20 +26,13 @@ def partition(n_runs: int, world: int, rank: int):
     return range(lo, lo + base + (1 if rank < extra else 0))
 
 
-def device_surrogate_variance(shape_T, n_vars, run_index, seed, complexify, rotated, n_rot, power,
-                              dtype="float64"):
-    """One surrogate run on the current CUDA device.  Returns the variance
-    spectrum (fp64 numpy) or None if the rotation did not converge.
-    dtype: storage precision of the Gaussian surrogate fields (see `rule_n`)."""
+def variance_of_fields(fields, complexify, rotated, n_rot, power):
+    """solve [+ rotate] + `_get_variance()` (sorted, array.py:771-779) of CENTRED real device fields
+    (one or two, T x S_k): the body of one Monte-Carlo run (array.py:1757-1764, :1935-1945).
+    Returns the variance spectrum (fp64 numpy, descending) or None if the rotation did not converge."""
     from . import device as D
     from . import engine as E
     t = D.torch()
-    fields = []
-    for f, S in enumerate(n_vars):
-        X = D.empty((shape_T, S), t.float32 if dtype == "float32" else t.float64)
-        D.fill_normal(X, seed, 2 * run_index + f)               # array.py:1756
-        D.center_columns(X)                                     # MCA ctor, array.py:199-207
-        fields.append(X)
     A = fields[0]
     B = fields[1] if len(fields) > 1 else None
     if not rotated:
@@ -56,9 +49,8 @@ def device_surrogate_variance(shape_T, n_vars, run_index, seed, complexify, rota
         except L.NotConvergedError:
             return None
         nl = E.complex_col_norms(Br, Bi, 0, s_left)
-        if B is None:
-            return nl ** 2
-        return nl * E.complex_col_norms(Br, Bi, s_left, Br.shape[0])
+        var = nl ** 2 if B is None else nl * E.complex_col_norms(Br, Bi, s_left, Br.shape[0])
+        return np.sort(var)[::-1]
     res = E.solve_real(A, B, want_vectors=True)
     p = min(n_rot, res.sigma.size)
     root = D.to_device(np.sqrt(res.sigma[:p]))
@@ -71,10 +63,24 @@ def device_surrogate_variance(shape_T, n_vars, run_index, seed, complexify, rota
     except L.NotConvergedError:
         return None                                             # array.py:1759-1763
     nl = np.sqrt(D.to_host(D.col_sumsq(Lrot, 0, s_left)))
-    if B is None:
-        return nl ** 2
-    nr = np.sqrt(D.to_host(D.col_sumsq(Lrot, s_left, Lrot.shape[0])))
-    return nl * nr
+    var = nl ** 2 if B is None else nl * np.sqrt(D.to_host(D.col_sumsq(Lrot, s_left, Lrot.shape[0])))
+    return np.sort(var)[::-1]
+
+
+def device_surrogate_variance(shape_T, n_vars, run_index, seed, complexify, rotated, n_rot, power,
+                              dtype="float64"):
+    """One surrogate run on the current CUDA device.  Returns the variance
+    spectrum (fp64 numpy) or None if the rotation did not converge.
+    dtype: storage precision of the Gaussian surrogate fields (see `rule_n`)."""
+    from . import device as D
+    t = D.torch()
+    fields = []
+    for f, S in enumerate(n_vars):
+        X = D.empty((shape_T, S), t.float32 if dtype == "float32" else t.float64)
+        D.fill_normal(X, seed, 2 * run_index + f)               # array.py:1756
+        D.center_columns(X)                                     # MCA ctor, array.py:199-207
+        fields.append(X)
+    return variance_of_fields(fields, complexify, rotated, n_rot, power)
 
 
 def gather_spectra(local: np.ndarray, valid: np.ndarray, n_runs: int, group=None):
