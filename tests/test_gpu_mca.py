@@ -392,6 +392,17 @@ def test_xmca_facade_wraps_engine_results():
     assert xm.explained_variance(4).name == "covariance fraction"
     r = xm.rule_n(3, 4, seed=1)
     assert r.dims == ("mode", "run") and r.shape == (4, 3) and list(r.coords["run"]) == [1, 2, 3]
+    # downstream wrappers (xarray.py:690-892, :1357-1439)
+    new = mk(a[:10], "a")
+    new.coords["time"] = t[:10]
+    pr = xm.predict(new, mk(b[:10], "b"), n=3)
+    assert pr["left"].dims == ("time", "mode") and pr["left"].shape == (10, 3)
+    hom, pv = xm.homogeneous_patterns(3)
+    assert hom["left"].dims == ("lat", "lon", "mode") and pv["right"].name == "prcp pvalues homogeneous patterns"
+    rec = xm.reconstructed_fields(mode=slice(1, 3))
+    assert rec["left"].dims == ("time", "lat", "lon") and rec["left"].shape == a.shape
+    bs = xm.bootstrapping(2, n_modes=3, disable_progress=True)
+    assert bs.dims == ("mode", "run") and bs.shape == (3, 2)
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])

@@ -163,3 +163,48 @@ class xMCA(MCA):
                                coords={"mode": self._modes(n_modes, sv.shape[0]),
                                        "run": np.arange(1, sv.shape[1] + 1)},
                                name="singular values")
+
+    # ----------------------------------------- callers downstream of the hot path
+    def _wrap_patterns(self, pats, pvals, n, suffix):
+        return (self._wrap_space(pats, n, suffix), self._wrap_space(pvals, n, "pvalues " + suffix))
+
+    def homogeneous_patterns(self, n=None, phase_shift=0):
+        """xarray.py:690-745."""
+        r, p = super().homogeneous_patterns(n=n, phase_shift=phase_shift)
+        return self._wrap_patterns(r, p, n, "homogeneous patterns")
+
+    def heterogeneous_patterns(self, n=None, phase_shift=0):
+        """xarray.py:747-802."""
+        r, p = super().heterogeneous_patterns(n=n, phase_shift=phase_shift)
+        return self._wrap_patterns(r, p, n, "heterogeneous patterns")
+
+    def reconstructed_fields(self, mode=slice(1, None), original_scale=True):
+        """xarray.py:804-833."""
+        xr = _xr()
+        rec = super().reconstructed_fields(mode=mode, original_scale=original_scale)
+        return {k: xr.DataArray(rec[k], dims=self._field_dims[k], coords=self._field_coords[k],
+                                name="reconstructed_{:}_field".format(k)) for k in self._keys}
+
+    def predict(self, left=None, right=None, n=None, scaling="None", phase_shift=0):
+        """xarray.py:835-892: DataArrays in, (time, mode) DataArrays out."""
+        xr = _xr()
+        data = dict(zip(self._keys, [left, right]))
+        try:
+            values = {k: (d if d is None else d.values) for k, d in data.items()}
+        except AttributeError as err:
+            raise ValueError("Please provide `xr.DataArray` to `left` and `right`") from err
+        pcs_new = super().predict(values.get("left"), values.get("right") if self._analysis["is_bivariate"] else None,
+                                  n, scaling, phase_shift)
+        return {k: xr.DataArray(pc, dims=("time", "mode"),
+                                coords={"time": data[k].coords["time"], "mode": list(range(1, pc.shape[1] + 1))})
+                for k, pc in pcs_new.items()}
+
+    def bootstrapping(self, n_runs, n_modes=20, axis=0, on_left=True, on_right=False, block_size=1, replace=True,
+                      strategy="standard", disable_progress=False):
+        """xarray.py:1357-1439 (the reference forwards axis=0 whatever is passed, :1419)."""
+        sv = super().bootstrapping(n_runs=n_runs, n_modes=n_modes, axis=0, on_left=on_left, on_right=on_right,
+                                   block_size=block_size, replace=replace, strategy=strategy,
+                                   disable_progress=disable_progress)
+        return _xr().DataArray(sv, dims=["mode", "run"],
+                               coords={"mode": self._modes(n_modes, len(sv)), "run": list(range(1, sv.shape[1] + 1))},
+                               name="singular values", attrs=self._attrs())
