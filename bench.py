@@ -256,9 +256,9 @@ def run_product(args, rank, world, local_rank):
 
     # ---- rule_n: surrogates sharded over the ranks, one all-gather ----------------------
     rn = None
-    if args.rule_n_runs > 0:
+    if args.rule_n_runs > 0 or args.rule_n_total > 0:
         model.solve(complexify=wo["complexify"])      # rule N of the unrotated model
-        n_runs = args.rule_n_runs * world
+        n_runs = args.rule_n_total if args.rule_n_total > 0 else args.rule_n_runs * world
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         model.rule_n(world, n_modes, seed=99)          # warm-up (allocator, kernel attributes)
@@ -271,7 +271,8 @@ def run_product(args, rank, world, local_rank):
         _lib.profile_begin()
         model.rule_n(world, n_modes, seed=4321)
         rn_prof = _lib.profile_end()
-        rn = {"surrogates_per_s": n_runs / (ms_rn / 1e3), "n_runs": n_runs, "runs_per_rank": args.rule_n_runs,
+        rn = {"surrogates_per_s": n_runs / (ms_rn / 1e3), "n_runs": n_runs,
+              "runs_per_rank": n_runs / world, "scaling": "strong" if args.rule_n_total > 0 else "weak",
               "ms_total": ms_rn, "shape": list(spectra.shape), "dtype": "f64",
               "collective": "1 all_gather (nccl)" if world > 1 else "none (1 rank)",
               "call_ms_one_surrogate": {k: round(v["ms"], 2) for k, v in
@@ -451,6 +452,8 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--rule-n-runs", type=int, default=1, help="surrogates per rank (0 = skip rule_n)")
+    ap.add_argument("--rule-n-total", type=int, default=0,
+                    help="strong-scaling rule_n: total number of surrogates split over the ranks (overrides --rule-n-runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 

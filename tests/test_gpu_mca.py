@@ -473,3 +473,44 @@ def test_full_size_config2_invariants(MCA):
     np.testing.assert_allclose(U["left"].T.astype(np.float64) @ U["right"] / (T - 1), np.eye(k), atol=5e-4)
     del C
     torch.cuda.empty_cache()
+
+
+def test_edge_inputs(MCA):
+    """Degenerate but legal inputs: constant (zero-variance) columns, tiny T, a single grid point,
+    integer and half-precision data (converted like numpy would), n larger than the rank."""
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((30, 12)).astype(np.float32)
+    B = rng.standard_normal((30, 7)).astype(np.float32)
+    A[:, 3] = 2.5                                     # constant column: zero after centring
+    m = MCA(A.copy(), B.copy())
+    m.solve()
+    ref = orc.solve(orc.make_model(A.copy(), B.copy()))
+    np.testing.assert_allclose(m.singular_values(), ref.sigma, atol=1e-5 * ref.sigma[0])
+    assert m.pcs(100)["left"].shape == (30, 7) and m.eofs(100)["right"].shape == (7, 7)   # n > rank is clipped
+    # tiny T (T - 1 = 2 degrees of freedom), T < S
+    A = rng.standard_normal((3, 9))
+    B = rng.standard_normal((3, 5))
+    m = MCA(A.copy(), B.copy())
+    m.solve()
+    ref = orc.solve(orc.make_model(A.copy(), B.copy()))
+    assert m._analysis["rank"] == 3
+    np.testing.assert_allclose(m.singular_values()[:2], ref.sigma[:2], rtol=1e-9)
+    assert m.singular_values()[2] < 1e-9 * m.singular_values()[0]
+    # a single grid point on one side
+    A = rng.standard_normal((40, 1))
+    B = rng.standard_normal((40, 6))
+    m = MCA(A.copy(), B.copy())
+    m.solve()
+    ref = orc.solve(orc.make_model(A.copy(), B.copy()))
+    np.testing.assert_allclose(m.singular_values(), ref.sigma, rtol=1e-9)
+    with pytest.raises(ValueError):
+        m.rotate(1)
+    # integer / half-precision input
+    Ai = rng.integers(-5, 6, size=(25, 8))
+    m = MCA(Ai.copy())
+    m.solve()
+    ref = orc.solve(orc.make_model(Ai.astype(np.float64)))
+    np.testing.assert_allclose(m.singular_values(5), ref.sigma[:5], rtol=1e-9)
+    m = MCA(rng.standard_normal((25, 8)).astype(np.float16))
+    m.solve()
+    assert np.isfinite(m.singular_values()).all()
