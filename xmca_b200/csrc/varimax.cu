@@ -84,8 +84,9 @@ __device__ int polar_jacobi(double* X, double* V, int pe, const unsigned char* r
         on[u] = pr < npairs;
         cp[u] = on[u] ? rr[step * pe + 2 * pr] : 0;
         cq[u] = on[u] ? rr[step * pe + 2 * pr + 1] : 1;
-        xp0[u] = X[cp[u] * VPP + lane]; xp1[u] = X[cp[u] * VPP + lane + 32];
-        xq0[u] = X[cq[u] * VPP + lane]; xq1[u] = X[cq[u] * VPP + lane + 32];
+        // (an idle pair slot must not read columns that another warp rotates in this step)
+        xp0[u] = on[u] ? X[cp[u] * VPP + lane] : 0.0; xp1[u] = on[u] ? X[cp[u] * VPP + lane + 32] : 0.0;
+        xq0[u] = on[u] ? X[cq[u] * VPP + lane] : 0.0; xq1[u] = on[u] ? X[cq[u] * VPP + lane + 32] : 0.0;
         al[u] = xp0[u] * xp0[u] + xp1[u] * xp1[u];
         be[u] = xq0[u] * xq0[u] + xq1[u] * xq1[u];
         ga[u] = xp0[u] * xq0[u] + xp1[u] * xq1[u];
