@@ -514,3 +514,31 @@ def test_edge_inputs(MCA):
     m = MCA(rng.standard_normal((25, 8)).astype(np.float16))
     m.solve()
     assert np.isfinite(m.singular_values()).all()
+
+
+def test_normalize_and_weights_on_the_device(MCA):
+    """normalize() / apply_weights() (array.py:317-365) scale the device fields; results equal the
+    numpy semantics of the reference (including the fp64 promotion by an fp64 weight array)."""
+    rng = np.random.default_rng(9)
+    A = (rng.standard_normal((60, 14)) * rng.uniform(0.5, 3.0, 14)).astype(np.float32)
+    B = (rng.standard_normal((60, 9)) * rng.uniform(0.5, 3.0, 9)).astype(np.float32)
+    m = MCA(A.copy(), B.copy())
+    m.normalize()
+    Ac, Bc = A - A.mean(0), B - B.mean(0)
+    np.testing.assert_allclose(m._fields["left"], Ac / A.std(0), atol=1e-5)
+    assert m._fields["left"].dtype == np.float32 and m._analysis["is_normalized"]
+    m.solve()
+    ref = orc.solve(orc.make_model((Ac / A.std(0)).astype(np.float32), (Bc / B.std(0)).astype(np.float32)))
+    np.testing.assert_allclose(m.singular_values(5), ref.sigma[:5], rtol=2e-5)
+    m2 = MCA(A.copy(), B.copy())
+    w = rng.uniform(0.2, 1.0, (1, 14))
+    m2.apply_weights(left=w)
+    assert m2._fields["left"].dtype == np.float64 and m2._fields["right"].dtype == np.float32
+    np.testing.assert_allclose(m2._fields["left"], Ac * w, atol=1e-5)
+    m2.apply_weights(right=0.5)
+    np.testing.assert_allclose(m2._fields["right"], Bc * 0.5, atol=1e-6)
+    wt = rng.uniform(0.5, 1.5, (60, 1))                    # varies in time: numpy broadcasting on the host
+    m2.apply_weights(left=wt)
+    np.testing.assert_allclose(m2._fields["left"], Ac * w * wt, atol=1e-5)
+    m2.solve()
+    assert m2.singular_values().dtype == np.float64

@@ -157,6 +157,10 @@ class MCA:
     def _field_dtype(self, k):
         """dtype of `_fields[k]` without materialising the host mirror."""
         real = self._field_means[k].dtype
+        if k in self._dev:
+            real = np.dtype(np.float32 if self._dev[k].dtype == D.f32() else np.float64)
+        elif k in self._host:
+            real = np.zeros(0, self._host[k].dtype).real.dtype
         if self._analysis["is_complex"]:
             return np.dtype(np.complex64 if real == np.float32 else np.complex128)
         return real
@@ -182,12 +186,38 @@ class MCA:
             return slice(lo, hi, n.step)
         raise ValueError("Invalid type {:}. Must be either int or slice.".format(type(n)))
 
+    def _scale_columns_device(self, scales, promote=True):
+        """fields[k] *= scales[k] (per-column factors, broadcast over time) on the device copies."""
+        dev = self._device_fields()
+        for k, sc in scales.items():
+            if k in dev and sc is not None:
+                cs = D.to_device(np.array(np.broadcast_to(np.asarray(sc, dtype=np.float64), (dev[k].shape[1],))))
+                # numpy promotion of `field * weights` (an fp64 weight ARRAY promotes an fp32 field)
+                up = promote and isinstance(sc, np.ndarray) and sc.dtype == np.float64 and sc.ndim > 0
+                dev[k] = D.scale_copy(dev[k], col_scale=cs, out_dtype=D.f64() if up else None)
+        self._host, self._devY = {}, {}               # host mirror / Hilbert transforms are rebuilt lazily
+
     def apply_weights(self, left=None, right=None):
-        w = {"left": 1 if left is None else left, "right": 1 if right is None else right}
+        """array.py:317-349: multiply the fields by weights.  Scalars and per-grid-point weights run on
+        the device; anything else (weights varying in time) takes numpy broadcasting on the host mirror."""
+        w = {"left": left, "right": right}
+        simple = all(v is None or np.ndim(v) == 0 or (np.ndim(v) <= 2 and np.size(v) == self._n_kept(k)
+                                                      and np.shape(v)[-1] == self._n_kept(k))
+                     for k, v in w.items() if k in self._keys)
+        if simple and L.cuda_available() and not self._analysis["is_complex"]:
+            self._scale_columns_device({k: (None if v is None else np.reshape(v, -1) if np.ndim(v) else v)
+                                        for k, v in w.items()})
+            return
+        w = {k: 1 if v is None else v for k, v in w.items()}
         self._fields = {k: f * w[k] for k, f in self._fields.items()}
 
     def normalize(self):
-        self._fields = {k: f / self._field_stds[k] for k, f in self._fields.items()}
+        """array.py:351-365: divide every grid point by its standard deviation."""
+        if L.cuda_available() and not self._analysis["is_complex"]:
+            self._scale_columns_device({k: 1.0 / self._field_stds[k].astype(np.float64) for k in self._keys},
+                                       promote=False)       # std has the field dtype: no promotion
+        else:
+            self._fields = {k: f / self._field_stds[k] for k, f in self._fields.items()}
         self._analysis["is_normalized"] = True
         self._analysis["is_coslat_corrected"] = False
         self._analysis["method"] = self._get_method_id()
@@ -240,7 +270,7 @@ class MCA:
             self._host = {}       # host mirror no longer matches the model (rebuilt lazily from the device)
         A = dev["left"]
         B = dev.get("right")
-        real_dtype = self._field_means["left"].dtype.type
+        real_dtype = np.float32 if A.dtype == D.f32() else np.float64
         try:
             if complexify:
                 sigma, vec, res = E.solve_complex(A, B)
