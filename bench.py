@@ -394,6 +394,11 @@ def cpu_baseline(workload, steps=1, warmup=0):
     wo = opts(workload)
     div = CPU_SAMPLE_DIV.get(workload, 4)
     cores = os.cpu_count() or 1
+    try:        # torchrun exports OMP_NUM_THREADS=1: give the reference all host cores anyway
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=cores)
+    except Exception:
+        pass
     _cpu_sample(256, 512, 512, 10, 10, 5)                       # BLAS/LAPACK warm-up
     ts = []
     for i in range(warmup + steps):
@@ -462,6 +467,20 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
+        if rank != 0:
+            return
+        # torchrun exports OMP_NUM_THREADS=1, which caps the BLAS thread pool when numpy is loaded: give the
+        # reference's CPU path all host cores by re-running this arm in a child with a clean thread environment
+        capped = [v for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS") if v in os.environ]
+        if capped and not os.environ.get("XMCA_BENCH_CHILD"):
+            env = {k: v for k, v in os.environ.items() if k not in capped}
+            env["XMCA_BENCH_CHILD"] = "1"
+            env["RANK"], env["WORLD_SIZE"] = "0", str(world)
+            res = subprocess.run([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env=env,
+                                 stdout=subprocess.PIPE, text=True)
+            sys.stdout.write(res.stdout)
+            sys.stdout.flush()
+            return
         out = run_reference(args, rank, world)
         if out is not None:
             print(json.dumps(out), flush=True)
