@@ -525,7 +525,12 @@ stein_kernel(int n, const double* __restrict__ d, const double* __restrict__ e,
 // Z[k, :] <- Q Z[k, :],  Q = H(0) H(1) ... H(n-2), reflector c stored in A[c, c+1:n].
 // One CTA per vector, vector kept in shared memory.
 constexpr int OR_THREADS = 512;
+constexpr int OR_REG = 16;                 // reflector elements per thread kept in registers (n <= 8192), the
+                                           // rest (longer reflectors) is read from global memory directly
 
+// The n - 1 reflectors are strictly sequential; what a step pays for is latency: the L2 read of the
+// reflector row, one block reduction, one barrier.  The NEXT reflector row is therefore prefetched
+// into registers while the current one is reduced and applied.
 __global__ void __launch_bounds__(OR_THREADS)
 ormtr_kernel(int n, const double* __restrict__ A, int64_t lda, const double* __restrict__ tau,
              double* __restrict__ Z, int64_t ldz) {
@@ -536,13 +541,30 @@ ormtr_kernel(int n, const double* __restrict__ A, int64_t lda, const double* __r
   for (int j = tid; j < n; j += OR_THREADS) zs[j] = z[j];
   __syncthreads();
   int par = 0;
+  double vn[OR_REG];                         // prefetched head of reflector c (elements tid + 512 q)
+  {
+    const int c = n - 2;
+    const double* v = A + (int64_t)c * lda + (c + 1);
+#pragma unroll
+    for (int q = 0; q < OR_REG; ++q) { const int j = tid + OR_THREADS * q; vn[q] = (c >= 0 && j < n - c - 1) ? v[j] : 0.0; }
+  }
   for (int c = n - 2; c >= 0; --c) {
-    const double tc = tau[c];
-    if (tc == 0.0) continue;                 // uniform
     const double* v = A + (int64_t)c * lda + (c + 1);
     const int n1 = n - c - 1;
+    double vc[OR_REG];
+#pragma unroll
+    for (int q = 0; q < OR_REG; ++q) vc[q] = vn[q];
+    if (c > 0) {                             // prefetch reflector c - 1
+      const double* v2 = A + (int64_t)(c - 1) * lda + c;
+#pragma unroll
+      for (int q = 0; q < OR_REG; ++q) { const int j = tid + OR_THREADS * q; vn[q] = (j < n1 + 1) ? v2[j] : 0.0; }
+    }
+    const double tc = tau[c];
+    if (tc == 0.0) continue;                 // uniform
     double dt = 0.0;
-    for (int j = tid; j < n1; j += OR_THREADS) dt = fma(v[j], zs[c + 1 + j], dt);
+#pragma unroll
+    for (int q = 0; q < OR_REG; ++q) { const int j = tid + OR_THREADS * q; if (j < n1) dt = fma(vc[q], zs[c + 1 + j], dt); }
+    for (int j = tid + OR_THREADS * OR_REG; j < n1; j += OR_THREADS) dt = fma(v[j], zs[c + 1 + j], dt);
     dt = warp_sum(dt);
     if (lane == 0) red[par][warp] = dt;
     __syncthreads();
@@ -550,7 +572,9 @@ ormtr_kernel(int n, const double* __restrict__ A, int64_t lda, const double* __r
 #pragma unroll
     for (int w = 0; w < OR_THREADS / 32; ++w) tot += red[par][w];
     const double f = -tc * tot;
-    for (int j = tid; j < n1; j += OR_THREADS) zs[c + 1 + j] = fma(f, v[j], zs[c + 1 + j]);
+#pragma unroll
+    for (int q = 0; q < OR_REG; ++q) { const int j = tid + OR_THREADS * q; if (j < n1) zs[c + 1 + j] = fma(f, vc[q], zs[c + 1 + j]); }
+    for (int j = tid + OR_THREADS * OR_REG; j < n1; j += OR_THREADS) zs[c + 1 + j] = fma(f, v[j], zs[c + 1 + j]);
     par ^= 1;
     __syncthreads();
   }
