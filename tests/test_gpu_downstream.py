@@ -140,3 +140,31 @@ def test_bootstrapping_of_a_rotated_model(MCA, live_next):
     np.testing.assert_allclose(got, ref, rtol=2e-3, atol=1e-4 * ref.max())
     with pytest.raises(ValueError):
         m.bootstrapping(2, block_size=7, disable_progress=True)
+
+
+@pytest.mark.parametrize("variant", ["plain", "rotated_normalized", "complex"])
+def test_load_analysis_round_trip(MCA, live_next, tmp_path, variant):
+    """test_integration_xarray.py:87-148 for the ndarray class: info.xmca + original-scale fields + unrotated
+    EOFs + singular values rebuild the model (array.py:1954-2012), including the re-run rotation."""
+    g = live_next
+    A, B = g["A/left"], g["A/right"]
+    m = MCA(A.copy(), B.copy())
+    if variant == "rotated_normalized":
+        m.normalize()
+    m.solve(complexify=(variant == "complex"))
+    if variant == "rotated_normalized":
+        m.rotate(5, 2)
+    m._create_info_file(str(tmp_path))
+    fields = {k: np.real(v) for k, v in m.fields(original_scale=True).items()}
+    eofs = m.eofs(rotated=False)
+    sv = m.singular_values()
+    m2 = MCA()
+    m2.load_analysis(str(tmp_path / "info.xmca"), fields=fields, eofs=eofs, singular_values=sv)
+    assert m2._analysis["rank"] == m._analysis["rank"] and m2._solve_info["route"] == "loaded"
+    np.testing.assert_array_equal(m2.singular_values(), sv)
+    e1, e2 = m.eofs(4), m2.eofs(4)
+    p1, p2 = m.pcs(4), m2.pcs(4)
+    for k in ("left", "right"):
+        np.testing.assert_allclose(np.nan_to_num(e2[k]), np.nan_to_num(e1[k]), atol=1e-4 * np.nanmax(np.abs(e1[k])))
+        np.testing.assert_allclose(p2[k], p1[k], atol=2e-4 * np.abs(p1[k]).max())
+    np.testing.assert_allclose(m2.variance(4), m.variance(4), rtol=1e-4)

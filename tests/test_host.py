@@ -190,3 +190,22 @@ def test_xmca_facade_constructor_and_metadata():
     w = np.sqrt(np.cos(np.deg2rad(lat)) + 1e-6)
     want = (da.values - da.values.mean(axis=0)) * w[None, :, None]
     np.testing.assert_allclose(m.fields()["left"].values, want, atol=1e-12)
+
+
+def test_info_file_round_trip(tmp_path):
+    """info.xmca (array.py:1629-1714): same `key : value` layout, values re-typed from the defaults."""
+    from xmca_b200 import MCA
+    rng = np.random.default_rng(1)
+    m = MCA(rng.standard_normal((20, 6)), rng.standard_normal((20, 4)))
+    m.set_field_names("sea surface temp", "precip")
+    m._analysis.update({"is_rotated": True, "n_rot": 7, "power": 2, "rank": 4, "is_complex": True,
+                        "total_covariance": 12.5, "is_normalized": True})
+    m._create_info_file(str(tmp_path))
+    text = (tmp_path / "info.xmca").read_text()
+    assert "\nleft                 : sea surface temp" in text and "\nn_rot                : 7" in text
+    assert m._get_file_names("nc")["eofs"]["left"] == "sea_surface_temp_eofs.nc"
+    m2 = MCA()
+    m2._set_info_from_file(str(tmp_path / "info.xmca"))
+    for k in ("is_rotated", "n_rot", "power", "rank", "is_complex", "is_bivariate", "is_normalized", "method"):
+        assert m2._analysis[k] == m._analysis[k], k
+    assert m2._analysis["total_covariance"] == 12.5 and m2._field_names["right"] == "precip"

@@ -14,6 +14,7 @@ Out of scope: plotting, save/load and the Hilbert ``extend`` options (``NotImple
 from __future__ import annotations
 
 import cmath
+import os
 import warnings
 
 import numpy as np
@@ -24,6 +25,7 @@ from . import _lib as L
 from . import device as D
 from . import engine as E
 from . import downstream as DS
+from . import storage as ST
 
 _SIDES = ("left", "right")
 
@@ -696,8 +698,24 @@ class MCA:
     def save_plot(self, *a, **k):
         self._out_of_scope("save_plot")
 
-    def save_analysis(self, *a, **k):
-        self._out_of_scope("save_analysis")
+    # ------------------------------------------------ checkpoint (info file + arrays)
+    def _get_analysis_path(self, path=None):
+        return ST.analysis_path(self, path)
 
-    def load_analysis(self, *a, **k):
-        self._out_of_scope("load_analysis")
+    def _create_analysis_path(self, path):
+        os.makedirs(self._get_analysis_path(path), exist_ok=True)
+
+    def _get_file_names(self, format):
+        return ST.file_names(self, format)
+
+    def _create_info_file(self, path):
+        ST.create_info_file(self, path)
+
+    def _set_info_from_file(self, path):
+        ST.set_info_from_file(self, path)
+
+    def _save_data(self, data_array, path, *args, **kwargs):
+        raise NotImplementedError("only works for `xarray`")           # array.py:1687-1688
+
+    def load_analysis(self, path, fields=None, eofs=None, singular_values=None):
+        ST.load_analysis(self, path, fields, eofs, singular_values)

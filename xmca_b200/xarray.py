@@ -208,3 +208,47 @@ class xMCA(MCA):
         return _xr().DataArray(sv, dims=["mode", "run"],
                                coords={"mode": self._modes(n_modes, len(sv)), "run": list(range(1, sv.shape[1] + 1))},
                                name="singular values", attrs=self._attrs())
+
+    # ------------------------------------------------------------ checkpoint (NetCDF)
+    def _save_data(self, data, path, engine="h5netcdf", *args, **kwargs):
+        """xarray.py:1239-1251 -- needs a DataArray backend with `to_netcdf` (real xarray)."""
+        import os
+        from .storage import secure_str
+        if not hasattr(data, "to_netcdf"):
+            raise NotImplementedError("saving needs xarray (+ h5netcdf); the active DataArray backend cannot write NetCDF")
+        out = os.path.join(path, secure_str(".".join([data.name, "nc"])))
+        data.to_netcdf(path=out, engine=engine, invalid_netcdf=(engine == "h5netcdf"), *args, **kwargs)
+
+    def save_analysis(self, path=None, engine="h5netcdf"):
+        """xarray.py:1253-1279: info.xmca + original-scale real fields, UNROTATED EOFs, singular values."""
+        path = self._get_analysis_path(path)
+        self._create_analysis_path(path)
+        self._create_info_file(path)
+        fields = self.fields(original_scale=True)
+        eofs = self.eofs(rotated=False)
+        self._save_data(self.singular_values(), path, engine)
+        for k in self._keys:
+            self._save_data(eofs[k], path, engine)
+            f = fields[k]
+            f.values = np.real(f.values)
+            self._save_data(f, path, engine)
+
+    def load_analysis(self, path, engine="h5netcdf"):
+        """xarray.py:1281-1314."""
+        import os
+        xr = _xr()
+        if not hasattr(xr, "open_dataarray"):
+            raise NotImplementedError("loading needs xarray (+ h5netcdf)")
+        self._set_info_from_file(path)
+        folder, _ = os.path.split(path)
+        names = self._get_file_names(format="nc")
+        sv = xr.open_dataarray(os.path.join(folder, names["singular"]), engine=engine).data
+        fields, eofs = {}, {}
+        for k in self._field_names:
+            eofs[k] = xr.open_dataarray(os.path.join(folder, names["eofs"][k]), engine=engine).data
+            f = xr.open_dataarray(os.path.join(folder, names["fields"][k]), engine=engine)
+            self._field_coords[k], self._field_dims[k] = f.coords, f.dims
+            fields[k] = f.data
+        MCA.load_analysis(self, path=path, fields=fields, eofs=eofs, singular_values=sv)
+        if self._analysis["is_coslat_corrected"]:
+            self.apply_coslat()
