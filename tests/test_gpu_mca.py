@@ -542,3 +542,23 @@ def test_normalize_and_weights_on_the_device(MCA):
     np.testing.assert_allclose(m2._fields["left"], Ac * w * wt, atol=1e-5)
     m2.solve()
     assert m2.singular_values().dtype == np.float64
+
+
+@pytest.mark.parametrize("shape", [(2600, 900, 1100), (900, 2500, 2000)])
+def test_default_route_at_moderate_size(MCA, shape):
+    """The default routing at a size where the tridiagonal route switches on by itself (rank >= 768), on its
+    direct (S < T) and Gram (T < S) sides, against the numpy oracle."""
+    T, S1, S2 = shape
+    A, B = orc.synthetic_fields(T, S1, S2, seed=71, k=12, dtype=np.float32)
+    m = MCA(A.copy(), B.copy())
+    m.solve()
+    assert m._solve_info["route"] == "tridiag"
+    ref = orc.solve(orc.make_model(A.copy(), B.copy()))
+    lead = ref.sigma > 1e-2 * ref.sigma[0]
+    np.testing.assert_allclose(m.singular_values()[lead], ref.sigma[lead], rtol=1e-5)
+    np.testing.assert_allclose(m.singular_values(), ref.sigma, atol=1e-5 * ref.sigma[0])
+    V, Vr = m._get_V(10, rotated=False), orc.get_V(ref, 10, rotated=False)
+    assert orc.subspace_angle(V["left"], Vr["left"]) < 1e-4 and orc.subspace_angle(V["right"], Vr["right"]) < 1e-4
+    m.rotate(8, 1)
+    orc.rotate(ref, 8, 1)
+    np.testing.assert_allclose(m.variance(8), orc.get_variance(ref, 8), rtol=1e-4)
