@@ -175,6 +175,10 @@ int xmca_ormtr(int64_t n, const double* d_A, int64_t lda, const double* d_tau, i
  *   one-sided spectrum Z^ = F x satisfies  Z_A^H Z_B = Z^_A^H Z^_B, so solve() runs on Z^.
  * xmca_embed_complex: real embedding [[Zr, -Zi], [Zi, Zr]] of the stacked [Zr; Zi] (2 rows_half x cols). */
 int xmca_hilbert_matrix(int64_t T, void* d_H, int h_dtype, int64_t ldh, double* d_taps, void* stream);
+/* rows x cols block at (row0, col0) of the length-N operator (d_taps: N doubles): the pieces of the 3T-long
+ * transform that the fore/back-cast extension of array.py:378-472 (extend='exp') needs. */
+int xmca_hilbert_block(int64_t N, int64_t rows, int64_t cols, int64_t row0, int64_t col0,
+                       void* d_H, int h_dtype, int64_t ldh, double* d_taps, void* stream);
 int64_t xmca_dft_rows(int64_t T);
 int xmca_dft_matrix(int64_t T, void* d_F, int f_dtype, int64_t ldf, void* stream);
 int xmca_embed_complex(const void* d_Z, int z_dtype, int64_t ldz, int64_t rows_half, int64_t cols,

@@ -56,6 +56,14 @@ def main():
     dump(out, "A/normalized", m, A, B, 5)
     m = MCA(A.copy(), B.copy()); m.solve(complexify=True)
     dump(out, "A/cplx", m, A, B, 4)
+    # complex solve on the exponentially extended series (array.py:378-411, :455-472)
+    m = MCA(A.copy(), B.copy()); m.solve(complexify=True, extend="exp", period=12)
+    out["A/cplx_exp/sigma"] = m.singular_values()
+    out["A/cplx_exp/field_left"] = m._fields["left"]
+    for k, v in m.eofs(4).items():
+        out["A/cplx_exp/eofs_" + k] = v
+    for k, v in m.pcs(4).items():
+        out["A/cplx_exp/pcs_" + k] = v
     # PCA
     C, _ = planted(60, (5, 9), (4,), seed=13)
     out["C/left"] = C

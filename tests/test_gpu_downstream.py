@@ -168,3 +168,27 @@ def test_load_analysis_round_trip(MCA, live_next, tmp_path, variant):
         np.testing.assert_allclose(np.nan_to_num(e2[k]), np.nan_to_num(e1[k]), atol=1e-4 * np.nanmax(np.abs(e1[k])))
         np.testing.assert_allclose(p2[k], p1[k], atol=2e-4 * np.abs(p1[k]).max())
     np.testing.assert_allclose(m2.variance(4), m.variance(4), rtol=1e-4)
+
+
+def test_complex_solve_with_exponential_extension(MCA, live_next):
+    """solve(complexify=True, extend='exp', period) -- array.py:378-411, :455-472: the Hilbert transform of
+    the fore/back-cast series as ONE T x T operator on the device, against the live reference."""
+    g = live_next
+    m = MCA(g["A/left"].copy(), g["A/right"].copy())
+    m.solve(complexify=True, extend="exp", period=12)
+    ref = g["A/cplx_exp/sigma"]
+    np.testing.assert_allclose(m.singular_values(30), ref[:30], rtol=5e-5)
+    np.testing.assert_allclose(m.singular_values(), ref, atol=2e-5 * ref[0])
+    zr = g["A/cplx_exp/field_left"]
+    np.testing.assert_allclose(m._fields["left"], zr, atol=2e-5 * np.abs(zr).max())
+    e, p = m.eofs(4), m.pcs(4)
+    er, pr = g["A/cplx_exp/eofs_left"], g["A/cplx_exp/pcs_left"]
+    np.testing.assert_allclose(_aligned(er, e["left"]), er, atol=1e-3 * np.nanmax(np.abs(er)), equal_nan=True)
+    np.testing.assert_allclose(_aligned(pr, p["left"]), pr, atol=1e-3 * np.abs(pr).max())
+    with pytest.raises(NotImplementedError):
+        m.solve(complexify=True, extend="theta", period=12)
+    with pytest.raises(ValueError):
+        m.solve(complexify=True, extend="bogus")
+    m.solve(complexify=True)                                  # back to the plain transform: caches are dropped
+    np.testing.assert_allclose(m.singular_values(10), orc.solve(orc.make_model(g["A/left"].copy(), g["A/right"].copy()),
+                                                                  complexify=True).sigma[:10], rtol=5e-5)

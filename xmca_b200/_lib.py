@@ -90,6 +90,7 @@ def load():
     lib.xmca_stein.argtypes = [i64, vp, vp, i64, vp, vp, i64, dbl, i32, vp, i64, vp, sz, vp]
     lib.xmca_ormtr.argtypes = [i64, vp, i64, vp, i64, vp, i64, vp]
     lib.xmca_hilbert_matrix.argtypes = [i64, vp, i32, i64, vp, vp]
+    lib.xmca_hilbert_block.argtypes = [i64, i64, i64, i64, i64, vp, i32, i64, vp, vp]
     lib.xmca_dft_rows.restype = i64
     lib.xmca_dft_rows.argtypes = [i64]
     lib.xmca_dft_matrix.argtypes = [i64, vp, i32, i64, vp]

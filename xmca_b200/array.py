@@ -9,7 +9,8 @@ library or a CUDA device ``solve`` raises.
 
 The callers either side of the path (``predict``, ``reconstructed_fields``, homogeneous /
 heterogeneous patterns, ``bootstrapping``: SURVEY.md section 8f) live in ``downstream.py``.
-Out of scope: plotting, save/load and the Hilbert ``extend`` options (``NotImplementedError``).
+Checkpointing (info file, ``load_analysis``) is in ``storage.py``.  Out of scope: plotting and the
+Theta-model Hilbert extension (``NotImplementedError``).
 """
 from __future__ import annotations
 
@@ -149,8 +150,14 @@ class MCA:
         analytic signal, array.py:464): one GEMM with the circulant operator, cached."""
         if k not in self._devY:
             X = self._device_fields()[k]
-            H = D.hilbert_matrix(X.shape[0], X.dtype)
-            self._devY[k], _ = D.apply_time_operator(H, X)
+            if self._analysis["extend"] == "exp":             # array.py:378-411, :455-472
+                H = D.hilbert_matrix_exp_extension(X.shape[0], float(self._analysis["theta_period"]), X.dtype)
+                Y, _ = D.apply_time_operator(H, X)
+                D.center_columns(Y)                           # remove_mean of the cropped signal (array.py:471)
+                self._devY[k] = Y
+            else:
+                H = D.hilbert_matrix(X.shape[0], X.dtype)
+                self._devY[k], _ = D.apply_time_operator(H, X)
         return self._devY[k]
 
     def _n_kept(self, k):
@@ -260,9 +267,15 @@ class MCA:
         if len(self._keys) == 0 or any(self._n_kept(k) == 0 for k in self._keys):
             raise RuntimeError("Fields are empty. Did you forget to load data?")
         L._torch()                # no CUDA device -> XmcaLibraryError: there is no CPU fallback
-        if extend:
-            raise NotImplementedError("Hilbert extension (extend='exp'|'theta') is outside the B200 "
-                                      "engine's scope (SURVEY.md section 2a #11).")
+        if extend == "theta":
+            raise NotImplementedError("the Theta-model extension needs statsmodels (per-column model fits, "
+                                      "array.py:367-376); use extend='exp' or extend=False")
+        if extend not in (False, None, "exp"):
+            raise ValueError("{:} is not a valid extension. Choose either `exp` or `theta`.".format(extend))
+        if bool(complexify) != bool(self._analysis["is_complex"]) or extend != self._analysis["extend"] \
+                or period != self._analysis["theta_period"]:
+            self._devY = {}       # cached Hilbert transforms belong to the previous setting
+            self._host = {k: v for k, v in self._host.items() if not np.iscomplexobj(v)}
         self._analysis["is_complex"] = bool(complexify)
         self._analysis["extend"] = extend
         self._analysis["theta_period"] = period
@@ -274,7 +287,11 @@ class MCA:
         B = dev.get("right")
         real_dtype = np.float32 if A.dtype == D.f32() else np.float64
         try:
-            if complexify:
+            if complexify and extend == "exp":
+                sigma, vec, res = E.solve_complex_time(A, self._hilbert_dev("left"), B,
+                                                       self._hilbert_dev("right") if B is not None else None)
+                self._dV = ("complex", vec)
+            elif complexify:
                 sigma, vec, res = E.solve_complex(A, B)
                 self._dV = ("complex", vec)
             else:

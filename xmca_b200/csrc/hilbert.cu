@@ -46,6 +46,18 @@ __global__ void circulant_kernel(int64_t T, const double* __restrict__ h, void* 
   }
 }
 
+// rows x cols block (row0, col0) of the N x N circulant: H[r][c] = h[((row0 + r) - (col0 + c)) mod N]
+__global__ void circulant_block_kernel(int64_t N, int64_t rows, int64_t cols, int64_t row0, int64_t col0,
+                                       const double* __restrict__ h, void* __restrict__ H, int dt, int64_t ld) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
+    int64_t k = ((row0 + r) - (col0 + c)) % N;
+    if (k < 0) k += N;
+    store_from_double(H, dt, r * ld + c, h[k]);
+  }
+}
+
 // rows 0..Tp-1: (w_f / sqrt(T)) cos(2 pi f t / T);  rows Tp..2Tp-1: -(w_f / sqrt(T)) sin(2 pi f t / T),  f = row + 1
 __global__ void dft_matrix_kernel(int64_t T, int64_t Tp, void* __restrict__ F, int dt, int64_t ld) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -94,6 +106,19 @@ extern "C" int xmca_hilbert_matrix(int64_t T, void* d_H, int h_dtype, int64_t ld
   hilbert_taps_kernel<<<(unsigned)((T + 127) / 128), 128, 0, st>>>(T, d_taps);
   XMCA_LAUNCHED();
   circulant_kernel<<<dim3((unsigned)((T + 255) / 256), rows_grid(T)), 256, 0, st>>>(T, d_taps, d_H, h_dtype, ldh);
+  XMCA_LAUNCHED();
+  return XMCA_OK;
+}
+
+extern "C" int xmca_hilbert_block(int64_t N, int64_t rows, int64_t cols, int64_t row0, int64_t col0,
+                                  void* d_H, int h_dtype, int64_t ldh, double* d_taps, void* stream) {
+  XMCA_REQUIRE(N >= 1 && rows >= 1 && cols >= 1 && row0 >= 0 && col0 >= 0 && row0 + rows <= N && col0 + cols <= N &&
+                   d_H && d_taps && ldh >= cols && dtype_ok(h_dtype), "xmca_hilbert_block: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  hilbert_taps_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(N, d_taps);
+  XMCA_LAUNCHED();
+  circulant_block_kernel<<<dim3((unsigned)((cols + 255) / 256), rows_grid(rows)), 256, 0, st>>>(
+      N, rows, cols, row0, col0, d_taps, d_H, h_dtype, ldh);
   XMCA_LAUNCHED();
   return XMCA_OK;
 }

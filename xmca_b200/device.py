@@ -295,6 +295,42 @@ def hilbert_matrix(T, dtype):
     return H
 
 
+def hilbert_block(N, rows, cols, row0, col0, dtype):
+    """rows x cols block at (row0, col0) of the length-N circulant Hilbert operator."""
+    lib = L.load()
+    H = empty((rows, cols), dtype)
+    taps = empty((N,), f64())
+    rc = lib.xmca_hilbert_block(N, rows, cols, row0, col0, L.ptr(H), L.dtype_code(H), cols, L.ptr(taps), L.stream_ptr())
+    L.check(rc, "xmca_hilbert_block")
+    return H
+
+
+def hilbert_matrix_exp_extension(T, theta, dtype):
+    """T x T operator M with  imag(analytic signal of the EXTENDED series)[T:2T] = M x  for the exponential
+    fore/back-cast of array.py:378-411 / :455-472 (extend='exp', period = theta): the series is extended to
+    [pre, x, post] (3T), transformed, and the middle third kept.  pre/post are linear in x -- three functionals
+    (slope with the reference's `xstd = mean(x)`, end of the regression line, offset) times three basis
+    vectors -- so  M = H_mid,mid + (H_mid,pre B_pre) F_pre + (H_mid,post B_post) F_post  (two rank-3 updates)."""
+    N = T
+    x = np.arange(N, dtype=np.float64)
+    xmean = (N - 1) / 2.0
+    s = (x - xmean) / (N * xmean ** 2)                    # slope = s . f   (array.py:384: xstd = np.mean(x))
+    lin = np.full(N, 1.0 / N) + s * xmean                 # linear_end = ymean + slope * xmean
+    off = -lin.copy()
+    off[-1] += 1.0                                        # offset = f[-1] - linear_end
+    F_post = np.stack([s, lin, off])                      # 3 x T
+    B_post = np.stack([x, np.ones(N), np.exp(-(x + 1.0) / theta)], axis=1)      # T x 3
+    F_pre, B_pre = F_post[:, ::-1].copy(), B_post[::-1].copy()                  # pre = extend(f[::-1])[::-1]
+    N3 = 3 * T
+    M = hilbert_block(N3, T, T, T, T, f64())
+    for col0, Bm, Fm in ((0, B_pre, F_pre), (2 * T, B_post, F_post)):
+        Hb = hilbert_block(N3, T, T, T, col0, f64())
+        U = matmul(Hb, to_device(Bm))                                            # T x 3
+        matmul(U, to_device(Fm), out=M, accumulate=True)
+        del Hb
+    return M if dtype == f64() else scale_copy(M, out_dtype=dtype)
+
+
 def dft_matrix(T, dtype):
     """Stacked [Re; Im] one-sided, weighted, orthonormally scaled DFT operator (2 floor(T/2) x T)."""
     lib = L.load()

@@ -460,6 +460,28 @@ def solve_complex(XA, XB, want_vectors=True):
     return sigma, ComplexVectors(res, n, rank), res
 
 
+def solve_complex_time(XA, YA, XB, YB):
+    """Complex solve from explicit analytic fields Z = X + iY (time domain), used when the Hilbert transform
+    is taken on a fore/back-cast extension (extend='exp'): the cropped signal is no longer confined to the
+    positive frequencies, so the real solver runs on the 2T x 2S embeddings [[X,-Y],[Y,X]] (both parts are
+    centred: two exact null vectors)."""
+    t = D.torch()
+    T, S1 = XA.shape
+    pca = XB is None
+    S2 = S1 if pca else XB.shape[1]
+    rank = min(T, S1, S2)
+    Ae = D.embed_complex(t.cat([XA, YA], dim=0).contiguous())
+    Be = None if pca else D.embed_complex(t.cat([XB, YB], dim=0).contiguous())
+    nb = np.zeros((2 * T, 2))
+    nb[:T, 0] = nb[T:, 1] = 1.0 / np.sqrt(T)
+    res = solve_real(Ae, Be, null_basis=D.to_device(nb), dof=T - 1)
+    s = res.sigma[0::2]
+    sigma = np.zeros(rank)
+    n = min(rank, s.size)
+    sigma[:n] = s[:n]
+    return sigma, ComplexVectors(res, n, rank), res
+
+
 class ComplexVectors:
     """Complex singular vectors out of the real-embedded solve: each pair of equal singular
     values {x, Jx} spans one complex vector, so the even-numbered embedded vectors are taken;
