@@ -85,6 +85,13 @@ def main():
     m.rotate(5, 1)
     np.random.seed(81)
     out["A/varimax/boot"] = m.bootstrapping(4, n_modes=4, on_left=True, on_right=True, disable_progress=True)
+    m = MCA(A.copy(), B.copy()); m.solve(complexify=True, extend="exp", period=12)
+    np.random.seed(82)
+    out["A/cplx_exp/boot"] = m.bootstrapping(3, n_modes=4, on_left=True, on_right=True, block_size=2,
+                                             disable_progress=True)
+    m = MCA(A.copy(), B.copy()); m.solve(complexify=True)
+    np.random.seed(83)
+    out["A/cplx/boot"] = m.bootstrapping(3, n_modes=4, on_left=True, on_right=False, disable_progress=True)
     np.savez_compressed(os.path.join(HERE, "live_next.npz"), **out)
     print("wrote live_next.npz with", len(out), "arrays")
 

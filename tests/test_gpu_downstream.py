@@ -192,3 +192,16 @@ def test_complex_solve_with_exponential_extension(MCA, live_next):
     m.solve(complexify=True)                                  # back to the plain transform: caches are dropped
     np.testing.assert_allclose(m.singular_values(10), orc.solve(orc.make_model(g["A/left"].copy(), g["A/right"].copy()),
                                                                   complexify=True).sigma[:10], rtol=5e-5)
+
+
+@pytest.mark.parametrize("key,seed,ext,kw", [
+    ("A/cplx_exp/boot", 82, "exp", dict(n_runs=3, n_modes=4, on_left=True, on_right=True, block_size=2)),
+    ("A/cplx/boot", 83, False, dict(n_runs=3, n_modes=4, on_left=True, on_right=False)),
+])
+def test_bootstrapping_of_complex_models(MCA, live_next, key, seed, ext, kw):
+    g = live_next
+    m = MCA(g["A/left"].copy(), g["A/right"].copy())
+    m.solve(complexify=True, extend=ext, period=12 if ext else 1)
+    np.random.seed(seed)
+    got = m.bootstrapping(disable_progress=True, **kw)
+    np.testing.assert_allclose(got, g[key], rtol=5e-4, atol=5e-5 * g[key].max())

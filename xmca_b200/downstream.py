@@ -217,8 +217,9 @@ def bootstrapping(self, n_runs, n_modes=20, axis=0, on_left=True, on_right=False
     self._require_solved("singular values")
     t = D.torch()
     complexify = self._analysis["is_complex"]
-    if self._analysis["extend"]:
-        raise NotImplementedError("Hilbert extension is outside the B200 engine's scope")
+    extend, period = self._analysis["extend"], self._analysis["theta_period"]
+    if extend == "theta":
+        raise NotImplementedError("the Theta-model extension needs statsmodels")
     is_rotated = self._analysis["is_rotated"]
     n_rot, power = self._analysis["n_rot"], self._analysis["power"]
     n_modes_max = int(min(self._analysis["rank"], n_modes, n_rot))
@@ -251,7 +252,7 @@ def bootstrapping(self, n_runs, n_modes=20, axis=0, on_left=True, on_right=False
                 F = X[k].clone()
                 D.center_columns(F)
                 fields.append(F)
-            var = variance_of_fields(fields, complexify, is_rotated, n_rot, power)
+            var = variance_of_fields(fields, complexify, is_rotated, n_rot, power, extend, period)
             if var is None:
                 continue                                                   # rotation did not converge (array.py:1939-1943)
             m = n_modes_max - mode

@@ -26,7 +26,25 @@ def partition(n_runs: int, world: int, rank: int):
     return range(lo, lo + base + (1 if rank < extra else 0))
 
 
-def variance_of_fields(fields, complexify, rotated, n_rot, power):
+def _complex_solve(fields, extend, period):
+    """Complex solve of centred real device fields: frequency-domain route, or the time-domain route on the
+    exponentially extended series (array.py:455-472) when extend == 'exp'."""
+    from . import device as D
+    from . import engine as E
+    A = fields[0]
+    B = fields[1] if len(fields) > 1 else None
+    if extend == "exp":
+        H = D.hilbert_matrix_exp_extension(A.shape[0], float(period), A.dtype)
+        Y = []
+        for X in fields:
+            y, _ = D.apply_time_operator(H, X)
+            D.center_columns(y)
+            Y.append(y)
+        return E.solve_complex_time(A, Y[0], B, Y[1] if B is not None else None)
+    return E.solve_complex(A, B)
+
+
+def variance_of_fields(fields, complexify, rotated, n_rot, power, extend=False, period=1):
     """solve [+ rotate] + `_get_variance()` (sorted, array.py:771-779) of CENTRED real device fields
     (one or two, T x S_k): the body of one Monte-Carlo run (array.py:1757-1764, :1935-1945).
     Returns the variance spectrum (fp64 numpy, descending) or None if the rotation did not converge."""
@@ -37,11 +55,11 @@ def variance_of_fields(fields, complexify, rotated, n_rot, power):
     B = fields[1] if len(fields) > 1 else None
     if not rotated:
         if complexify:
-            sigma, _, _ = E.solve_complex(A, B, want_vectors=False)
+            sigma, _, _ = _complex_solve(fields, extend, period)
             return sigma
         return E.solve_real(A, B, want_vectors=False).sigma
     if complexify:
-        sigma, vec, _ = E.solve_complex(A, B)
+        sigma, vec, _ = _complex_solve(fields, extend, period)
         p = min(n_rot, sigma.size)
         keys = ["left", "right"][:len(fields)]
         try:
