@@ -71,6 +71,7 @@ __device__ __forceinline__ void small_matmul(const double* X, int xs_i, int xs_k
 __device__ int polar_jacobi(double* X, double* V, int pe, const unsigned char* rr, double* s_max, double stop2) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int npairs = pe >> 1;
+  const bool fast = stop2 > 1e-13;           // the full-accuracy polish keeps fp64 reductions
   int sweeps = 0;
   while (sweeps < 40) {
     double cmax2 = 0.0;
@@ -91,13 +92,44 @@ __device__ int polar_jacobi(double* X, double* V, int pe, const unsigned char* r
         be[u] = xq0[u] * xq0[u] + xq1[u] * xq1[u];
         ga[u] = xp0[u] * xq0[u] + xp1[u] * xq1[u];
       }
+      if (fast) {
+        // in-loop sweeps (stop at cosine 1e-3): the three sums only steer the rotation angle, so they
+        // are reduced in fp32 -- half the shuffle traffic on the crossbar the column loads/stores share.
+        // Scaled by 1/al so that products of norms cannot overflow the fp32 range.
+        // The six sums of a warp (two pairs x {al, be, ga}) go through ONE transposed butterfly: 4 + 2 + 1
+        // exchange shuffles halve the value count while summing lanes, two plain steps finish, and six
+        // broadcasts hand every lane all sums: 15 shuffles instead of 30.
+        float x8[8] = {(float)al[0], (float)be[0], (float)ga[0], 0.0f, (float)al[1], (float)be[1], (float)ga[1], 0.0f};
+        float y4[4], z2[2];
+        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
+        for (int k = 0; k < 4; ++k) {
+          const float keep = b4 ? x8[k + 4] : x8[k], send = b4 ? x8[k] : x8[k + 4];
+          y4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          al[u] += __shfl_xor_sync(0xffffffffu, al[u], o);
-          be[u] += __shfl_xor_sync(0xffffffffu, be[u], o);
-          ga[u] += __shfl_xor_sync(0xffffffffu, ga[u], o);
+        for (int k = 0; k < 2; ++k) {
+          const float keep = b3 ? y4[k + 2] : y4[k], send = b3 ? y4[k] : y4[k + 2];
+          z2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+        float r1 = (b2 ? z2[1] : z2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? z2[0] : z2[1], 4);
+        r1 += __shfl_xor_sync(0xffffffffu, r1, 2);
+        r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
+        // lane l now holds the total of value index v = (l >> 2) & 7 with bit order b2 + 2 b3 + 4 b4
+        // (v = k_low + 2 k_mid + 4 k_high as selected above): value v sits in lanes 4 v .. 4 v + 3
+        al[0] = (double)__shfl_sync(0xffffffffu, r1, 0);  be[0] = (double)__shfl_sync(0xffffffffu, r1, 4);
+        ga[0] = (double)__shfl_sync(0xffffffffu, r1, 8);
+        al[1] = (double)__shfl_sync(0xffffffffu, r1, 16); be[1] = (double)__shfl_sync(0xffffffffu, r1, 20);
+        ga[1] = (double)__shfl_sync(0xffffffffu, r1, 24);
+      } else {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            al[u] += __shfl_xor_sync(0xffffffffu, al[u], o);
+            be[u] += __shfl_xor_sync(0xffffffffu, be[u], o);
+            ga[u] += __shfl_xor_sync(0xffffffffu, ga[u], o);
+          }
         }
       }
 #pragma unroll
