@@ -174,7 +174,7 @@ def test_cholesky_rejects_indefinite(D):
         D.cholesky(D.to_device(G))
 
 
-@pytest.mark.parametrize("n", [5, 64, 200, 777, 1500])
+@pytest.mark.parametrize("n", [5, 64, 200, 777, 1500, 4700])
 def test_tridiagonal_eigensolver(D, n):
     """sytrd + stebz give all eigenvalues; stein + ormtr the leading eigenvectors (also inside
     exactly degenerate clusters)."""

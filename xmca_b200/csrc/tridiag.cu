@@ -27,6 +27,8 @@ constexpr int TD_WARPS = TD_THREADS / 32;
 constexpr int TD_K2 = 2 * TD_NB;          // row length of the [V | W] panel buffers
 constexpr int TD_PART = TD_K2 + 8;        // per-CTA reduction slots: [0] ssq, [1..128] p, [130] w.v
 constexpr int TD_MAXF = 16;               // max column split of one row in the symv
+constexpr int TD_TS = 64;                 // tile size of the tile-major trailing matrix (= panel width)
+constexpr int TD_TILE_MIN = 4096;         // tile-major one-triangle passes while the trailing size exceeds this
 
 struct SytrdParams {
   double* A; int64_t lda; int n;
@@ -34,7 +36,9 @@ struct SytrdParams {
   double* VW;          // n x 128 row-major: [V | W]
   double* WV;          // n x 128 row-major: [W | V]
   double* u;           // n
-  double* wraw;        // TD_MAXF x n
+  double* wraw;        // slots x n: row partials of A v (slots = column split, or tile columns when tiled)
+  double* cpart;       // NT x n: mirrored (column) partials of A v, tiled mode
+  double* tiles;       // tile-major lower triangle of the trailing matrix (tiled mode), 64 x 64 tiles
   double* wpre;        // n
   double* part;        // grid x TD_PART
   double* d; double* e; double* tau;
@@ -75,6 +79,36 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
   __syncthreads();
 }
 
+// tile (I, J), J <= I, of the tile-major lower triangle: 64 x 64 doubles, row-major, contiguous
+__device__ __forceinline__ int64_t tile_off(int I, int J) { return ((int64_t)I * (I + 1) / 2 + J) * (TD_TS * TD_TS); }
+
+// sums of 8 per-lane values over the 32 lanes of a warp with 9 shuffles: afterwards every lane l holds the
+// total of x[(l >> 2) & 7]
+__device__ __forceinline__ double warp_reduce8(double (&x)[8], int lane) {
+  double y[4], z[2];
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double keep = b4 ? x[k + 4] : x[k], send = b4 ? x[k] : x[k + 4];
+    y[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const double keep = b3 ? y[k + 2] : y[k], send = b3 ? y[k] : y[k + 2];
+    z[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  const double keep = b2 ? z[1] : z[0], send = b2 ? z[0] : z[1];
+  double r = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  r += __shfl_xor_sync(0xffffffffu, r, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
+}
+
+// TILED: the trailing matrix lives in P.tiles (tile-major, lower triangle, diagonal tiles full) and y = A v
+// reads every tile ONCE -- each tile feeds the row sums of its block row and, mirrored, the column sums of
+// its block column -- half the HBM bytes of the row-major pass, in contiguous 32 KB pieces.  Partial sums go
+// to per-tile-row / per-tile-column slots (deterministic).  P.A then only receives the reflectors.
+template <bool TILED>
 __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams P) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ double vs[];                 // current Householder vector (n doubles)
@@ -111,7 +145,9 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
         for (int t = lane; t < i; t += 32) acc = fma(vw[t], Wc[t], fma(vw[TD_NB + t], Vc[t], acc));
         acc = warp_sum(acc);
         if (lane == 0) {
-          const double ur = P.A[(int64_t)c * lda + r] - acc;
+          const double a_cr = TILED ? P.tiles[tile_off(r / TD_TS, c / TD_TS) + (int64_t)(r % TD_TS) * TD_TS + c % TD_TS]
+                                    : P.A[(int64_t)c * lda + r];
+          const double ur = a_cr - acc;
           P.u[r] = ur;
           if (r == c) P.d[c] = ur;
           if (r >= c + 2) ssq = fma(ur, ur, ssq);
@@ -141,8 +177,51 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
     if (blockIdx.x == 0 && tid == 0) { P.e[c] = beta; P.tau[c] = tau; }
     __syncthreads();
 
-    // column split so that every warp of the grid gets >= ~4 row pieces of >= 256 elements
     int F = 1;
+    if (TILED) {
+      const int NT = (n + TD_TS - 1) / TD_TS, IB = (c + 1) / TD_TS, m = NT - IB;
+      const int items = m * (m + 1) / 2;
+      // v by GLOBAL index, zero outside the active range (this also masks the retired rows / columns of block IB)
+      auto vget = [&](int g) -> double { return (g > c && g < n) ? vs[g - c - 1] : 0.0; };
+      for (int item = gw; item < items; item += NW) {
+        int Ir = (int)((sqrt(8.0 * (double)item + 1.0) - 1.0) * 0.5);
+        while (Ir * (Ir + 1) / 2 > item) --Ir;
+        while ((Ir + 1) * (Ir + 2) / 2 <= item) ++Ir;
+        const int I = IB + Ir, J = IB + (item - Ir * (Ir + 1) / 2);
+        const double* tp = P.tiles + tile_off(I, J) + lane;
+        const bool diag = (I == J);
+        const double vc0 = vget(TD_TS * J + lane), vc1 = vget(TD_TS * J + 32 + lane);
+        double ca0 = 0.0, ca1 = 0.0;
+#pragma unroll 1
+        for (int rg = 0; rg < TD_TS / 8; ++rg) {
+          double a0[8], a1[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            a0[k] = __ldcs(tp + (rg * 8 + k) * TD_TS);
+            a1[k] = __ldcs(tp + (rg * 8 + k) * TD_TS + 32);
+          }
+          double x8[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            x8[k] = fma(a0[k], vc0, a1[k] * vc1);
+            if (!diag) {
+              const double vr = vget(TD_TS * I + rg * 8 + k);
+              ca0 = fma(a0[k], vr, ca0);
+              ca1 = fma(a1[k], vr, ca1);
+            }
+          }
+          const double rsum = warp_reduce8(x8, lane);
+          const int gr = TD_TS * I + rg * 8 + ((lane >> 2) & 7);
+          if (!(lane & 3) && gr > c && gr < n) P.wraw[(int64_t)J * n + gr] = rsum;
+        }
+        if (!diag) {
+          const int g0 = TD_TS * J + lane, g1 = g0 + 32;
+          if (g0 > c && g0 < n) P.cpart[(int64_t)I * n + g0] = ca0;
+          if (g1 > c && g1 < n) P.cpart[(int64_t)I * n + g1] = ca1;
+        }
+      }
+    } else {
+    // column split so that every warp of the grid gets >= ~4 row pieces of >= 256 elements
     while (F < TD_MAXF && (int64_t)n1 * F < 4LL * NW && n1 / (2 * F) >= 256) F *= 2;
     const int len = ((n1 + F - 1) / F + 31) & ~31;
     {
@@ -167,6 +246,7 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
         double sum = warp_sum(((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7)));
         if (lane == 0) P.wraw[(int64_t)q * n + c + 1 + rr] = sum;
       }
+    }
     }
     if (i > 0) {
       double pa[4] = {0.0, 0.0, 0.0, 0.0};
@@ -224,7 +304,12 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
         double acc = 0.0;
         const double* vw = P.VW + (int64_t)r * TD_K2;
         for (int t = lane; t < i; t += 32) acc = fma(vw[t], pv[TD_NB + t], fma(vw[TD_NB + t], pv[t], acc));
-        double wr = (lane < F) ? P.wraw[(int64_t)lane * n + r] : 0.0;
+        double wr = 0.0;
+        if (TILED) {
+          const int NT = (n + TD_TS - 1) / TD_TS, IB = (c + 1) / TD_TS, I = r / TD_TS;
+          for (int J = IB + lane; J <= I; J += 32) wr += P.wraw[(int64_t)J * n + r];           // tiles (I, J <= I)
+          for (int I2 = I + 1 + lane; I2 < NT; I2 += 32) wr += P.cpart[(int64_t)I2 * n + r];   // mirrored: tiles (I2 > I, I)
+        } else if (lane < F) wr = P.wraw[(int64_t)lane * n + r];
         const double tot = warp_sum(wr - acc);
         if (lane == 0) {
           const double wp = tau * tot;
@@ -260,6 +345,108 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
   }
   if (blockIdx.x == 0 && tid == 0 && P.clk)
     for (int q = 0; q < 5; ++q) P.clk[q] += (unsigned long long)tk[q];
+}
+
+// ------------------------------------------------------------------ tile-major helpers
+// row-major symmetric S (both triangles) -> tile-major lower triangle (diagonal tiles full, zero padded)
+__global__ void to_tiles_kernel(const double* __restrict__ A, int64_t lda, int n, int NT, double* __restrict__ tiles) {
+  const int t = blockIdx.x;                       // linear tile index: I (I + 1) / 2 + J
+  int I = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+  while (I * (I + 1) / 2 > t) --I;
+  while ((I + 1) * (I + 2) / 2 <= t) ++I;
+  const int J = t - I * (I + 1) / 2;
+  double* tp = tiles + (int64_t)t * (TD_TS * TD_TS);
+  for (int e = threadIdx.x; e < TD_TS * TD_TS; e += blockDim.x) {
+    const int r = TD_TS * I + (e >> 6), c = TD_TS * J + (e & 63);
+    tp[e] = (r < n && c < n) ? A[(int64_t)r * lda + c] : 0.0;
+  }
+}
+
+// tile-major -> row-major for the trailing block rows / columns >= 64 * I0 (both triangles)
+__global__ void from_tiles_kernel(const double* __restrict__ tiles, int I0, int NT, int n, double* __restrict__ A,
+                                  int64_t lda) {
+  __shared__ double buf[TD_TS][TD_TS + 1];
+  const int m = NT - I0, t = blockIdx.x;          // tiles (I0 + Ir, I0 + Jr), Jr <= Ir
+  int Ir = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+  while (Ir * (Ir + 1) / 2 > t) --Ir;
+  while ((Ir + 1) * (Ir + 2) / 2 <= t) ++Ir;
+  (void)m;
+  const int I = I0 + Ir, J = I0 + (t - Ir * (Ir + 1) / 2);
+  const double* tp = tiles + tile_off(I, J);
+  for (int e = threadIdx.x; e < TD_TS * TD_TS; e += blockDim.x) {
+    const int rr = e >> 6, cc = e & 63;
+    const double v = tp[e];
+    buf[rr][cc] = v;
+    const int r = TD_TS * I + rr, c = TD_TS * J + cc;
+    if (r < n && c < n) A[(int64_t)r * lda + c] = v;
+  }
+  if (I == J) return;
+  __syncthreads();
+  for (int e = threadIdx.x; e < TD_TS * TD_TS; e += blockDim.x) {      // mirrored tile, coalesced through smem
+    const int cc = e >> 6, rr = e & 63;
+    const int r = TD_TS * I + rr, c = TD_TS * J + cc;
+    if (r < n && c < n) A[(int64_t)c * lda + r] = buf[rr][cc];
+  }
+}
+
+// Trailing update of the tile-major matrix after a panel: tile(I, J) -= VW_I WV_J^T (= V W^T + W V^T) for
+// all tiles I0 <= J <= I.  One CTA of 4 warps per tile: 64 x 64 x 128 on the DMMA pipe (32 x 32 warp tiles),
+// operand slabs of 16 k in XOR-swizzled shared memory, the tile itself is one contiguous 32 KB read-modify-write.
+constexpr int TU_LD = TD_TS + 4;
+__global__ void __launch_bounds__(128)
+syr2k_tiles_kernel(const double* __restrict__ VW, const double* __restrict__ WV, int I0, int n, double* __restrict__ tiles) {
+  __shared__ double As[16][TU_LD];
+  __shared__ double Bs[16][TU_LD];
+  const int t = blockIdx.x;
+  int Ir = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+  while (Ir * (Ir + 1) / 2 > t) --Ir;
+  while ((Ir + 1) * (Ir + 2) / 2 <= t) ++Ir;
+  const int I = I0 + Ir, J = I0 + (t - Ir * (Ir + 1) / 2);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int wm = (warp & 1) * 32, wn = (warp >> 1) * 32;
+  double c[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { c[i][j][0] = 0.0; c[i][j][1] = 0.0; }
+  const int kk = tid & 15, mrow = tid >> 4;       // loader: 16 consecutive k of rows mrow + 8 i
+  for (int k0 = 0; k0 < TD_K2; k0 += 16) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rl = mrow + 8 * i;
+      const int ra = TD_TS * I + rl, rb = TD_TS * J + rl;
+      As[kk][rl ^ ((kk >> 2) & 3)] = ra < n ? VW[(int64_t)ra * TD_K2 + k0 + kk] : 0.0;
+      Bs[kk][rl ^ ((kk >> 2) & 3)] = rb < n ? WV[(int64_t)rb * TD_K2 + k0 + kk] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < 16; ks += 4) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        a[i] = As[ks + tig][(wm + 8 * i + gid) ^ ((ks >> 2) & 3)];
+        b[i] = Bs[ks + tig][(wn + 8 * i + gid) ^ ((ks >> 2) & 3)];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(c[i][j][0]), "+d"(c[i][j][1]) : "d"(a[i]), "d"(b[j]));
+    }
+    __syncthreads();
+  }
+  double* tp = tiles + tile_off(I, J);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double2* q = reinterpret_cast<double2*>(tp + (wm + 8 * i + gid) * TD_TS + wn + 8 * j + 2 * tig);
+      double2 d = *q;
+      d.x -= c[i][j][0]; d.y -= c[i][j][1];
+      *q = d;
+    }
 }
 
 // ------------------------------------------------------------------ bisection
@@ -583,8 +770,9 @@ ormtr_kernel(int n, const double* __restrict__ A, int64_t lda, const double* __r
 
 static int sytrd_grid(size_t smem, int* grid_out) {
   int occ = 0;
-  XMCA_CUDA(cudaFuncSetAttribute(sytrd_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  XMCA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sytrd_panel_kernel, TD_THREADS, smem));
+  XMCA_CUDA(cudaFuncSetAttribute(sytrd_panel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  XMCA_CUDA(cudaFuncSetAttribute(sytrd_panel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  XMCA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sytrd_panel_kernel<true>, TD_THREADS, smem));
   if (occ < 1) return fail(XMCA_CUDA_ERROR, "sytrd panel kernel does not fit on an SM", __FILE__, __LINE__);
   *grid_out = sm_count();
   return XMCA_OK;
@@ -598,11 +786,23 @@ using namespace xmca;
 
 extern "C" int64_t xmca_sytrd_max_n(void) { return 26000; }
 
+// tile-major mode is used for the leading panels of large problems (trailing size > TD_TILE_MIN)
+static bool sytrd_tiled(int64_t n) {
+  static const bool off = getenv("XMCA_SYTRD_NO_TILES") != nullptr;
+  return !off && n >= TD_TILE_MIN + 8 * TD_TS;
+}
+static int64_t sytrd_nt(int64_t n) { return (n + TD_TS - 1) / TD_TS; }
+static size_t sytrd_wraw_slots(int64_t n) { return sytrd_tiled(n) ? (size_t)(sytrd_nt(n) > TD_MAXF ? sytrd_nt(n) : TD_MAXF) : TD_MAXF; }
+
 extern "C" size_t xmca_sytrd_workspace_bytes(int64_t n) {
   size_t b = 0;
   b += 2 * al256((size_t)n * TD_K2 * 8);          // VW, WV
   b += al256((size_t)n * 8) * 2;                  // u, wpre
-  b += al256((size_t)n * TD_MAXF * 8);            // wraw
+  b += al256((size_t)n * sytrd_wraw_slots(n) * 8);   // row partials
+  if (sytrd_tiled(n)) {
+    b += al256((size_t)n * sytrd_nt(n) * 8);                                               // mirrored partials
+    b += al256((size_t)(sytrd_nt(n) * (sytrd_nt(n) + 1) / 2) * TD_TS * TD_TS * 8);         // tile-major lower triangle
+  }
   b += al256((size_t)(148 * 2) * TD_PART * 8);    // partials
   b += 256;                                       // phase clocks
   b += al256((size_t)(n / TD_NB + 2) * 4);       // one barrier counter per panel launch
@@ -630,7 +830,14 @@ extern "C" int xmca_sytrd(int64_t n, double* d_A, int64_t lda, double* d_d, doub
   P.WV = reinterpret_cast<double*>(ws + o); o += al256((size_t)n * TD_K2 * 8);
   P.u = reinterpret_cast<double*>(ws + o); o += al256((size_t)n * 8);
   P.wpre = reinterpret_cast<double*>(ws + o); o += al256((size_t)n * 8);
-  P.wraw = reinterpret_cast<double*>(ws + o); o += al256((size_t)n * TD_MAXF * 8);
+  P.wraw = reinterpret_cast<double*>(ws + o); o += al256((size_t)n * sytrd_wraw_slots(n) * 8);
+  P.cpart = nullptr; P.tiles = nullptr;
+  const bool tiled_mode = sytrd_tiled(n);
+  const int NT = (int)sytrd_nt(n);
+  if (tiled_mode) {
+    P.cpart = reinterpret_cast<double*>(ws + o); o += al256((size_t)n * NT * 8);
+    P.tiles = reinterpret_cast<double*>(ws + o); o += al256((size_t)(NT * (NT + 1) / 2) * TD_TS * TD_TS * 8);
+  }
   P.part = reinterpret_cast<double*>(ws + o); o += al256((size_t)(148 * 2) * TD_PART * 8);
   P.clk = reinterpret_cast<unsigned long long*>(ws + o); o += 256;
   unsigned int* bars = reinterpret_cast<unsigned int*>(ws + o);
@@ -639,22 +846,42 @@ extern "C" int xmca_sytrd(int64_t n, double* d_A, int64_t lda, double* d_d, doub
   P.d = d_d; P.e = d_e; P.tau = d_tau;
   XMCA_CUDA(cudaMemsetAsync(d_tau, 0, (size_t)n * 8, st));
 
+  bool in_tiles = false;
+  if (tiled_mode) {
+    to_tiles_kernel<<<(unsigned)(NT * (NT + 1) / 2), 256, 0, st>>>(d_A, lda, (int)n, NT, P.tiles);
+    XMCA_LAUNCHED();
+    in_tiles = true;
+  }
   for (int64_t j0 = 0; j0 < n; j0 += TD_NB) {
     const int nb = (int)((n - j0 < TD_NB) ? (n - j0) : TD_NB);
+    if (in_tiles && n - j0 <= TD_TILE_MIN) {
+      // the trailing matrix now fits the L2: back to the row-major layout (both triangles) for the rest
+      const int I0 = (int)(j0 / TD_TS), m = NT - I0;
+      from_tiles_kernel<<<(unsigned)(m * (m + 1) / 2), 256, 0, st>>>(P.tiles, I0, NT, (int)n, d_A, lda);
+      XMCA_LAUNCHED();
+      in_tiles = false;
+    }
     P.j0 = (int)j0; P.nb = nb;
     P.bar = bars + j0 / TD_NB;
     // (only the last panel can be short, and it has no trailing block to update)
     void* args[] = {&P};
-    XMCA_CUDA(cudaLaunchCooperativeKernel((void*)sytrd_panel_kernel, dim3(grid), dim3(TD_THREADS), args, smem, st));
+    const void* fn = in_tiles ? (const void*)sytrd_panel_kernel<true> : (const void*)sytrd_panel_kernel<false>;
+    XMCA_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(TD_THREADS), args, smem, st));
     XMCA_LAUNCHED();
     const int64_t r0 = j0 + nb;
     if (r0 < n) {
-      // trailing update  A22 -= V W^T + W V^T  =  [V | W] [W | V]^T   (dsyr2k, full square kept)
-      const int64_t m = n - r0;
-      rc = xmca_gemm_ex(1, 1, m, m, TD_K2, -1.0, P.VW + r0 * TD_K2, XMCA_F64, TD_K2, P.WV + r0 * TD_K2, XMCA_F64,
-                        TD_K2, d_A + r0 * lda + r0, XMCA_F64, lda, 1, XMCA_F64, 1, nullptr, 0, XMCA_GEMM_SYMMETRIC,
-                        stream);
-      if (rc != XMCA_OK) return rc;
+      if (in_tiles) {
+        const int I0 = (int)(r0 / TD_TS), m = NT - I0;
+        syr2k_tiles_kernel<<<(unsigned)(m * (m + 1) / 2), 128, 0, st>>>(P.VW, P.WV, I0, (int)n, P.tiles);
+        XMCA_LAUNCHED();
+      } else {
+        // trailing update  A22 -= V W^T + W V^T  =  [V | W] [W | V]^T   (dsyr2k, full square kept)
+        const int64_t m = n - r0;
+        rc = xmca_gemm_ex(1, 1, m, m, TD_K2, -1.0, P.VW + r0 * TD_K2, XMCA_F64, TD_K2, P.WV + r0 * TD_K2, XMCA_F64,
+                          TD_K2, d_A + r0 * lda + r0, XMCA_F64, lda, 1, XMCA_F64, 1, nullptr, 0, XMCA_GEMM_SYMMETRIC,
+                          stream);
+        if (rc != XMCA_OK) return rc;
+      }
     }
   }
   if (getenv("XMCA_SYTRD_TRACE")) {
