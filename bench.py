@@ -63,6 +63,11 @@ def workload_string(workload):
         workload, "complex " if o["complexify"] else "", T, S1, S2, np.dtype(o["dtype"]).name, n_rot, o["power"], n_modes)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of sytrd_panel_kernel<true> (ncu --set full, n = 8192,
+# panel 9 of 128) next to the algorithmic bytes of that launch (64 columns x n'^2 x 4 B)
+SYTRD_NCU_TRAFFIC = {"traffic": None, "traffic_algorithmic_same_launch": None,
+                     "traffic_note": "see profiles/r1_ncu_summary.md"}
+
 CPU_SAMPLE_DIV = {"c2": 4, "half": 2, "small": 1, "c3": 8, "c3half": 4, "c5": 16, "c5half": 8}
 
 
@@ -309,12 +314,16 @@ def run_product(args, rank, world, local_rank):
     if "xmca_sytrd" in prof:
         v = prof["xmca_sytrd"]
         n_eig = min(T, S1, S2)
-        sbytes = n_eig ** 3 * 8.0 / 3.0          # one streaming pass over the trailing matrix per column (y = A v)
+        # every element of the symmetric trailing matrix once per Householder column (y = A v): n^3 * 8 / 6 bytes;
+        # the tile-major pass reads exactly that while the trailing matrix exceeds the L2, the L2-resident tail
+        # (n' <= 4096) reads full rows from the cache
+        sbytes = n_eig ** 3 * 8.0 / 6.0
         roof_list["xmca_sytrd"] = {"bound": "hbm", "achieved": sbytes * v["calls"] / v["ms"] / 1e6,
                                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "bytes_per_call": sbytes, "n": n_eig,
-                                   "kernel": "sytrd_panel_kernel (+ rank-128 trailing update)",
-                                   "note": "algorithmic bytes n^3*8/3 = the y = A v pass of every Householder column; "
-                                           "the time is the whole xmca_sytrd call (panel kernels + trailing updates)"}
+                                   "kernel": "sytrd_panel_kernel<tiled> (+ tiled rank-128 trailing update)",
+                                   "note": "algorithmic bytes n^3*8/6 = one triangle of the trailing matrix per Householder "
+                                           "column; the time is the whole xmca_sytrd call (panel kernels, grid barriers, "
+                                           "trailing updates, layout conversions)"}
     for name in ("xmca_gemm_ex", "xmca_gemm"):
         if name in prof:
             v = prof[name]
@@ -331,11 +340,8 @@ def run_product(args, rank, world, local_rank):
     roof.update({"kernel": roof.get("kernel", dom), "call": dom, "share_of_step": shares[dom]["share"],
                  "peak_source": peaks["source"]})
     if dom == "xmca_sytrd":
-        # one `ncu --set full` capture of sytrd_panel_kernel (profiles/r1_ncu_summary.md): launch 9 of 128 at
-        # n = 8192 read 30.34 GB + wrote 0.10 GB of DRAM for 29.9 GB of algorithmic bytes (64 columns x n'^2 x 8 B)
-        roof.update({"traffic": 30.44e9, "traffic_algorithmic_same_launch": 29.9e9,
-                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE panel launch (ncu, n=8192, "
-                                     "panel 9/128); `achieved` averages all panel launches and trailing updates of a call"})
+        # one `ncu --set full` capture of the tiled panel kernel (profiles/r1_ncu_summary.md)
+        roof.update(SYTRD_NCU_TRAFFIC)
     else:
         roof.setdefault("traffic", None)
 
