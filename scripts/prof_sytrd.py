@@ -22,3 +22,7 @@ for r in range(reps):
     t = e0.elapsed_time(e1)
     print("n=%d: sytrd %.1f ms (%.0f GB/s on n^3*8/3 algorithmic bytes), stebz %.1f ms" %
           (n, t, n ** 3 * 8 / 3 / t / 1e6, e1.elapsed_time(e2)), flush=True)
+if os.environ.get("XMCA_PROF_CHECK"):
+    ref = torch.linalg.eigvalsh(S0).flip(0)
+    print("variant %s: max |lambda - eigvalsh| / lambda_max = %.3e" %
+          (os.environ.get("XMCA_SYTRD_VARIANT", "default"), float((w - ref).abs().max() / ref.abs().max())), flush=True)

@@ -28,6 +28,7 @@ constexpr int TD_K2 = 2 * TD_NB;          // row length of the [V | W] panel buf
 constexpr int TD_PART = TD_K2 + 8;        // per-CTA reduction slots: [0] ssq, [1..128] p, [130] w.v
 constexpr int TD_MAXF = 16;               // max column split of one row in the symv
 constexpr int TD_TS = 64;                 // tile size of the tile-major trailing matrix (= panel width)
+constexpr int TD_DEFAULT_VARIANT = 3;     // see XMCA_SYTRD_VARIANT in xmca_sytrd
 constexpr int TD_TILE_MIN = 4096;         // tile-major one-triangle passes while the trailing size exceeds this
 
 struct SytrdParams {
@@ -44,6 +45,7 @@ struct SytrdParams {
   double* d; double* e; double* tau;
   unsigned long long* clk;   // [8] per-phase clock totals of CTA 0 (XMCA_SYTRD_TRACE)
   unsigned int* bar;         // arrival counter of this launch's grid barrier (zeroed by the host)
+  int slot_t;                // tiled mode: partial sums in ONE transposed array wraw[r * NT + K] (coalesced reads)
 };
 
 __device__ __forceinline__ double block_sum_1024(double v, double* red) {
@@ -108,7 +110,10 @@ __device__ __forceinline__ double warp_reduce8(double (&x)[8], int lane) {
 // reads every tile ONCE -- each tile feeds the row sums of its block row and, mirrored, the column sums of
 // its block column -- half the HBM bytes of the row-major pass, in contiguous 32 KB pieces.  Partial sums go
 // to per-tile-row / per-tile-column slots (deterministic).  P.A then only receives the reflectors.
-template <bool TILED>
+// TWO: two grid barriers per column instead of three -- v^T A v is accumulated during the streaming pass, so
+// alpha = -tau^2/2 (v^T A v - 2 (V^T v).(W^T v)) is known right after the second barrier and w is stored at once;
+// every CTA recomputes w for the first active row (the only entry the next column needs from another CTA).
+template <bool TILED, bool TWO>
 __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams P) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ double vs[];                 // current Householder vector (n doubles)
@@ -116,6 +121,7 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
   __shared__ double Vc[TD_NB], Wc[TD_NB];        // row c of V and W
   __shared__ double pv[TD_K2];                   // p1 = V^T v (first 64), p2 = W^T v (last 64)
   __shared__ double psum[8][TD_K2];
+  __shared__ double s_wfirst;                    // TWO: w of the first active row of the previous column
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = gridDim.x;
@@ -132,25 +138,44 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
     const int n1 = n - c - 1;
     // ------------------------------------------------------------ phase A: column c
     if (tid < i) {
-      if (tid == i - 1) { Vc[tid] = 1.0; Wc[tid] = P.wpre[c] + alpha2_prev; }
+      if (tid == i - 1) { Vc[tid] = 1.0; Wc[tid] = TWO ? s_wfirst : P.wpre[c] + alpha2_prev; }
       else { Vc[tid] = P.VW[(int64_t)c * TD_K2 + tid]; Wc[tid] = P.VW[(int64_t)c * TD_K2 + TD_NB + tid]; }
     }
     __syncthreads();
     double ssq = 0.0;
     {
+      // two rows per trip: all loads of both rows are in flight before the first reduction (the phase is
+      // pure latency: ~1.7 rows per warp)
       int r = c + ((gw - c % NW) + NW) % NW;      // first row >= c with r % NW == gw
-      for (; r < n; r += NW) {
-        double acc = 0.0;
-        const double* vw = P.VW + (int64_t)r * TD_K2;
-        for (int t = lane; t < i; t += 32) acc = fma(vw[t], Wc[t], fma(vw[TD_NB + t], Vc[t], acc));
-        acc = warp_sum(acc);
+      for (; r < n; r += 2 * NW) {
+        const int rb = r + NW;
+        const bool hb = rb < n;
+        double acr0 = 0.0, acr1 = 0.0;
         if (lane == 0) {
-          const double a_cr = TILED ? P.tiles[tile_off(r / TD_TS, c / TD_TS) + (int64_t)(r % TD_TS) * TD_TS + c % TD_TS]
-                                    : P.A[(int64_t)c * lda + r];
-          const double ur = a_cr - acc;
-          P.u[r] = ur;
-          if (r == c) P.d[c] = ur;
-          if (r >= c + 2) ssq = fma(ur, ur, ssq);
+          acr0 = TILED ? P.tiles[tile_off(r / TD_TS, c / TD_TS) + (int64_t)(r % TD_TS) * TD_TS + c % TD_TS]
+                       : P.A[(int64_t)c * lda + r];
+          if (hb) acr1 = TILED ? P.tiles[tile_off(rb / TD_TS, c / TD_TS) + (int64_t)(rb % TD_TS) * TD_TS + c % TD_TS]
+                               : P.A[(int64_t)c * lda + rb];
+        }
+        double acc0 = 0.0, acc1 = 0.0;
+        const double* vw0 = P.VW + (int64_t)r * TD_K2;
+        const double* vw1 = P.VW + (int64_t)(hb ? rb : r) * TD_K2;
+        for (int t = lane; t < i; t += 32) {
+          const double wc = Wc[t], vc = Vc[t];
+          acc0 = fma(vw0[t], wc, fma(vw0[TD_NB + t], vc, acc0));
+          acc1 = fma(vw1[t], wc, fma(vw1[TD_NB + t], vc, acc1));
+        }
+        acc0 = warp_sum(acc0); acc1 = warp_sum(acc1);
+        if (lane == 0) {
+          const double u0 = acr0 - acc0;
+          P.u[r] = u0;
+          if (r == c) P.d[c] = u0;
+          if (r >= c + 2) ssq = fma(u0, u0, ssq);
+          if (hb) {
+            const double u1 = acr1 - acc1;
+            P.u[rb] = u1;
+            if (rb >= c + 2) ssq = fma(u1, u1, ssq);
+          }
         }
       }
     }
@@ -178,6 +203,8 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
     __syncthreads();
 
     int F = 1;
+    double q = 0.0;                               // TWO: this thread's share of v^T (A v)
+    const int NTs = (n + TD_TS - 1) / TD_TS;
     if (TILED) {
       const int NT = (n + TD_TS - 1) / TD_TS, IB = (c + 1) / TD_TS, m = NT - IB;
       const int items = m * (m + 1) / 2;
@@ -212,12 +239,16 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
           }
           const double rsum = warp_reduce8(x8, lane);
           const int gr = TD_TS * I + rg * 8 + ((lane >> 2) & 7);
-          if (!(lane & 3) && gr > c && gr < n) P.wraw[(int64_t)J * n + gr] = rsum;
+          if (!(lane & 3) && gr > c && gr < n) {
+            if (P.slot_t) P.wraw[(int64_t)gr * NTs + J] = rsum; else P.wraw[(int64_t)J * n + gr] = rsum;
+            if (TWO) q = fma(vs[gr - c - 1], rsum, q);
+          }
         }
         if (!diag) {
           const int g0 = TD_TS * J + lane, g1 = g0 + 32;
-          if (g0 > c && g0 < n) P.cpart[(int64_t)I * n + g0] = ca0;
-          if (g1 > c && g1 < n) P.cpart[(int64_t)I * n + g1] = ca1;
+          if (g0 > c && g0 < n) { if (P.slot_t) P.wraw[(int64_t)g0 * NTs + I] = ca0; else P.cpart[(int64_t)I * n + g0] = ca0; }
+          if (g1 > c && g1 < n) { if (P.slot_t) P.wraw[(int64_t)g1 * NTs + I] = ca1; else P.cpart[(int64_t)I * n + g1] = ca1; }
+          if (TWO) q = fma(ca0, vc0, fma(ca1, vc1, q));
         }
       }
     } else {
@@ -227,8 +258,8 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
     {
       const int64_t items = (int64_t)n1 * F;
       for (int64_t item = gw; item < items; item += NW) {
-        const int rr = (int)(item / F), q = (int)(item - (int64_t)rr * F);
-        const int s0 = q * len, s1 = min(n1, s0 + len);
+        const int rr = (int)(item / F), qq = (int)(item - (int64_t)rr * F);
+        const int s0 = qq * len, s1 = min(n1, s0 + len);
         const double* row = P.A + (int64_t)(c + 1 + rr) * lda + (c + 1);
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0, a5 = 0.0, a6 = 0.0, a7 = 0.0;
         int s = s0 + lane;
@@ -244,9 +275,16 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
         }
         for (; s < s1; s += 32) a0 = fma(row[s], vs[s], a0);
         double sum = warp_sum(((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7)));
-        if (lane == 0) P.wraw[(int64_t)q * n + c + 1 + rr] = sum;
+        if (lane == 0) {
+          P.wraw[(int64_t)qq * n + c + 1 + rr] = sum;
+          if (TWO) q = fma(sum, vs[rr], q);
+        }
       }
     }
+    }
+    if (TWO) {
+      q = block_sum_1024(q, red);
+      if (tid == 0) P.part[(int64_t)blockIdx.x * TD_PART + 131] = q;
     }
     if (i > 0) {
       double pa[4] = {0.0, 0.0, 0.0, 0.0};
@@ -286,7 +324,18 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
     if (i > 0) {
       const int idx = tid & (TD_K2 - 1), gq = tid >> 7;        // 8 groups of CTAs
       double s = 0.0;
-      for (int g = gq; g < G; g += 8) s += P.part[(int64_t)g * TD_PART + 1 + idx];
+      if ((idx & (TD_NB - 1)) < i) {                           // (entries >= i of p1 / p2 are zero)
+        for (int g0 = gq; g0 < G; g0 += 8 * 20) {              // 20 independent loads in flight
+          double tmp[20];
+#pragma unroll
+          for (int k = 0; k < 20; ++k) {
+            const int g = g0 + 8 * k;
+            tmp[k] = (g < G) ? P.part[(int64_t)g * TD_PART + 1 + idx] : 0.0;
+          }
+#pragma unroll
+          for (int k = 0; k < 20; ++k) s += tmp[k];
+        }
+      }
       psum[gq][idx] = s;
       __syncthreads();
       if (tid < TD_K2) {
@@ -297,24 +346,72 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
       }
       __syncthreads();
     }
+    // w before the alpha correction for row r: this lane's share (to be summed over the warp, times tau)
+    auto row_part = [&](int r) -> double {
+      double acc = 0.0;
+      const double* vw = P.VW + (int64_t)r * TD_K2;
+      for (int t = lane; t < i; t += 32) acc = fma(vw[t], pv[TD_NB + t], fma(vw[TD_NB + t], pv[t], acc));
+      double wr = 0.0;
+      if (TILED) {
+        const int IB = (c + 1) / TD_TS, I = r / TD_TS;
+        if (P.slot_t) {
+          for (int K = IB + lane; K < NTs; K += 32) wr += P.wraw[(int64_t)r * NTs + K];         // one contiguous run
+        } else {
+          for (int J = IB + lane; J <= I; J += 32) wr += P.wraw[(int64_t)J * n + r];           // tiles (I, J <= I)
+          for (int I2 = I + 1 + lane; I2 < NTs; I2 += 32) wr += P.cpart[(int64_t)I2 * n + r];  // mirrored: tiles (I2 > I, I)
+        }
+      } else if (lane < F) wr = P.wraw[(int64_t)lane * n + r];
+      return wr - acc;
+    };
+    double alpha2;
+    if (TWO) {
+      double pp = 0.0;
+      for (int t = lane; t < i; t += 32) pp = fma(pv[t], pv[TD_NB + t], pp);
+      pp = warp_sum(pp);
+      const double vAv = grid_slot_sum(P.part, 131, G, red);
+      alpha2 = -0.5 * tau * tau * (vAv - 2.0 * pp);
+      // two rows per trip (loads of both in flight before the reductions); warp 0 of every CTA also takes
+      // the first active row, whose w the next column needs from shared memory
+      int r = c + 1 + ((gw - (c + 1) % NW) + NW) % NW;
+      bool extra = (warp == 0);
+      while (r < n || extra) {
+        int ra, rb = -1;
+        bool ea = false, eb = false;
+        if (r < n) { ra = r; r += NW; } else { ra = c + 1; ea = true; extra = false; }
+        if (r < n) { rb = r; r += NW; } else if (extra) { rb = c + 1; eb = true; extra = false; }
+        double pa0 = row_part(ra), pa1 = (rb >= 0) ? row_part(rb) : 0.0;
+        pa0 = tau * warp_sum(pa0); pa1 = tau * warp_sum(pa1);
+        if (lane == 0) {
+          const double v0 = vs[ra - c - 1], w0 = fma(alpha2, v0, pa0);
+          if (ea) s_wfirst = w0;
+          else {
+            P.VW[(int64_t)ra * TD_K2 + i] = v0;        P.VW[(int64_t)ra * TD_K2 + TD_NB + i] = w0;
+            P.WV[(int64_t)ra * TD_K2 + i] = w0;        P.WV[(int64_t)ra * TD_K2 + TD_NB + i] = v0;
+          }
+          if (rb >= 0) {
+            const double v1 = vs[rb - c - 1], w1 = fma(alpha2, v1, pa1);
+            if (eb) s_wfirst = w1;
+            else {
+              P.VW[(int64_t)rb * TD_K2 + i] = v1;      P.VW[(int64_t)rb * TD_K2 + TD_NB + i] = w1;
+              P.WV[(int64_t)rb * TD_K2 + i] = w1;      P.WV[(int64_t)rb * TD_K2 + TD_NB + i] = v1;
+            }
+          }
+        }
+      }
+      { long long c1 = clock64(); tk[3] += c1 - c0; c0 = c1; }
+    } else {
     double dotacc = 0.0;
     {
       int r = c + 1 + ((gw - (c + 1) % NW) + NW) % NW;
-      for (; r < n; r += NW) {
-        double acc = 0.0;
-        const double* vw = P.VW + (int64_t)r * TD_K2;
-        for (int t = lane; t < i; t += 32) acc = fma(vw[t], pv[TD_NB + t], fma(vw[TD_NB + t], pv[t], acc));
-        double wr = 0.0;
-        if (TILED) {
-          const int NT = (n + TD_TS - 1) / TD_TS, IB = (c + 1) / TD_TS, I = r / TD_TS;
-          for (int J = IB + lane; J <= I; J += 32) wr += P.wraw[(int64_t)J * n + r];           // tiles (I, J <= I)
-          for (int I2 = I + 1 + lane; I2 < NT; I2 += 32) wr += P.cpart[(int64_t)I2 * n + r];   // mirrored: tiles (I2 > I, I)
-        } else if (lane < F) wr = P.wraw[(int64_t)lane * n + r];
-        const double tot = warp_sum(wr - acc);
+      for (; r < n; r += 2 * NW) {
+        const int rb = r + NW;
+        const bool hb = rb < n;
+        double p0 = row_part(r), p1 = hb ? row_part(rb) : 0.0;
+        p0 = tau * warp_sum(p0); p1 = tau * warp_sum(p1);
         if (lane == 0) {
-          const double wp = tau * tot;
-          P.wpre[r] = wp;
-          dotacc = fma(wp, vs[r - c - 1], dotacc);
+          P.wpre[r] = p0;
+          dotacc = fma(p0, vs[r - c - 1], dotacc);
+          if (hb) { P.wpre[rb] = p1; dotacc = fma(p1, vs[rb - c - 1], dotacc); }
         }
       }
     }
@@ -326,7 +423,7 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
 
     // ------------------------------------------------------------ phase D: finish w, store panel column i
     const double dot = grid_slot_sum(P.part, 130, G, red);
-    const double alpha2 = -0.5 * tau * dot;
+    alpha2 = -0.5 * tau * dot;
     {
       int r = c + 1 + ((gw - (c + 1) % NW) + NW) % NW;
       for (; r < n; r += NW) {
@@ -337,6 +434,7 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
           P.WV[(int64_t)r * TD_K2 + i] = w;          P.WV[(int64_t)r * TD_K2 + TD_NB + i] = v;
         }
       }
+    }
     }
     alpha2_prev = alpha2;
     __syncwarp();
@@ -770,9 +868,11 @@ ormtr_kernel(int n, const double* __restrict__ A, int64_t lda, const double* __r
 
 static int sytrd_grid(size_t smem, int* grid_out) {
   int occ = 0;
-  XMCA_CUDA(cudaFuncSetAttribute(sytrd_panel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  XMCA_CUDA(cudaFuncSetAttribute(sytrd_panel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  XMCA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sytrd_panel_kernel<true>, TD_THREADS, smem));
+  XMCA_CUDA(cudaFuncSetAttribute(sytrd_panel_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  XMCA_CUDA(cudaFuncSetAttribute(sytrd_panel_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  XMCA_CUDA(cudaFuncSetAttribute(sytrd_panel_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  XMCA_CUDA(cudaFuncSetAttribute(sytrd_panel_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  XMCA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sytrd_panel_kernel<true, true>, TD_THREADS, smem));
   if (occ < 1) return fail(XMCA_CUDA_ERROR, "sytrd panel kernel does not fit on an SM", __FILE__, __LINE__);
   *grid_out = sm_count();
   return XMCA_OK;
@@ -846,6 +946,11 @@ extern "C" int xmca_sytrd(int64_t n, double* d_A, int64_t lda, double* d_d, doub
   P.d = d_d; P.e = d_e; P.tau = d_tau;
   XMCA_CUDA(cudaMemsetAsync(d_tau, 0, (size_t)n * 8, st));
 
+  // XMCA_SYTRD_VARIANT (bit mask, for A/B measurements): 1 = two barriers per column, 2 = transposed slot array
+  const char* var_env = getenv("XMCA_SYTRD_VARIANT");
+  const int variant = var_env ? atoi(var_env) : TD_DEFAULT_VARIANT;
+  const bool two = variant & 1;
+  P.slot_t = (variant & 2) ? 1 : 0;
   bool in_tiles = false;
   if (tiled_mode) {
     to_tiles_kernel<<<(unsigned)(NT * (NT + 1) / 2), 256, 0, st>>>(d_A, lda, (int)n, NT, P.tiles);
@@ -865,7 +970,8 @@ extern "C" int xmca_sytrd(int64_t n, double* d_A, int64_t lda, double* d_d, doub
     P.bar = bars + j0 / TD_NB;
     // (only the last panel can be short, and it has no trailing block to update)
     void* args[] = {&P};
-    const void* fn = in_tiles ? (const void*)sytrd_panel_kernel<true> : (const void*)sytrd_panel_kernel<false>;
+    const void* fn = two ? (in_tiles ? (const void*)sytrd_panel_kernel<true, true> : (const void*)sytrd_panel_kernel<false, true>)
+                         : (in_tiles ? (const void*)sytrd_panel_kernel<true, false> : (const void*)sytrd_panel_kernel<false, false>);
     XMCA_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(TD_THREADS), args, smem, st));
     XMCA_LAUNCHED();
     const int64_t r0 = j0 + nb;
