@@ -28,7 +28,7 @@ constexpr int TD_K2 = 2 * TD_NB;          // row length of the [V | W] panel buf
 constexpr int TD_PART = TD_K2 + 8;        // per-CTA reduction slots: [0] ssq, [1..128] p, [130] w.v
 constexpr int TD_MAXF = 16;               // max column split of one row in the symv
 constexpr int TD_TS = 64;                 // tile size of the tile-major trailing matrix (= panel width)
-constexpr int TD_DEFAULT_VARIANT = 3;     // see XMCA_SYTRD_VARIANT in xmca_sytrd
+constexpr int TD_DEFAULT_VARIANT = 7;     // see XMCA_SYTRD_VARIANT in xmca_sytrd
 constexpr int TD_TILE_MIN = 4096;         // tile-major one-triangle passes while the trailing size exceeds this
 
 struct SytrdParams {
@@ -46,6 +46,7 @@ struct SytrdParams {
   unsigned long long* clk;   // [8] per-phase clock totals of CTA 0 (XMCA_SYTRD_TRACE)
   unsigned int* bar;         // arrival counter of this launch's grid barrier (zeroed by the host)
   int slot_t;                // tiled mode: partial sums in ONE transposed array wraw[r * NT + K] (coalesced reads)
+  int bar_ra;                // grid barrier by red.release / ld.acquire instead of fence + atomic + fence
 };
 
 __device__ __forceinline__ double block_sum_1024(double v, double* red) {
@@ -69,14 +70,23 @@ __device__ __forceinline__ double grid_slot_sum(const double* part, int slot, in
 // Grid-wide barrier for the co-resident CTAs of a cooperative launch: one monotonically increasing
 // arrival counter per launch, release/acquire through __threadfence; about half the latency of
 // cooperative_groups' grid.sync(), which is paid three times per column.
-__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& epoch) {
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& epoch, int release_acquire = 0) {
   __syncthreads();
   if (threadIdx.x == 0) {
     epoch += gridDim.x;
-    __threadfence();
-    atomicAdd(counter, 1u);
-    while (*((volatile unsigned int*)counter) < epoch) { }
-    __threadfence();
+    if (release_acquire) {
+      // the CTA barrier above orders the other threads' writes before this release (cumulativity)
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+      unsigned int seen;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+      } while (seen < epoch);
+    } else {
+      __threadfence();
+      atomicAdd(counter, 1u);
+      while (*((volatile unsigned int*)counter) < epoch) { }
+      __threadfence();
+    }
   }
   __syncthreads();
 }
@@ -120,7 +130,7 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
   __shared__ double red[32];
   __shared__ double Vc[TD_NB], Wc[TD_NB];        // row c of V and W
   __shared__ double pv[TD_K2];                   // p1 = V^T v (first 64), p2 = W^T v (last 64)
-  __shared__ double psum[8][TD_K2];
+  __shared__ double psum[16][TD_K2];
   __shared__ double s_wfirst;                    // TWO: w of the first active row of the previous column
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -183,12 +193,19 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
     ssq = block_sum_1024(ssq, red);
     if (tid == 0) P.part[(int64_t)blockIdx.x * TD_PART] = ssq;
     { long long c1 = clock64(); tk[0] += c1 - c0; c0 = c1; }
-    grid_barrier(P.bar, epoch);                   // #1
+    grid_barrier(P.bar, epoch, P.bar_ra);                   // #1
     { long long c1 = clock64(); tk[1] += c1 - c0; c0 = c1; }
 
     // ------------------------------------------------------------ phase B: reflector, A v
-    const double xnorm2 = grid_slot_sum(P.part, 0, G, red);
+    // (the loads of u are issued before the norm reduction, whose latency they then share)
+    double ureg[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int j = tid + TD_THREADS * k;
+      ureg[k] = (j < n1) ? P.u[c + 1 + j] : 0.0;
+    }
     const double alpha = P.u[c + 1];
+    const double xnorm2 = grid_slot_sum(P.part, 0, G, red);
     double beta, tau, scale;
     if (xnorm2 == 0.0) { beta = alpha; tau = 0.0; scale = 0.0; }
     else {
@@ -196,11 +213,16 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
       tau = (beta - alpha) / beta;
       scale = 1.0 / (alpha - beta);
     }
-    for (int j = tid; j < n1; j += TD_THREADS) vs[j] = (j == 0) ? 1.0 : P.u[c + 1 + j] * scale;
-    for (int j = blockIdx.x * TD_THREADS + tid; j < n1; j += G * TD_THREADS)
-      P.A[(int64_t)c * lda + c + 1 + j] = (j == 0) ? 1.0 : P.u[c + 1 + j] * scale;     // reflector storage
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int j = tid + TD_THREADS * k;
+      if (j < n1) vs[j] = (j == 0) ? 1.0 : ureg[k] * scale;
+    }
+    for (int j = tid + 8 * TD_THREADS; j < n1; j += TD_THREADS) vs[j] = P.u[c + 1 + j] * scale;
     if (blockIdx.x == 0 && tid == 0) { P.e[c] = beta; P.tau[c] = tau; }
     __syncthreads();
+    for (int j = blockIdx.x * TD_THREADS + tid; j < n1; j += G * TD_THREADS)
+      P.A[(int64_t)c * lda + c + 1 + j] = vs[j];                                       // reflector storage
 
     int F = 1;
     double q = 0.0;                               // TWO: this thread's share of v^T (A v)
@@ -282,49 +304,58 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
       }
     }
     }
-    if (TWO) {
-      q = block_sum_1024(q, red);
-      if (tid == 0) P.part[(int64_t)blockIdx.x * TD_PART + 131] = q;
-    }
-    if (i > 0) {
+    if (i > 0 || TWO) {
       double pa[4] = {0.0, 0.0, 0.0, 0.0};
       int r = c + 1 + ((gw - (c + 1) % NW) + NW) % NW;
-      for (; r < n; r += NW) {
-        const double vr = vs[r - c - 1];
-        const double* vw = P.VW + (int64_t)r * TD_K2;
+      for (; r < n; r += 2 * NW) {                 // two rows per trip (8 independent loads)
+        const int rb = r + NW;
+        const bool hb = rb < n;
+        const double vr0 = vs[r - c - 1], vr1 = hb ? vs[rb - c - 1] : 0.0;
+        const double* vw0 = P.VW + (int64_t)r * TD_K2;
+        const double* vw1 = P.VW + (int64_t)(hb ? rb : r) * TD_K2;
+        double x0[4], x1[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int idx = lane + 32 * k;
-          if ((idx & (TD_NB - 1)) < i) pa[k] = fma(vw[idx], vr, pa[k]);
+          const bool on = (idx & (TD_NB - 1)) < i;
+          x0[k] = on ? vw0[idx] : 0.0;
+          x1[k] = on ? vw1[idx] : 0.0;
         }
-      }
-      // CTA reduction of the 32 per-warp partial vectors, 8 warps at a time
-      for (int pass = 0; pass < 4; ++pass) {
-        __syncthreads();
-        if ((warp >> 3) == pass) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) psum[warp & 7][lane + 32 * k] = pa[k];
+        for (int k = 0; k < 4; ++k) pa[k] = fma(x0[k], vr0, fma(x1[k], vr1, pa[k]));
+      }
+      if (TWO) {
+        // v^T A v rides in entry 127 of the p vector (p2[63], always zero: a panel has at most 63 earlier columns)
+        q = warp_sum(q);
+        if (lane == 31) pa[3] = q;
+      }
+      // CTA reduction of the 32 per-warp partial vectors, 16 warps at a time
+      for (int pass = 0; pass < 2; ++pass) {
+        __syncthreads();
+        if ((warp >> 4) == pass) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) psum[warp & 15][lane + 32 * k] = pa[k];
         }
         __syncthreads();
         if (tid < TD_K2) {
-          double s = 0.0;
+          double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-          for (int w = 0; w < 8; ++w) s += psum[w][tid];
-          pv[tid] = (pass == 0 ? 0.0 : pv[tid]) + s;
+          for (int w = 0; w < 8; ++w) { s0 += psum[w][tid]; s1 += psum[w + 8][tid]; }
+          pv[tid] = (pass == 0 ? 0.0 : pv[tid]) + (s0 + s1);
         }
       }
       __syncthreads();
       if (tid < TD_K2) P.part[(int64_t)blockIdx.x * TD_PART + 1 + tid] = pv[tid];
     }
     { long long c1 = clock64(); tk[2] += c1 - c0; c0 = c1; }
-    grid_barrier(P.bar, epoch);                   // #2
+    grid_barrier(P.bar, epoch, P.bar_ra);                   // #2
     { long long c1 = clock64(); tk[1] += c1 - c0; c0 = c1; }
 
     // ------------------------------------------------------------ phase C: w (before the alpha correction)
-    if (i > 0) {
+    if (i > 0 || TWO) {
       const int idx = tid & (TD_K2 - 1), gq = tid >> 7;        // 8 groups of CTAs
       double s = 0.0;
-      if ((idx & (TD_NB - 1)) < i) {                           // (entries >= i of p1 / p2 are zero)
+      if ((idx & (TD_NB - 1)) < i || (TWO && idx == TD_K2 - 1)) {   // (entries >= i of p1 / p2 are zero)
         for (int g0 = gq; g0 < G; g0 += 8 * 20) {              // 20 independent loads in flight
           double tmp[20];
 #pragma unroll
@@ -368,7 +399,7 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
       double pp = 0.0;
       for (int t = lane; t < i; t += 32) pp = fma(pv[t], pv[TD_NB + t], pp);
       pp = warp_sum(pp);
-      const double vAv = grid_slot_sum(P.part, 131, G, red);
+      const double vAv = pv[TD_K2 - 1];
       alpha2 = -0.5 * tau * tau * (vAv - 2.0 * pp);
       // two rows per trip (loads of both in flight before the reductions); warp 0 of every CTA also takes
       // the first active row, whose w the next column needs from shared memory
@@ -418,7 +449,7 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
     dotacc = block_sum_1024(dotacc, red);
     if (tid == 0) P.part[(int64_t)blockIdx.x * TD_PART + 130] = dotacc;
     { long long c1 = clock64(); tk[3] += c1 - c0; c0 = c1; }
-    grid_barrier(P.bar, epoch);                   // #3
+    grid_barrier(P.bar, epoch, P.bar_ra);                   // #3
     { long long c1 = clock64(); tk[1] += c1 - c0; c0 = c1; }
 
     // ------------------------------------------------------------ phase D: finish w, store panel column i
@@ -946,11 +977,13 @@ extern "C" int xmca_sytrd(int64_t n, double* d_A, int64_t lda, double* d_d, doub
   P.d = d_d; P.e = d_e; P.tau = d_tau;
   XMCA_CUDA(cudaMemsetAsync(d_tau, 0, (size_t)n * 8, st));
 
-  // XMCA_SYTRD_VARIANT (bit mask, for A/B measurements): 1 = two barriers per column, 2 = transposed slot array
+  // XMCA_SYTRD_VARIANT (bit mask, for A/B measurements): 1 = two barriers per column, 2 = transposed slot array,
+  // 4 = release/acquire grid barrier
   const char* var_env = getenv("XMCA_SYTRD_VARIANT");
   const int variant = var_env ? atoi(var_env) : TD_DEFAULT_VARIANT;
   const bool two = variant & 1;
   P.slot_t = (variant & 2) ? 1 : 0;
+  P.bar_ra = (variant & 4) ? 1 : 0;
   bool in_tiles = false;
   if (tiled_mode) {
     to_tiles_kernel<<<(unsigned)(NT * (NT + 1) / 2), 256, 0, st>>>(d_A, lda, (int)n, NT, P.tiles);
