@@ -1,9 +1,7 @@
-# A/B timing of the xmca_sytrd variants (XMCA_SYTRD_VARIANT bit mask: 1 = two barriers per column, 2 = transposed slots,
-# 4 = release/acquire grid barrier)
+# A/B timing of xmca_sytrd tuning knobs: XMCA_SYTRD_TILE_MIN (tile-major while the trailing size exceeds it),
+# XMCA_SYTRD_KEEP_MB (plain instead of evict-first loads once the trailing matrix is at most this large)
 set -x
-for v in 7 0; do
-  XMCA_SYTRD_VARIANT=$v XMCA_PROF_CHECK=1 XMCA_SYTRD_TRACE=1 timeout 300 python scripts/prof_sytrd.py 8192 3 2>&1 | tail -5
+for cfg in "4096 0" "4096 88" "2048 88" "1024 88" "2048 0" "512 88" "1024 110"; do
+  set -- $cfg
+  XMCA_SYTRD_TILE_MIN=$1 XMCA_SYTRD_KEEP_MB=$2 XMCA_PROF_CHECK=1 timeout 300 python scripts/prof_sytrd.py 8192 3 2>&1 | tail -2
 done
-XMCA_PROF_CHECK=1 timeout 300 python scripts/prof_sytrd.py 16384 2 2>&1 | tail -3
-XMCA_PROF_CHECK=1 timeout 300 python scripts/prof_sytrd.py 3000 2 2>&1 | tail -3
-XMCA_PROF_CHECK=1 timeout 300 python scripts/prof_sytrd.py 25000 1 2>&1 | tail -3

@@ -29,6 +29,7 @@ constexpr int TD_PART = TD_K2 + 8;        // per-CTA reduction slots: [0] ssq, [
 constexpr int TD_MAXF = 16;               // max column split of one row in the symv
 constexpr int TD_TS = 64;                 // tile size of the tile-major trailing matrix (= panel width)
 constexpr int TD_DEFAULT_VARIANT = 7;     // see XMCA_SYTRD_VARIANT in xmca_sytrd
+constexpr double TD_KEEP_MB = 88.0;       // trailing matrices up to this size are kept L2-resident (plain loads)
 constexpr int TD_TILE_MIN = 4096;         // tile-major one-triangle passes while the trailing size exceeds this
 
 struct SytrdParams {
@@ -47,7 +48,12 @@ struct SytrdParams {
   unsigned int* bar;         // arrival counter of this launch's grid barrier (zeroed by the host)
   int slot_t;                // tiled mode: partial sums in ONE transposed array wraw[r * NT + K] (coalesced reads)
   int bar_ra;                // grid barrier by red.release / ld.acquire instead of fence + atomic + fence
+  int keep_l2;               // trailing matrix fits the L2: plain loads (stay resident) instead of evict-first
 };
+
+// streaming load of the trailing matrix: evict-first while it is larger than the L2 (it is read once per column
+// and must not push the panel buffers / partial vectors out), plain once it fits
+__device__ __forceinline__ double ld_trail(const double* p, int keep) { return keep ? *p : __ldcs(p); }
 
 __device__ __forceinline__ double block_sum_1024(double v, double* red) {
   // all threads get the sum; red: 32 doubles of shared memory
@@ -140,7 +146,7 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
   const int64_t lda = P.lda;
   double alpha2_prev = 0.0;
   unsigned int epoch = 0;
-  long long tk[5] = {0, 0, 0, 0, 0};
+  long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // [5] reflector set-up, [6] streaming pass, both also inside [2]
 
   for (int i = 0; i < P.nb; ++i) {
     long long c0 = clock64();
@@ -223,6 +229,8 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
     __syncthreads();
     for (int j = blockIdx.x * TD_THREADS + tid; j < n1; j += G * TD_THREADS)
       P.A[(int64_t)c * lda + c + 1 + j] = vs[j];                                       // reflector storage
+    long long cb = clock64();
+    tk[5] += cb - c0;
 
     int F = 1;
     double q = 0.0;                               // TWO: this thread's share of v^T (A v)
@@ -246,8 +254,8 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
           double a0[8], a1[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            a0[k] = __ldcs(tp + (rg * 8 + k) * TD_TS);
-            a1[k] = __ldcs(tp + (rg * 8 + k) * TD_TS + 32);
+            a0[k] = ld_trail(tp + (rg * 8 + k) * TD_TS, P.keep_l2);
+            a1[k] = ld_trail(tp + (rg * 8 + k) * TD_TS + 32, P.keep_l2);
           }
           double x8[8];
 #pragma unroll
@@ -288,8 +296,9 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
         for (; s + 224 < s1; s += 256) {
           // streaming loads (evict-first): the trailing matrix is read once per column and must not
           // push the panel buffers / partial vectors out of the caches
-          const double x0 = __ldcs(row + s), x1 = __ldcs(row + s + 32), x2 = __ldcs(row + s + 64), x3 = __ldcs(row + s + 96);
-          const double x4 = __ldcs(row + s + 128), x5 = __ldcs(row + s + 160), x6 = __ldcs(row + s + 192), x7 = __ldcs(row + s + 224);
+          const int kp = P.keep_l2;
+          const double x0 = ld_trail(row + s, kp), x1 = ld_trail(row + s + 32, kp), x2 = ld_trail(row + s + 64, kp), x3 = ld_trail(row + s + 96, kp);
+          const double x4 = ld_trail(row + s + 128, kp), x5 = ld_trail(row + s + 160, kp), x6 = ld_trail(row + s + 192, kp), x7 = ld_trail(row + s + 224, kp);
           a0 = fma(x0, vs[s], a0);       a1 = fma(x1, vs[s + 32], a1);
           a2 = fma(x2, vs[s + 64], a2);  a3 = fma(x3, vs[s + 96], a3);
           a4 = fma(x4, vs[s + 128], a4); a5 = fma(x5, vs[s + 160], a5);
@@ -304,6 +313,7 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
       }
     }
     }
+    { const long long cb2 = clock64(); tk[6] += cb2 - cb; }
     if (i > 0 || TWO) {
       double pa[4] = {0.0, 0.0, 0.0, 0.0};
       int r = c + 1 + ((gw - (c + 1) % NW) + NW) % NW;
@@ -473,7 +483,7 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
     { long long c1 = clock64(); tk[4] += c1 - c0; c0 = c1; }
   }
   if (blockIdx.x == 0 && tid == 0 && P.clk)
-    for (int q = 0; q < 5; ++q) P.clk[q] += (unsigned long long)tk[q];
+    for (int q = 0; q < 8; ++q) P.clk[q] += (unsigned long long)tk[q];
 }
 
 // ------------------------------------------------------------------ tile-major helpers
@@ -918,9 +928,14 @@ using namespace xmca;
 extern "C" int64_t xmca_sytrd_max_n(void) { return 26000; }
 
 // tile-major mode is used for the leading panels of large problems (trailing size > TD_TILE_MIN)
+static int64_t sytrd_tile_min() {
+  static const char* e = getenv("XMCA_SYTRD_TILE_MIN");      // (tuning knob)
+  static const int64_t v = e ? atoll(e) / TD_TS * TD_TS : TD_TILE_MIN;
+  return v < 2 * TD_TS ? 2 * TD_TS : v;
+}
 static bool sytrd_tiled(int64_t n) {
   static const bool off = getenv("XMCA_SYTRD_NO_TILES") != nullptr;
-  return !off && n >= TD_TILE_MIN + 8 * TD_TS;
+  return !off && n >= sytrd_tile_min() + 8 * TD_TS;
 }
 static int64_t sytrd_nt(int64_t n) { return (n + TD_TS - 1) / TD_TS; }
 static size_t sytrd_wraw_slots(int64_t n) { return sytrd_tiled(n) ? (size_t)(sytrd_nt(n) > TD_MAXF ? sytrd_nt(n) : TD_MAXF) : TD_MAXF; }
@@ -992,7 +1007,7 @@ extern "C" int xmca_sytrd(int64_t n, double* d_A, int64_t lda, double* d_d, doub
   }
   for (int64_t j0 = 0; j0 < n; j0 += TD_NB) {
     const int nb = (int)((n - j0 < TD_NB) ? (n - j0) : TD_NB);
-    if (in_tiles && n - j0 <= TD_TILE_MIN) {
+    if (in_tiles && n - j0 <= sytrd_tile_min()) {
       // the trailing matrix now fits the L2: back to the row-major layout (both triangles) for the rest
       const int I0 = (int)(j0 / TD_TS), m = NT - I0;
       from_tiles_kernel<<<(unsigned)(m * (m + 1) / 2), 256, 0, st>>>(P.tiles, I0, NT, (int)n, d_A, lda);
@@ -1001,6 +1016,11 @@ extern "C" int xmca_sytrd(int64_t n, double* d_A, int64_t lda, double* d_d, doub
     }
     P.j0 = (int)j0; P.nb = nb;
     P.bar = bars + j0 / TD_NB;
+    {
+      const double m = (double)(n - j0), bytes = in_tiles ? m * m * 4.0 : m * m * 8.0;
+      static const char* ke = getenv("XMCA_SYTRD_KEEP_MB");  // (tuning knob)
+      P.keep_l2 = bytes <= (ke ? atof(ke) : TD_KEEP_MB) * 1e6;
+    }
     // (only the last panel can be short, and it has no trailing block to update)
     void* args[] = {&P};
     const void* fn = two ? (in_tiles ? (const void*)sytrd_panel_kernel<true, true> : (const void*)sytrd_panel_kernel<false, true>)
@@ -1024,11 +1044,11 @@ extern "C" int xmca_sytrd(int64_t n, double* d_A, int64_t lda, double* d_d, doub
     }
   }
   if (getenv("XMCA_SYTRD_TRACE")) {
-    unsigned long long h[5];
+    unsigned long long h[8];
     XMCA_CUDA(cudaMemcpyAsync(h, P.clk, sizeof h, cudaMemcpyDeviceToHost, st));
     XMCA_CUDA(cudaStreamSynchronize(st));
-    fprintf(stderr, "[xmca sytrd] n=%lld clocks (CTA 0): column update %.3e | grid syncs %.3e | reflector+symv+p %.3e | w %.3e | store %.3e\n",
-            (long long)n, (double)h[0], (double)h[1], (double)h[2], (double)h[3], (double)h[4]);
+    fprintf(stderr, "[xmca sytrd] n=%lld clocks (CTA 0): column update %.3e | grid syncs %.3e | reflector+symv+p %.3e | w %.3e | store %.3e || inside symv: set-up %.3e, streaming %.3e\n",
+            (long long)n, (double)h[0], (double)h[1], (double)h[2], (double)h[3], (double)h[4], (double)h[5], (double)h[6]);
   }
   return XMCA_OK;
 }
