@@ -145,6 +145,11 @@ int xmca_trsm_lt(int64_t n, int64_t nrhs, const double* d_L, int64_t ldl, const 
  *   destroyed; on return d_d (n) / d_e (n-1) hold the tridiagonal, row c of d_A
  *   (columns c+1..n-1) holds Householder vector c (leading 1 stored) and d_tau
  *   (n) its scalar:  Q = H(0) H(1) ... H(n-2),  H(c) = I - tau_c v_c v_c^T.
+ * xmca_sytrd_batched: batch = 1 or 2 problems of the same size n in ONE sequence of launches, each on half
+ *   of the SMs with its own grid barrier: while one streams its trailing matrix the other is in its
+ *   latency-bound phases (column update, reflector, reductions).  This is what the independent surrogate
+ *   runs of rule_n (array.py:1753-1765) use.  Problem 1 lives stride_a doubles behind d_A and stride_v
+ *   doubles behind d_d / d_e / d_tau; d_workspace: batch * xmca_sytrd_workspace_bytes(n).
  * xmca_stebz: all n eigenvalues, DESCENDING, into d_w (d_scratch: n + 8 doubles).
  *   Synchronises `stream` once (Gershgorin bounds come back to the host).
  * xmca_stein: eigenvectors of the tridiagonal for the k eigenvalues d_lambda
@@ -157,6 +162,9 @@ int64_t xmca_sytrd_max_n(void);
 size_t xmca_sytrd_workspace_bytes(int64_t n);
 int xmca_sytrd(int64_t n, double* d_A, int64_t lda, double* d_d, double* d_e, double* d_tau,
                void* d_workspace, size_t workspace_bytes, void* stream);
+int xmca_sytrd_batched(int64_t n, int batch, double* d_A, int64_t lda, int64_t stride_a, double* d_d,
+                       double* d_e, double* d_tau, int64_t stride_v, void* d_workspace,
+                       size_t workspace_bytes, void* stream);
 int xmca_stebz(int64_t n, const double* d_d, const double* d_e, double* d_w, double* d_scratch,
                void* stream);
 size_t xmca_stein_workspace_bytes(int64_t n, int64_t n_clusters);

@@ -1,7 +1,5 @@
-# A/B timing of xmca_sytrd tuning knobs: XMCA_SYTRD_TILE_MIN (tile-major while the trailing size exceeds it),
-# XMCA_SYTRD_KEEP_MB (plain instead of evict-first loads once the trailing matrix is at most this large)
+# A/B timing of the batched tridiagonalisation: phase offset between the two groups (clocks)
 set -x
-for cfg in "4096 0" "4096 88" "2048 88" "1024 88" "2048 0" "512 88" "1024 110"; do
-  set -- $cfg
-  XMCA_SYTRD_TILE_MIN=$1 XMCA_SYTRD_KEEP_MB=$2 XMCA_PROF_CHECK=1 timeout 300 python scripts/prof_sytrd.py 8192 3 2>&1 | tail -2
+for dl in 0 15000 30000 45000 60000; do
+  XMCA_SYTRD_BATCH_DELAY=$dl XMCA_PROF_PAIR=1 timeout 300 python scripts/prof_sytrd.py 8192 2 2>&1 | tail -1
 done

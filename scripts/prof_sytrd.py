@@ -26,3 +26,17 @@ if os.environ.get("XMCA_PROF_CHECK"):
     ref = torch.linalg.eigvalsh(S0).flip(0)
     print("variant %s: max |lambda - eigvalsh| / lambda_max = %.3e" %
           (os.environ.get("XMCA_SYTRD_VARIANT", "default"), float((w - ref).abs().max() / ref.abs().max())), flush=True)
+if os.environ.get("XMCA_PROF_PAIR"):
+    # two problems per batched call against two single calls
+    for r in range(reps):
+        Sp = torch.stack([S0, S0.flip(0).flip(1).contiguous()]).contiguous()
+        torch.cuda.synchronize()
+        e0, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(2))
+        e0.record()
+        d2, e2_, tau2 = D.sytrd_pair(Sp)
+        e1.record()
+        torch.cuda.synchronize()
+        t2 = e0.elapsed_time(e1)
+        w2 = D.stebz(d2[0], e2_[0, :n - 1])
+        print("n=%d: batched pair %.1f ms = %.1f ms per problem (single: %.1f ms); max |lambda_pair - lambda_single| / lambda_max = %.2e"
+              % (n, t2, t2 / 2, t, float((w2 - w).abs().max() / w.abs().max())), flush=True)

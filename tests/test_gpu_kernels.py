@@ -206,6 +206,33 @@ def test_tridiagonal_eigensolver(D, n):
     np.testing.assert_allclose(S @ X, X * w[:m], atol=1e-10 * ref[0])
 
 
+@pytest.mark.parametrize("n", [130, 1500, 4700])
+def test_batched_tridiagonalisation(D, n):
+    """xmca_sytrd_batched (two problems, half of the SMs each) against the single-problem call and numpy."""
+    r = _rng(n + 1)
+    mats = []
+    for k in range(2):
+        Q, _ = np.linalg.qr(r.standard_normal((n, n)))
+        lam = np.sort(r.uniform(0.5, 2.0, n) * np.logspace(0, -3 - k, n))[::-1]
+        S = (Q * lam) @ Q.T
+        mats.append(0.5 * (S + S.T))
+    Sp = D.to_device(np.stack(mats))
+    d, e, tau = D.sytrd_pair(Sp)
+    for k in range(2):
+        ref = np.linalg.eigvalsh(mats[k])[::-1]
+        w = D.to_host(D.stebz(d[k], e[k, :n - 1]))
+        np.testing.assert_allclose(w, ref, atol=5e-14 * n * ref[0])
+        d1, e1, _ = D.sytrd(D.to_device(mats[k]))
+        w1 = D.to_host(D.stebz(d1, e1))
+        np.testing.assert_allclose(w, w1, atol=2e-14 * n * ref[0])
+        # reflectors of the batched call reproduce eigenvectors of the ORIGINAL matrix
+        m = 6
+        starts = np.arange(m + 1)
+        Z = D.stein(d[k], e[k, :n - 1], w[:m], starts, w[0])
+        X = D.to_host(D.ormtr(Sp[k], tau[k], Z)).T
+        np.testing.assert_allclose(mats[k] @ X, X * w[:m], atol=1e-10 * ref[0])
+
+
 def test_gemm_structure_flags(D):
     """Symmetric-result and triangular-operand shortcuts give the same numbers as the plain product."""
     r = _rng(5)

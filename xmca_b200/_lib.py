@@ -84,6 +84,7 @@ def load():
     lib.xmca_sytrd_workspace_bytes.restype = sz
     lib.xmca_sytrd_workspace_bytes.argtypes = [i64]
     lib.xmca_sytrd.argtypes = [i64, vp, i64, vp, vp, vp, vp, sz, vp]
+    lib.xmca_sytrd_batched.argtypes = [i64, i32, vp, i64, i64, vp, vp, vp, i64, vp, sz, vp]
     lib.xmca_stebz.argtypes = [i64, vp, vp, vp, vp, vp]
     lib.xmca_stein_workspace_bytes.restype = sz
     lib.xmca_stein_workspace_bytes.argtypes = [i64, i64]

@@ -49,6 +49,7 @@ struct SytrdParams {
   int slot_t;                // tiled mode: partial sums in ONE transposed array wraw[r * NT + K] (coalesced reads)
   int bar_ra;                // grid barrier by red.release / ld.acquire instead of fence + atomic + fence
   int keep_l2;               // trailing matrix fits the L2: plain loads (stay resident) instead of evict-first
+  int64_t bs_a, bs_v, bs_ws; // batched launch: distance of problem 1 behind problem 0 (doubles, doubles, BYTES)
 };
 
 // streaming load of the trailing matrix: evict-first while it is larger than the L2 (it is read once per column
@@ -76,10 +77,10 @@ __device__ __forceinline__ double grid_slot_sum(const double* part, int slot, in
 // Grid-wide barrier for the co-resident CTAs of a cooperative launch: one monotonically increasing
 // arrival counter per launch, release/acquire through __threadfence; about half the latency of
 // cooperative_groups' grid.sync(), which is paid three times per column.
-__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& epoch, int release_acquire = 0) {
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& epoch, int release_acquire, int nctas) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    epoch += gridDim.x;
+    epoch += (unsigned)nctas;
     if (release_acquire) {
       // the CTA barrier above orders the other threads' writes before this release (cumulativity)
       asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
@@ -129,7 +130,7 @@ __device__ __forceinline__ double warp_reduce8(double (&x)[8], int lane) {
 // TWO: two grid barriers per column instead of three -- v^T A v is accumulated during the streaming pass, so
 // alpha = -tau^2/2 (v^T A v - 2 (V^T v).(W^T v)) is known right after the second barrier and w is stored at once;
 // every CTA recomputes w for the first active row (the only entry the next column needs from another CTA).
-template <bool TILED, bool TWO>
+template <bool TILED, bool TWO, bool BATCH>
 __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams P) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ double vs[];                 // current Householder vector (n doubles)
@@ -140,8 +141,22 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
   __shared__ double s_wfirst;                    // TWO: w of the first active row of the previous column
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int G = gridDim.x;
-  const int NW = G * TD_WARPS, gw = blockIdx.x * TD_WARPS + warp;
+  // BATCH: two independent problems of the same size in one launch, half of the grid each (own barrier counter);
+  // while one group streams its trailing matrix the other is in its latency-bound phases.  Problem 1 lives at
+  // fixed strides behind problem 0 (matrix, d / e / tau, workspace).
+  const int Gdim = BATCH ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int grp = BATCH ? (int)(blockIdx.x >= (unsigned)Gdim) : 0;
+  const int bx = (int)blockIdx.x - grp * Gdim;
+  const int64_t ows = BATCH ? grp * P.bs_ws : 0, oa = BATCH ? grp * P.bs_a : 0, ov = BATCH ? grp * P.bs_v : 0;
+  auto wsp = [&](double* q) { return reinterpret_cast<double*>(reinterpret_cast<char*>(q) + ows); };
+  double* const qVW = wsp(P.VW); double* const qWV = wsp(P.WV); double* const qu = wsp(P.u);
+  double* const qwraw = wsp(P.wraw); double* const qcpart = wsp(P.cpart); double* const qtiles = wsp(P.tiles);
+  double* const qwpre = wsp(P.wpre); double* const qpart = wsp(P.part);
+  double* const qA = P.A + oa; double* const qd = P.d + ov; double* const qe = P.e + ov; double* const qtau = P.tau + ov;
+  unsigned long long* const qclk = P.clk ? reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(P.clk) + ows) : nullptr;
+  unsigned int* const qbar = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(P.bar) + ows);
+  const int G = Gdim;
+  const int NW = G * TD_WARPS, gw = bx * TD_WARPS + warp;
   const int n = P.n;
   const int64_t lda = P.lda;
   double alpha2_prev = 0.0;
@@ -154,8 +169,8 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
     const int n1 = n - c - 1;
     // ------------------------------------------------------------ phase A: column c
     if (tid < i) {
-      if (tid == i - 1) { Vc[tid] = 1.0; Wc[tid] = TWO ? s_wfirst : P.wpre[c] + alpha2_prev; }
-      else { Vc[tid] = P.VW[(int64_t)c * TD_K2 + tid]; Wc[tid] = P.VW[(int64_t)c * TD_K2 + TD_NB + tid]; }
+      if (tid == i - 1) { Vc[tid] = 1.0; Wc[tid] = TWO ? s_wfirst : qwpre[c] + alpha2_prev; }
+      else { Vc[tid] = qVW[(int64_t)c * TD_K2 + tid]; Wc[tid] = qVW[(int64_t)c * TD_K2 + TD_NB + tid]; }
     }
     __syncthreads();
     double ssq = 0.0;
@@ -168,14 +183,14 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
         const bool hb = rb < n;
         double acr0 = 0.0, acr1 = 0.0;
         if (lane == 0) {
-          acr0 = TILED ? P.tiles[tile_off(r / TD_TS, c / TD_TS) + (int64_t)(r % TD_TS) * TD_TS + c % TD_TS]
-                       : P.A[(int64_t)c * lda + r];
-          if (hb) acr1 = TILED ? P.tiles[tile_off(rb / TD_TS, c / TD_TS) + (int64_t)(rb % TD_TS) * TD_TS + c % TD_TS]
-                               : P.A[(int64_t)c * lda + rb];
+          acr0 = TILED ? qtiles[tile_off(r / TD_TS, c / TD_TS) + (int64_t)(r % TD_TS) * TD_TS + c % TD_TS]
+                       : qA[(int64_t)c * lda + r];
+          if (hb) acr1 = TILED ? qtiles[tile_off(rb / TD_TS, c / TD_TS) + (int64_t)(rb % TD_TS) * TD_TS + c % TD_TS]
+                               : qA[(int64_t)c * lda + rb];
         }
         double acc0 = 0.0, acc1 = 0.0;
-        const double* vw0 = P.VW + (int64_t)r * TD_K2;
-        const double* vw1 = P.VW + (int64_t)(hb ? rb : r) * TD_K2;
+        const double* vw0 = qVW + (int64_t)r * TD_K2;
+        const double* vw1 = qVW + (int64_t)(hb ? rb : r) * TD_K2;
         for (int t = lane; t < i; t += 32) {
           const double wc = Wc[t], vc = Vc[t];
           acc0 = fma(vw0[t], wc, fma(vw0[TD_NB + t], vc, acc0));
@@ -184,12 +199,12 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
         acc0 = warp_sum(acc0); acc1 = warp_sum(acc1);
         if (lane == 0) {
           const double u0 = acr0 - acc0;
-          P.u[r] = u0;
-          if (r == c) P.d[c] = u0;
+          qu[r] = u0;
+          if (r == c) qd[c] = u0;
           if (r >= c + 2) ssq = fma(u0, u0, ssq);
           if (hb) {
             const double u1 = acr1 - acc1;
-            P.u[rb] = u1;
+            qu[rb] = u1;
             if (rb >= c + 2) ssq = fma(u1, u1, ssq);
           }
         }
@@ -197,9 +212,9 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
     }
     if (n1 == 0) break;                           // last column: only its diagonal entry
     ssq = block_sum_1024(ssq, red);
-    if (tid == 0) P.part[(int64_t)blockIdx.x * TD_PART] = ssq;
+    if (tid == 0) qpart[(int64_t)bx * TD_PART] = ssq;
     { long long c1 = clock64(); tk[0] += c1 - c0; c0 = c1; }
-    grid_barrier(P.bar, epoch, P.bar_ra);                   // #1
+    grid_barrier(qbar, epoch, P.bar_ra, G);                   // #1
     { long long c1 = clock64(); tk[1] += c1 - c0; c0 = c1; }
 
     // ------------------------------------------------------------ phase B: reflector, A v
@@ -208,10 +223,10 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int j = tid + TD_THREADS * k;
-      ureg[k] = (j < n1) ? P.u[c + 1 + j] : 0.0;
+      ureg[k] = (j < n1) ? qu[c + 1 + j] : 0.0;
     }
-    const double alpha = P.u[c + 1];
-    const double xnorm2 = grid_slot_sum(P.part, 0, G, red);
+    const double alpha = qu[c + 1];
+    const double xnorm2 = grid_slot_sum(qpart, 0, G, red);
     double beta, tau, scale;
     if (xnorm2 == 0.0) { beta = alpha; tau = 0.0; scale = 0.0; }
     else {
@@ -224,11 +239,11 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
       const int j = tid + TD_THREADS * k;
       if (j < n1) vs[j] = (j == 0) ? 1.0 : ureg[k] * scale;
     }
-    for (int j = tid + 8 * TD_THREADS; j < n1; j += TD_THREADS) vs[j] = P.u[c + 1 + j] * scale;
-    if (blockIdx.x == 0 && tid == 0) { P.e[c] = beta; P.tau[c] = tau; }
+    for (int j = tid + 8 * TD_THREADS; j < n1; j += TD_THREADS) vs[j] = qu[c + 1 + j] * scale;
+    if (bx == 0 && tid == 0) { qe[c] = beta; qtau[c] = tau; }
     __syncthreads();
-    for (int j = blockIdx.x * TD_THREADS + tid; j < n1; j += G * TD_THREADS)
-      P.A[(int64_t)c * lda + c + 1 + j] = vs[j];                                       // reflector storage
+    for (int j = bx * TD_THREADS + tid; j < n1; j += G * TD_THREADS)
+      qA[(int64_t)c * lda + c + 1 + j] = vs[j];                                       // reflector storage
     long long cb = clock64();
     tk[5] += cb - c0;
 
@@ -245,7 +260,7 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
         while (Ir * (Ir + 1) / 2 > item) --Ir;
         while ((Ir + 1) * (Ir + 2) / 2 <= item) ++Ir;
         const int I = IB + Ir, J = IB + (item - Ir * (Ir + 1) / 2);
-        const double* tp = P.tiles + tile_off(I, J) + lane;
+        const double* tp = qtiles + tile_off(I, J) + lane;
         const bool diag = (I == J);
         const double vc0 = vget(TD_TS * J + lane), vc1 = vget(TD_TS * J + 32 + lane);
         double ca0 = 0.0, ca1 = 0.0;
@@ -270,14 +285,14 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
           const double rsum = warp_reduce8(x8, lane);
           const int gr = TD_TS * I + rg * 8 + ((lane >> 2) & 7);
           if (!(lane & 3) && gr > c && gr < n) {
-            if (P.slot_t) P.wraw[(int64_t)gr * NTs + J] = rsum; else P.wraw[(int64_t)J * n + gr] = rsum;
+            if (P.slot_t) qwraw[(int64_t)gr * NTs + J] = rsum; else qwraw[(int64_t)J * n + gr] = rsum;
             if (TWO) q = fma(vs[gr - c - 1], rsum, q);
           }
         }
         if (!diag) {
           const int g0 = TD_TS * J + lane, g1 = g0 + 32;
-          if (g0 > c && g0 < n) { if (P.slot_t) P.wraw[(int64_t)g0 * NTs + I] = ca0; else P.cpart[(int64_t)I * n + g0] = ca0; }
-          if (g1 > c && g1 < n) { if (P.slot_t) P.wraw[(int64_t)g1 * NTs + I] = ca1; else P.cpart[(int64_t)I * n + g1] = ca1; }
+          if (g0 > c && g0 < n) { if (P.slot_t) qwraw[(int64_t)g0 * NTs + I] = ca0; else qcpart[(int64_t)I * n + g0] = ca0; }
+          if (g1 > c && g1 < n) { if (P.slot_t) qwraw[(int64_t)g1 * NTs + I] = ca1; else qcpart[(int64_t)I * n + g1] = ca1; }
           if (TWO) q = fma(ca0, vc0, fma(ca1, vc1, q));
         }
       }
@@ -290,7 +305,7 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
       for (int64_t item = gw; item < items; item += NW) {
         const int rr = (int)(item / F), qq = (int)(item - (int64_t)rr * F);
         const int s0 = qq * len, s1 = min(n1, s0 + len);
-        const double* row = P.A + (int64_t)(c + 1 + rr) * lda + (c + 1);
+        const double* row = qA + (int64_t)(c + 1 + rr) * lda + (c + 1);
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0, a5 = 0.0, a6 = 0.0, a7 = 0.0;
         int s = s0 + lane;
         for (; s + 224 < s1; s += 256) {
@@ -307,7 +322,7 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
         for (; s < s1; s += 32) a0 = fma(row[s], vs[s], a0);
         double sum = warp_sum(((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7)));
         if (lane == 0) {
-          P.wraw[(int64_t)qq * n + c + 1 + rr] = sum;
+          qwraw[(int64_t)qq * n + c + 1 + rr] = sum;
           if (TWO) q = fma(sum, vs[rr], q);
         }
       }
@@ -321,8 +336,8 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
         const int rb = r + NW;
         const bool hb = rb < n;
         const double vr0 = vs[r - c - 1], vr1 = hb ? vs[rb - c - 1] : 0.0;
-        const double* vw0 = P.VW + (int64_t)r * TD_K2;
-        const double* vw1 = P.VW + (int64_t)(hb ? rb : r) * TD_K2;
+        const double* vw0 = qVW + (int64_t)r * TD_K2;
+        const double* vw1 = qVW + (int64_t)(hb ? rb : r) * TD_K2;
         double x0[4], x1[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -355,10 +370,10 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
         }
       }
       __syncthreads();
-      if (tid < TD_K2) P.part[(int64_t)blockIdx.x * TD_PART + 1 + tid] = pv[tid];
+      if (tid < TD_K2) qpart[(int64_t)bx * TD_PART + 1 + tid] = pv[tid];
     }
     { long long c1 = clock64(); tk[2] += c1 - c0; c0 = c1; }
-    grid_barrier(P.bar, epoch, P.bar_ra);                   // #2
+    grid_barrier(qbar, epoch, P.bar_ra, G);                   // #2
     { long long c1 = clock64(); tk[1] += c1 - c0; c0 = c1; }
 
     // ------------------------------------------------------------ phase C: w (before the alpha correction)
@@ -371,7 +386,7 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
 #pragma unroll
           for (int k = 0; k < 20; ++k) {
             const int g = g0 + 8 * k;
-            tmp[k] = (g < G) ? P.part[(int64_t)g * TD_PART + 1 + idx] : 0.0;
+            tmp[k] = (g < G) ? qpart[(int64_t)g * TD_PART + 1 + idx] : 0.0;
           }
 #pragma unroll
           for (int k = 0; k < 20; ++k) s += tmp[k];
@@ -390,18 +405,18 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
     // w before the alpha correction for row r: this lane's share (to be summed over the warp, times tau)
     auto row_part = [&](int r) -> double {
       double acc = 0.0;
-      const double* vw = P.VW + (int64_t)r * TD_K2;
+      const double* vw = qVW + (int64_t)r * TD_K2;
       for (int t = lane; t < i; t += 32) acc = fma(vw[t], pv[TD_NB + t], fma(vw[TD_NB + t], pv[t], acc));
       double wr = 0.0;
       if (TILED) {
         const int IB = (c + 1) / TD_TS, I = r / TD_TS;
         if (P.slot_t) {
-          for (int K = IB + lane; K < NTs; K += 32) wr += P.wraw[(int64_t)r * NTs + K];         // one contiguous run
+          for (int K = IB + lane; K < NTs; K += 32) wr += qwraw[(int64_t)r * NTs + K];         // one contiguous run
         } else {
-          for (int J = IB + lane; J <= I; J += 32) wr += P.wraw[(int64_t)J * n + r];           // tiles (I, J <= I)
-          for (int I2 = I + 1 + lane; I2 < NTs; I2 += 32) wr += P.cpart[(int64_t)I2 * n + r];  // mirrored: tiles (I2 > I, I)
+          for (int J = IB + lane; J <= I; J += 32) wr += qwraw[(int64_t)J * n + r];           // tiles (I, J <= I)
+          for (int I2 = I + 1 + lane; I2 < NTs; I2 += 32) wr += qcpart[(int64_t)I2 * n + r];  // mirrored: tiles (I2 > I, I)
         }
-      } else if (lane < F) wr = P.wraw[(int64_t)lane * n + r];
+      } else if (lane < F) wr = qwraw[(int64_t)lane * n + r];
       return wr - acc;
     };
     double alpha2;
@@ -426,15 +441,15 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
           const double v0 = vs[ra - c - 1], w0 = fma(alpha2, v0, pa0);
           if (ea) s_wfirst = w0;
           else {
-            P.VW[(int64_t)ra * TD_K2 + i] = v0;        P.VW[(int64_t)ra * TD_K2 + TD_NB + i] = w0;
-            P.WV[(int64_t)ra * TD_K2 + i] = w0;        P.WV[(int64_t)ra * TD_K2 + TD_NB + i] = v0;
+            qVW[(int64_t)ra * TD_K2 + i] = v0;        qVW[(int64_t)ra * TD_K2 + TD_NB + i] = w0;
+            qWV[(int64_t)ra * TD_K2 + i] = w0;        qWV[(int64_t)ra * TD_K2 + TD_NB + i] = v0;
           }
           if (rb >= 0) {
             const double v1 = vs[rb - c - 1], w1 = fma(alpha2, v1, pa1);
             if (eb) s_wfirst = w1;
             else {
-              P.VW[(int64_t)rb * TD_K2 + i] = v1;      P.VW[(int64_t)rb * TD_K2 + TD_NB + i] = w1;
-              P.WV[(int64_t)rb * TD_K2 + i] = w1;      P.WV[(int64_t)rb * TD_K2 + TD_NB + i] = v1;
+              qVW[(int64_t)rb * TD_K2 + i] = v1;      qVW[(int64_t)rb * TD_K2 + TD_NB + i] = w1;
+              qWV[(int64_t)rb * TD_K2 + i] = w1;      qWV[(int64_t)rb * TD_K2 + TD_NB + i] = v1;
             }
           }
         }
@@ -450,29 +465,29 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
         double p0 = row_part(r), p1 = hb ? row_part(rb) : 0.0;
         p0 = tau * warp_sum(p0); p1 = tau * warp_sum(p1);
         if (lane == 0) {
-          P.wpre[r] = p0;
+          qwpre[r] = p0;
           dotacc = fma(p0, vs[r - c - 1], dotacc);
-          if (hb) { P.wpre[rb] = p1; dotacc = fma(p1, vs[rb - c - 1], dotacc); }
+          if (hb) { qwpre[rb] = p1; dotacc = fma(p1, vs[rb - c - 1], dotacc); }
         }
       }
     }
     dotacc = block_sum_1024(dotacc, red);
-    if (tid == 0) P.part[(int64_t)blockIdx.x * TD_PART + 130] = dotacc;
+    if (tid == 0) qpart[(int64_t)bx * TD_PART + 130] = dotacc;
     { long long c1 = clock64(); tk[3] += c1 - c0; c0 = c1; }
-    grid_barrier(P.bar, epoch, P.bar_ra);                   // #3
+    grid_barrier(qbar, epoch, P.bar_ra, G);                   // #3
     { long long c1 = clock64(); tk[1] += c1 - c0; c0 = c1; }
 
     // ------------------------------------------------------------ phase D: finish w, store panel column i
-    const double dot = grid_slot_sum(P.part, 130, G, red);
+    const double dot = grid_slot_sum(qpart, 130, G, red);
     alpha2 = -0.5 * tau * dot;
     {
       int r = c + 1 + ((gw - (c + 1) % NW) + NW) % NW;
       for (; r < n; r += NW) {
         if (lane == 0) {
           const double v = vs[r - c - 1];
-          const double w = fma(alpha2, v, P.wpre[r]);
-          P.VW[(int64_t)r * TD_K2 + i] = v;          P.VW[(int64_t)r * TD_K2 + TD_NB + i] = w;
-          P.WV[(int64_t)r * TD_K2 + i] = w;          P.WV[(int64_t)r * TD_K2 + TD_NB + i] = v;
+          const double w = fma(alpha2, v, qwpre[r]);
+          qVW[(int64_t)r * TD_K2 + i] = v;          qVW[(int64_t)r * TD_K2 + TD_NB + i] = w;
+          qWV[(int64_t)r * TD_K2 + i] = w;          qWV[(int64_t)r * TD_K2 + TD_NB + i] = v;
         }
       }
     }
@@ -482,8 +497,8 @@ __global__ void __launch_bounds__(TD_THREADS, 1) sytrd_panel_kernel(SytrdParams 
     __syncthreads();
     { long long c1 = clock64(); tk[4] += c1 - c0; c0 = c1; }
   }
-  if (blockIdx.x == 0 && tid == 0 && P.clk)
-    for (int q = 0; q < 8; ++q) P.clk[q] += (unsigned long long)tk[q];
+  if (bx == 0 && tid == 0 && qclk)
+    for (int q = 0; q < 8; ++q) qclk[q] += (unsigned long long)tk[q];
 }
 
 // ------------------------------------------------------------------ tile-major helpers
@@ -909,11 +924,13 @@ ormtr_kernel(int n, const double* __restrict__ A, int64_t lda, const double* __r
 
 static int sytrd_grid(size_t smem, int* grid_out) {
   int occ = 0;
-  XMCA_CUDA(cudaFuncSetAttribute(sytrd_panel_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  XMCA_CUDA(cudaFuncSetAttribute(sytrd_panel_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  XMCA_CUDA(cudaFuncSetAttribute(sytrd_panel_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  XMCA_CUDA(cudaFuncSetAttribute(sytrd_panel_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  XMCA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sytrd_panel_kernel<true, true>, TD_THREADS, smem));
+  XMCA_CUDA(cudaFuncSetAttribute(sytrd_panel_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  XMCA_CUDA(cudaFuncSetAttribute(sytrd_panel_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  XMCA_CUDA(cudaFuncSetAttribute(sytrd_panel_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  XMCA_CUDA(cudaFuncSetAttribute(sytrd_panel_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  XMCA_CUDA(cudaFuncSetAttribute(sytrd_panel_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  XMCA_CUDA(cudaFuncSetAttribute(sytrd_panel_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  XMCA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sytrd_panel_kernel<true, true, true>, TD_THREADS, smem));
   if (occ < 1) return fail(XMCA_CUDA_ERROR, "sytrd panel kernel does not fit on an SM", __FILE__, __LINE__);
   *grid_out = sm_count();
   return XMCA_OK;
@@ -955,22 +972,22 @@ extern "C" size_t xmca_sytrd_workspace_bytes(int64_t n) {
   return b;
 }
 
-extern "C" int xmca_sytrd(int64_t n, double* d_A, int64_t lda, double* d_d, double* d_e, double* d_tau,
-                          void* d_workspace, size_t workspace_bytes, void* stream) {
-  XMCA_REQUIRE(n >= 1 && d_A && d_d && d_e && d_tau && d_workspace, "xmca_sytrd: bad argument");
-  XMCA_REQUIRE(lda >= n, "xmca_sytrd: lda < n");
-  XMCA_REQUIRE(n <= xmca_sytrd_max_n(), "xmca_sytrd: n too large for the shared-memory Householder vector");
-  XMCA_REQUIRE(workspace_bytes >= xmca_sytrd_workspace_bytes(n), "xmca_sytrd: workspace too small");
+// batch = 1 or 2 problems of the same size; problem 1 at fixed strides behind problem 0
+static int sytrd_impl(int64_t n, int batch, double* d_A, int64_t lda, int64_t stride_a, double* d_d, double* d_e,
+                      double* d_tau, int64_t stride_v, void* d_workspace, size_t workspace_bytes, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = (size_t)n * 8;
   int grid = 0;
   int rc = sytrd_grid(smem, &grid);
   if (rc != XMCA_OK) return rc;
   XMCA_REQUIRE(grid <= 148 * 2, "xmca_sytrd: grid larger than the workspace plan");
+  if (batch == 2) grid &= ~1;                      // two equal groups of CTAs
+  const size_t ws_one = xmca_sytrd_workspace_bytes(n);
 
   char* ws = reinterpret_cast<char*>(d_workspace);
   SytrdParams P;
   P.A = d_A; P.lda = lda; P.n = (int)n;
+  P.bs_a = stride_a; P.bs_v = stride_v; P.bs_ws = (int64_t)ws_one;
   size_t o = 0;
   P.VW = reinterpret_cast<double*>(ws + o); o += al256((size_t)n * TD_K2 * 8);
   P.WV = reinterpret_cast<double*>(ws + o); o += al256((size_t)n * TD_K2 * 8);
@@ -987,22 +1004,27 @@ extern "C" int xmca_sytrd(int64_t n, double* d_A, int64_t lda, double* d_d, doub
   P.part = reinterpret_cast<double*>(ws + o); o += al256((size_t)(148 * 2) * TD_PART * 8);
   P.clk = reinterpret_cast<unsigned long long*>(ws + o); o += 256;
   unsigned int* bars = reinterpret_cast<unsigned int*>(ws + o);
-  XMCA_CUDA(cudaMemsetAsync(P.clk, 0, 64, st));
-  XMCA_CUDA(cudaMemsetAsync(bars, 0, (size_t)(n / TD_NB + 2) * 4, st));
+  const size_t off_clk = (size_t)(reinterpret_cast<char*>(P.clk) - ws);
+  for (int b = 0; b < batch; ++b) {
+    XMCA_CUDA(cudaMemsetAsync(ws + b * ws_one + off_clk, 0, 256 + (size_t)(n / TD_NB + 2) * 4, st));   // clocks + barrier counters
+    XMCA_CUDA(cudaMemsetAsync(d_tau + b * stride_v, 0, (size_t)n * 8, st));
+  }
   P.d = d_d; P.e = d_e; P.tau = d_tau;
-  XMCA_CUDA(cudaMemsetAsync(d_tau, 0, (size_t)n * 8, st));
+  auto ws_of = [&](double* q, int b) { return reinterpret_cast<double*>(reinterpret_cast<char*>(q) + (size_t)b * ws_one); };
 
   // XMCA_SYTRD_VARIANT (bit mask, for A/B measurements): 1 = two barriers per column, 2 = transposed slot array,
   // 4 = release/acquire grid barrier
   const char* var_env = getenv("XMCA_SYTRD_VARIANT");
-  const int variant = var_env ? atoi(var_env) : TD_DEFAULT_VARIANT;
+  const int variant = (var_env ? atoi(var_env) : TD_DEFAULT_VARIANT) | (batch == 2 ? 1 : 0);
   const bool two = variant & 1;
   P.slot_t = (variant & 2) ? 1 : 0;
   P.bar_ra = (variant & 4) ? 1 : 0;
   bool in_tiles = false;
   if (tiled_mode) {
-    to_tiles_kernel<<<(unsigned)(NT * (NT + 1) / 2), 256, 0, st>>>(d_A, lda, (int)n, NT, P.tiles);
-    XMCA_LAUNCHED();
+    for (int b = 0; b < batch; ++b) {
+      to_tiles_kernel<<<(unsigned)(NT * (NT + 1) / 2), 256, 0, st>>>(d_A + b * stride_a, lda, (int)n, NT, ws_of(P.tiles, b));
+      XMCA_LAUNCHED();
+    }
     in_tiles = true;
   }
   for (int64_t j0 = 0; j0 < n; j0 += TD_NB) {
@@ -1010,36 +1032,42 @@ extern "C" int xmca_sytrd(int64_t n, double* d_A, int64_t lda, double* d_d, doub
     if (in_tiles && n - j0 <= sytrd_tile_min()) {
       // the trailing matrix now fits the L2: back to the row-major layout (both triangles) for the rest
       const int I0 = (int)(j0 / TD_TS), m = NT - I0;
-      from_tiles_kernel<<<(unsigned)(m * (m + 1) / 2), 256, 0, st>>>(P.tiles, I0, NT, (int)n, d_A, lda);
-      XMCA_LAUNCHED();
+      for (int b = 0; b < batch; ++b) {
+        from_tiles_kernel<<<(unsigned)(m * (m + 1) / 2), 256, 0, st>>>(ws_of(P.tiles, b), I0, NT, (int)n, d_A + b * stride_a, lda);
+        XMCA_LAUNCHED();
+      }
       in_tiles = false;
     }
     P.j0 = (int)j0; P.nb = nb;
     P.bar = bars + j0 / TD_NB;
     {
-      const double m = (double)(n - j0), bytes = in_tiles ? m * m * 4.0 : m * m * 8.0;
+      const double m = (double)(n - j0), bytes = (in_tiles ? m * m * 4.0 : m * m * 8.0) * batch;
       static const char* ke = getenv("XMCA_SYTRD_KEEP_MB");  // (tuning knob)
       P.keep_l2 = bytes <= (ke ? atof(ke) : TD_KEEP_MB) * 1e6;
     }
     // (only the last panel can be short, and it has no trailing block to update)
     void* args[] = {&P};
-    const void* fn = two ? (in_tiles ? (const void*)sytrd_panel_kernel<true, true> : (const void*)sytrd_panel_kernel<false, true>)
-                         : (in_tiles ? (const void*)sytrd_panel_kernel<true, false> : (const void*)sytrd_panel_kernel<false, false>);
+    const void* fn;
+    if (batch == 2) fn = in_tiles ? (const void*)sytrd_panel_kernel<true, true, true> : (const void*)sytrd_panel_kernel<false, true, true>;
+    else fn = two ? (in_tiles ? (const void*)sytrd_panel_kernel<true, true, false> : (const void*)sytrd_panel_kernel<false, true, false>)
+                  : (in_tiles ? (const void*)sytrd_panel_kernel<true, false, false> : (const void*)sytrd_panel_kernel<false, false, false>);
     XMCA_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(TD_THREADS), args, smem, st));
     XMCA_LAUNCHED();
     const int64_t r0 = j0 + nb;
     if (r0 < n) {
-      if (in_tiles) {
-        const int I0 = (int)(r0 / TD_TS), m = NT - I0;
-        syr2k_tiles_kernel<<<(unsigned)(m * (m + 1) / 2), 128, 0, st>>>(P.VW, P.WV, I0, (int)n, P.tiles);
-        XMCA_LAUNCHED();
-      } else {
-        // trailing update  A22 -= V W^T + W V^T  =  [V | W] [W | V]^T   (dsyr2k, full square kept)
-        const int64_t m = n - r0;
-        rc = xmca_gemm_ex(1, 1, m, m, TD_K2, -1.0, P.VW + r0 * TD_K2, XMCA_F64, TD_K2, P.WV + r0 * TD_K2, XMCA_F64,
-                          TD_K2, d_A + r0 * lda + r0, XMCA_F64, lda, 1, XMCA_F64, 1, nullptr, 0, XMCA_GEMM_SYMMETRIC,
-                          stream);
-        if (rc != XMCA_OK) return rc;
+      for (int b = 0; b < batch; ++b) {
+        if (in_tiles) {
+          const int I0 = (int)(r0 / TD_TS), m = NT - I0;
+          syr2k_tiles_kernel<<<(unsigned)(m * (m + 1) / 2), 128, 0, st>>>(ws_of(P.VW, b), ws_of(P.WV, b), I0, (int)n, ws_of(P.tiles, b));
+          XMCA_LAUNCHED();
+        } else {
+          // trailing update  A22 -= V W^T + W V^T  =  [V | W] [W | V]^T   (dsyr2k, full square kept)
+          const int64_t m = n - r0;
+          rc = xmca_gemm_ex(1, 1, m, m, TD_K2, -1.0, ws_of(P.VW, b) + r0 * TD_K2, XMCA_F64, TD_K2, ws_of(P.WV, b) + r0 * TD_K2,
+                            XMCA_F64, TD_K2, d_A + b * stride_a + r0 * lda + r0, XMCA_F64, lda, 1, XMCA_F64, 1, nullptr, 0,
+                            XMCA_GEMM_SYMMETRIC, stream);
+          if (rc != XMCA_OK) return rc;
+        }
       }
     }
   }
@@ -1047,10 +1075,32 @@ extern "C" int xmca_sytrd(int64_t n, double* d_A, int64_t lda, double* d_d, doub
     unsigned long long h[8];
     XMCA_CUDA(cudaMemcpyAsync(h, P.clk, sizeof h, cudaMemcpyDeviceToHost, st));
     XMCA_CUDA(cudaStreamSynchronize(st));
-    fprintf(stderr, "[xmca sytrd] n=%lld clocks (CTA 0): column update %.3e | grid syncs %.3e | reflector+symv+p %.3e | w %.3e | store %.3e || inside symv: set-up %.3e, streaming %.3e\n",
-            (long long)n, (double)h[0], (double)h[1], (double)h[2], (double)h[3], (double)h[4], (double)h[5], (double)h[6]);
+    fprintf(stderr, "[xmca sytrd] n=%lld batch=%d clocks (CTA 0): column update %.3e | grid syncs %.3e | reflector+symv+p %.3e | w %.3e | store %.3e || inside symv: set-up %.3e, streaming %.3e\n",
+            (long long)n, batch, (double)h[0], (double)h[1], (double)h[2], (double)h[3], (double)h[4], (double)h[5], (double)h[6]);
   }
+  (void)workspace_bytes;
   return XMCA_OK;
+}
+
+extern "C" int xmca_sytrd(int64_t n, double* d_A, int64_t lda, double* d_d, double* d_e, double* d_tau,
+                          void* d_workspace, size_t workspace_bytes, void* stream) {
+  XMCA_REQUIRE(n >= 1 && d_A && d_d && d_e && d_tau && d_workspace, "xmca_sytrd: bad argument");
+  XMCA_REQUIRE(lda >= n, "xmca_sytrd: lda < n");
+  XMCA_REQUIRE(n <= xmca_sytrd_max_n(), "xmca_sytrd: n too large for the shared-memory Householder vector");
+  XMCA_REQUIRE(workspace_bytes >= xmca_sytrd_workspace_bytes(n), "xmca_sytrd: workspace too small");
+  return sytrd_impl(n, 1, d_A, lda, 0, d_d, d_e, d_tau, 0, d_workspace, workspace_bytes, stream);
+}
+
+extern "C" int xmca_sytrd_batched(int64_t n, int batch, double* d_A, int64_t lda, int64_t stride_a, double* d_d,
+                                  double* d_e, double* d_tau, int64_t stride_v, void* d_workspace,
+                                  size_t workspace_bytes, void* stream) {
+  XMCA_REQUIRE(n >= 1 && d_A && d_d && d_e && d_tau && d_workspace, "xmca_sytrd_batched: bad argument");
+  XMCA_REQUIRE(batch == 1 || batch == 2, "xmca_sytrd_batched: batch must be 1 or 2");
+  XMCA_REQUIRE(lda >= n, "xmca_sytrd_batched: lda < n");
+  XMCA_REQUIRE(batch == 1 || (stride_a >= n * lda && stride_v >= n), "xmca_sytrd_batched: strides too small");
+  XMCA_REQUIRE(n <= xmca_sytrd_max_n(), "xmca_sytrd_batched: n too large for the shared-memory Householder vector");
+  XMCA_REQUIRE(workspace_bytes >= (size_t)batch * xmca_sytrd_workspace_bytes(n), "xmca_sytrd_batched: workspace too small");
+  return sytrd_impl(n, batch, d_A, lda, stride_a, d_d, d_e, d_tau, stride_v, d_workspace, workspace_bytes, stream);
 }
 
 extern "C" int xmca_stebz(int64_t n, const double* d_d, const double* d_e, double* d_w, double* d_scratch,

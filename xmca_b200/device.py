@@ -245,6 +245,22 @@ def sytrd(S):
     return d, e, tau
 
 
+def sytrd_pair(S2):
+    """Two tridiagonalisations of the same size in one batched call (S2: 2 x n x n fp64, contiguous,
+    DESTROYED).  Returns (d, e, tau) as 2 x n device tensors (e: the first n - 1 entries of each row)."""
+    lib = L.load()
+    t = torch()
+    assert S2.dtype == t.float64 and S2.dim() == 3 and S2.shape[0] == 2 and S2.shape[1] == S2.shape[2] and S2.is_contiguous()
+    n = S2.shape[1]
+    d, e, tau = empty((2, n), t.float64), zeros((2, n), t.float64), empty((2, n), t.float64)
+    ws_bytes = 2 * lib.xmca_sytrd_workspace_bytes(n)
+    ws = empty((ws_bytes,), t.uint8)
+    rc = lib.xmca_sytrd_batched(n, 2, L.ptr(S2), n, n * n, L.ptr(d), L.ptr(e), L.ptr(tau), n, L.ptr(ws), ws_bytes,
+                                L.stream_ptr())
+    L.check(rc, "xmca_sytrd_batched")
+    return d, e, tau
+
+
 def stebz(d, e):
     """All eigenvalues of the symmetric tridiagonal (d, e), descending (device fp64)."""
     lib = L.load()

@@ -211,7 +211,7 @@ class TridiagResult:
 
     route = "tridiag"
 
-    def __init__(self, A, B, null_basis=None, dof=None):
+    def __init__(self, A, B, null_basis=None, dof=None, defer=False):
         T, S1 = A.shape
         self.A, self.B = A, B
         self.pca = B is None
@@ -263,8 +263,15 @@ class TridiagResult:
                 self.C = D.matmul(Xs, Xl, trans_a=True, alpha=1.0 / dof)          # S_short x S_long
                 S = D.matmul(self.C, self.C, trans_b=True, symmetric=True)
         self.n = S.shape[0]
-        self.d, self.e, self.tau = D.sytrd(S)
-        self.Q = S                                                            # rows now hold the reflectors
+        self._S = S
+        if not defer:                  # (deferred: `solve_real_pair` tridiagonalises two models in one batched call)
+            self._finish(*D.sytrd(S), S)
+
+    def _finish(self, d, e, tau, Q):
+        """Spectrum from the tridiagonal form (d, e, tau) of S; Q: the matrix whose rows hold the reflectors."""
+        self._S = None
+        self.d, self.e, self.tau = d, e, tau
+        self.Q = Q
         lam = D.to_host(D.stebz(self.d, self.e))
         if not np.isfinite(lam).all():
             raise np.linalg.LinAlgError("non-finite spectrum")
@@ -436,6 +443,34 @@ def spectrum_embedding(X, F=None):
         F = D.dft_matrix(X.shape[0], X.dtype)
     ZZ, _ = D.apply_time_operator(F, X)
     return D.embed_complex(ZZ)
+
+
+def solve_real_pair(A0, B0, A1, B1):
+    """Two independent real solves of the same shape (the surrogate runs of rule_n, array.py:1753-1765).
+    On the tridiagonal route both symmetric matrices are reduced by ONE batched call (xmca_sytrd_batched:
+    half of the SMs each, so one streams while the other is in its latency-bound phases); otherwise two
+    plain `solve_real` calls.  Returns the two results."""
+    T, S1 = A0.shape
+    pca = B0 is None
+    S2 = S1 if pca else B0.shape[1]
+    rank = min(T, S1, S2)
+    same = A0.shape == A1.shape and A0.dtype == A1.dtype and (pca == (B1 is None)) and (pca or B0.shape == B1.shape)
+    if not (same and TRIDIAG_MIN_N <= rank <= D.sytrd_max_n()):
+        return solve_real(A0, B0), solve_real(A1, B1)
+    try:
+        r0 = TridiagResult(A0, B0, defer=True)
+        r1 = TridiagResult(A1, B1, defer=True)
+    except np.linalg.LinAlgError:
+        return solve_real(A0, B0), solve_real(A1, B1)
+    n = r0.n
+    Sp = D.empty((2, n, n), D.f64())
+    Sp[0].copy_(r0._S)
+    Sp[1].copy_(r1._S)
+    r0._S = r1._S = None
+    d, e, tau = D.sytrd_pair(Sp)
+    r0._finish(d[0], e[0, :max(n - 1, 1)], tau[0], Sp[0])
+    r1._finish(d[1], e[1, :max(n - 1, 1)], tau[1], Sp[1])
+    return r0, r1
 
 
 def solve_complex(XA, XB, want_vectors=True):

@@ -69,7 +69,14 @@ def variance_of_fields(fields, complexify, rotated, n_rot, power, extend=False, 
         nl = E.complex_col_norms(Br, Bi, 0, s_left)
         var = nl ** 2 if B is None else nl * E.complex_col_norms(Br, Bi, s_left, Br.shape[0])
         return np.sort(var)[::-1]
-    res = E.solve_real(A, B, want_vectors=True)
+    return _rotated_variance(E.solve_real(A, B, want_vectors=True), B is None, n_rot, power)
+
+
+def _rotated_variance(res, pca, n_rot, power):
+    """rotate + sorted variance (array.py:823-834, :771-779) from a real solve result; None if not converged."""
+    from . import device as D
+    from . import engine as E
+    t = D.torch()
     p = min(n_rot, res.sigma.size)
     root = D.to_device(np.sqrt(res.sigma[:p]))
     Vp = res.vectors(p)
@@ -81,15 +88,11 @@ def variance_of_fields(fields, complexify, rotated, n_rot, power, extend=False, 
     except L.NotConvergedError:
         return None                                             # array.py:1759-1763
     nl = np.sqrt(D.to_host(D.col_sumsq(Lrot, 0, s_left)))
-    var = nl ** 2 if B is None else nl * np.sqrt(D.to_host(D.col_sumsq(Lrot, s_left, Lrot.shape[0])))
+    var = nl ** 2 if pca else nl * np.sqrt(D.to_host(D.col_sumsq(Lrot, s_left, Lrot.shape[0])))
     return np.sort(var)[::-1]
 
 
-def device_surrogate_variance(shape_T, n_vars, run_index, seed, complexify, rotated, n_rot, power,
-                              dtype="float64"):
-    """One surrogate run on the current CUDA device.  Returns the variance
-    spectrum (fp64 numpy) or None if the rotation did not converge.
-    dtype: storage precision of the Gaussian surrogate fields (see `rule_n`)."""
+def _surrogate_fields(shape_T, n_vars, run_index, seed, dtype):
     from . import device as D
     t = D.torch()
     fields = []
@@ -98,7 +101,31 @@ def device_surrogate_variance(shape_T, n_vars, run_index, seed, complexify, rota
         D.fill_normal(X, seed, 2 * run_index + f)               # array.py:1756
         D.center_columns(X)                                     # MCA ctor, array.py:199-207
         fields.append(X)
+    return fields
+
+
+def device_surrogate_variance(shape_T, n_vars, run_index, seed, complexify, rotated, n_rot, power,
+                              dtype="float64"):
+    """One surrogate run on the current CUDA device.  Returns the variance
+    spectrum (fp64 numpy) or None if the rotation did not converge.
+    dtype: storage precision of the Gaussian surrogate fields (see `rule_n`)."""
+    fields = _surrogate_fields(shape_T, n_vars, run_index, seed, dtype)
     return variance_of_fields(fields, complexify, rotated, n_rot, power)
+
+
+def device_surrogate_variance_pair(shape_T, n_vars, run_a, run_b, seed, rotated, n_rot, power, dtype="float64"):
+    """Two real surrogate runs at once: the runs are independent (array.py:1753-1765), so their two symmetric
+    eigenproblems go through ONE batched tridiagonalisation (engine.solve_real_pair).  Same Philox streams as
+    the single-run path, hence the same surrogates.  Returns the two spectra (None where not converged)."""
+    from . import engine as E
+    fa = _surrogate_fields(shape_T, n_vars, run_a, seed, dtype)
+    fb = _surrogate_fields(shape_T, n_vars, run_b, seed, dtype)
+    pca = len(n_vars) == 1
+    ra, rb = E.solve_real_pair(fa[0], None if pca else fa[1], fb[0], None if pca else fb[1])
+    del fa, fb
+    if not rotated:
+        return ra.sigma, rb.sigma
+    return _rotated_variance(ra, pca, n_rot, power), _rotated_variance(rb, pca, n_rot, power)
 
 
 def gather_spectra(local: np.ndarray, valid: np.ndarray, n_runs: int, group=None):
@@ -132,13 +159,16 @@ def gather_spectra(local: np.ndarray, valid: np.ndarray, n_runs: int, group=None
     return np.concatenate(cols, axis=1) if cols else np.zeros((modes, 0))
 
 
-def rule_n(model, n_runs, n_modes=None, seed=None, group=None, _surrogate_fn=None, surrogate_dtype=None):
+def rule_n(model, n_runs, n_modes=None, seed=None, group=None, _surrogate_fn=None, surrogate_dtype=None,
+           pair_runs=True):
     """Sharded Rule N for an ``xmca_b200.MCA`` model (array.py:1716-1771).
 
     surrogate_dtype: the reference draws float64 surrogates whatever the model's dtype
     (array.py:1756); a conscious deviation here: the surrogates follow the MODEL's field dtype
     (fp32 model -> fp32 Gaussian fields, Gram matrices on the tensor cores), which changes nothing
-    statistically; pass "float64" for the reference's behaviour.  The returned spectra are fp64."""
+    statistically; pass "float64" for the reference's behaviour.  The returned spectra are fp64.
+    pair_runs: real models process their runs two at a time through one batched tridiagonalisation
+    (same surrogates, same spectra to rounding; see `device_surrogate_variance_pair`)."""
     import torch.distributed as dist
     T = model._n_observations["left"]
     n_vars = [model._n_variables[k] for k in model._keys]
@@ -160,12 +190,25 @@ def rule_n(model, n_runs, n_modes=None, seed=None, group=None, _surrogate_fn=Non
     modes = ref.size
     local = np.full((modes, len(mine)), np.nan)
     valid = np.zeros(len(mine), dtype=bool)
-    for j, i in enumerate(mine):
-        spec = fn(T, n_vars, i, seed, complexify, rotated, n_rot, power, **extra)
+    def store(j, spec):
         if spec is None:
-            continue
+            return
         spec = np.asarray(spec, dtype=np.float64)
         local[:spec.size, j] = spec * (ref.sum() / spec.sum())   # column-wise rescale, array.py:1768-1769
         valid[j] = True
+
+    runs = list(mine)
+    j = 0
+    pairs = _surrogate_fn is None and not complexify and pair_runs
+    while j < len(runs):
+        if pairs and j + 1 < len(runs):
+            sa, sb = device_surrogate_variance_pair(T, n_vars, runs[j], runs[j + 1], seed, rotated, n_rot, power,
+                                                    dtype=surrogate_dtype)
+            store(j, sa)
+            store(j + 1, sb)
+            j += 2
+        else:
+            store(j, fn(T, n_vars, runs[j], seed, complexify, rotated, n_rot, power, **extra))
+            j += 1
     sv = gather_spectra(local, valid, n_runs, group)
     return sv[model._get_slice(n_modes)]
