@@ -282,8 +282,7 @@ def run_product(args, rank, world, local_rank):
               "runs_per_rank": n_runs / world, "scaling": "strong" if args.rule_n_total > 0 else "weak",
               "ms_total": ms_rn, "shape": list(spectra.shape), "dtype": "f64",
               "collective": "1 all_gather (nccl)" if world > 1 else "none (1 rank)",
-              "runs_in_flight": "real models: two surrogates per batched tridiagonalisation (xmca_sytrd_batched) "
-                                "when a rank owns >= 2 runs",
+              "runs_in_flight": "two surrogates per batched tridiagonalisation (xmca_sytrd_batched) when a rank owns >= 2 runs",
               "call_ms_one_surrogate": {k: round(v["ms"], 2) for k, v in
                                         sorted(rn_prof.items(), key=lambda kv: -kv[1]["ms"])}}
 

@@ -219,15 +219,16 @@ def test_rule_n_distribution_matches_oracle(MCA):
     np.testing.assert_array_equal(got, again)              # counter-based RNG: reproducible
 
 
+@pytest.mark.parametrize("complexify", [False, True])
 @pytest.mark.parametrize("rotated", [False, True])
-def test_rule_n_paired_runs_equal_single_runs(MCA, monkeypatch, rotated):
+def test_rule_n_paired_runs_equal_single_runs(MCA, monkeypatch, rotated, complexify):
     """rule_n processes real surrogates two at a time through the batched tridiagonalisation: same Philox
     streams, so the spectra equal the one-at-a-time result to rounding (odd run count: last run single)."""
     from xmca_b200 import engine as E
     monkeypatch.setattr(E, "TRIDIAG_MIN_N", 64)
     A, B = orc.synthetic_fields(150, 260, 200, seed=5, k=6, dtype=np.float64)
     m = MCA(A.copy(), B.copy())
-    m.solve()
+    m.solve(complexify=complexify)
     if rotated:
         m.rotate(6, 1)
     from xmca_b200 import rule_n as RN

@@ -445,7 +445,7 @@ def spectrum_embedding(X, F=None):
     return D.embed_complex(ZZ)
 
 
-def solve_real_pair(A0, B0, A1, B1):
+def solve_real_pair(A0, B0, A1, B1, null_basis=None, dof=None):
     """Two independent real solves of the same shape (the surrogate runs of rule_n, array.py:1753-1765).
     On the tridiagonal route both symmetric matrices are reduced by ONE batched call (xmca_sytrd_batched:
     half of the SMs each, so one streams while the other is in its latency-bound phases); otherwise two
@@ -455,13 +455,14 @@ def solve_real_pair(A0, B0, A1, B1):
     S2 = S1 if pca else B0.shape[1]
     rank = min(T, S1, S2)
     same = A0.shape == A1.shape and A0.dtype == A1.dtype and (pca == (B1 is None)) and (pca or B0.shape == B1.shape)
+    single = lambda A, B: solve_real(A, B, null_basis=null_basis, dof=dof)
     if not (same and TRIDIAG_MIN_N <= rank <= D.sytrd_max_n()):
-        return solve_real(A0, B0), solve_real(A1, B1)
+        return single(A0, B0), single(A1, B1)
     try:
-        r0 = TridiagResult(A0, B0, defer=True)
-        r1 = TridiagResult(A1, B1, defer=True)
+        r0 = TridiagResult(A0, B0, null_basis, dof, defer=True)
+        r1 = TridiagResult(A1, B1, null_basis, dof, defer=True)
     except np.linalg.LinAlgError:
-        return solve_real(A0, B0), solve_real(A1, B1)
+        return single(A0, B0), single(A1, B1)
     n = r0.n
     Sp = D.empty((2, n, n), D.f64())
     Sp[0].copy_(r0._S)
@@ -493,6 +494,26 @@ def solve_complex(XA, XB, want_vectors=True):
     n = min(rank, s.size)
     sigma[:n] = s[:n]               # modes beyond the T/2 positive frequencies are exactly zero
     return sigma, ComplexVectors(res, n, rank), res
+
+
+def solve_complex_pair(XA0, XB0, XA1, XB1):
+    """Two independent complex solves of the same shape (see `solve_complex`) sharing one batched
+    tridiagonalisation (`solve_real_pair`).  Returns two (sigma, ComplexVectors, embedded result) triples."""
+    T, S1 = XA0.shape
+    pca = XB0 is None
+    S2 = S1 if pca else XB0.shape[1]
+    rank = min(T, S1, S2)
+    F = D.dft_matrix(T, XA0.dtype)
+    emb = [(spectrum_embedding(XA, F), None if pca else spectrum_embedding(XB, F)) for XA, XB in ((XA0, XB0), (XA1, XB1))]
+    del F
+    out = []
+    for res in solve_real_pair(emb[0][0], emb[0][1], emb[1][0], emb[1][1], null_basis=0, dof=T - 1):
+        s = res.sigma[0::2]
+        sigma = np.zeros(rank)
+        n = min(rank, s.size)
+        sigma[:n] = s[:n]
+        out.append((sigma, ComplexVectors(res, n, rank), res))
+    return out
 
 
 def solve_complex_time(XA, YA, XB, YB):

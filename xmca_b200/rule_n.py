@@ -60,15 +60,7 @@ def variance_of_fields(fields, complexify, rotated, n_rot, power, extend=False, 
         return E.solve_real(A, B, want_vectors=False).sigma
     if complexify:
         sigma, vec, _ = _complex_solve(fields, extend, period)
-        p = min(n_rot, sigma.size)
-        keys = ["left", "right"][:len(fields)]
-        try:
-            Br, Bi, s_left, _, _, _ = E.rotate_complex(vec.vectors(p), sigma, keys, p, power)
-        except L.NotConvergedError:
-            return None
-        nl = E.complex_col_norms(Br, Bi, 0, s_left)
-        var = nl ** 2 if B is None else nl * E.complex_col_norms(Br, Bi, s_left, Br.shape[0])
-        return np.sort(var)[::-1]
+        return _rotated_variance_complex(sigma, vec, len(fields), n_rot, power)
     return _rotated_variance(E.solve_real(A, B, want_vectors=True), B is None, n_rot, power)
 
 
@@ -113,14 +105,35 @@ def device_surrogate_variance(shape_T, n_vars, run_index, seed, complexify, rota
     return variance_of_fields(fields, complexify, rotated, n_rot, power)
 
 
-def device_surrogate_variance_pair(shape_T, n_vars, run_a, run_b, seed, rotated, n_rot, power, dtype="float64"):
-    """Two real surrogate runs at once: the runs are independent (array.py:1753-1765), so their two symmetric
+def _rotated_variance_complex(sigma, vec, n_fields, n_rot, power):
+    from . import engine as E
+    p = min(n_rot, sigma.size)
+    keys = ["left", "right"][:n_fields]
+    try:
+        Br, Bi, s_left, _, _, _ = E.rotate_complex(vec.vectors(p), sigma, keys, p, power)
+    except L.NotConvergedError:
+        return None
+    nl = E.complex_col_norms(Br, Bi, 0, s_left)
+    var = nl ** 2 if n_fields == 1 else nl * E.complex_col_norms(Br, Bi, s_left, Br.shape[0])
+    return np.sort(var)[::-1]
+
+
+def device_surrogate_variance_pair(shape_T, n_vars, run_a, run_b, seed, rotated, n_rot, power, dtype="float64",
+                                   complexify=False):
+    """Two surrogate runs at once: the runs are independent (array.py:1753-1765), so their two symmetric
     eigenproblems go through ONE batched tridiagonalisation (engine.solve_real_pair).  Same Philox streams as
     the single-run path, hence the same surrogates.  Returns the two spectra (None where not converged)."""
     from . import engine as E
     fa = _surrogate_fields(shape_T, n_vars, run_a, seed, dtype)
     fb = _surrogate_fields(shape_T, n_vars, run_b, seed, dtype)
     pca = len(n_vars) == 1
+    if complexify:
+        (sa, va, _), (sb, vb, _) = E.solve_complex_pair(fa[0], None if pca else fa[1], fb[0], None if pca else fb[1])
+        del fa, fb
+        if not rotated:
+            return sa, sb
+        return (_rotated_variance_complex(sa, va, len(n_vars), n_rot, power),
+                _rotated_variance_complex(sb, vb, len(n_vars), n_rot, power))
     ra, rb = E.solve_real_pair(fa[0], None if pca else fa[1], fb[0], None if pca else fb[1])
     del fa, fb
     if not rotated:
@@ -167,7 +180,7 @@ def rule_n(model, n_runs, n_modes=None, seed=None, group=None, _surrogate_fn=Non
     (array.py:1756); a conscious deviation here: the surrogates follow the MODEL's field dtype
     (fp32 model -> fp32 Gaussian fields, Gram matrices on the tensor cores), which changes nothing
     statistically; pass "float64" for the reference's behaviour.  The returned spectra are fp64.
-    pair_runs: real models process their runs two at a time through one batched tridiagonalisation
+    pair_runs: the runs are processed two at a time through one batched tridiagonalisation
     (same surrogates, same spectra to rounding; see `device_surrogate_variance_pair`)."""
     import torch.distributed as dist
     T = model._n_observations["left"]
@@ -199,11 +212,11 @@ def rule_n(model, n_runs, n_modes=None, seed=None, group=None, _surrogate_fn=Non
 
     runs = list(mine)
     j = 0
-    pairs = _surrogate_fn is None and not complexify and pair_runs
+    pairs = _surrogate_fn is None and pair_runs
     while j < len(runs):
         if pairs and j + 1 < len(runs):
             sa, sb = device_surrogate_variance_pair(T, n_vars, runs[j], runs[j + 1], seed, rotated, n_rot, power,
-                                                    dtype=surrogate_dtype)
+                                                    dtype=surrogate_dtype, complexify=complexify)
             store(j, sa)
             store(j + 1, sb)
             j += 2
