@@ -117,7 +117,7 @@ static CholPlan chol_plan(int64_t n, int64_t nrhs) {
   size_t o = 0;
   p.off_inv = o;   o += (size_t)p.nblk * CB * CB * sizeof(double);
   int64_t w = nrhs > CB ? nrhs : CB;
-  p.off_panel = o; o += ((size_t)n * CB + (size_t)CB * w) * sizeof(double);
+  p.off_panel = o; o += (2 * (size_t)n * CB + (size_t)CB * w) * sizeof(double);   // two panel buffers (look-ahead)
   p.off_flag = o;  o += 256;
   p.total = o;
   return p;
@@ -140,30 +140,71 @@ extern "C" int xmca_cholesky(int64_t n, double* d_A, int64_t lda, double* d_invd
   XMCA_REQUIRE(workspace_bytes >= pl.total, "xmca_cholesky: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = reinterpret_cast<char*>(d_workspace);
-  double* panel = reinterpret_cast<double*>(ws + pl.off_panel);
+  double* panels[2] = {reinterpret_cast<double*>(ws + pl.off_panel), reinterpret_cast<double*>(ws + pl.off_panel) + (size_t)n * CB};
   int* flag = reinterpret_cast<int*>(ws + pl.off_flag);
   XMCA_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
   const size_t diag_smem = 2 * CB * (CB + 1) * sizeof(double);
   XMCA_CUDA(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)diag_smem));
-  for (int64_t b = 0; b < pl.nblk; ++b) {
+  // Look-ahead: the critical chain (diagonal block -> panel -> update of the NEXT block column) runs on an
+  // internal HIGH-priority stream; the rest of each trailing update (block columns >= b + 2) stays on the caller's
+  // stream, one step behind, under the next step's chain.  The stream / event objects live for the call only.
+  cudaStream_t chain = nullptr;
+  cudaEvent_t ev_panel = nullptr, ev_bulk = nullptr;
+  int prio_lo = 0, prio_hi = 0;
+  XMCA_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  XMCA_CUDA(cudaStreamCreateWithPriority(&chain, cudaStreamNonBlocking, prio_hi));
+  XMCA_CUDA(cudaEventCreateWithFlags(&ev_panel, cudaEventDisableTiming));
+  XMCA_CUDA(cudaEventCreateWithFlags(&ev_bulk, cudaEventDisableTiming));
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(chain);
+    cudaEventDestroy(ev_panel); cudaEventDestroy(ev_bulk); cudaStreamDestroy(chain);
+  };
+  int rc = XMCA_OK;
+  // the chain starts after everything already queued on the caller's stream (the matrix, the flag reset)
+  if (cudaEventRecord(ev_bulk, st) != cudaSuccess || cudaStreamWaitEvent(chain, ev_bulk, 0) != cudaSuccess) rc = XMCA_CUDA_ERROR;
+  bool bulk_pending = false;
+  for (int64_t b = 0; b < pl.nblk && rc == XMCA_OK; ++b) {
     const int64_t k0 = b * CB;
     const int nb = (int)((n - k0) < CB ? (n - k0) : CB);
     double* inv = d_invdiag + (size_t)b * CB * CB;
-    chol_diag_kernel<<<1, 256, diag_smem, st>>>(d_A, lda, k0, nb, inv, flag, min_pivot > 0.0 ? min_pivot : 0.0);
-    XMCA_LAUNCHED();
+    double* panel = panels[b & 1];
+    chol_diag_kernel<<<1, 256, diag_smem, chain>>>(d_A, lda, k0, nb, inv, flag, min_pivot > 0.0 ? min_pivot : 0.0);
+    if (cudaGetLastError() != cudaSuccess) { rc = XMCA_CUDA_ERROR; break; }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     const int64_t rem = n - k0 - nb;
     if (rem <= 0) break;
     // panel: L_ik = A_ik inv(L_kk)^T   (rem x nb) -> workspace, then back in place
     double* Aik = d_A + (k0 + nb) * lda + k0;
-    int rc = xmca_gemm(1, 1, rem, nb, nb, 1.0, Aik, XMCA_F64, lda, inv, XMCA_F64, CB, panel, XMCA_F64, CB, 0,
-                       XMCA_F64, 1, nullptr, 0, stream);
-    if (rc != XMCA_OK) return rc;
-    if ((rc = copy_block(panel, CB, Aik, lda, rem, nb, st)) != XMCA_OK) return rc;
-    // trailing update: A_ij -= L_ik L_jk^T (tiles on or below the diagonal; only the lower half is used later)
+    rc = xmca_gemm(1, 1, rem, nb, nb, 1.0, Aik, XMCA_F64, lda, inv, XMCA_F64, CB, panel, XMCA_F64, CB, 0,
+                   XMCA_F64, 1, nullptr, 0, (void*)chain);
+    if (rc != XMCA_OK) break;
+    if ((rc = copy_block(panel, CB, Aik, lda, rem, nb, chain)) != XMCA_OK) break;
+    if (cudaEventRecord(ev_panel, chain) != cudaSuccess) { rc = XMCA_CUDA_ERROR; break; }
+    // the previous step's bulk update also touched block column b + 1: it has to land first
+    if (bulk_pending && cudaStreamWaitEvent(chain, ev_bulk, 0) != cudaSuccess) { rc = XMCA_CUDA_ERROR; break; }
+    // trailing update  A_ij -= L_ik L_jk^T  (tiles on or below the diagonal): the next block column on the chain ...
     double* Att = d_A + (k0 + nb) * lda + (k0 + nb);
-    rc = xmca_gemm_ex(1, 1, rem, rem, nb, -1.0, panel, XMCA_F64, CB, panel, XMCA_F64, CB, Att, XMCA_F64, lda, 1,
-                      XMCA_F64, 1, nullptr, 0, XMCA_GEMM_LOWER_ONLY, stream);
-    if (rc != XMCA_OK) return rc;
+    const int64_t c1 = rem < CB ? rem : CB;
+    rc = xmca_gemm_ex(1, 1, rem, c1, nb, -1.0, panel, XMCA_F64, CB, panel, XMCA_F64, CB, Att, XMCA_F64, lda, 1,
+                      XMCA_F64, 1, nullptr, 0, 0, (void*)chain);       // (the strict upper part is zeroed at the end)
+    if (rc != XMCA_OK) break;
+    // ... and the remaining block columns on the caller's stream
+    const int64_t rem2 = rem - c1;
+    if (rem2 > 0) {
+      if (cudaStreamWaitEvent(st, ev_panel, 0) != cudaSuccess) { rc = XMCA_CUDA_ERROR; break; }
+      rc = xmca_gemm_ex(1, 1, rem2, rem2, nb, -1.0, panel + c1 * CB, XMCA_F64, CB, panel + c1 * CB, XMCA_F64, CB,
+                        Att + c1 * lda + c1, XMCA_F64, lda, 1, XMCA_F64, 1, nullptr, 0, XMCA_GEMM_LOWER_ONLY, stream);
+      if (rc != XMCA_OK) break;
+      if (cudaEventRecord(ev_bulk, st) != cudaSuccess) { rc = XMCA_CUDA_ERROR; break; }
+      bulk_pending = true;
+    }
+  }
+  // join: the caller's stream continues after the chain
+  if (rc == XMCA_OK && (cudaEventRecord(ev_panel, chain) != cudaSuccess || cudaStreamWaitEvent(st, ev_panel, 0) != cudaSuccess))
+    rc = XMCA_CUDA_ERROR;
+  if (rc != XMCA_OK) {
+    cleanup();
+    return rc == XMCA_CUDA_ERROR ? fail(XMCA_CUDA_ERROR, "xmca_cholesky: CUDA error in the block loop", __FILE__, __LINE__) : rc;
   }
   {
     dim3 grid((unsigned)((n + 127) / 128), yblocks(n));
@@ -171,8 +212,10 @@ extern "C" int xmca_cholesky(int64_t n, double* d_A, int64_t lda, double* d_invd
     XMCA_LAUNCHED();
   }
   int h_flag = 0;
-  XMCA_CUDA(cudaMemcpyAsync(&h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
-  XMCA_CUDA(cudaStreamSynchronize(st));
+  cudaError_t ce = cudaMemcpyAsync(&h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+  cleanup();
+  XMCA_CUDA(ce);
   if (info_out) *info_out = h_flag;
   if (h_flag != 0)
     return fail(XMCA_NUMERIC, "xmca_cholesky: matrix is not (numerically) positive definite", __FILE__, __LINE__);
