@@ -20,61 +20,79 @@ namespace xmca {
 
 constexpr int CB = 64;
 
-// One CTA, 256 threads.  A: n x n row-major (lda), block starting at (k0, k0) of
-// size nb (<= 64).  Writes L_kk in place (strict upper part of the block zeroed)
-// and inv(L_kk) (lower triangular, padded to 64 x 64 with an identity tail) to inv.
-// flag[0] is set to 1 + (failing column) when a pivot is not above min_pivot / finite.
-__global__ void __launch_bounds__(256)
+// One CTA of 64 threads (two warps, synchronised by a named barrier).  A: n x n row-major (lda), block starting
+// at (k0, k0) of size nb (<= 64).  Writes L_kk in place (strict upper part of the block zeroed) and inv(L_kk)
+// (lower triangular, padded to 64 x 64 with an identity tail) to inv.  flag[0] is set to k0 + 1 + (failing
+// column) when a pivot is not above min_pivot / finite.
+// The block is on the critical path of the whole factorisation (n / 64 strictly sequential launches), so both
+// parts are written for latency: thread i keeps ROW i of the block in registers and the factorisation is
+// right-looking (per column: pivot, scale, then 63 - j independent FMAs per thread); the inverse is a
+// column-oriented forward substitution with thread c holding column c of the right-hand side in registers.
+__device__ __forceinline__ void bar64() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+
+__global__ void __launch_bounds__(CB)
 chol_diag_kernel(double* __restrict__ A, int64_t lda, int64_t k0, int nb, double* __restrict__ inv,
                  int* __restrict__ flag, double min_pivot) {
-  extern __shared__ double chol_sm[];
-  double (*Ls)[CB + 1] = reinterpret_cast<double (*)[CB + 1]>(chol_sm);
-  double (*Is)[CB + 1] = reinterpret_cast<double (*)[CB + 1]>(chol_sm + CB * (CB + 1));
+  __shared__ double Ls[CB][CB + 1];
+  __shared__ double colbuf[CB], rdiag[CB];
+  __shared__ double s_rinv;
   __shared__ int s_bad;
   const int tid = threadIdx.x;
   if (tid == 0) s_bad = 0;
-  for (int e = tid; e < CB * CB; e += 256) {
-    int i = e >> 6, j = e & 63;
+  for (int e = tid; e < CB * CB; e += CB) {
+    const int i = e >> 6, j = e & 63;
     Ls[i][j] = (i < nb && j < nb && j <= i) ? A[(k0 + i) * lda + k0 + j] : ((i == j) ? 1.0 : 0.0);
   }
-  __syncthreads();
-  // left-looking factorisation, thread i owns row i: per column one dot product of length j per
-  // thread (operands in shared memory, row j broadcast) and two barriers -- the block is on the
-  // critical path of the whole factorisation (n / 64 strictly sequential launches)
-  for (int j = 0; j < nb; ++j) {
-    double sdot = 0.0;
-    if (tid >= j && tid < nb) {
-      sdot = Ls[tid][j];
-      for (int k = 0; k < j; ++k) sdot = fma(-Ls[tid][k], Ls[j][k], sdot);
-    }
-    __syncthreads();
+  bar64();
+  double row[CB];
+#pragma unroll
+  for (int k = 0; k < CB; ++k) row[k] = Ls[tid][k];
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < CB; ++j) {
     if (tid == j) {
-      if (!(sdot > min_pivot) || !isfinite(sdot)) s_bad = j + 1;
-      Ls[j][j] = sqrt(sdot);
+      const double d = row[j];
+      if (!(d > min_pivot) || !isfinite(d)) s_bad = j + 1;
+      const double piv = sqrt(d);
+      row[j] = piv;
+      const double r = 1.0 / piv;
+      s_rinv = r;
+      rdiag[j] = r;
     }
-    __syncthreads();
-    if (s_bad) break;                              // uniform
-    if (tid > j && tid < nb) Ls[tid][j] = sdot / Ls[j][j];
-    __syncthreads();                               // row j + 1 is read by every thread next
+    bar64();
+    if (s_bad) { bad = true; break; }              // uniform
+    if (tid > j) { row[j] *= s_rinv; colbuf[tid] = row[j]; }
+    bar64();
+    if (tid > j) {
+      const double lij = row[j];
+#pragma unroll
+      for (int k = j + 1; k < CB; ++k)
+        if (k <= tid) row[k] = fma(-lij, colbuf[k], row[k]);
+    }
   }
-  if (s_bad) {
+  if (bad) {
     if (tid == 0) atomicCAS(flag, 0, (int)(k0 + s_bad));
     return;
   }
-  // inverse of the lower-triangular block: column c of inv solves L x = e_c (forward substitution)
-  if (tid < CB) {
-    const int c = tid;
-    for (int i = 0; i < CB; ++i) {
-      double s = (i == c) ? 1.0 : 0.0;
-      for (int k = c; k < i; ++k) s -= Ls[i][k] * Is[k][c];
-      Is[i][c] = (i >= c) ? s / Ls[i][i] : 0.0;
-    }
+#pragma unroll
+  for (int k = 0; k < CB; ++k) Ls[tid][k] = (k <= tid) ? row[k] : 0.0;
+  bar64();
+  // inverse: column c = tid of inv solves L x = e_c; x_k = s_k / L_kk, then s_i -= L_ik x_k for all i > k
+  double sv[CB];
+#pragma unroll
+  for (int i = 0; i < CB; ++i) sv[i] = (i == tid) ? 1.0 : 0.0;
+#pragma unroll
+  for (int k = 0; k < CB; ++k) {
+    const double xk = sv[k] * rdiag[k];
+    sv[k] = xk;
+#pragma unroll
+    for (int i = k + 1; i < CB; ++i) sv[i] = fma(-Ls[i][k], xk, sv[i]);
   }
-  __syncthreads();
-  for (int e = tid; e < CB * CB; e += 256) {
-    int i = e >> 6, j = e & 63;
-    inv[e] = Is[i][j];
-    if (i < nb && j < nb) A[(k0 + i) * lda + k0 + j] = (j <= i) ? Ls[i][j] : 0.0;
+#pragma unroll
+  for (int i = 0; i < CB; ++i) inv[i * CB + tid] = (i >= tid) ? sv[i] : 0.0;
+  for (int e = tid; e < CB * CB; e += CB) {
+    const int i = e >> 6, j = e & 63;
+    if (i < nb && j < nb) A[(k0 + i) * lda + k0 + j] = Ls[i][j];
   }
 }
 
@@ -143,8 +161,6 @@ extern "C" int xmca_cholesky(int64_t n, double* d_A, int64_t lda, double* d_invd
   double* panels[2] = {reinterpret_cast<double*>(ws + pl.off_panel), reinterpret_cast<double*>(ws + pl.off_panel) + (size_t)n * CB};
   int* flag = reinterpret_cast<int*>(ws + pl.off_flag);
   XMCA_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
-  const size_t diag_smem = 2 * CB * (CB + 1) * sizeof(double);
-  XMCA_CUDA(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)diag_smem));
   // Look-ahead: the critical chain (diagonal block -> panel -> update of the NEXT block column) runs on an
   // internal HIGH-priority stream; the rest of each trailing update (block columns >= b + 2) stays on the caller's
   // stream, one step behind, under the next step's chain.  The stream / event objects live for the call only.
@@ -168,7 +184,7 @@ extern "C" int xmca_cholesky(int64_t n, double* d_A, int64_t lda, double* d_invd
     const int nb = (int)((n - k0) < CB ? (n - k0) : CB);
     double* inv = d_invdiag + (size_t)b * CB * CB;
     double* panel = panels[b & 1];
-    chol_diag_kernel<<<1, 256, diag_smem, chain>>>(d_A, lda, k0, nb, inv, flag, min_pivot > 0.0 ? min_pivot : 0.0);
+    chol_diag_kernel<<<1, CB, 0, chain>>>(d_A, lda, k0, nb, inv, flag, min_pivot > 0.0 ? min_pivot : 0.0);
     if (cudaGetLastError() != cudaSuccess) { rc = XMCA_CUDA_ERROR; break; }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     const int64_t rem = n - k0 - nb;
