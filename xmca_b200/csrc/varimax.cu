@@ -60,6 +60,72 @@ __device__ __forceinline__ void small_matmul(const double* X, int xs_i, int xs_k
   }
 }
 
+// max over the CTA (every thread gets it); red: one double per warp
+__device__ __forceinline__ double block_max(double v, double* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double m = red[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, red[w]);
+  __syncthreads();
+  return m;
+}
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double m = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m += red[w];      // fixed order: identical on every CTA
+  __syncthreads();
+  return m;
+}
+
+// Polar factor of a matrix X with NEARLY orthogonal columns (all cosines <= ~1e-3), without rotations:
+//   polar(X) = X G^{-1/2},  G = X^T X = D + E  (D = diag(s_j^2), E small)
+// and G^{-1/2} to second order in E through the divided differences of f(x) = x^{-1/2} (Daleckii-Krein):
+//   Z_ij = [i = j] / s_i  -  Et_ij / (s_i s_j)  +  sum_k Et_ik Et_kj (s_i + s_j + s_k) / (s_k s_i s_j (s_i + s_j)),
+//   Et_ij = E_ij / (s_i + s_j)
+// (f[a, b] = -1 / (ra rb (ra + rb)),  f[a, b, c] = (ra + rb + rc) / (ra rb rc (ra + rb)(rb + rc)(ra + rc)), r = sqrt).
+// The error is third order in the cosines: <= ~1e-8 here, where one more Jacobi sweep would cost 5x as much.
+// In: Et (row-major 64 x 64, zero diagonal / padding), s[64].  Out: Z (row-major 64 x 64); returns
+// sum_ij Z_ij G_ij = trace(polar(X)^T X) = the sum of the singular values.
+__device__ __noinline__ double gram_inv_sqrt2(const double* Et, const double* s, double* Z, int p, double* red) {
+  const int j = threadIdx.x & 63, ig = threadIdx.x >> 6;
+  double f[8], h[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { f[q] = 0.0; h[q] = 0.0; }
+  if (j < p) {
+    for (int k = 0; k < p; ++k) {
+      const double y = Et[k * VP + j];
+      const double yk = s[k] > 0.0 ? y / s[k] : 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const double x = Et[(ig + 8 * q) * VP + k];
+        f[q] = fma(x, yk, f[q]);
+        h[q] = fma(x, y, h[q]);
+      }
+    }
+  }
+  double dd = 0.0;
+  const double sj = s[j];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int i = ig + 8 * q;
+    const double si = s[i];
+    double z = 0.0;
+    if (i < p && j < p && si > 0.0 && sj > 0.0) {
+      const double et = Et[i * VP + j], ssum = si + sj, rij = 1.0 / (si * sj);
+      z = ((i == j) ? 1.0 / si : 0.0) - et * rij + (ssum * f[q] + h[q]) * rij / ssum;
+      dd = fma(z, (i == j) ? si * si : et * ssum, dd);
+    }
+    Z[i * VP + j] = z;
+  }
+  return block_sum(dd, red);
+}
+
 // One-sided Jacobi on the columns of X (p x p), accumulating V.  Both are held COLUMN-major
 // with stride VPP (X[c * VPP + r]) so that a warp reads a column without bank conflicts.
 // pe = p rounded up to even (column p is a zero column when p is odd).
@@ -68,12 +134,13 @@ __device__ __forceinline__ void small_matmul(const double* X, int xs_i, int xs_k
 // reductions, a division and two square roots), so one step serves all pe/2 <= 32 pairs of
 // the round.  A sweep whose largest cosine (before rotating) is <= 1e-6 leaves cosines of
 // ~1e-12: no confirming sweep is run.  Returns the number of sweeps used.
-__device__ int polar_jacobi(double* X, double* V, int pe, const unsigned char* rr, double* s_max, double stop2) {
+__device__ int polar_jacobi(double* X, double* V, int pe, const unsigned char* rr, double* s_max, double stop2,
+                            int max_sweeps = 40) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int npairs = pe >> 1;
   const bool fast = stop2 > 1e-13;           // the full-accuracy polish keeps fp64 reductions
   int sweeps = 0;
-  while (sweeps < 40) {
+  while (sweeps < max_sweeps) {
     double cmax2 = 0.0;
     for (int step = 0; step < pe - 1; ++step) {
       int cp[2], cq[2];
@@ -387,13 +454,40 @@ __global__ void __launch_bounds__(VTHREADS, 1) varimax_kernel(VarimaxParams P) {
     small_matmul(Vs, VPP, 1, Ts, VPP, 1, Xs, VPP, 1, p);   // computed as X^T = V^T T^T: Z(j,i) = sum_k V^T(j,k) T^T(k,i)
     __syncthreads();
     { long long c1 = clock64(); tk[3] += c1 - c0; c0 = c1; }
-    // Inexact polar factor inside the iteration: sweeps stop once every cosine seen before a sweep is
-    // <= 1e-3 (the sweep itself leaves ~1e-6); V is warm-started, so while T settles the residual
-    // shrinks quadratically from one outer iteration to the next.  The converged rotation is polished
-    // to full accuracy below.
-    svd_sweeps += polar_jacobi(Xs, Vs, pe, rr, s_max, 1e-6);
-    { long long c1 = clock64(); tk[4] += c1 - c0; c0 = c1; }
+    // Polar factor inside the iteration: X = T V (V warm-started) already has nearly orthogonal columns.  The
+    // Gram matrix G = X^T X tells exactly how nearly: while a cosine exceeds 1e-3 one Jacobi sweep is applied
+    // (X and V rotated); then polar(X) = X G^{-1/2} comes from the second-order expansion above (error ~1e-8)
+    // and R = polar(X) V^T.  The converged rotation is polished to full accuracy by Jacobi sweeps below.
+    double d_new = 0.0;
+    for (int guard = 0; guard < 40; ++guard) {
+      small_matmul(Xs, VPP, 1, Xs, 1, VPP, Ws, VP, 1, p);            // G(i,j) = x_i . x_j
+      __syncthreads();
+      if (tid < VP) cs[tid] = (tid < p) ? sqrt(Ws[tid * VP + tid]) : 0.0;
+      __syncthreads();
+      double m2 = 0.0;
+      for (int e = tid; e < VP * VP; e += VTHREADS) {
+        const int i = e >> 6, j = e & 63;
+        const double den = cs[i] * cs[j];
+        if (i != j && i < p && j < p && den > 0.0) { const double c = Ws[e] / den; m2 = fmax(m2, c * c); }
+      }
+      m2 = block_max(m2, s_max);
+      if (m2 <= 1e-6) break;
+      svd_sweeps += polar_jacobi(Xs, Vs, pe, rr, s_max, 1e-6, 1);
+      __syncthreads();
+    }
+    for (int e = tid; e < VP * VP; e += VTHREADS) {                  // G -> Et in place
+      const int i = e >> 6, j = e & 63;
+      const double ssum = cs[i] + cs[j];
+      Ws[e] = (i != j && i < p && j < p && ssum > 0.0) ? Ws[e] / ssum : 0.0;
+    }
     __syncthreads();
+    d_new = gram_inv_sqrt2(Ws, cs, Rs, p, s_max);                    // Rs = Z
+    __syncthreads();
+    small_matmul(Rs, VP, 1, Vs, VPP, 1, Ws, VP, 1, p);               // Y = Z V^T:  Y(i,l) = sum_j Z(i,j) V(l,j)
+    __syncthreads();
+    small_matmul(Xs, 1, VPP, Ws, VP, 1, Rs, VP, 1, p);               // R = X Y
+    __syncthreads();
+    { long long c1 = clock64(); tk[4] += c1 - c0; c0 = c1; }
     auto finish_polar = [&]() {
       // sigma_j = ||x_j||, U = X / sigma (in place), R = U V^T, d = sum sigma
       const int warp = tid >> 5, lane = tid & 31;
@@ -413,7 +507,7 @@ __global__ void __launch_bounds__(VTHREADS, 1) varimax_kernel(VarimaxParams P) {
       __syncthreads();
       return dd;
     };
-    d = finish_polar();
+    d = d_new;
     if (fabs(d - d_old) / d < P.tol) {
       // converged: redo the last polar factor to full accuracy (cosines <= 1e-11 before the final sweep)
       small_matmul(Vs, VPP, 1, Ts, VPP, 1, Xs, VPP, 1, p);          // X = T V with the accumulated V
