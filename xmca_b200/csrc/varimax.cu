@@ -36,28 +36,38 @@ struct VarimaxParams {
   double* B; int64_t ldb; double* R; double* out;   // out: [0]=iterations [1]=converged [2]=d [3]=svd sweeps total
 };
 
-// Z[i][j] = sum_k X(i,k) Y(k,j) for i, j, k < p (padded entries -> 0), 64 x 64 output by the whole
-// CTA: thread -> column j and 8 rows (8 independent accumulators hide the DFMA latency).
-// Element access: X(i,k) = X[i * xs_i + k * xs_k], Y(k,j) = Y[k * ys_k + j * ys_j] (so transposed
-// / padded operands are expressed through strides); Z is written at Z[i * zs_i + j * zs_j].
+// Z[i][j] = sum_k X(i,k) Y(k,j) for i, j, k < p (padded entries -> 0), 64 x 64 output by the first 256 threads
+// of the CTA: a 4 x 4 register block per thread (rows 4 ty + r, columns tx + 16 c), so that one k step of a warp
+// costs 8 shared-memory wavefronts for 512 FMAs -- the products are bound by the shared-memory crossbar, not by
+// the fp64 pipe.  Element access: X(i,k) = X[i * xs_i + k * xs_k], Y(k,j) = Y[k * ys_k + j * ys_j] (transposed /
+// padded operands are expressed through strides); Z is written at Z[i * zs_i + j * zs_j].
 __device__ __forceinline__ void small_matmul(const double* X, int xs_i, int xs_k, const double* Y, int ys_k, int ys_j,
                                              double* Z, int zs_i, int zs_j, int p) {
-  const int j = threadIdx.x & 63, ig = threadIdx.x >> 6;     // VTHREADS / 64 = 8 row groups
-  double acc[8];
+  if (threadIdx.x >= 256) return;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double acc[4][4];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) acc[q] = 0.0;
-  if (j < p) {
-    for (int k = 0; k < p; ++k) {
-      const double y = Y[k * ys_k + j * ys_j];
+  for (int r = 0; r < 4; ++r)
 #pragma unroll
-      for (int q = 0; q < 8; ++q) acc[q] = fma(X[(ig + 8 * q) * xs_i + k * xs_k], y, acc[q]);
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+  for (int k = 0; k < p; ++k) {
+    double a[4], b[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) a[r] = X[(4 * ty + r) * xs_i + k * xs_k];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) b[c] = Y[k * ys_k + (tx + 16 * c) * ys_j];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = fma(a[r], b[c], acc[r][c]);
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int i = 4 * ty + r, j = tx + 16 * c;
+      Z[i * zs_i + j * zs_j] = (i < p && j < p) ? acc[r][c] : 0.0;
     }
-  }
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const int i = ig + 8 * q;
-    Z[i * zs_i + j * zs_j] = (i < p && j < p) ? acc[q] : 0.0;
-  }
 }
 
 // max over the CTA (every thread gets it); red: one double per warp
@@ -93,35 +103,42 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 // In: Et (row-major 64 x 64, zero diagonal / padding), s[64].  Out: Z (row-major 64 x 64); returns
 // sum_ij Z_ij G_ij = trace(polar(X)^T X) = the sum of the singular values.
 __device__ __noinline__ double gram_inv_sqrt2(const double* Et, const double* s, double* Z, int p, double* red) {
-  const int j = threadIdx.x & 63, ig = threadIdx.x >> 6;
-  double f[8], h[8];
+  double dd = 0.0;
+  if (threadIdx.x < 256) {
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double f[4][4], h[4][4];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) { f[q] = 0.0; h[q] = 0.0; }
-  if (j < p) {
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { f[r][c] = 0.0; h[r][c] = 0.0; }
     for (int k = 0; k < p; ++k) {
-      const double y = Et[k * VP + j];
-      const double yk = s[k] > 0.0 ? y / s[k] : 0.0;
+      const double rk = s[k] > 0.0 ? 1.0 / s[k] : 0.0;
+      double a[4], b[4];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const double x = Et[(ig + 8 * q) * VP + k];
-        f[q] = fma(x, yk, f[q]);
-        h[q] = fma(x, y, h[q]);
+      for (int r = 0; r < 4; ++r) a[r] = Et[(4 * ty + r) * VP + k];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) b[c] = Et[k * VP + tx + 16 * c];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const double ak = a[r] * rk;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { f[r][c] = fma(ak, b[c], f[r][c]); h[r][c] = fma(a[r], b[c], h[r][c]); }
       }
     }
-  }
-  double dd = 0.0;
-  const double sj = s[j];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const int i = ig + 8 * q;
-    const double si = s[i];
-    double z = 0.0;
-    if (i < p && j < p && si > 0.0 && sj > 0.0) {
-      const double et = Et[i * VP + j], ssum = si + sj, rij = 1.0 / (si * sj);
-      z = ((i == j) ? 1.0 / si : 0.0) - et * rij + (ssum * f[q] + h[q]) * rij / ssum;
-      dd = fma(z, (i == j) ? si * si : et * ssum, dd);
-    }
-    Z[i * VP + j] = z;
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int i = 4 * ty + r, j = tx + 16 * c;
+        const double si = s[i], sj = s[j];
+        double z = 0.0;
+        if (i < p && j < p && si > 0.0 && sj > 0.0) {
+          const double et = Et[i * VP + j], ssum = si + sj, rij = 1.0 / (si * sj);
+          z = ((i == j) ? 1.0 / si : 0.0) - et * rij + (ssum * f[r][c] + h[r][c]) * rij / ssum;
+          dd = fma(z, (i == j) ? si * si : et * ssum, dd);
+        }
+        Z[i * VP + j] = z;
+      }
   }
   return block_sum(dd, red);
 }
