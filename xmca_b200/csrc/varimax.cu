@@ -151,8 +151,10 @@ __device__ __noinline__ double gram_inv_sqrt2(const double* Et, const double* s,
 // reductions, a division and two square roots), so one step serves all pe/2 <= 32 pairs of
 // the round.  A sweep whose largest cosine (before rotating) is <= 1e-6 leaves cosines of
 // ~1e-12: no confirming sweep is run.  Returns the number of sweeps used.
+// skip2: pairs whose squared cosine is below it are left alone (the in-loop caller finishes with an expansion that
+// is accurate for cosines up to ~1e-3, so only the few larger ones need a rotation).
 __device__ int polar_jacobi(double* X, double* V, int pe, const unsigned char* rr, double* s_max, double stop2,
-                            int max_sweeps = 40) {
+                            int max_sweeps = 40, double skip2 = 1e-30) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int npairs = pe >> 1;
   const bool fast = stop2 > 1e-13;           // the full-accuracy polish keeps fp64 reductions
@@ -221,7 +223,7 @@ __device__ int polar_jacobi(double* X, double* V, int pe, const unsigned char* r
         if (!on[u]) continue;
         // |cos| = |ga| / sqrt(al be), compared and recorded through its square (no sqrt / division)
         const double ab = al[u] * be[u], g2 = ga[u] * ga[u];
-        if (g2 > 1e-30 * ab && fabs(ga[u]) > 1e-300) {
+        if (g2 > skip2 * ab && fabs(ga[u]) > 1e-300) {
           cmax2 = fmax(cmax2, g2 * fast_rcp(ab));
           // The rotation angle only steers convergence: zeta and t in fp32 (hardware MUFU ops);
           // c = 1/sqrt(1 + t^2), s = c t in fp64, so the rotation is orthogonal to rounding.
@@ -489,7 +491,7 @@ __global__ void __launch_bounds__(VTHREADS, 1) varimax_kernel(VarimaxParams P) {
       }
       m2 = block_max(m2, s_max);
       if (m2 <= 1e-6) break;
-      svd_sweeps += polar_jacobi(Xs, Vs, pe, rr, s_max, 1e-6, 1);
+      svd_sweeps += polar_jacobi(Xs, Vs, pe, rr, s_max, 1e-6, 1, 1e-8);
       __syncthreads();
     }
     for (int e = tid; e < VP * VP; e += VTHREADS) {                  // G -> Et in place
