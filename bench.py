@@ -65,10 +65,10 @@ def workload_string(workload):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of sytrd_panel_kernel<true> (ncu --set full, n = 8192,
 # panel 9 of 128) next to the algorithmic bytes of that launch (64 columns x n'^2 x 4 B)
-SYTRD_NCU_TRAFFIC = {"traffic": 15.38e9, "traffic_algorithmic_same_launch": 14.95e9,
-                     "traffic_note": "ONE panel launch (ncu --set full, n = 8192, panel 9/128): 15.21 GB read + 0.18 GB written "
-                                     "for 14.95 GB of algorithmic bytes; `achieved` averages all panel launches, barriers and "
-                                     "trailing updates of a call (profiles/r1_ncu_summary.md)"}
+SYTRD_NCU_TRAFFIC = {"traffic": 15.36e9, "traffic_algorithmic_same_launch": 14.95e9,
+                     "traffic_note": "ONE panel launch (ncu --set full, n = 8192, panel 9/128, 3.84 ms): 15.21 GB read + 0.15 GB "
+                                     "written for 14.95 GB of algorithmic bytes = 4.0 TB/s; `achieved` averages all panel "
+                                     "launches, barriers and trailing updates of a call (profiles/r1_ncu_summary.md)"}
 
 CPU_SAMPLE_DIV = {"c2": 4, "half": 2, "small": 1, "c3": 8, "c3half": 4, "c5": 16, "c5half": 8}
 
