@@ -445,7 +445,7 @@ def spectrum_embedding(X, F=None):
     return D.embed_complex(ZZ)
 
 
-def solve_real_pair(A0, B0, A1, B1, null_basis=None, dof=None):
+def solve_real_pair(A0, B0, A1, B1, null_basis=None, dof=None, want_vectors=True):
     """Two independent real solves of the same shape (the surrogate runs of rule_n, array.py:1753-1765).
     On the tridiagonal route both symmetric matrices are reduced by ONE batched call (xmca_sytrd_batched:
     half of the SMs each, so one streams while the other is in its latency-bound phases); otherwise two
@@ -455,7 +455,7 @@ def solve_real_pair(A0, B0, A1, B1, null_basis=None, dof=None):
     S2 = S1 if pca else B0.shape[1]
     rank = min(T, S1, S2)
     same = A0.shape == A1.shape and A0.dtype == A1.dtype and (pca == (B1 is None)) and (pca or B0.shape == B1.shape)
-    single = lambda A, B: solve_real(A, B, null_basis=null_basis, dof=dof)
+    single = lambda A, B: solve_real(A, B, want_vectors=want_vectors, null_basis=null_basis, dof=dof)
     if not (same and TRIDIAG_MIN_N <= rank <= D.sytrd_max_n()):
         return single(A0, B0), single(A1, B1)
     try:
@@ -496,7 +496,7 @@ def solve_complex(XA, XB, want_vectors=True):
     return sigma, ComplexVectors(res, n, rank), res
 
 
-def solve_complex_pair(XA0, XB0, XA1, XB1):
+def solve_complex_pair(XA0, XB0, XA1, XB1, want_vectors=True):
     """Two independent complex solves of the same shape (see `solve_complex`) sharing one batched
     tridiagonalisation (`solve_real_pair`).  Returns two (sigma, ComplexVectors, embedded result) triples."""
     T, S1 = XA0.shape
@@ -507,7 +507,8 @@ def solve_complex_pair(XA0, XB0, XA1, XB1):
     emb = [(spectrum_embedding(XA, F), None if pca else spectrum_embedding(XB, F)) for XA, XB in ((XA0, XB0), (XA1, XB1))]
     del F
     out = []
-    for res in solve_real_pair(emb[0][0], emb[0][1], emb[1][0], emb[1][1], null_basis=0, dof=T - 1):
+    for res in solve_real_pair(emb[0][0], emb[0][1], emb[1][0], emb[1][1], null_basis=0, dof=T - 1,
+                               want_vectors=want_vectors):
         s = res.sigma[0::2]
         sigma = np.zeros(rank)
         n = min(rank, s.size)

@@ -128,13 +128,14 @@ def device_surrogate_variance_pair(shape_T, n_vars, run_a, run_b, seed, rotated,
     fb = _surrogate_fields(shape_T, n_vars, run_b, seed, dtype)
     pca = len(n_vars) == 1
     if complexify:
-        (sa, va, _), (sb, vb, _) = E.solve_complex_pair(fa[0], None if pca else fa[1], fb[0], None if pca else fb[1])
+        (sa, va, _), (sb, vb, _) = E.solve_complex_pair(fa[0], None if pca else fa[1], fb[0], None if pca else fb[1],
+                                                        want_vectors=rotated)
         del fa, fb
         if not rotated:
             return sa, sb
         return (_rotated_variance_complex(sa, va, len(n_vars), n_rot, power),
                 _rotated_variance_complex(sb, vb, len(n_vars), n_rot, power))
-    ra, rb = E.solve_real_pair(fa[0], None if pca else fa[1], fb[0], None if pca else fb[1])
+    ra, rb = E.solve_real_pair(fa[0], None if pca else fa[1], fb[0], None if pca else fb[1], want_vectors=rotated)
     del fa, fb
     if not rotated:
         return ra.sigma, rb.sigma
