@@ -12,7 +12,8 @@
  *     keeps a pointer after the call returns and never allocates persistent
  *     device memory.  Scratch space is caller-supplied: ask the matching
  *     *_workspace_bytes() function first.
- *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it (or on a stream
+ *     forked from and joined back onto it inside the call: xmca_cholesky).
  *     Calls that need a device->host decision (convergence tests) synchronise
  *     that stream internally and say so.
  *   - matrices are dense, real.  Complex fields are handled by the host as
@@ -124,7 +125,9 @@ int xmca_jacobi_svd(int64_t m, int64_t n, double* d_Kc, int64_t ldk,
  *   64 x 64 diagonal blocks (xmca_cholesky_invdiag_bytes).  Returns XMCA_NUMERIC
  *   (info_out = 1 + failing column) if a pivot is not above min_pivot (>= 0): the
  *   matrix is not numerically positive definite.
- *   Synchronises `stream` once at the end to read that flag.
+ *   Synchronises `stream` once at the end to read that flag.  Look-ahead: the chain diagonal block ->
+ *   panel -> next block column runs on an internal high-priority stream that is forked from and joined
+ *   back onto `stream` inside the call (the bulk trailing updates stay on `stream`).
  * xmca_trsm_lt: solves L^T W = R in place (R: n x nrhs row-major, ldr). */
 size_t xmca_cholesky_workspace_bytes(int64_t n);
 size_t xmca_cholesky_invdiag_bytes(int64_t n);
