@@ -1,0 +1,103 @@
+"""Design prototype (numpy, NOT part of the shipped path, imported by nothing): two-stage reduction of a
+symmetric matrix to tridiagonal form, the planned replacement of the one-stage `xmca_sytrd` for single solves.
+
+  stage 1  dense -> band (bandwidth b): blocked Householder QR of each (m x b) sub-diagonal panel, two-sided
+           compact-WY update of the trailing matrix -- everything but the panel QR is GEMM shaped
+           (W = A22 V T, X = W - 1/2 V (T^T (V^T W)), A22 -= X V^T + V X^T): 4/3 n^3 flops on the fp64 DMMA pipe
+           instead of n^3 8/6 bytes of latency-ridden matrix-vector passes.
+  stage 2  band -> tridiagonal by bulge chasing (Bischof / Lang / Sun): per column one length-b reflector and a
+           chain of (n - j) / b chase steps on b x 3b windows: 6 n^2 b flops, L2 / shared-memory resident,
+           parallel as a wavefront of sweeps (sweep j + 1 may run two windows behind sweep j).
+
+Run:  python scripts/proto/two_stage_sytrd.py [n] [b]   -> checks the eigenvalues of both stages against numpy and
+prints the flop / task counts the DESIGN.md estimate uses.
+"""
+import sys
+import numpy as np
+
+
+def house(x):
+    """v (v[0] = 1), tau, beta with (I - tau v v^T) x = beta e_0  (LAPACK dlarfg convention)."""
+    alpha, xnorm = x[0], np.linalg.norm(x[1:])
+    if xnorm == 0.0:
+        v = np.zeros_like(x); v[0] = 1.0
+        return v, 0.0, alpha
+    beta = -np.copysign(np.hypot(alpha, xnorm), alpha)
+    v = x / (alpha - beta); v[0] = 1.0
+    return v, (beta - alpha) / beta, beta
+
+
+def panel_qr(P):
+    """Householder QR of the m x b panel: returns V (m x b, unit lower trapezoidal), T (b x b upper, compact WY:
+    Q = I - V T V^T) and R (b x b upper triangular)."""
+    m, b = P.shape
+    P = P.copy()
+    V = np.zeros((m, b)); taus = np.zeros(b)
+    for j in range(min(b, m)):
+        v, tau, beta = house(P[j:, j])
+        V[j:, j] = v; taus[j] = tau
+        P[j:, j:] -= tau * np.outer(v, v @ P[j:, j:])
+    T = np.zeros((b, b))
+    for j in range(b):                       # dlarft, forward / columnwise
+        T[j, j] = taus[j]
+        if j:
+            T[:j, j] = -taus[j] * (T[:j, :j] @ (V[:, :j].T @ V[:, j]))
+    return V, T, np.triu(P[:b, :])
+
+
+def stage1_dense_to_band(A, b):
+    """Returns the band matrix (full storage, entries beyond bandwidth b zero) and the flop count of the GEMMs."""
+    A = A.copy(); n = A.shape[0]; flops = 0
+    for k in range(0, n - b - 1, b):
+        m = n - k - b
+        V, T, R = panel_qr(A[k + b:, k:k + b])
+        A[k + b:, k:k + b] = 0.0
+        A[k + b:k + b + R.shape[0], k:k + b] = R[:min(m, b), :]
+        A[k:k + b, k + b:] = A[k + b:, k:k + b].T
+        A22 = A[k + b:, k + b:]
+        W = A22 @ V @ T                                           # symm: 2 m^2 b
+        X = W - 0.5 * V @ (T.T @ (V.T @ W))
+        A22 -= X @ V.T + V @ X.T                                  # syr2k: 2 m^2 b
+        flops += 4 * m * m * b
+    return A, flops
+
+
+def stage2_band_to_tridiag(B, b):
+    """Bulge chasing on the full-storage band matrix; returns (d, e) and the number of chase tasks (windows)."""
+    B = B.copy(); n = B.shape[0]; tasks = 0
+    for j in range(n - 2):
+        # eliminate column j below the sub-diagonal, then chase the bulge down the band
+        col, r0 = j, j + 1
+        while r0 < n - 1:
+            r1 = min(r0 + b, n)
+            x = B[r0:r1, col]
+            if np.all(x[1:] == 0.0):
+                break
+            v, tau, beta = house(x)
+            # two-sided application on the window touched by rows / columns r0:r1 (everything else is zero there)
+            lo, hi = max(col, r0 - b), min(n, r1 + b)
+            Hw = B[r0:r1, lo:hi]
+            Hw -= tau * np.outer(v, v @ Hw)
+            Hc = B[lo:hi, r0:r1]
+            Hc -= tau * np.outer(Hc @ v, v)
+            tasks += 1
+            # the reflector filled a bulge below the band in columns r0:r1: its first column is chased next
+            col, r0 = r0, r1
+    return np.diag(B).copy(), np.diag(B, -1).copy(), tasks
+
+
+if __name__ == "__main__":
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 192
+    b = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+    rng = np.random.default_rng(0)
+    S = rng.standard_normal((n, n)); S = S @ S.T / n
+    ref = np.linalg.eigvalsh(S)
+    Bm, flops = stage1_dense_to_band(S, b)
+    i, j = np.indices((n, n))
+    assert np.abs(Bm[np.abs(i - j) > b]).max() < 1e-12 * np.abs(S).max(), "stage 1 left entries outside the band"
+    print("stage 1: band eigenvalues vs numpy %.2e, GEMM flops %.3g (4/3 n^3 = %.3g)"
+          % (np.abs(np.linalg.eigvalsh(Bm) - ref).max() / ref.max(), flops, 4 / 3 * n ** 3))
+    d, e, tasks = stage2_band_to_tridiag(Bm, b)
+    Tm = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
+    print("stage 2: tridiagonal eigenvalues vs numpy %.2e, chase tasks %d (n^2 / (2 b) = %d)"
+          % (np.abs(np.linalg.eigvalsh(Tm) - ref).max() / ref.max(), tasks, n * n // (2 * b)))
