@@ -144,6 +144,20 @@ def _rule_n_worker(rank, world, port, out_dir):
 
     got = rule_n(m, 11, n_modes=4, seed=17, _surrogate_fn=stub)
     np.save(os.path.join(out_dir, "r%d.npy" % rank), got)
+
+    # the same runs two at a time (what the GPU path does): identical bookkeeping, also with an odd number of
+    # runs on a rank and a dropped run inside a pair
+    calls = []
+
+    def pair_stub(T, n_vars, run_a, run_b, seed, rot, n_rot, power, dtype=None, complexify=False):
+        calls.append((run_a, run_b))
+        return (stub(T, n_vars, run_a, seed, complexify, rot, n_rot, power),
+                stub(T, n_vars, run_b, seed, complexify, rot, n_rot, power))
+
+    paired = rule_n(m, 11, n_modes=4, seed=17, _surrogate_fn=stub, _pair_fn=pair_stub)
+    np.testing.assert_array_equal(paired, got)
+    mine = list(__import__("xmca_b200.rule_n", fromlist=["partition"]).partition(11, world, rank))
+    assert calls == [(mine[k], mine[k + 1]) for k in range(0, len(mine) - 1, 2)]
     dist.destroy_process_group()
 
 

@@ -174,7 +174,7 @@ def gather_spectra(local: np.ndarray, valid: np.ndarray, n_runs: int, group=None
 
 
 def rule_n(model, n_runs, n_modes=None, seed=None, group=None, _surrogate_fn=None, surrogate_dtype=None,
-           pair_runs=True):
+           pair_runs=True, _pair_fn=None):
     """Sharded Rule N for an ``xmca_b200.MCA`` model (array.py:1716-1771).
 
     surrogate_dtype: the reference draws float64 surrogates whatever the model's dtype
@@ -213,11 +213,12 @@ def rule_n(model, n_runs, n_modes=None, seed=None, group=None, _surrogate_fn=Non
 
     runs = list(mine)
     j = 0
-    pairs = _surrogate_fn is None and pair_runs
+    pairs = (_surrogate_fn is None or _pair_fn is not None) and pair_runs
+    pair_fn = _pair_fn or device_surrogate_variance_pair
     while j < len(runs):
         if pairs and j + 1 < len(runs):
-            sa, sb = device_surrogate_variance_pair(T, n_vars, runs[j], runs[j + 1], seed, rotated, n_rot, power,
-                                                    dtype=surrogate_dtype, complexify=complexify)
+            sa, sb = pair_fn(T, n_vars, runs[j], runs[j + 1], seed, rotated, n_rot, power,
+                             dtype=surrogate_dtype, complexify=complexify)
             store(j, sa)
             store(j + 1, sb)
             j += 2
