@@ -9,6 +9,18 @@ symmetric matrix to tridiagonal form, the planned replacement of the one-stage `
            chain of (n - j) / b chase steps on b x 3b windows: 6 n^2 b flops, L2 / shared-memory resident,
            parallel as a wavefront of sweeps (sweep j + 1 may run two windows behind sweep j).
 
+Planned GPU mapping (round 2):
+  stage 1  panel QR by one cooperative kernel (TSQR-free: the panel is m x 64, column norms by grid reduction as in
+           today's sytrd_panel_kernel but on 64 columns of a TALL panel only -- O(m b) bytes per column instead of
+           O(m^2)); W = A22 V T and the rank-2b update on xmca_gemm_ex (DMMA), A22 kept tile-major / lower only.
+  stage 2  band in a (2b + 1) x n array (8.4 MB at n = 8192, b = 64: L2 resident).  One persistent CTA per sweep
+           (sweeps handed out in order from an atomic counter); task k of sweep j waits on a progress flag until
+           sweep j - 1 has finished task k + 2, then generates its length-b reflector (warp reduction) and applies it
+           to its b x 3b window from both sides in shared memory, publishes its own progress (release store).
+           ~n / (3b) sweeps are in flight; ~64 tasks of 1-2 us per sweep.  Eigenvalues-only callers (rule_n, the
+           unrotated spectrum) stop here; for vectors the reflectors are stored (n^2 / 2 doubles) and applied to
+           the m requested vectors as diamond-shaped compact-WY blocks (b sweeps x one chase position each).
+
 Run:  python scripts/proto/two_stage_sytrd.py [n] [b]   -> checks the eigenvalues of both stages against numpy and
 prints the flop / task counts the DESIGN.md estimate uses.
 """
