@@ -278,7 +278,26 @@ def run_product(args, rank, world, local_rank):
         _lib.profile_begin()
         model.rule_n(world, n_modes, seed=4321)
         rn_prof = _lib.profile_end()
+        # The reference draws float64 surrogates whatever the model's dtype (array.py:1756); the engine's default
+        # follows the model's field dtype (fp32 here: Gram matrices on the tensor cores).  Time the reference's
+        # choice as well, so that both numbers stand next to each other.
+        rn64 = None
+        if np.dtype(wo["dtype"]) == np.float32:
+            try:
+                model.rule_n(2 * world, n_modes, seed=98, surrogate_dtype="float64")        # warm-up
+                barrier()
+                e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e2.record()
+                sp64 = model.rule_n(n_runs, n_modes, seed=1234, surrogate_dtype="float64")
+                e3.record()
+                barrier()
+                ms64 = reduce_max(e2.elapsed_time(e3))
+                rn64 = {"surrogates_per_s": n_runs / (ms64 / 1e3), "ms_total": ms64, "shape": list(sp64.shape)}
+            except Exception as exc:                   # this leg must never take the bench line down
+                rn64 = {"error": "%s: %s" % (type(exc).__name__, exc)}
         rn = {"surrogates_per_s": n_runs / (ms_rn / 1e3), "n_runs": n_runs,
+              "surrogate_dtype": "%s (the model's field dtype; see float64_surrogates for the reference's choice)" % np.dtype(wo["dtype"]).name,
+              "float64_surrogates": rn64,
               "runs_per_rank": n_runs / world, "scaling": "strong" if args.rule_n_total > 0 else "weak",
               "ms_total": ms_rn, "shape": list(spectra.shape), "dtype": "f64",
               "collective": "1 all_gather (nccl)" if world > 1 else "none (1 rank)",
