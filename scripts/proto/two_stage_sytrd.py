@@ -113,3 +113,66 @@ if __name__ == "__main__":
     Tm = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
     print("stage 2: tridiagonal eigenvalues vs numpy %.2e, chase tasks %d (n^2 / (2 b) = %d)"
           % (np.abs(np.linalg.eigvalsh(Tm) - ref).max() / ref.max(), tasks, n * n // (2 * b)))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Stage 2 again, on the storage the kernel will use: AB[d, j] = A[j + d, j], d = 0 .. 2b (lower band + bulge room).
+# One task = three dense sub-blocks around the reflector's index range I = [r0, r1):
+#   left   A[I, lo:r0]   <- H A[I, lo:r0]        (b x <= b; its first column is the one being eliminated)
+#   diag   A[I, I]       <- H A[I, I] H          (symmetric b x b, lower part stored)
+#   below  A[r1:hi, I]   <- A[r1:hi, I] H        (<= b x b; fills the next bulge)
+def to_band_storage(B, b):
+    n = B.shape[0]
+    AB = np.zeros((2 * b + 1, n))
+    for d in range(2 * b + 1):
+        AB[d, :n - d] = np.diag(B, -d)
+    return AB
+
+
+def stage2_band_storage(AB, b):
+    AB = AB.copy(); n = AB.shape[1]
+
+    def get(r, c):            # r >= c
+        return AB[r - c, c]
+
+    for j in range(n - 2):
+        col, r0 = j, j + 1
+        while r0 < n - 1:
+            r1 = min(r0 + b, n); m = r1 - r0
+            x = np.array([get(r0 + i, col) for i in range(m)])
+            if np.all(x[1:] == 0.0):
+                break
+            v, tau, beta = house(x)
+            lo, hi = max(col, r0 - b), min(n, r1 + b)
+            # left block: rows I, columns lo .. r0 - 1
+            for c in range(lo, r0):
+                colv = np.array([get(r0 + i, c) for i in range(m)])
+                colv -= tau * v * (v @ colv)
+                for i in range(m):
+                    AB[r0 + i - c, c] = colv[i]
+            # diagonal block (symmetric, two-sided): D <- D - v w^T - w v^T,  w = tau D v - (tau^2 v^T D v / 2) v
+            D = np.zeros((m, m))
+            for i in range(m):
+                for k in range(i + 1):
+                    D[i, k] = D[k, i] = get(r0 + i, r0 + k)
+            p = tau * (D @ v)
+            w = p - 0.5 * tau * (v @ p) * v
+            D -= np.outer(v, w) + np.outer(w, v)
+            for i in range(m):
+                for k in range(i + 1):
+                    AB[i - k, r0 + k] = D[i, k]
+            # block below: rows r1 .. hi - 1, columns I
+            for r in range(r1, hi):
+                rowv = np.array([get(r, r0 + k) for k in range(m)])
+                rowv -= tau * (rowv @ v) * v
+                for k in range(m):
+                    AB[r - r0 - k, r0 + k] = rowv[k]
+            col, r0 = r0, r1
+    return AB[0].copy(), AB[1, :n - 1].copy()
+
+
+if __name__ == "__main__":
+    d2, e2 = stage2_band_storage(to_band_storage(Bm, b), b)
+    T2 = np.diag(d2) + np.diag(e2, 1) + np.diag(e2, -1)
+    print("stage 2 on band storage (left / diagonal / below blocks): eigenvalues vs numpy %.2e; max |d - d_full| %.2e"
+          % (np.abs(np.linalg.eigvalsh(T2) - ref).max() / ref.max(), np.abs(d2 - d).max()))
