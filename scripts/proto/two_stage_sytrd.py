@@ -176,3 +176,54 @@ if __name__ == "__main__":
     T2 = np.diag(d2) + np.diag(e2, 1) + np.diag(e2, -1)
     print("stage 2 on band storage (left / diagonal / below blocks): eigenvalues vs numpy %.2e; max |d - d_full| %.2e"
           % (np.abs(np.linalg.eigvalsh(T2) - ref).max() / ref.max(), np.abs(d2 - d).max()))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Eigenvectors: S = Q1 B Q1^T (stage 1, block reflectors per panel), B = Q2 T Q2^T (stage 2, one reflector per
+# task, in task order).  An eigenvector z of T goes back as x = Q1 (Q2 z): the stage-2 reflectors are applied in
+# REVERSE task order (each touches rows r0:r1 only -- reflectors of one chase position from b consecutive sweeps
+# touch overlapping ranges and can be merged into one compact-WY block: the "diamond" blocking), then the stage-1
+# block reflectors in reverse panel order (GEMMs).
+def two_stage_with_vectors(S, b, m):
+    n = S.shape[0]
+    A = S.copy(); q1 = []
+    for k in range(0, n - b - 1, b):
+        V, T, R = panel_qr(A[k + b:, k:k + b])
+        q1.append((k + b, V, T))
+        A[k + b:, k:k + b] = 0.0
+        A[k + b:k + b + R.shape[0], k:k + b] = R[:min(n - k - b, b), :]
+        A[k:k + b, k + b:] = A[k + b:, k:k + b].T
+        A22 = A[k + b:, k + b:]
+        W = A22 @ V @ T
+        X = W - 0.5 * V @ (T.T @ (V.T @ W))
+        A22 -= X @ V.T + V @ X.T
+    q2 = []
+    for j in range(n - 2):
+        col, r0 = j, j + 1
+        while r0 < n - 1:
+            r1 = min(r0 + b, n)
+            x = A[r0:r1, col]
+            if np.all(x[1:] == 0.0):
+                break
+            v, tau, beta = house(x.copy())
+            lo, hi = max(col, r0 - b), min(n, r1 + b)
+            Hw = A[r0:r1, lo:hi]; Hw -= tau * np.outer(v, v @ Hw)
+            Hc = A[lo:hi, r0:r1]; Hc -= tau * np.outer(Hc @ v, v)
+            q2.append((r0, v, tau))
+            col, r0 = r0, r1
+    d, e = np.diag(A).copy(), np.diag(A, -1).copy()
+    lam, Z = np.linalg.eigh(np.diag(d) + np.diag(e, 1) + np.diag(e, -1))
+    lam, Z = lam[::-1][:m], Z[:, ::-1][:, :m].copy()
+    for r0, v, tau in reversed(q2):                       # x <- H x  on rows r0 : r0 + len(v)
+        blk = Z[r0:r0 + v.size]
+        blk -= tau * np.outer(v, v @ blk)
+    for r0, V, T in reversed(q1):                         # x <- (I - V T V^T) x  on rows r0 :
+        blk = Z[r0:]
+        blk -= V @ (T @ (V.T @ blk))
+    return lam, Z
+
+
+if __name__ == "__main__":
+    lam, X = two_stage_with_vectors(S, b, 6)
+    print("vectors through both stages: max |S x - lambda x| / lambda_max = %.2e, |X^T X - I| = %.2e"
+          % (np.abs(S @ X - X * lam).max() / lam[0], np.abs(X.T @ X - np.eye(6)).max()))
