@@ -1,0 +1,47 @@
+"""CPU checks of the numpy design prototypes under scripts/proto/ (the two-stage tridiagonalisation planned next,
+DESIGN.md 6b).  They are not on the product path; the tests only keep the documented algorithms reproducible."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "scripts", "proto"))
+
+
+def _spd(n, seed):
+    r = np.random.default_rng(seed)
+    S = r.standard_normal((n, n))
+    return S @ S.T / n
+
+
+def test_two_stage_reduction_keeps_the_spectrum_and_vectors():
+    import two_stage_sytrd as P
+    n, b = 70, 6
+    S = _spd(n, 0)
+    ref = np.linalg.eigvalsh(S)
+    Bm, _ = P.stage1_dense_to_band(S, b)
+    i, j = np.indices((n, n))
+    assert np.abs(Bm[np.abs(i - j) > b]).max() < 1e-12
+    np.testing.assert_allclose(np.linalg.eigvalsh(Bm), ref, atol=1e-13 * ref.max())
+    d, e, tasks = P.stage2_band_to_tridiag(Bm, b)
+    T = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
+    np.testing.assert_allclose(np.linalg.eigvalsh(T), ref, atol=1e-13 * ref.max())
+    d2, e2 = P.stage2_band_storage(P.to_band_storage(Bm, b), b)
+    T2 = np.diag(d2) + np.diag(e2, 1) + np.diag(e2, -1)
+    np.testing.assert_allclose(np.linalg.eigvalsh(T2), ref, atol=1e-13 * ref.max())
+    lam, X = P.two_stage_with_vectors(S, b, 5)
+    np.testing.assert_allclose(S @ X, X * lam, atol=1e-12 * lam[0])
+
+
+def test_bulge_chasing_sweeps_may_overlap_with_lag_two():
+    import two_stage_sytrd as P
+    import bulge_chase_schedule as C
+    n, b = 48, 4
+    Bm, _ = P.stage1_dense_to_band(_spd(n, 1), b)
+    seq = C.chase(Bm, b)
+    par, width = C.chase(Bm, b, lag=2, seed=3)
+    np.testing.assert_array_equal(par, seq)          # bit for bit: the rule orders every conflicting pair of tasks
+    assert width >= 3                                # and several sweeps are in flight
+    bad, _ = C.chase(Bm, b, lag=0, seed=3)
+    assert np.abs(bad - seq).max() > 1e-6            # without the lag the sweeps trample on each other
