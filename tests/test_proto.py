@@ -34,6 +34,18 @@ def test_two_stage_reduction_keeps_the_spectrum_and_vectors():
     np.testing.assert_allclose(S @ X, X * lam, atol=1e-12 * lam[0])
 
 
+def test_stage1_panels_by_choleskyqr2_and_householder_reconstruction():
+    import stage1_cholqr_panels as Q
+    M = Q.engine_matrix(96, 200, seed=2, k=6)
+    M = 0.5 * (M + M.T)
+    ref = np.linalg.eigvalsh(M)
+    Bm, breakdowns, orth = Q.stage1(M, 8)
+    assert breakdowns == 0 and orth < 1e-13
+    i, j = np.indices(M.shape)
+    assert np.abs(Bm[np.abs(i - j) > 8]).max() == 0.0
+    np.testing.assert_allclose(np.linalg.eigvalsh(Bm), ref, atol=1e-13 * ref.max())
+
+
 def test_bulge_chasing_sweeps_may_overlap_with_lag_two():
     import two_stage_sytrd as P
     import bulge_chase_schedule as C
