@@ -57,3 +57,35 @@ def test_bulge_chasing_sweeps_may_overlap_with_lag_two():
     assert width >= 3                                # and several sweeps are in flight
     bad, _ = C.chase(Bm, b, lag=0, seed=3)
     assert np.abs(bad - seq).max() > 1e-6            # without the lag the sweeps trample on each other
+
+
+def test_varimax_polar_expansion_is_third_order():
+    """The arithmetic of varimax.cu's in-loop polar factor (gram_inv_sqrt2): at the kernel's threshold (largest
+    cosine 1e-3) the factor is good to ~1e-8 and the sum of singular values far below the 1e-8 stop tolerance."""
+    import varimax_polar_expansion as V
+    rng = np.random.default_rng(5)
+    errs = []
+    for eps in (1.2e-3, 1.2e-4):
+        X = V.nearly_orthogonal(40, eps, rng)
+        G = X.T @ X
+        sn = np.sqrt(np.diag(G))
+        cmax = np.abs(G / np.outer(sn, sn) - np.eye(40)).max()
+        P, d = V.polar_by_expansion(X)
+        u, sv, vt = np.linalg.svd(X)
+        errs.append((cmax, np.abs(P - u @ vt).max(), abs(d - sv.sum()) / sv.sum()))
+    (c0, e0, d0), (c1, e1, d1) = errs
+    assert c0 < 1.5e-3 and e0 < 5e-8 and d0 < 1e-9
+    assert e1 < e0 * (c1 / c0) ** 3 * 20             # third order in the cosines
+
+
+def test_two_barrier_alpha_identity():
+    """tridiag.cu (two-barrier column step): alpha = -tau/2 * w_pre^T v equals -tau^2/2 * (v^T A v - 2 (V^T v).(W^T v))
+    with w_pre = tau (A v - V (W^T v) - W (V^T v)) -- the form that needs no third grid-wide reduction."""
+    rng = np.random.default_rng(6)
+    n, i = 60, 7
+    A = rng.standard_normal((n, n)); A = A + A.T
+    V, W = rng.standard_normal((n, i)), rng.standard_normal((n, i))
+    v = rng.standard_normal(n); tau = 1.3
+    p1, p2 = V.T @ v, W.T @ v
+    w_pre = tau * (A @ v - V @ p2 - W @ p1)
+    np.testing.assert_allclose(-0.5 * tau * (w_pre @ v), -0.5 * tau * tau * (v @ A @ v - 2.0 * (p1 @ p2)), rtol=1e-12)
