@@ -177,6 +177,29 @@ int xmca_stein(int64_t n, const double* d_d, const double* d_e, int64_t k, const
 int xmca_ormtr(int64_t n, const double* d_A, int64_t lda, const double* d_tau, int64_t k,
                double* d_Z, int64_t ldz, void* stream);
 
+/* ---- two-stage symmetric tridiagonalisation (fp64; csrc/sbr.cu + csrc/sbtrd.cu) --------------
+ * Same seam as xmca_sytrd (np.linalg.svd of array.py:479 / :570), compute-bound instead of HBM-bound:
+ *   stage 1  dense -> band (bandwidth 64): panels by shifted CholeskyQR3 + Householder reconstruction,
+ *            trailing matrix  A22 <- A22 - X Y^T - Y X^T  with Z = A22 Y and the rank-128 update on the
+ *            fp64 DMMA pipe (4/3 n^3 flops, all GEMM shaped);
+ *   stage 2  band -> tridiagonal by bulge chasing on the L2-resident band (one persistent CTA per
+ *            sweep, task windows in registers, release/acquire progress flags between sweeps).
+ * xmca_sytrd2: d_A (n x n row-major, symmetric, BOTH triangles) is destroyed.  On return d_d (n) / d_e (n - 1)
+ *   hold the tridiagonal; d_A holds the stage-1 block reflectors Y_p (m x 64, dense, in the place of panel p,
+ *   below the band) and -- when want_vectors != 0 -- the stage-2 reflectors in its strict upper triangle
+ *   (row j: sweep j, leading entry of every reflector replaced by its tau); d_tfac (xmca_sytrd2_tfac_bytes)
+ *   receives the 64 x 64 triangular factors T_p of  W_p = I - Y_p T_p Y_p^T.
+ *   Returns XMCA_NUMERIC if a panel factorisation broke down (non-finite input / exactly rank-deficient
+ *   panel): the caller falls back to xmca_sytrd.  Synchronises `stream` once at the end to read that flag.
+ * xmca_ormtr2: rows of d_Z (k x n) <- Q row with Q = Q1 Q2 from xmca_sytrd2 (eigenvectors of the tridiagonal ->
+ *   eigenvectors of the original matrix; array.py:584 for the modes that are asked for). */
+size_t xmca_sytrd2_workspace_bytes(int64_t n);
+size_t xmca_sytrd2_tfac_bytes(int64_t n);
+int xmca_sytrd2(int64_t n, double* d_A, int64_t lda, double* d_d, double* d_e, double* d_tfac,
+                int want_vectors, void* d_workspace, size_t workspace_bytes, void* stream);
+int xmca_ormtr2(int64_t n, const double* d_A, int64_t lda, const double* d_tfac, int64_t k,
+                double* d_Z, int64_t ldz, void* stream);
+
 /* ---- analytic signal (Hilbert transform along time) ----------------------
  * Replaces scipy.signal.hilbert(field, axis=0) of array.py:464 by two linear operators that
  * are applied to the T x S field as GEMMs (xmca_tc_gemm_nt for fp32 fields, xmca_gemm for fp64):

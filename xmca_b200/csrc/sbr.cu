@@ -1,0 +1,915 @@
+// Stage 1 of the two-stage symmetric tridiagonalisation (fp64): dense symmetric S -> symmetric band matrix of
+// bandwidth 64 by blocked orthogonal similarity transformations, every O(n^3) part GEMM shaped (fp64 DMMA pipe),
+// plus the drivers of the whole two-stage solver (stage 2: sbtrd.cu).
+//
+// Replaces np.linalg.svd of array.py:479 / :570 (engine.py: sigma(C)^2 = eigenvalues of ONE symmetric matrix)
+// -- the one-stage xmca_sytrd (tridiag.cu) streams the trailing matrix once per column and is bound by HBM and
+// per-column latency; here the 4/3 n^3 flops are products with K = 64 / 128.
+//
+// Panel k (columns kb .. kb + 63, rows r0 = kb + 64 .. n - 1, m rows):
+//   P = Q R by shifted CholeskyQR3 (Fukaya et al. 2020): three passes of Gram matrix (deterministic two-level
+//       sum) -> 64 x 64 Cholesky (one CTA) -> triangular solve per row; the tiny shift of the first pass bounds the
+//       condition number the second pass sees, so no pass can break down on a numerically full-rank panel;
+//   compact WY form of an orthogonal W = I - Y T Y^T with W [I; 0] = Q diag(s) by Householder RECONSTRUCTION
+//       (Ballard et al. 2015): LU of [I; 0] - Q diag(s) with the signs chosen so that every pivot is >= 1;
+//   two-sided update of the trailing matrix  A22 <- W^T A22 W = A22 - X Y^T - Y X^T,
+//       Z = A22 Y (DMMA, split-K), X = (Z - 1/2 Y T^T (Y^T Z)) T, rank-128 update on xmca_gemm_ex (DMMA, lower tiles
+//       computed, upper mirrored).
+//   R diag(s) goes to the band array; Y stays in the panel's place in S (dense m x 64), T in the caller's `tfac`.
+// The last panel (m < 64 rows) is done by one CTA with plain Householder reflectors.
+#include "common.cuh"
+#include <math.h>
+
+namespace xmca {
+
+constexpr int PB = 64;              // panel width = bandwidth
+constexpr int PLD = PB + 1;         // shared-memory pitch
+constexpr int BLD = 2 * PB;         // doubles per band column (same as sbtrd.cu)
+constexpr int PT = 256;             // threads of the chunk kernels
+constexpr int NRED = 16;            // CTAs of the reduction kernels (256 elements each)
+
+int sb_chase(double* AB, int n, int* counters, double* V2, int64_t ldv, double* d, double* e, cudaStream_t st);
+int sb_apply_q2(const double* V2, int64_t ldv, int n, double* Z, int64_t ldz, int kvec, cudaStream_t st);
+
+__device__ __forceinline__ void bar64() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+
+// ------------------------------------------------------------------ small dense helpers (one CTA)
+// 64 x 64 (pitch PLD) from / to global (pitch 64), all threads of the CTA
+__device__ __forceinline__ void load64(double (*s)[PLD], const double* __restrict__ g, int tid, int nthreads) {
+  for (int e = tid; e < PB * PB; e += nthreads) s[e >> 6][e & 63] = g[e];
+}
+
+// rows solve  q L^T = x  in registers (thread = row): q[c] = (x[c] - sum_{k<c} q[k] L[c][k]) * rdiag[c]
+__device__ __forceinline__ void solve_lt(double (&x)[PB], const double (*Ls)[PLD], const double* rdiag) {
+#pragma unroll
+  for (int c = 0; c < PB; ++c) {
+    double acc = x[c];
+#pragma unroll
+    for (int k = 0; k < c; ++k) acc = fma(-x[k], Ls[c][k], acc);
+    x[c] = acc * rdiag[c];
+  }
+}
+// rows solve  y U = t  (U upper, rows of Us): y[c] = (t[c] - sum_{k<c} y[k] U[k][c]) * ru[c]
+__device__ __forceinline__ void solve_u(double (&x)[PB], const double (*Us)[PLD], const double* ru) {
+#pragma unroll
+  for (int c = 0; c < PB; ++c) {
+    double acc = x[c];
+#pragma unroll
+    for (int k = 0; k < c; ++k) acc = fma(-x[k], Us[k][c], acc);
+    x[c] = acc * ru[c];
+  }
+}
+
+// 64 x 64 += over rows:  G[i][j] = sum_r A[r][i] B[r][j], 256 threads, thread (ty, tx) owns i = ty + 16 a, j = tx + 16 b
+__device__ __forceinline__ void tile_atb(const double (*A)[PLD], const double (*B)[PLD], int rows, int tid,
+                                         double (&acc)[4][4]) {
+  const int tx = tid & 15, ty = tid >> 4;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+  for (int r = 0; r < rows; ++r) {
+    double av[4], bv[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) { av[a] = A[r][ty + 16 * a]; bv[a] = B[r][tx + 16 * a]; }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+  }
+}
+
+// ------------------------------------------------------------------ (1) optional solve + Gram partial per 64-row chunk
+// X: m x 64 (ldx).  If Lf != null: Q = X L^-T is written to Qout (pitch 64) first.  Gpart[chunk] = Q_chunk^T Q_chunk.
+// One extra CTA (blockIdx.x == nch) multiplies two lower-triangular factors when Ma != null: Mout = Ma Mb.
+__global__ void __launch_bounds__(PT)
+sbr_gram_kernel(const double* X, int64_t ldx, int m, const double* __restrict__ Lf,
+                double* Qout, double* __restrict__ Gpart, int nch,
+                const double* __restrict__ Ma, const double* __restrict__ Mb, double* __restrict__ Mout) {
+  extern __shared__ double smem[];
+  double (*Xs)[PLD] = reinterpret_cast<double (*)[PLD]>(smem);
+  double (*Ls)[PLD] = reinterpret_cast<double (*)[PLD]>(smem + PB * PLD);
+  __shared__ double rdiag[PB];
+  const int tid = threadIdx.x;
+  if ((int)blockIdx.x == nch) {                       // lower x lower product (accumulated R^T of the passes)
+    if (!Ma) return;
+    load64(Xs, Ma, tid, PT);
+    load64(Ls, Mb, tid, PT);
+    __syncthreads();
+    for (int e = tid; e < PB * PB; e += PT) {
+      const int i = e >> 6, c = e & 63;
+      double s = 0.0;
+      for (int k = c; k <= i; ++k) s = fma(Xs[i][k], Ls[k][c], s);
+      Mout[e] = s;
+    }
+    return;
+  }
+  const int r0 = blockIdx.x * PB, rows = min(PB, m - r0);
+  for (int e = tid; e < PB * PB; e += PT) {
+    const int r = e >> 6, c = e & 63;
+    Xs[r][c] = r < rows ? X[(int64_t)(r0 + r) * ldx + c] : 0.0;
+  }
+  if (Lf) {
+    load64(Ls, Lf, tid, PT);
+    __syncthreads();
+    if (tid < PB) rdiag[tid] = 1.0 / Ls[tid][tid];
+    __syncthreads();
+    if (tid < PB) {
+      double x[PB];
+#pragma unroll
+      for (int c = 0; c < PB; ++c) x[c] = Xs[tid][c];
+      solve_lt(x, Ls, rdiag);
+#pragma unroll
+      for (int c = 0; c < PB; ++c) Xs[tid][c] = x[c];
+    }
+    __syncthreads();
+    for (int e = tid; e < PB * PB; e += PT) {
+      const int r = e >> 6, c = e & 63;
+      if (r < rows) Qout[(int64_t)(r0 + r) * PB + c] = Xs[r][c];
+    }
+  } else {
+    __syncthreads();
+  }
+  double acc[4][4];
+  tile_atb(Xs, Xs, rows, tid, acc);
+  double* G = Gpart + (int64_t)blockIdx.x * PB * PB;
+  const int tx = tid & 15, ty = tid >> 4;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) G[(ty + 16 * a) * PB + tx + 16 * b] = acc[a][b];
+}
+
+// ------------------------------------------------------------------ (2) sum of the partials + factorisation (last CTA)
+// mode 0: G + shift I = L L^T (first pass)   1: G = L L^T   2: as 1, then Householder reconstruction of the top block
+// mode 3: C1 = T^T G (no factorisation; G = Y^T Z)
+struct RedParams {
+  const double* part; int npart; double* G; int* ticket; int mode; int m;
+  double* Lout;            // modes 0-2: Cholesky factor (lower, 64 x 64)
+  const double* Qtop;      // mode 2: top 64 rows of the current Q (pitch 64)
+  double* LU;              // mode 2: strict lower = Y1, upper = U
+  double* sign;            // mode 2: 64 signs
+  const double* Tm;        // mode 3
+  double* C1;              // mode 3
+  int* fail;
+};
+
+__global__ void __launch_bounds__(PT) sbr_reduce_kernel(RedParams P) {
+  __shared__ double Ls[PB][PLD];
+  __shared__ double colbuf[PB], rdiag[PB];
+  __shared__ double s_b0, s_b1;
+  __shared__ int s_last;
+  const int tid = threadIdx.x;
+  {
+    const int e = blockIdx.x * PT + tid;
+    double s = 0.0;
+    for (int p = 0; p < P.npart; ++p) s += __ldcg(P.part + (int64_t)p * PB * PB + e);
+    P.G[e] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(P.ticket, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (tid == 0) *P.ticket = 0;                        // re-armed for the next launch (stream ordered)
+  if (P.mode == 3) {                                  // C1 = T^T C0, T upper triangular
+    for (int e = tid; e < PB * PB; e += PT) Ls[e >> 6][e & 63] = __ldcg(P.G + e);
+    __syncthreads();
+    for (int e = tid; e < PB * PB; e += PT) {
+      const int i = e >> 6, j = e & 63;
+      double s = 0.0;
+      for (int k = 0; k <= i; ++k) s = fma(__ldg(P.Tm + k * PB + i), Ls[k][j], s);
+      P.C1[e] = s;
+    }
+    return;
+  }
+  if (tid >= PB) return;                              // the factorisations run on two warps (named barrier)
+  double row[PB];
+#pragma unroll
+  for (int k = 0; k < PB; ++k) row[k] = __ldcg(P.G + tid * PB + k);
+  if (P.mode == 0) {                                  // shift = 11 (m b + b (b + 1)) u trace(G)
+    double dg = 0.0;                                  // (static indices only: `row` must stay in registers)
+#pragma unroll
+    for (int k = 0; k < PB; ++k) dg = k == tid ? row[k] : dg;
+    colbuf[tid] = dg;
+    bar64();
+    double tr = 0.0;
+    for (int k = 0; k < PB; ++k) tr += colbuf[k];
+    double nd = dg + 11.0 * ((double)P.m * PB + PB * (PB + 1)) * 1.1102230246251565e-16 * tr;
+    if (!(tr > 0.0) || !isfinite(tr)) { nd = 1.0; if (tid == 0) atomicExch(P.fail, 1); }
+#pragma unroll
+    for (int k = 0; k < PB; ++k) row[k] = k == tid ? nd : row[k];
+    bar64();
+  }
+  // right-looking Cholesky, thread = row (lower part kept)
+#pragma unroll
+  for (int j = 0; j < PB; ++j) {
+    if (tid == j) {
+      double d = row[j];
+      if (!(d > 0.0) || !isfinite(d)) { d = 1.0; atomicExch(P.fail, 2); }
+      const double piv = sqrt(d);
+      row[j] = piv;
+      s_b0 = 1.0 / piv;
+    }
+    bar64();
+    if (tid > j) { row[j] *= s_b0; colbuf[tid] = row[j]; }
+    bar64();
+    if (tid > j) {
+      const double lij = row[j];
+#pragma unroll
+      for (int k = j + 1; k < PB; ++k)
+        if (k <= tid) row[k] = fma(-lij, colbuf[k], row[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < PB; ++k) {
+    const double v = k <= tid ? row[k] : 0.0;
+    Ls[tid][k] = v;
+    P.Lout[tid * PB + k] = v;
+  }
+  if (P.mode != 2) return;
+  // ---- Householder reconstruction on the top block: A = -(Qtop L^-T), LU without pivoting of A diag(s) + I
+  {
+    double dg = 1.0;
+#pragma unroll
+    for (int k = 0; k < PB; ++k) dg = k == tid ? row[k] : dg;
+    rdiag[tid] = 1.0 / dg;
+  }
+  bar64();
+#pragma unroll
+  for (int k = 0; k < PB; ++k) row[k] = P.Qtop[tid * PB + k];
+  solve_lt(row, Ls, rdiag);
+#pragma unroll
+  for (int k = 0; k < PB; ++k) row[k] = -row[k];
+#pragma unroll
+  for (int j = 0; j < PB; ++j) {
+    if (tid == j) {
+      const double a = row[j];
+      const double s = a >= 0.0 ? 1.0 : -1.0;
+      s_b0 = s;
+      s_b1 = 1.0 / (s * a + 1.0);
+      P.sign[j] = s;
+#pragma unroll
+      for (int k = j + 1; k < PB; ++k) colbuf[k] = row[k];
+    }
+    bar64();
+    row[j] *= s_b0;
+    if (tid == j) row[j] += 1.0;
+    if (tid > j) {
+      const double l = row[j] * s_b1;
+      row[j] = l;
+#pragma unroll
+      for (int k = j + 1; k < PB; ++k) row[k] = fma(-l, colbuf[k], row[k]);
+    }
+    bar64();
+  }
+#pragma unroll
+  for (int k = 0; k < PB; ++k) P.LU[tid * PB + k] = row[k];
+}
+
+// ------------------------------------------------------------------ (3) Y = reconstruction applied to all rows
+// chunk CTAs: rows of Y.  Top block (chunk 0): Y1 (unit lower) from LU.  Other rows: y = ((q L3^-T) * (-s)) U^-1.
+// Y goes to Ybuf (pitch 64) and to the panel's place in S (pitch lda).
+// CTA nch: T = U Y1^-T -> Tout.   CTA nch + 1: R = diag(s) (M12 L3)^T -> band array (rows r0 .., columns kb ..).
+__global__ void __launch_bounds__(PT)
+sbr_applyfinal_kernel(const double* __restrict__ Q, int m, const double* __restrict__ L3, const double* __restrict__ LU,
+                      const double* __restrict__ sign, double* __restrict__ Ybuf, double* __restrict__ Sp, int64_t lda,
+                      int nch, double* __restrict__ Tout, const double* __restrict__ M12, double* __restrict__ AB,
+                      int kb) {
+  extern __shared__ double smem[];
+  double (*Ls)[PLD] = reinterpret_cast<double (*)[PLD]>(smem);
+  double (*Us)[PLD] = reinterpret_cast<double (*)[PLD]>(smem + PB * PLD);
+  double (*Xs)[PLD] = reinterpret_cast<double (*)[PLD]>(smem + 2 * PB * PLD);
+  __shared__ double rdiag[PB], ru[PB], sg[PB];
+  const int tid = threadIdx.x;
+  if ((int)blockIdx.x == nch) {                       // T: T Y1^T = U  (forward in c, thread = row of T)
+    load64(Us, LU, tid, PT);
+    __syncthreads();
+    if (tid < PB) {
+      double t[PB];
+#pragma unroll
+      for (int c = 0; c < PB; ++c) {
+        double acc = c >= tid ? Us[tid][c] : 0.0;
+#pragma unroll
+        for (int k = 0; k < c; ++k) acc = fma(-t[k], Us[c][k], acc);     // t[k] = 0 for k < tid; Us[c][k], k < c: Y1
+        t[c] = c >= tid ? acc : 0.0;
+      }
+#pragma unroll
+      for (int c = 0; c < PB; ++c) Tout[tid * PB + c] = t[c];
+    }
+    return;
+  }
+  if ((int)blockIdx.x == nch + 1) {                   // R = diag(s) (M12 L3)^T, written into the band
+    load64(Ls, M12, tid, PT);
+    load64(Us, L3, tid, PT);
+    if (tid < PB) sg[tid] = sign[tid];
+    __syncthreads();
+    for (int e = tid; e < PB * PB; e += PT) {
+      const int c = e >> 6, i = e & 63;               // M[c][i], i <= c  ->  R[i][c]
+      if (i > c) continue;
+      double s = 0.0;
+      for (int k = i; k <= c; ++k) s = fma(Ls[c][k], Us[k][i], s);
+      AB[(int64_t)(kb + c) * BLD + (PB + i - c)] = sg[i] * s;
+    }
+    return;
+  }
+  const int r0 = blockIdx.x * PB, rows = min(PB, m - r0);
+  if (blockIdx.x == 0) {
+    for (int e = tid; e < PB * PB; e += PT) {
+      const int r = e >> 6, c = e & 63;
+      if (r >= rows) continue;
+      const double v = c < r ? LU[e] : (c == r ? 1.0 : 0.0);
+      Ybuf[(int64_t)r * PB + c] = v;
+      Sp[(int64_t)r * lda + c] = v;
+    }
+    return;
+  }
+  load64(Ls, L3, tid, PT);
+  load64(Us, LU, tid, PT);
+  for (int e = tid; e < PB * PB; e += PT) {
+    const int r = e >> 6, c = e & 63;
+    Xs[r][c] = r < rows ? Q[(int64_t)(r0 + r) * PB + c] : 0.0;
+  }
+  if (tid < PB) sg[tid] = sign[tid];
+  __syncthreads();
+  if (tid < PB) { rdiag[tid] = 1.0 / Ls[tid][tid]; ru[tid] = 1.0 / Us[tid][tid]; }
+  __syncthreads();
+  if (tid < PB) {
+    double x[PB];
+#pragma unroll
+    for (int c = 0; c < PB; ++c) x[c] = Xs[tid][c];
+    solve_lt(x, Ls, rdiag);
+#pragma unroll
+    for (int c = 0; c < PB; ++c) x[c] *= -sg[c];
+    solve_u(x, Us, ru);
+#pragma unroll
+    for (int c = 0; c < PB; ++c) Xs[tid][c] = x[c];
+  }
+  __syncthreads();
+  for (int e = tid; e < PB * PB; e += PT) {
+    const int r = e >> 6, c = e & 63;
+    if (r >= rows) continue;
+    const double v = Xs[r][c];
+    Ybuf[(int64_t)(r0 + r) * PB + c] = v;
+    Sp[(int64_t)(r0 + r) * lda + c] = v;
+  }
+}
+
+// ------------------------------------------------------------------ (4) Z = A22 Y on the DMMA pipe, split-K partials
+// A: m x m row-major (lda, both triangles valid), Y: m x 64 (pitch 64).  CTA tile 128 x 64, k chunk per blockIdx.y.
+constexpr int SY_BM = 128, SY_BK = 16, SY_T = 256, SY_LDA = SY_BM + 4, SY_LDB = PB + 4;
+
+__global__ void __launch_bounds__(SY_T, 2)
+sbr_symm_kernel(const double* __restrict__ A, int64_t lda, int m, const double* __restrict__ Y,
+                double* __restrict__ Zp, int kchunk) {
+  __shared__ double As[SY_BK][SY_LDA];
+  __shared__ double Bs[SY_BK][SY_LDB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
+  const int m0 = blockIdx.x * SY_BM;
+  const int kb = blockIdx.y * kchunk, ke = min(m, kb + kchunk);
+  double c[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { c[i][j][0] = 0.0; c[i][j][1] = 0.0; }
+  const int akk = tid & 15, ar = tid >> 4;            // A slab: 16 consecutive k of row ar + 16 i
+  const int bn = tid & 63, bk = tid >> 6;             // Y slab: row k = bk + 4 i, column bn
+  double ra[8], rb[4];
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = m0 + ar + 16 * i, k = k0 + akk;
+      ra[i] = (r < m && k < ke) ? A[(int64_t)r * lda + k] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = k0 + bk + 4 * i;
+      rb[i] = k < ke ? Y[(int64_t)k * PB + bn] : 0.0;
+    }
+  };
+  if (kb < ke) gload(kb);
+  for (int k0 = kb; k0 < ke; k0 += SY_BK) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) As[akk][(ar + 16 * i) ^ ((akk >> 2) & 3)] = ra[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) Bs[bk + 4 * i][bn ^ (((bk + 4 * i) >> 2) & 3)] = rb[i];
+    __syncthreads();
+    if (k0 + SY_BK < ke) gload(k0 + SY_BK);
+#pragma unroll
+    for (int ks = 0; ks < SY_BK; ks += 4) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        a[i] = As[ks + tig][(wm + 8 * i + gid) ^ ((ks >> 2) & 3)];
+        b[i] = Bs[ks + tig][(wn + 8 * i + gid) ^ ((ks >> 2) & 3)];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(c[i][j][0]), "+d"(c[i][j][1]) : "d"(a[i]), "d"(b[j]));
+    }
+    __syncthreads();
+  }
+  double* Zo = Zp + (int64_t)blockIdx.y * m * PB;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = m0 + wm + 8 * i + gid;
+    if (r >= m) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = wn + 8 * j + 2 * tig;
+      *reinterpret_cast<double2*>(Zo + (int64_t)r * PB + n) = make_double2(c[i][j][0], c[i][j][1]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ (5) Z = sum of the split-K partials, partial Y^T Z
+__global__ void __launch_bounds__(PT)
+sbr_yz_kernel(const double* __restrict__ Zp, int split, int m, const double* __restrict__ Ybuf,
+              double* __restrict__ Zbuf, double* __restrict__ Gpart) {
+  extern __shared__ double smem[];
+  double (*Ys)[PLD] = reinterpret_cast<double (*)[PLD]>(smem);
+  double (*Zs)[PLD] = reinterpret_cast<double (*)[PLD]>(smem + PB * PLD);
+  const int tid = threadIdx.x;
+  const int r0 = blockIdx.x * PB, rows = min(PB, m - r0);
+  for (int e = tid; e < PB * PB; e += PT) {
+    const int r = e >> 6, c = e & 63;
+    double z = 0.0, y = 0.0;
+    if (r < rows) {
+      const int64_t off = (int64_t)(r0 + r) * PB + c;
+      for (int s = 0; s < split; ++s) z += Zp[(int64_t)s * m * PB + off];
+      y = Ybuf[off];
+      Zbuf[off] = z;
+    }
+    Ys[r][c] = y;
+    Zs[r][c] = z;
+  }
+  __syncthreads();
+  double acc[4][4];
+  tile_atb(Ys, Zs, rows, tid, acc);
+  double* G = Gpart + (int64_t)blockIdx.x * PB * PB;
+  const int tx = tid & 15, ty = tid >> 4;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) G[(ty + 16 * a) * PB + tx + 16 * b] = acc[a][b];
+}
+
+// ------------------------------------------------------------------ (7) X = (Z - 1/2 Y C1) T; operands of the rank-128 update
+// XY = [X | Y], YX = [Y | X]  (m x 128 each):  A22 -= XY YX^T = X Y^T + Y X^T
+__global__ void __launch_bounds__(PT)
+sbr_xbuild_kernel(const double* __restrict__ Zbuf, const double* __restrict__ Ybuf, int m,
+                  const double* __restrict__ C1, const double* __restrict__ Tm,
+                  double* __restrict__ XY, double* __restrict__ YX) {
+  extern __shared__ double smem[];
+  double (*Ys)[PLD] = reinterpret_cast<double (*)[PLD]>(smem);
+  double (*Zs)[PLD] = reinterpret_cast<double (*)[PLD]>(smem + PB * PLD);
+  double (*Cs)[PLD] = reinterpret_cast<double (*)[PLD]>(smem + 2 * PB * PLD);
+  const int tid = threadIdx.x;
+  const int r0 = blockIdx.x * PB, rows = min(PB, m - r0);
+  for (int e = tid; e < PB * PB; e += PT) {
+    const int r = e >> 6, c = e & 63;
+    const int64_t off = (int64_t)(r0 + r) * PB + c;
+    Ys[r][c] = r < rows ? Ybuf[off] : 0.0;
+    Zs[r][c] = r < rows ? Zbuf[off] : 0.0;
+    Cs[r][c] = C1[e];
+  }
+  __syncthreads();
+  // A1 = Z - 1/2 Y C1 (thread owns 16 elements: row r = tid >> 2, columns (tid & 3) + 4 q)
+  const int r = tid >> 2, cq = tid & 3;
+  double a1[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) a1[q] = 0.0;
+  for (int k = 0; k < PB; ++k) {
+    const double y = Ys[r][k];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) a1[q] = fma(y, Cs[k][cq + 4 * q], a1[q]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 16; ++q) Zs[r][cq + 4 * q] -= 0.5 * a1[q];
+  for (int e = tid; e < PB * PB; e += PT) Cs[e >> 6][e & 63] = Tm[e];
+  __syncthreads();
+  // X = A1 T (T upper triangular)
+#pragma unroll
+  for (int q = 0; q < 16; ++q) a1[q] = 0.0;
+  for (int k = 0; k < PB; ++k) {
+    const double z = Zs[r][k];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) a1[q] = fma(z, Cs[k][cq + 4 * q], a1[q]);   // T[k][c] = 0 for c < k
+  }
+  if (r < rows) {
+    double* xy = XY + (int64_t)(r0 + r) * 2 * PB;
+    double* yx = YX + (int64_t)(r0 + r) * 2 * PB;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int c = cq + 4 * q;
+      const double y = Ys[r][c];
+      xy[c] = a1[q];  xy[PB + c] = y;
+      yx[c] = y;      yx[PB + c] = a1[q];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ (9) last panel, m < 64 rows: one CTA, plain Householder
+// P = S[r0 .., kb .. kb + 63] (m x 64), A22 = S[r0 .., r0 ..] (m x m).  Writes R into the band, A22 back (both
+// triangles), Y (m x 64 dense) into the panel's place, T (64 x 64) to Tout.
+__global__ void __launch_bounds__(PT)
+sbr_tail_kernel(double* __restrict__ S, int64_t lda, int n, int kb, double* __restrict__ AB, double* __restrict__ Tout) {
+  extern __shared__ double smem[];
+  double (*Ps)[PLD] = reinterpret_cast<double (*)[PLD]>(smem);
+  double (*As)[PLD] = reinterpret_cast<double (*)[PLD]>(smem + PB * PLD);
+  double (*Ys)[PLD] = reinterpret_cast<double (*)[PLD]>(smem + 2 * PB * PLD);
+  double (*Ts)[PLD] = reinterpret_cast<double (*)[PLD]>(smem + 3 * PB * PLD);
+  __shared__ double taus[PB], dots[PB], zz[PB];
+  __shared__ double s_tau;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r0 = kb + PB, m = n - r0;
+  for (int e = tid; e < PB * PB; e += PT) {
+    const int r = e >> 6, c = e & 63;
+    Ps[r][c] = r < m ? S[(int64_t)(r0 + r) * lda + kb + c] : 0.0;
+    As[r][c] = (r < m && c < m) ? S[(int64_t)(r0 + r) * lda + r0 + c] : 0.0;
+    Ys[r][c] = 0.0;
+    Ts[r][c] = 0.0;
+  }
+  if (tid < PB) taus[tid] = 0.0;
+  __syncthreads();
+  const int nref = min(m - 1, PB);
+  for (int c = 0; c < nref; ++c) {
+    if (warp == 0) {                                  // reflector from Ps[c .. m - 1][c]
+      const int i0 = c + lane, i1 = c + lane + 32;
+      double x0 = i0 < m ? Ps[i0][c] : 0.0, x1 = i1 < m ? Ps[i1][c] : 0.0;
+      const double alpha = __shfl_sync(0xffffffffu, x0, 0);
+      const double ssq = warp_sum((lane == 0 ? 0.0 : x0 * x0) + x1 * x1);
+      double tau = 0.0, beta = alpha, sc = 0.0;
+      if (ssq != 0.0) {
+        const double nrm = sqrt(fma(alpha, alpha, ssq));
+        beta = alpha >= 0.0 ? -nrm : nrm;
+        tau = (beta - alpha) / beta;
+        sc = 1.0 / (alpha - beta);
+      }
+      if (i0 < m) { Ys[i0][c] = lane == 0 ? 1.0 : x0 * sc; Ps[i0][c] = lane == 0 ? beta : 0.0; }
+      if (i1 < m) { Ys[i1][c] = x1 * sc; Ps[i1][c] = 0.0; }
+      if (lane == 0) { s_tau = tau; taus[c] = tau; }
+    }
+    __syncthreads();
+    const double tau = s_tau;
+    if (tau != 0.0) {
+      // left on the remaining panel columns and on A22: thread per column
+      if (tid < PB) {
+        if (tid > c) {
+          double dsum = 0.0;
+          for (int i = c; i < m; ++i) dsum = fma(Ys[i][c], Ps[i][tid], dsum);
+          dsum *= tau;
+          for (int i = c; i < m; ++i) Ps[i][tid] = fma(-dsum, Ys[i][c], Ps[i][tid]);
+        }
+      } else if (tid < 2 * PB) {
+        const int cc = tid - PB;
+        if (cc < m) {
+          double dsum = 0.0;
+          for (int i = c; i < m; ++i) dsum = fma(Ys[i][c], As[i][cc], dsum);
+          dsum *= tau;
+          for (int i = c; i < m; ++i) As[i][cc] = fma(-dsum, Ys[i][c], As[i][cc]);
+        }
+      }
+      __syncthreads();
+      if (tid < m) {                                  // right on A22: thread per row
+        double dsum = 0.0;
+        for (int i = c; i < m; ++i) dsum = fma(As[tid][i], Ys[i][c], dsum);
+        dsum *= tau;
+        for (int i = c; i < m; ++i) As[tid][i] = fma(-dsum, Ys[i][c], As[tid][i]);
+      }
+    }
+    __syncthreads();
+  }
+  // T (dlarft, forward columnwise): T[j][j] = tau_j, T[0:j, j] = -tau_j T[0:j, 0:j] (Y[:, 0:j]^T Y[:, j])
+  for (int j = 0; j < nref; ++j) {
+    if (tid < j) {
+      double s = 0.0;
+      for (int i = j; i < m; ++i) s = fma(Ys[i][tid], Ys[i][j], s);
+      zz[tid] = s;
+    }
+    __syncthreads();
+    if (tid < j) {
+      double s = 0.0;
+      for (int k = tid; k < j; ++k) s = fma(Ts[tid][k], zz[k], s);
+      dots[tid] = -taus[j] * s;
+    }
+    __syncthreads();
+    if (tid < j) Ts[tid][j] = dots[tid];
+    if (tid == j) Ts[j][j] = taus[j];
+    __syncthreads();
+  }
+  for (int e = tid; e < PB * PB; e += PT) {
+    const int r = e >> 6, c = e & 63;
+    Tout[e] = Ts[r][c];
+    if (r < m) {
+      S[(int64_t)(r0 + r) * lda + kb + c] = Ys[r][c];
+      if (c < m) S[(int64_t)(r0 + r) * lda + r0 + c] = As[r][c];
+      if (r <= c) AB[(int64_t)(kb + c) * BLD + (PB + r - c)] = Ps[r][c];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ (10) band array from the reduced matrix
+// AB[c][d] = A[c + d][c], d = 0 .. 64: diagonal blocks from S; the sub-diagonal blocks of factored panels were
+// written by the panel kernels (R diag(s)); beyond the last panel straight from S.
+__global__ void sbr_band_extract_kernel(const double* __restrict__ S, int64_t lda, int n, int npanels,
+                                        double* __restrict__ AB) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (int)(idx / (PB + 1)), d = (int)(idx % (PB + 1));
+  if (c >= n) return;
+  const int r = c + d;
+  if (r >= n) return;
+  const int k = c / PB;
+  if (r >= (k + 1) * PB && k < npanels) return;
+  AB[(int64_t)c * BLD + d] = S[(int64_t)r * lda + c];
+}
+
+// ------------------------------------------------------------------ (11) back-transformation through stage 1
+// rows of Z <- Q1 row, Q1 = W_0 W_1 ... (panel order), W_p = I - Y_p T_p Y_p^T acting on rows r0_p ..: last panel first.
+// One CTA per NV vectors (shared memory); per panel two passes over Y (u = Y^T z; z -= Y (T u)).
+template <int NV>
+__global__ void __launch_bounds__(512)
+sbr_apply_q1_kernel(const double* __restrict__ S, int64_t lda, const double* __restrict__ tfac, int n, int npanels,
+                    double* __restrict__ Z, int64_t ldz, int kvec) {
+  extern __shared__ double smem[];
+  double* zs = smem;                                  // NV x n
+  double (*Ts)[PLD] = reinterpret_cast<double (*)[PLD]>(smem + (size_t)NV * n);
+  double* pa = smem + (size_t)NV * n + PB * PLD;      // NV x 8 x 64 partials
+  double* uu = pa + NV * 8 * PB;                      // NV x 64
+  const int tid = threadIdx.x;
+  const int v0 = blockIdx.x * NV;
+  for (int a = 0; a < NV; ++a)
+    for (int i = tid; i < n; i += 512) zs[a * n + i] = (v0 + a < kvec) ? Z[(int64_t)(v0 + a) * ldz + i] : 0.0;
+  __syncthreads();
+  const int c = tid & 63, g = tid >> 6;
+  for (int p = npanels - 1; p >= 0; --p) {
+    const int r0 = (p + 1) * PB, m = n - r0;
+    const double* Y = S + (int64_t)r0 * lda + (int64_t)p * PB;
+    for (int e = tid; e < PB * PB; e += 512) Ts[e >> 6][e & 63] = tfac[(int64_t)p * PB * PB + e];
+    // u = Y^T z
+    double acc[NV];
+#pragma unroll
+    for (int a = 0; a < NV; ++a) acc[a] = 0.0;
+#pragma unroll 4
+    for (int r = g; r < m; r += 8) {
+      const double y = __ldg(Y + (int64_t)r * lda + c);
+#pragma unroll
+      for (int a = 0; a < NV; ++a) acc[a] = fma(y, zs[a * n + r0 + r], acc[a]);
+    }
+#pragma unroll
+    for (int a = 0; a < NV; ++a) pa[(a * 8 + g) * PB + c] = acc[a];
+    __syncthreads();
+    if (tid < NV * PB) {
+      const int a = tid >> 6;
+      double s = 0.0;
+#pragma unroll
+      for (int gg = 0; gg < 8; ++gg) s += pa[(a * 8 + gg) * PB + c];
+      uu[a * PB + c] = s;
+    }
+    __syncthreads();
+    // u2 = T u  (T upper): partial over columns k = g, g + 8, ...
+#pragma unroll
+    for (int a = 0; a < NV; ++a) acc[a] = 0.0;
+    for (int k = g; k < PB; k += 8) {
+      const double t = Ts[c][k];                       // zero for k < c
+#pragma unroll
+      for (int a = 0; a < NV; ++a) acc[a] = fma(t, uu[a * PB + k], acc[a]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < NV; ++a) pa[(a * 8 + g) * PB + c] = acc[a];
+    __syncthreads();
+    if (tid < NV * PB) {
+      const int a = tid >> 6;
+      double s = 0.0;
+#pragma unroll
+      for (int gg = 0; gg < 8; ++gg) s += pa[(a * 8 + gg) * PB + c];
+      uu[a * PB + c] = s;
+    }
+    __syncthreads();
+    // z -= Y u2: thread (row sub = tid >> 3, segment = tid & 7 -> 8 columns), 64 rows per trip
+    {
+      const int seg = tid & 7, rs = tid >> 3;
+      double u2[NV][8];
+#pragma unroll
+      for (int a = 0; a < NV; ++a)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) u2[a][q] = uu[a * PB + 8 * seg + q];
+      for (int rb = 0; rb < m; rb += 64) {
+        const int r = rb + rs;
+        double dsum[NV];
+#pragma unroll
+        for (int a = 0; a < NV; ++a) dsum[a] = 0.0;
+        if (r < m) {
+          const double* yr = Y + (int64_t)r * lda + 8 * seg;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const double y = __ldg(yr + q);
+#pragma unroll
+            for (int a = 0; a < NV; ++a) dsum[a] = fma(y, u2[a][q], dsum[a]);
+          }
+        }
+#pragma unroll
+        for (int a = 0; a < NV; ++a) {
+          double s = dsum[a];
+          s += __shfl_xor_sync(0xffffffffu, s, 1);
+          s += __shfl_xor_sync(0xffffffffu, s, 2);
+          s += __shfl_xor_sync(0xffffffffu, s, 4);
+          if (seg == 0 && r < m) zs[a * n + r0 + r] -= s;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (int a = 0; a < NV; ++a)
+    if (v0 + a < kvec)
+      for (int i = tid; i < n; i += 512) Z[(int64_t)(v0 + a) * ldz + i] = zs[a * n + i];
+}
+
+// ------------------------------------------------------------------ host side
+static size_t al256(size_t b) { return (b + 255) / 256 * 256; }
+
+static int sbr_npanels(int64_t n) {                  // panels with m = n - (k + 1) 64 >= 2 rows
+  int k = 0;
+  while (n - (int64_t)(k + 1) * PB >= 2) ++k;
+  return k;
+}
+
+struct SbrPlan {
+  size_t off_ab, off_q, off_y, off_z, off_xy, off_yx, off_zp, off_gpart, off_small, off_ints, total;
+  int max_split;
+};
+
+static SbrPlan sbr_plan(int64_t n) {
+  SbrPlan p;
+  p.max_split = 16;
+  const size_t nn = (size_t)n;
+  size_t o = 0;
+  p.off_ab = o;    o += al256(nn * BLD * 8);
+  p.off_q = o;     o += al256(nn * PB * 8);
+  p.off_y = o;     o += al256(nn * PB * 8);
+  p.off_z = o;     o += al256(nn * PB * 8);
+  p.off_xy = o;    o += al256(nn * 2 * PB * 8);
+  p.off_yx = o;    o += al256(nn * 2 * PB * 8);
+  p.off_zp = o;    o += al256((size_t)p.max_split * nn * PB * 8);
+  p.off_gpart = o; o += al256(((nn + PB - 1) / PB + 1) * PB * PB * 8);
+  p.off_small = o; o += al256(16 * PB * PB * 8);
+  p.off_ints = o;  o += al256((nn + 64) * 4);
+  p.total = o;
+  return p;
+}
+
+}  // namespace xmca
+
+using namespace xmca;
+
+extern "C" size_t xmca_sytrd2_workspace_bytes(int64_t n) { return n > 0 ? sbr_plan(n).total : 0; }
+extern "C" size_t xmca_sytrd2_tfac_bytes(int64_t n) {
+  const int np = n > 0 ? sbr_npanels(n) : 0;
+  return (size_t)(np > 0 ? np : 1) * PB * PB * sizeof(double);
+}
+
+extern "C" int xmca_sytrd2(int64_t n, double* d_A, int64_t lda, double* d_d, double* d_e, double* d_tfac,
+                           int want_vectors, void* d_workspace, size_t workspace_bytes, void* stream) {
+  XMCA_REQUIRE(n >= 1 && n <= 26000, "xmca_sytrd2: n out of range");
+  XMCA_REQUIRE(d_A && d_d && d_e && d_tfac && d_workspace, "xmca_sytrd2: null pointer");
+  XMCA_REQUIRE(lda >= n, "xmca_sytrd2: lda < n");
+  const SbrPlan pl = sbr_plan(n);
+  XMCA_REQUIRE(workspace_bytes >= pl.total, "xmca_sytrd2: workspace too small");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  char* ws = reinterpret_cast<char*>(d_workspace);
+  double* AB = reinterpret_cast<double*>(ws + pl.off_ab);
+  double* Qb = reinterpret_cast<double*>(ws + pl.off_q);
+  double* Yb = reinterpret_cast<double*>(ws + pl.off_y);
+  double* Zb = reinterpret_cast<double*>(ws + pl.off_z);
+  double* XY = reinterpret_cast<double*>(ws + pl.off_xy);
+  double* YX = reinterpret_cast<double*>(ws + pl.off_yx);
+  double* Zp = reinterpret_cast<double*>(ws + pl.off_zp);
+  double* Gpart = reinterpret_cast<double*>(ws + pl.off_gpart);
+  double* small = reinterpret_cast<double*>(ws + pl.off_small);
+  double* G = small, *L1 = small + 4096, *L2 = small + 2 * 4096, *L3 = small + 3 * 4096, *LU = small + 4 * 4096,
+        *M12 = small + 5 * 4096, *C1 = small + 6 * 4096, *sign = small + 7 * 4096;
+  int* ints = reinterpret_cast<int*>(ws + pl.off_ints);
+  int* ticket = ints, *fail = ints + 1, *counters = ints + 8;
+
+  XMCA_CUDA(cudaMemsetAsync(AB, 0, sizeof(double) * (size_t)n * BLD, st));
+  XMCA_CUDA(cudaMemsetAsync(ints, 0, 32, st));
+  const int np = sbr_npanels(n);
+  const size_t sm2 = 2 * PB * PLD * sizeof(double), sm3 = 3 * PB * PLD * sizeof(double), sm4 = 4 * PB * PLD * sizeof(double);
+  XMCA_CUDA(cudaFuncSetAttribute(sbr_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+  XMCA_CUDA(cudaFuncSetAttribute(sbr_yz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+  XMCA_CUDA(cudaFuncSetAttribute(sbr_applyfinal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
+  XMCA_CUDA(cudaFuncSetAttribute(sbr_xbuild_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
+  XMCA_CUDA(cudaFuncSetAttribute(sbr_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4));
+  const int nsm = sm_count();
+
+  for (int p = 0; p < np; ++p) {
+    const int kb = p * PB, r0 = kb + PB, m = (int)n - r0;
+    double* Tp = d_tfac + (int64_t)p * PB * PB;
+    if (m < PB) {
+      sbr_tail_kernel<<<1, PT, sm4, st>>>(d_A, lda, (int)n, kb, AB, Tp);
+      XMCA_LAUNCHED();
+      continue;
+    }
+    const int nch = (m + PB - 1) / PB;
+    double* Pp = d_A + (int64_t)r0 * lda + kb;        // the panel, m x 64, pitch lda
+    RedParams R;
+    R.part = Gpart; R.npart = nch; R.G = G; R.ticket = ticket; R.m = m; R.Qtop = Qb; R.LU = LU; R.sign = sign;
+    R.Tm = Tp; R.C1 = C1; R.fail = fail;
+    // pass 1 (shifted), 2, 3
+    sbr_gram_kernel<<<nch, PT, sm2, st>>>(Pp, lda, m, nullptr, nullptr, Gpart, nch, nullptr, nullptr, nullptr);
+    XMCA_LAUNCHED();
+    R.mode = 0; R.Lout = L1;
+    sbr_reduce_kernel<<<NRED, PT, 0, st>>>(R);
+    XMCA_LAUNCHED();
+    sbr_gram_kernel<<<nch, PT, sm2, st>>>(Pp, lda, m, L1, Qb, Gpart, nch, nullptr, nullptr, nullptr);
+    XMCA_LAUNCHED();
+    R.mode = 1; R.Lout = L2;
+    sbr_reduce_kernel<<<NRED, PT, 0, st>>>(R);
+    XMCA_LAUNCHED();
+    sbr_gram_kernel<<<nch + 1, PT, sm2, st>>>(Qb, PB, m, L2, Qb, Gpart, nch, L1, L2, M12);
+    XMCA_LAUNCHED();
+    R.mode = 2; R.Lout = L3;
+    sbr_reduce_kernel<<<NRED, PT, 0, st>>>(R);
+    XMCA_LAUNCHED();
+    sbr_applyfinal_kernel<<<nch + 2, PT, sm3, st>>>(Qb, m, L3, LU, sign, Yb, Pp, lda, nch, Tp, M12, AB, kb);
+    XMCA_LAUNCHED();
+    // Z = A22 Y
+    const int tiles = (m + SY_BM - 1) / SY_BM;
+    int split = (2 * nsm + tiles - 1) / tiles;
+    if (split > pl.max_split) split = pl.max_split;
+    if (split > (m + 127) / 128) split = (m + 127) / 128;
+    if (split < 1) split = 1;
+    int kchunk = ((m + split - 1) / split + SY_BK - 1) / SY_BK * SY_BK;
+    split = (m + kchunk - 1) / kchunk;
+    double* A22 = d_A + (int64_t)r0 * lda + r0;
+    sbr_symm_kernel<<<dim3(tiles, split), SY_T, 0, st>>>(A22, lda, m, Yb, Zp, kchunk);
+    XMCA_LAUNCHED();
+    sbr_yz_kernel<<<nch, PT, sm2, st>>>(Zp, split, m, Yb, Zb, Gpart);
+    XMCA_LAUNCHED();
+    R.mode = 3;
+    sbr_reduce_kernel<<<NRED, PT, 0, st>>>(R);
+    XMCA_LAUNCHED();
+    sbr_xbuild_kernel<<<nch, PT, sm3, st>>>(Zb, Yb, m, C1, Tp, XY, YX);
+    XMCA_LAUNCHED();
+    // A22 -= XY YX^T  (symmetric result: lower tiles computed, upper mirrored)
+    int rc = xmca_gemm_ex(1, 1, m, m, 2 * PB, -1.0, XY, XMCA_F64, 2 * PB, YX, XMCA_F64, 2 * PB, A22, XMCA_F64, lda, 1,
+                          XMCA_F64, 1, nullptr, 0, XMCA_GEMM_SYMMETRIC, stream);
+    if (rc != XMCA_OK) return rc;
+  }
+  {
+    const int64_t tot = n * (PB + 1);
+    sbr_band_extract_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(d_A, lda, (int)n, np, AB);
+    XMCA_LAUNCHED();
+  }
+  // stage 2; the reflectors go to the strict upper triangle of A (row j, columns > j), free after stage 1
+  if (!(want_vectors & 4)) {                         // (bit 2: stop after stage 1 -- diagnostics, scripts/check_sytrd2.py)
+    int rc = sb_chase(AB, (int)n, counters, (want_vectors & 1) ? d_A : nullptr, lda, d_d, d_e, st);
+    if (rc != XMCA_OK) return rc;
+  }
+  int h_fail = 0;
+  XMCA_CUDA(cudaMemcpyAsync(&h_fail, fail, sizeof(int), cudaMemcpyDeviceToHost, st));
+  XMCA_CUDA(cudaStreamSynchronize(st));
+  if (h_fail)
+    return ::xmca::fail(XMCA_NUMERIC, "xmca_sytrd2: panel factorisation broke down (matrix not finite or panel rank deficient)",
+                        __FILE__, __LINE__);
+  return XMCA_OK;
+}
+
+extern "C" int xmca_ormtr2(int64_t n, const double* d_A, int64_t lda, const double* d_tfac, int64_t k,
+                           double* d_Z, int64_t ldz, void* stream) {
+  XMCA_REQUIRE(n >= 1 && k >= 0 && d_A && d_tfac && d_Z && ldz >= n, "xmca_ormtr2: bad argument");
+  if (k == 0) return XMCA_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = sb_apply_q2(d_A, lda, (int)n, d_Z, ldz, (int)k, st);
+  if (rc != XMCA_OK) return rc;
+  const int np = sbr_npanels(n);
+  if (np == 0) return XMCA_OK;
+  const size_t extra = (PB * PLD + 2 * 8 * PB + 2 * PB) * sizeof(double);
+  const size_t one = sizeof(double) * (size_t)n;
+  if (2 * one + extra <= 200 * 1024) {
+    const size_t sm = 2 * one + extra;
+    XMCA_CUDA(cudaFuncSetAttribute(sbr_apply_q1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    sbr_apply_q1_kernel<2><<<(unsigned)((k + 1) / 2), 512, sm, st>>>(d_A, lda, d_tfac, (int)n, np, d_Z, ldz, (int)k);
+  } else {
+    const size_t sm = one + extra;
+    XMCA_REQUIRE(sm <= 227 * 1024, "xmca_ormtr2: n too large for the shared-memory vector");
+    XMCA_CUDA(cudaFuncSetAttribute(sbr_apply_q1_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    sbr_apply_q1_kernel<1><<<(unsigned)k, 512, sm, st>>>(d_A, lda, d_tfac, (int)n, np, d_Z, ldz, (int)k);
+  }
+  XMCA_LAUNCHED();
+  return XMCA_OK;
+}
+
+// diagnostics (scripts/check_sytrd2.py): stage 2 alone on a caller-built band array (n x 128 doubles, see sbtrd.cu)
+extern "C" int xmca_dbg_band_chase(int64_t n, double* d_AB, double* d_d, double* d_e, double* d_V2, int64_t ldv,
+                                   int* d_counters, void* stream) {
+  return sb_chase(d_AB, (int)n, d_counters, d_V2, ldv, d_d, d_e, reinterpret_cast<cudaStream_t>(stream));
+}

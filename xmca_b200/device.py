@@ -261,6 +261,34 @@ def sytrd_pair(S2):
     return d, e, tau
 
 
+def sytrd2(S, want_vectors=True):
+    """Two-stage tridiagonalisation (dense -> band 64 on the DMMA pipe -> tridiagonal by bulge chasing) of the
+    symmetric fp64 matrix S (n x n, both triangles, DESTROYED: it then holds both reflector sets).
+    Returns (d, e, tfac).  Raises LinAlgError if a panel factorisation broke down."""
+    lib = L.load()
+    t = torch()
+    n = S.shape[0]
+    assert S.dtype == t.float64 and S.shape[1] == n
+    d, e = empty((n,), t.float64), zeros((max(n - 1, 1),), t.float64)
+    tfac = empty((lib.xmca_sytrd2_tfac_bytes(n) // 8,), t.float64)
+    ws_bytes = lib.xmca_sytrd2_workspace_bytes(n)
+    ws = empty((ws_bytes,), t.uint8)
+    rc = lib.xmca_sytrd2(n, L.ptr(S), _ld(S), L.ptr(d), L.ptr(e), L.ptr(tfac), 1 if want_vectors else 0,
+                         L.ptr(ws), ws_bytes, L.stream_ptr())
+    L.check(rc, "xmca_sytrd2")
+    return d, e, tfac
+
+
+def ormtr2(S_reflectors, tfac, Z):
+    """Rows of Z <- Q row (in place), Q = Q1 Q2 from `sytrd2`."""
+    lib = L.load()
+    n = S_reflectors.shape[0]
+    rc = lib.xmca_ormtr2(n, L.ptr(S_reflectors), _ld(S_reflectors), L.ptr(tfac), Z.shape[0], L.ptr(Z), _ld(Z),
+                         L.stream_ptr())
+    L.check(rc, "xmca_ormtr2")
+    return Z
+
+
 def stebz(d, e):
     """All eigenvalues of the symmetric tridiagonal (d, e), descending (device fp64)."""
     lib = L.load()
