@@ -14,7 +14,7 @@ from xmca_b200 import _lib as L, device as D
 lib = L.load()
 raw = lib._raw
 raw.xmca_dbg_band_chase.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
-                                    C.c_void_p]
+                                    C.c_void_p, C.c_void_p]
 B = 64
 
 
@@ -67,7 +67,7 @@ def check_stage2(n, seed=0, vectors=True):
     V2 = D.zeros((n, n), D.f64())
     cnt = torch.zeros(n + 8, dtype=torch.int32, device="cuda")
     rc = raw.xmca_dbg_band_chase(n, L.ptr(AB), L.ptr(d), L.ptr(e), L.ptr(V2) if vectors else None, n, L.ptr(cnt),
-                                 L.stream_ptr())
+                                 None, L.stream_ptr())
     torch.cuda.synchronize()
     dh, eh = D.to_host(d), D.to_host(e)
     lam = tri_eigs(dh, eh)
@@ -196,7 +196,33 @@ def timing(n, reps=3):
     print("timing n=%d: %s" % (n, {k: (round(v, 3) if v > 1e-3 else v) for k, v in out.items()}), flush=True)
 
 
+def chase_profile(n):
+    """phase clocks of the bulge-chasing kernel (thread 0 of every CTA, summed over tasks)"""
+    Bm = band_of(spd(n, 5))
+    AB0 = D.to_device(to_ab(Bm))
+    for vec in (False, True):
+        AB = AB0.clone()
+        d, e = D.empty((n,), D.f64()), D.zeros((n,), D.f64())
+        V2 = D.zeros((n, n), D.f64()) if vec else None
+        cnt = torch.zeros(n + 8, dtype=torch.int32, device="cuda")
+        prof = torch.zeros(8, dtype=torch.int64, device="cuda")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        raw.xmca_dbg_band_chase(n, L.ptr(AB), L.ptr(d), L.ptr(e), L.ptr(V2), n, L.ptr(cnt), L.ptr(prof), L.stream_ptr())
+        e1.record()
+        torch.cuda.synchronize()
+        p = prof.cpu().numpy()
+        nt = max(int(p[6]), 1)
+        names = ["wait", "load", "matvec", "update+larfg", "store", "publish"]
+        print("chase n=%d vectors=%s: %.2f ms, %d tasks; clocks/task: %s" % (
+            n, vec, e0.elapsed_time(e1), nt, ", ".join("%s %.0f" % (a, p[i] / nt) for i, a in enumerate(names))), flush=True)
+
+
 if __name__ == "__main__":
+    if "prof" in sys.argv:
+        chase_profile(8192)
+        sys.exit(0)
     quick = "quick" in sys.argv
     if "tiny" in sys.argv:             # for compute-sanitizer
         for n in (3, 66, 130):
@@ -214,3 +240,4 @@ if __name__ == "__main__":
         timing(2048, reps=2)
         timing(4096, reps=2)
         timing(8192, reps=3)
+

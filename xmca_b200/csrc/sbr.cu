@@ -26,9 +26,10 @@ constexpr int PB = 64;              // panel width = bandwidth
 constexpr int PLD = PB + 1;         // shared-memory pitch
 constexpr int BLD = 2 * PB;         // doubles per band column (same as sbtrd.cu)
 constexpr int PT = 256;             // threads of the chunk kernels
-constexpr int NRED = 16;            // CTAs of the reduction kernels (256 elements each)
+constexpr int NRED = 64;            // CTAs of the reduction kernels (64 elements each, 4 threads per element)
 
-int sb_chase(double* AB, int n, int* counters, double* V2, int64_t ldv, double* d, double* e, cudaStream_t st);
+int sb_chase(double* AB, int n, int* counters, double* V2, int64_t ldv, double* d, double* e, cudaStream_t st,
+             long long* prof = nullptr);
 int sb_apply_q2(const double* V2, int64_t ldv, int n, double* Z, int64_t ldz, int kvec, cudaStream_t st);
 
 __device__ __forceinline__ void bar64() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
@@ -39,24 +40,25 @@ __device__ __forceinline__ void load64(double (*s)[PLD], const double* __restric
   for (int e = tid; e < PB * PB; e += nthreads) s[e >> 6][e & 63] = g[e];
 }
 
-// rows solve  q L^T = x  in registers (thread = row): q[c] = (x[c] - sum_{k<c} q[k] L[c][k]) * rdiag[c]
+// rows solve  q L^T = x  in registers (thread = row), right-looking: once q[c] is final every later entry is updated
+// with an independent FMA (no long dependent chain):  q[c] = x[c] / L[c][c];  x[k] -= q[c] L[k][c], k > c
 __device__ __forceinline__ void solve_lt(double (&x)[PB], const double (*Ls)[PLD], const double* rdiag) {
 #pragma unroll
   for (int c = 0; c < PB; ++c) {
-    double acc = x[c];
+    const double q = x[c] * rdiag[c];
+    x[c] = q;
 #pragma unroll
-    for (int k = 0; k < c; ++k) acc = fma(-x[k], Ls[c][k], acc);
-    x[c] = acc * rdiag[c];
+    for (int k = c + 1; k < PB; ++k) x[k] = fma(-q, Ls[k][c], x[k]);
   }
 }
-// rows solve  y U = t  (U upper, rows of Us): y[c] = (t[c] - sum_{k<c} y[k] U[k][c]) * ru[c]
+// rows solve  y U = t  (U upper, rows of Us):  y[c] = t[c] / U[c][c];  t[k] -= y[c] U[c][k], k > c
 __device__ __forceinline__ void solve_u(double (&x)[PB], const double (*Us)[PLD], const double* ru) {
 #pragma unroll
   for (int c = 0; c < PB; ++c) {
-    double acc = x[c];
+    const double y = x[c] * ru[c];
+    x[c] = y;
 #pragma unroll
-    for (int k = 0; k < c; ++k) acc = fma(-x[k], Us[k][c], acc);
-    x[c] = acc * ru[c];
+    for (int k = c + 1; k < PB; ++k) x[k] = fma(-y, Us[c][k], x[k]);
   }
 }
 
@@ -155,16 +157,30 @@ struct RedParams {
 };
 
 __global__ void __launch_bounds__(PT) sbr_reduce_kernel(RedParams P) {
-  __shared__ double Ls[PB][PLD];
+  extern __shared__ double smem[];
+  double (*Ls)[PLD] = reinterpret_cast<double (*)[PLD]>(smem);
+  double (*Ts)[PLD] = reinterpret_cast<double (*)[PLD]>(smem + PB * PLD);
   __shared__ double colbuf[PB], rdiag[PB];
   __shared__ double s_b0, s_b1;
   __shared__ int s_last;
   const int tid = threadIdx.x;
   {
-    const int e = blockIdx.x * PT + tid;
-    double s = 0.0;
-    for (int p = 0; p < P.npart; ++p) s += __ldcg(P.part + (int64_t)p * PB * PB + e);
-    P.G[e] = s;
+    // 64 elements per CTA, 4 threads per element (each a quarter of the partials, fixed order -> deterministic)
+    const int e = blockIdx.x * (PT / 4) + (tid >> 2), part = tid & 3;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int p = part;
+    for (; p + 12 < P.npart; p += 16) {
+      const double a0 = __ldcg(P.part + (int64_t)p * PB * PB + e);
+      const double a1 = __ldcg(P.part + (int64_t)(p + 4) * PB * PB + e);
+      const double a2 = __ldcg(P.part + (int64_t)(p + 8) * PB * PB + e);
+      const double a3 = __ldcg(P.part + (int64_t)(p + 12) * PB * PB + e);
+      s0 += a0; s1 += a1; s2 += a2; s3 += a3;
+    }
+    for (; p < P.npart; p += 4) s0 += __ldcg(P.part + (int64_t)p * PB * PB + e);
+    double s = (s0 + s1) + (s2 + s3);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (part == 0) P.G[e] = s;
   }
   __threadfence();
   __syncthreads();
@@ -174,14 +190,19 @@ __global__ void __launch_bounds__(PT) sbr_reduce_kernel(RedParams P) {
   __threadfence();
   if (tid == 0) *P.ticket = 0;                        // re-armed for the next launch (stream ordered)
   if (P.mode == 3) {                                  // C1 = T^T C0, T upper triangular
-    for (int e = tid; e < PB * PB; e += PT) Ls[e >> 6][e & 63] = __ldcg(P.G + e);
+    for (int e = tid; e < PB * PB; e += PT) { Ls[e >> 6][e & 63] = __ldcg(P.G + e); Ts[e >> 6][e & 63] = P.Tm[e]; }
     __syncthreads();
-    for (int e = tid; e < PB * PB; e += PT) {
-      const int i = e >> 6, j = e & 63;
-      double s = 0.0;
-      for (int k = 0; k <= i; ++k) s = fma(__ldg(P.Tm + k * PB + i), Ls[k][j], s);
-      P.C1[e] = s;
+    const int i = tid >> 2, jq = tid & 3;             // row i, columns jq + 4 q
+    double acc[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) acc[q] = 0.0;
+    for (int k = 0; k <= i; ++k) {
+      const double t = Ts[k][i];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) acc[q] = fma(t, Ls[k][jq + 4 * q], acc[q]);
     }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) P.C1[i * PB + jq + 4 * q] = acc[q];
     return;
   }
   if (tid >= PB) return;                              // the factorisations run on two warps (named barrier)
@@ -208,9 +229,9 @@ __global__ void __launch_bounds__(PT) sbr_reduce_kernel(RedParams P) {
     if (tid == j) {
       double d = row[j];
       if (!(d > 0.0) || !isfinite(d)) { d = 1.0; atomicExch(P.fail, 2); }
-      const double piv = sqrt(d);
-      row[j] = piv;
-      s_b0 = 1.0 / piv;
+      const double rinv = fast_rsqrt(d);              // (~1e-15; sqrt + divide would sit on the critical path 64 times)
+      row[j] = d * rinv;
+      s_b0 = rinv;
     }
     bar64();
     if (tid > j) { row[j] *= s_b0; colbuf[tid] = row[j]; }
@@ -248,7 +269,7 @@ __global__ void __launch_bounds__(PT) sbr_reduce_kernel(RedParams P) {
       const double a = row[j];
       const double s = a >= 0.0 ? 1.0 : -1.0;
       s_b0 = s;
-      s_b1 = 1.0 / (s * a + 1.0);
+      s_b1 = fast_rcp(s * a + 1.0);
       P.sign[j] = s;
 #pragma unroll
       for (int k = j + 1; k < PB; ++k) colbuf[k] = row[k];
@@ -289,11 +310,12 @@ sbr_applyfinal_kernel(const double* __restrict__ Q, int m, const double* __restr
     if (tid < PB) {
       double t[PB];
 #pragma unroll
-      for (int c = 0; c < PB; ++c) {
-        double acc = c >= tid ? Us[tid][c] : 0.0;
+      for (int c = 0; c < PB; ++c) t[c] = c >= tid ? Us[tid][c] : 0.0;
 #pragma unroll
-        for (int k = 0; k < c; ++k) acc = fma(-t[k], Us[c][k], acc);     // t[k] = 0 for k < tid; Us[c][k], k < c: Y1
-        t[c] = c >= tid ? acc : 0.0;
+      for (int c = 0; c < PB; ++c) {                   // t[c] final; later entries: t[c2] -= t[c] Y1[c2][c]
+        const double tc = t[c];
+#pragma unroll
+        for (int c2 = c + 1; c2 < PB; ++c2) t[c2] = fma(-tc, Us[c2][c], t[c2]);
       }
 #pragma unroll
       for (int c = 0; c < PB; ++c) Tout[tid * PB + c] = t[c];
@@ -437,17 +459,30 @@ sbr_yz_kernel(const double* __restrict__ Zp, int split, int m, const double* __r
   double (*Zs)[PLD] = reinterpret_cast<double (*)[PLD]>(smem + PB * PLD);
   const int tid = threadIdx.x;
   const int r0 = blockIdx.x * PB, rows = min(PB, m - r0);
-  for (int e = tid; e < PB * PB; e += PT) {
-    const int r = e >> 6, c = e & 63;
-    double z = 0.0, y = 0.0;
-    if (r < rows) {
-      const int64_t off = (int64_t)(r0 + r) * PB + c;
-      for (int s = 0; s < split; ++s) z += Zp[(int64_t)s * m * PB + off];
-      y = Ybuf[off];
-      Zbuf[off] = z;
+  {
+    double z[16], y[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int e = tid + q * PT, r = e >> 6;
+      const int64_t off = (int64_t)(r0 + r) * PB + (e & 63);
+      z[q] = 0.0;
+      y[q] = r < rows ? Ybuf[off] : 0.0;
     }
-    Ys[r][c] = y;
-    Zs[r][c] = z;
+    for (int s = 0; s < split; ++s) {
+      const double* zp = Zp + (int64_t)s * m * PB;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int e = tid + q * PT, r = e >> 6;
+        if (r < rows) z[q] += zp[(int64_t)(r0 + r) * PB + (e & 63)];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int e = tid + q * PT, r = e >> 6, c = e & 63;
+      if (r < rows) Zbuf[(int64_t)(r0 + r) * PB + c] = z[q];
+      Ys[r][c] = y[q];
+      Zs[r][c] = z[q];
+    }
   }
   __syncthreads();
   double acc[4][4];
@@ -653,15 +688,23 @@ sbr_apply_q1_kernel(const double* __restrict__ S, int64_t lda, const double* __r
     const int r0 = (p + 1) * PB, m = n - r0;
     const double* Y = S + (int64_t)r0 * lda + (int64_t)p * PB;
     for (int e = tid; e < PB * PB; e += 512) Ts[e >> 6][e & 63] = tfac[(int64_t)p * PB * PB + e];
-    // u = Y^T z
+    // u = Y^T z  (16 independent loads per thread in flight)
     double acc[NV];
 #pragma unroll
     for (int a = 0; a < NV; ++a) acc[a] = 0.0;
-#pragma unroll 4
-    for (int r = g; r < m; r += 8) {
-      const double y = __ldg(Y + (int64_t)r * lda + c);
+    for (int rb = g; rb < m; rb += 8 * 16) {
+      double y[16];
 #pragma unroll
-      for (int a = 0; a < NV; ++a) acc[a] = fma(y, zs[a * n + r0 + r], acc[a]);
+      for (int t = 0; t < 16; ++t) {
+        const int r = rb + 8 * t;
+        y[t] = r < m ? __ldg(Y + (int64_t)r * lda + c) : 0.0;
+      }
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        const int r = min(rb + 8 * t, m - 1);            // (y is zero beyond m)
+#pragma unroll
+        for (int a = 0; a < NV; ++a) acc[a] = fma(y[t], zs[a * n + r0 + r], acc[a]);
+      }
     }
 #pragma unroll
     for (int a = 0; a < NV; ++a) pa[(a * 8 + g) * PB + c] = acc[a];
@@ -702,27 +745,28 @@ sbr_apply_q1_kernel(const double* __restrict__ S, int64_t lda, const double* __r
       for (int a = 0; a < NV; ++a)
 #pragma unroll
         for (int q = 0; q < 8; ++q) u2[a][q] = uu[a * PB + 8 * seg + q];
-      for (int rb = 0; rb < m; rb += 64) {
-        const int r = rb + rs;
-        double dsum[NV];
+      for (int rb = 0; rb < m; rb += 128) {              // two blocks of 64 rows per trip: 16 loads in flight
+        double yv[2][8];
 #pragma unroll
-        for (int a = 0; a < NV; ++a) dsum[a] = 0.0;
-        if (r < m) {
+        for (int h = 0; h < 2; ++h) {
+          const int r = rb + 64 * h + rs;
           const double* yr = Y + (int64_t)r * lda + 8 * seg;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const double y = __ldg(yr + q);
-#pragma unroll
-            for (int a = 0; a < NV; ++a) dsum[a] = fma(y, u2[a][q], dsum[a]);
-          }
+          for (int q = 0; q < 8; ++q) yv[h][q] = r < m ? __ldg(yr + q) : 0.0;
         }
 #pragma unroll
-        for (int a = 0; a < NV; ++a) {
-          double s = dsum[a];
-          s += __shfl_xor_sync(0xffffffffu, s, 1);
-          s += __shfl_xor_sync(0xffffffffu, s, 2);
-          s += __shfl_xor_sync(0xffffffffu, s, 4);
-          if (seg == 0 && r < m) zs[a * n + r0 + r] -= s;
+        for (int h = 0; h < 2; ++h) {
+          const int r = rb + 64 * h + rs;
+#pragma unroll
+          for (int a = 0; a < NV; ++a) {
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) s = fma(yv[h][q], u2[a][q], s);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            if (seg == 0 && r < m) zs[a * n + r0 + r] -= s;
+          }
         }
       }
     }
@@ -804,6 +848,7 @@ extern "C" int xmca_sytrd2(int64_t n, double* d_A, int64_t lda, double* d_d, dou
   const int np = sbr_npanels(n);
   const size_t sm2 = 2 * PB * PLD * sizeof(double), sm3 = 3 * PB * PLD * sizeof(double), sm4 = 4 * PB * PLD * sizeof(double);
   XMCA_CUDA(cudaFuncSetAttribute(sbr_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+  XMCA_CUDA(cudaFuncSetAttribute(sbr_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
   XMCA_CUDA(cudaFuncSetAttribute(sbr_yz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
   XMCA_CUDA(cudaFuncSetAttribute(sbr_applyfinal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
   XMCA_CUDA(cudaFuncSetAttribute(sbr_xbuild_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
@@ -827,17 +872,17 @@ extern "C" int xmca_sytrd2(int64_t n, double* d_A, int64_t lda, double* d_d, dou
     sbr_gram_kernel<<<nch, PT, sm2, st>>>(Pp, lda, m, nullptr, nullptr, Gpart, nch, nullptr, nullptr, nullptr);
     XMCA_LAUNCHED();
     R.mode = 0; R.Lout = L1;
-    sbr_reduce_kernel<<<NRED, PT, 0, st>>>(R);
+    sbr_reduce_kernel<<<NRED, PT, sm2, st>>>(R);
     XMCA_LAUNCHED();
     sbr_gram_kernel<<<nch, PT, sm2, st>>>(Pp, lda, m, L1, Qb, Gpart, nch, nullptr, nullptr, nullptr);
     XMCA_LAUNCHED();
     R.mode = 1; R.Lout = L2;
-    sbr_reduce_kernel<<<NRED, PT, 0, st>>>(R);
+    sbr_reduce_kernel<<<NRED, PT, sm2, st>>>(R);
     XMCA_LAUNCHED();
     sbr_gram_kernel<<<nch + 1, PT, sm2, st>>>(Qb, PB, m, L2, Qb, Gpart, nch, L1, L2, M12);
     XMCA_LAUNCHED();
     R.mode = 2; R.Lout = L3;
-    sbr_reduce_kernel<<<NRED, PT, 0, st>>>(R);
+    sbr_reduce_kernel<<<NRED, PT, sm2, st>>>(R);
     XMCA_LAUNCHED();
     sbr_applyfinal_kernel<<<nch + 2, PT, sm3, st>>>(Qb, m, L3, LU, sign, Yb, Pp, lda, nch, Tp, M12, AB, kb);
     XMCA_LAUNCHED();
@@ -855,7 +900,7 @@ extern "C" int xmca_sytrd2(int64_t n, double* d_A, int64_t lda, double* d_d, dou
     sbr_yz_kernel<<<nch, PT, sm2, st>>>(Zp, split, m, Yb, Zb, Gpart);
     XMCA_LAUNCHED();
     R.mode = 3;
-    sbr_reduce_kernel<<<NRED, PT, 0, st>>>(R);
+    sbr_reduce_kernel<<<NRED, PT, sm2, st>>>(R);
     XMCA_LAUNCHED();
     sbr_xbuild_kernel<<<nch, PT, sm3, st>>>(Zb, Yb, m, C1, Tp, XY, YX);
     XMCA_LAUNCHED();
@@ -894,7 +939,7 @@ extern "C" int xmca_ormtr2(int64_t n, const double* d_A, int64_t lda, const doub
   if (np == 0) return XMCA_OK;
   const size_t extra = (PB * PLD + 2 * 8 * PB + 2 * PB) * sizeof(double);
   const size_t one = sizeof(double) * (size_t)n;
-  if (2 * one + extra <= 200 * 1024) {
+  if (2 * one + extra <= 200 * 1024 && k > sm_count()) {
     const size_t sm = 2 * one + extra;
     XMCA_CUDA(cudaFuncSetAttribute(sbr_apply_q1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     sbr_apply_q1_kernel<2><<<(unsigned)((k + 1) / 2), 512, sm, st>>>(d_A, lda, d_tfac, (int)n, np, d_Z, ldz, (int)k);
@@ -910,6 +955,6 @@ extern "C" int xmca_ormtr2(int64_t n, const double* d_A, int64_t lda, const doub
 
 // diagnostics (scripts/check_sytrd2.py): stage 2 alone on a caller-built band array (n x 128 doubles, see sbtrd.cu)
 extern "C" int xmca_dbg_band_chase(int64_t n, double* d_AB, double* d_d, double* d_e, double* d_V2, int64_t ldv,
-                                   int* d_counters, void* stream) {
-  return sb_chase(d_AB, (int)n, d_counters, d_V2, ldv, d_d, d_e, reinterpret_cast<cudaStream_t>(stream));
+                                   int* d_counters, long long* d_prof, void* stream) {
+  return sb_chase(d_AB, (int)n, d_counters, d_V2, ldv, d_d, d_e, reinterpret_cast<cudaStream_t>(stream), d_prof);
 }

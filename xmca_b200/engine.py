@@ -32,6 +32,11 @@ TRIDIAG_MIN_N = 768
 # ... and it computes singular vectors on demand for requests of up to this many leading modes;
 # larger requests (e.g. the full `_V` of the reference) fall back to the Jacobi routes.
 TRIDIAG_MAX_VECTORS = 512
+# Tridiagonalisation: "two_stage" (xmca_sytrd2: dense -> band on the DMMA pipe -> bulge chasing; the default) or
+# "one_stage" (xmca_sytrd: BLAS-2, HBM bound; also the fallback when a panel factorisation of the two-stage
+# reduction reports a breakdown).  XMCA_SYTRD=one_stage in the environment selects the old path (A/B runs).
+import os as _os
+SYTRD_MODE = _os.environ.get("XMCA_SYTRD", "two_stage")
 
 
 class SolveResult:
@@ -224,8 +229,19 @@ class TridiagResult:
         self.frob2 = None
         self._cache = (0, None)
         self._full = None
-        dof = self.dof
-        self.n_null = 0
+        self.n_null = 0 if isinstance(null_basis, int) or not self.gram_side else \
+            (null_basis.shape[1] if null_basis is not None else 1)
+        S = self._build_S()
+        self.n = S.shape[0]
+        self._S = S
+        if not defer:                  # (deferred: `solve_real_pair` reduces the two models of a pair itself)
+            self.reduce()
+
+    def _build_S(self):
+        A, B, null_basis, dof = self.A, self.B, self.null_basis, self.dof
+        T, S1 = A.shape
+        S2 = S1 if self.pca else B.shape[1]
+
         def gram(X, alpha=1.0):
             """X X^T (T x T, fp64): tcgen05 3xTF32 with fp64 chunk accumulation for fp32 fields,
             fp64 DMMA product otherwise."""
@@ -238,7 +254,6 @@ class TridiagResult:
                 Nb = None
             else:
                 Nb = null_basis if null_basis is not None else D.to_device(np.full((T, 1), 1.0 / np.sqrt(T)))
-                self.n_null = Nb.shape[1]
             if self.pca:
                 S = gram(A, 1.0 / dof)
             else:
@@ -262,15 +277,25 @@ class TridiagResult:
                 Xs, Xl = (A, B) if self.left_short else (B, A)
                 self.C = D.matmul(Xs, Xl, trans_a=True, alpha=1.0 / dof)          # S_short x S_long
                 S = D.matmul(self.C, self.C, trans_b=True, symmetric=True)
-        self.n = S.shape[0]
-        self._S = S
-        if not defer:                  # (deferred: `solve_real_pair` tridiagonalises two models in one batched call)
-            self._finish(*D.sytrd(S), S)
+        return S
 
-    def _finish(self, d, e, tau, Q):
-        """Spectrum from the tridiagonal form (d, e, tau) of S; Q: the matrix whose rows hold the reflectors."""
+    def reduce(self):
+        """S = Q T Q^T.  Two-stage reduction (xmca_sytrd2); if one of its panel factorisations reports a breakdown
+        (exactly rank-deficient panel, non-finite data) S is formed again and reduced by the one-stage xmca_sytrd."""
+        S = self._S
+        if SYTRD_MODE == "two_stage":
+            try:
+                d, e, tfac = D.sytrd2(S)
+                return self._finish(d, e, None, S, tfac)
+            except np.linalg.LinAlgError:
+                S = self._S = self._build_S()
+        self._finish(*D.sytrd(S), S)
+
+    def _finish(self, d, e, tau, Q, tfac=None):
+        """Spectrum from the tridiagonal form (d, e) of S; Q: the matrix that holds the reflectors (one-stage: rows +
+        tau; two-stage: panel reflectors below the band, sweep reflectors above the diagonal, + tfac)."""
         self._S = None
-        self.d, self.e, self.tau = d, e, tau
+        self.d, self.e, self.tau, self.tfac = d, e, tau, tfac
         self.Q = Q
         lam = D.to_host(D.stebz(self.d, self.e))
         if not np.isfinite(lam).all():
@@ -291,6 +316,8 @@ class TridiagResult:
         gap = 2.2e-16 * tnorm / (1e-7 if self.out_dtype == D.f32() else 1e-10)
         starts = [0] + [i for i in range(1, m) if lam[i - 1] - lam[i] > gap] + [m]
         Z = D.stein(self.d, self.e, lam, np.asarray(starts), tnorm, iterations=2)
+        if self.tfac is not None:
+            return D.ormtr2(self.Q, self.tfac, Z)
         return D.ormtr(self.Q, self.tau, Z)
 
     def vectors(self, m):
@@ -463,6 +490,10 @@ def solve_real_pair(A0, B0, A1, B1, null_basis=None, dof=None, want_vectors=True
         r1 = TridiagResult(A1, B1, null_basis, dof, defer=True)
     except np.linalg.LinAlgError:
         return single(A0, B0), single(A1, B1)
+    if SYTRD_MODE == "two_stage":
+        r0.reduce()
+        r1.reduce()
+        return r0, r1
     n = r0.n
     Sp = D.empty((2, n, n), D.f64())
     Sp[0].copy_(r0._S)
