@@ -234,6 +234,22 @@ gemm_dmma_kernel(int64_t M, int64_t N, int64_t K, double alpha,
     __syncthreads();
   }
 
+  // accumulate: every old value is loaded before the first store (a load after a store to the same array cannot be
+  // hoisted by the compiler, and 32 dependent DRAM round trips per thread used to cost more than the tile's MMAs)
+  if (!partial && accumulate) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t m = m0 + wm + 8 * i + gid;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int64_t n = n0 + wn + 8 * j + 2 * tig + e;
+          const double old = (m < M && n < N) ? load_as_double(D, ddt, m * ldd + n) : 0.0;
+          c[i][j][e] = fma(alpha, c[i][j][e], old);
+        }
+    }
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int64_t m = m0 + wm + 8 * i + gid;
@@ -247,8 +263,7 @@ gemm_dmma_kernel(int64_t M, int64_t N, int64_t K, double alpha,
         if (partial) {
           partial[((int64_t)blockIdx.z * M + m) * N + n] = c[i][j][e];
         } else {
-          double v = alpha * c[i][j][e];
-          if (accumulate) v += load_as_double(D, ddt, m * ldd + n);
+          const double v = accumulate ? c[i][j][e] : alpha * c[i][j][e];
           store_from_double(D, ddt, m * ldd + n, v);
           if ((flags & XMCA_GEMM_SYMMETRIC) && n0 < m0) store_from_double(D, ddt, n * ldd + m, v);
         }

@@ -19,6 +19,8 @@
 // The last panel (m < 64 rows) is done by one CTA with plain Householder reflectors.
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
+#include <vector>
 
 namespace xmca {
 
@@ -26,7 +28,7 @@ constexpr int PB = 64;              // panel width = bandwidth
 constexpr int PLD = PB + 1;         // shared-memory pitch
 constexpr int BLD = 2 * PB;         // doubles per band column (same as sbtrd.cu)
 constexpr int PT = 256;             // threads of the chunk kernels
-constexpr int NRED = 64;            // CTAs of the reduction kernels (64 elements each, 4 threads per element)
+constexpr int NRED = 256;           // CTAs of the reduction kernels (16 elements each, 16 threads per element)
 
 int sb_chase(double* AB, int n, int* counters, double* V2, int64_t ldv, double* d, double* e, cudaStream_t st,
              long long* prof = nullptr);
@@ -40,25 +42,297 @@ __device__ __forceinline__ void load64(double (*s)[PLD], const double* __restric
   for (int e = tid; e < PB * PB; e += nthreads) s[e >> 6][e & 63] = g[e];
 }
 
-// rows solve  q L^T = x  in registers (thread = row), right-looking: once q[c] is final every later entry is updated
-// with an independent FMA (no long dependent chain):  q[c] = x[c] / L[c][c];  x[k] -= q[c] L[k][c], k > c
-__device__ __forceinline__ void solve_lt(double (&x)[PB], const double (*Ls)[PLD], const double* rdiag) {
+// ---- 64 x 64 factorisations / triangular solves, blocked by 8 (shared memory, 256 threads).
+// Measured dead ends: rows in registers with the 64-step recurrence fully unrolled (~100 KB of straight-line code per
+// solve, runs at instruction-fetch speed: 45-65 us per factorisation), element-wise rolled loops in shared memory
+// (every step re-reads the matrix: bound by shared-memory bandwidth / latency, 50 us).  Here every 8 x 8 diagonal
+// block is factorised and inverted in REGISTERS by every thread redundantly (no broadcast, no barrier inside the
+// 8-step chain; ~500 instructions that are re-executed eight times), the rest is 8-wide rank updates.
+// Dinv[cb * 64 + ii * 8 + jj]: inverse of diagonal block cb.
+constexpr int NB8 = 8;
+
+// Cholesky A = L L^T (lower part in place; the upper part is not touched), Dinv: inverses of the diagonal blocks of L.
+__device__ __forceinline__ void chol64_blocked(double (*A)[PLD], double* Dinv, int tid, int* fail) {
+  const int ti = tid >> 4, tk = tid & 15;
+  for (int cb = 0; cb < NB8; ++cb) {
+    const int j0 = 8 * cb;
+    double a[8][8], li[8][8];
 #pragma unroll
-  for (int c = 0; c < PB; ++c) {
-    const double q = x[c] * rdiag[c];
-    x[c] = q;
+    for (int ii = 0; ii < 8; ++ii)
 #pragma unroll
-    for (int k = c + 1; k < PB; ++k) x[k] = fma(-q, Ls[k][c], x[k]);
+      for (int jj = 0; jj <= ii; ++jj) a[ii][jj] = A[j0 + ii][j0 + jj];
+    bool bad = false;
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      double d = a[jj][jj];
+      if (!(d > 0.0) || !isfinite(d)) { d = 1.0; bad = true; }
+      const double rinv = fast_rsqrt(d);
+      a[jj][jj] = d * rinv;
+      li[jj][jj] = rinv;
+#pragma unroll
+      for (int ii = jj + 1; ii < 8; ++ii) a[ii][jj] *= rinv;
+#pragma unroll
+      for (int kk = jj + 1; kk < 8; ++kk)
+#pragma unroll
+        for (int ii = kk; ii < 8; ++ii) a[ii][kk] = fma(-a[ii][jj], a[kk][jj], a[ii][kk]);
+    }
+    if (bad && tid == 0) atomicExch(fail, 2);
+    // inverse of the 8 x 8 lower block: column jj of Li by forward substitution
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj)
+#pragma unroll
+      for (int ii = jj + 1; ii < 8; ++ii) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int k = jj; k < ii; ++k) sacc = fma(a[ii][k], li[k][jj], sacc);
+        li[ii][jj] = -sacc * li[ii][ii];
+      }
+    if (tid == 0) {
+#pragma unroll
+      for (int ii = 0; ii < 8; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) Dinv[cb * 64 + ii * 8 + jj] = jj <= ii ? li[ii][jj] : 0.0;
+    }
+    // panel: L[i][j0 .. j0 + 7] = A[i][j0 ..] Lkk^-T for the rows below the block (thread = row)
+    if (tid < PB && tid >= j0 + 8) {
+      double x[8], l[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) x[k] = A[tid][j0 + k];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int k = 0; k <= jj; ++k) sacc = fma(x[k], li[jj][k], sacc);
+        l[jj] = sacc;
+      }
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) A[tid][j0 + jj] = l[jj];
+    }
+    __syncthreads();
+    if (tid == 0) {                                  // (after the barrier: every thread has read the original block)
+#pragma unroll
+      for (int ii = 0; ii < 8; ++ii)
+#pragma unroll
+        for (int jj = 0; jj <= ii; ++jj) A[j0 + ii][j0 + jj] = a[ii][jj];
+    }
+    // trailing update: A[i][k] -= sum_jj L[i][j0 + jj] L[k][j0 + jj], rows ti + 16 a, columns tk + 16 b
+    if (cb < NB8 - 1) {
+      double lr[4][8], lc[4][8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) { lr[q][jj] = A[ti + 16 * q][j0 + jj]; lc[q][jj] = A[tk + 16 * q][j0 + jj]; }
+#pragma unroll
+      for (int qa = 0; qa < 4; ++qa)
+#pragma unroll
+        for (int qb = 0; qb < 4; ++qb) {
+          const int i = ti + 16 * qa, k = tk + 16 * qb;
+          if (k >= j0 + 8 && i >= k) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) sacc = fma(lr[qa][jj], lc[qb][jj], sacc);
+            A[i][k] -= sacc;
+          }
+        }
+    }
+    __syncthreads();
   }
 }
-// rows solve  y U = t  (U upper, rows of Us):  y[c] = t[c] / U[c][c];  t[k] -= y[c] U[c][k], k > c
-__device__ __forceinline__ void solve_u(double (&x)[PB], const double (*Us)[PLD], const double* ru) {
+
+// X <- X L^-T (rows of X; L lower in Ls, Dinv = inverses of its diagonal blocks).  Thread (r = tid >> 2, kq = tid & 3):
+// the four threads of a row compute the diagonal-block step redundantly and share the trailing blocks.
+__device__ __forceinline__ void rows_trsm_lt(double (*Xs)[PLD], const double (*Ls)[PLD], const double* Dinv, int tid) {
+  const int r = tid >> 2, kq = tid & 3;
+  for (int cb = 0; cb < NB8; ++cb) {
+    const int j0 = 8 * cb;
+    double x[8], q[8];
 #pragma unroll
-  for (int c = 0; c < PB; ++c) {
-    const double y = x[c] * ru[c];
-    x[c] = y;
+    for (int k = 0; k < 8; ++k) x[k] = Xs[r][j0 + k];
 #pragma unroll
-    for (int k = c + 1; k < PB; ++k) x[k] = fma(-y, Us[c][k], x[k]);
+    for (int jj = 0; jj < 8; ++jj) {
+      double sacc = 0.0;
+#pragma unroll
+      for (int k = 0; k <= jj; ++k) sacc = fma(x[k], Dinv[cb * 64 + jj * 8 + k], sacc);
+      q[jj] = sacc;
+    }
+    __syncwarp();
+    if (kq == 0) {
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) Xs[r][j0 + jj] = q[jj];
+    }
+    for (int tb = cb + 1 + kq; tb < NB8; tb += 4) {
+      const int t0 = 8 * tb;
+      double y[8];
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) y[kk] = Xs[r][t0 + kk];
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk)
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) y[kk] = fma(-q[jj], Ls[t0 + kk][j0 + jj], y[kk]);
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) Xs[r][t0 + kk] = y[kk];
+    }
+    __syncwarp();
+  }
+}
+// X <- X U^-1 (U upper in Us, Uinv = inverses of its diagonal blocks)
+__device__ __forceinline__ void rows_trsm_u(double (*Xs)[PLD], const double (*Us)[PLD], const double* Uinv, int tid) {
+  const int r = tid >> 2, kq = tid & 3;
+  for (int cb = 0; cb < NB8; ++cb) {
+    const int j0 = 8 * cb;
+    double x[8], q[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = Xs[r][j0 + k];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      double sacc = 0.0;
+#pragma unroll
+      for (int k = 0; k <= jj; ++k) sacc = fma(x[k], Uinv[cb * 64 + k * 8 + jj], sacc);
+      q[jj] = sacc;
+    }
+    __syncwarp();
+    if (kq == 0) {
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) Xs[r][j0 + jj] = q[jj];
+    }
+    for (int tb = cb + 1 + kq; tb < NB8; tb += 4) {
+      const int t0 = 8 * tb;
+      double y[8];
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) y[kk] = Xs[r][t0 + kk];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj)
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) y[kk] = fma(-q[jj], Us[j0 + jj][t0 + kk], y[kk]);
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) Xs[r][t0 + kk] = y[kk];
+    }
+    __syncwarp();
+  }
+}
+
+// LU without pivoting of  A diag(s) + I  with the signs s_j chosen on the fly so that every pivot is >= 1
+// (Householder reconstruction).  In place: strict lower part = L (unit diagonal implied), upper part = U;
+// Linv / Uinv: inverses of the diagonal blocks of L / U; sg: the 64 signs.
+__device__ __forceinline__ void lu64_sign_blocked(double (*A)[PLD], double* Linv, double* Uinv, double* sg, int tid) {
+  const int ti = tid >> 4, tk = tid & 15;
+  for (int cb = 0; cb < NB8; ++cb) {
+    const int j0 = 8 * cb;
+    double a[8][8], li[8][8], ui[8][8], sv[8];
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii)
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) a[ii][jj] = A[j0 + ii][j0 + jj];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      const double s = a[jj][jj] >= 0.0 ? 1.0 : -1.0;
+      sv[jj] = s;
+#pragma unroll
+      for (int ii = 0; ii < 8; ++ii) a[ii][jj] *= s;                 // column jj scaled in every row of the block
+      a[jj][jj] += 1.0;
+      const double rp = fast_rcp(a[jj][jj]);
+      ui[jj][jj] = rp;
+#pragma unroll
+      for (int ii = jj + 1; ii < 8; ++ii) a[ii][jj] *= rp;
+#pragma unroll
+      for (int ii = jj + 1; ii < 8; ++ii)
+#pragma unroll
+        for (int kk = jj + 1; kk < 8; ++kk) a[ii][kk] = fma(-a[ii][jj], a[jj][kk], a[ii][kk]);
+    }
+    // Li = inverse of the unit lower block, Ui = inverse of the upper block
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      li[jj][jj] = 1.0;
+#pragma unroll
+      for (int ii = jj + 1; ii < 8; ++ii) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int k = jj; k < ii; ++k) sacc = fma(a[ii][k], li[k][jj], sacc);
+        li[ii][jj] = -sacc;
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj)                                    // column jj of Ui: rows jj - 1 .. 0
+#pragma unroll
+      for (int ii = jj - 1; ii >= 0; --ii) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int k = ii + 1; k <= jj; ++k) sacc = fma(a[ii][k], ui[k][jj], sacc);
+        ui[ii][jj] = -sacc * ui[ii][ii];
+      }
+    if (tid == 0) {
+#pragma unroll
+      for (int ii = 0; ii < 8; ++ii) {
+        sg[j0 + ii] = sv[ii];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          Linv[cb * 64 + ii * 8 + jj] = jj <= ii ? li[ii][jj] : 0.0;
+          Uinv[cb * 64 + ii * 8 + jj] = jj >= ii ? ui[ii][jj] : 0.0;
+        }
+      }
+    }
+    if (tid < PB) {
+      if (tid >= j0 + 8) {                             // column panel: L[i][blk] = (A[i][blk] * s) Ukk^-1
+        double x[8], l[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = A[tid][j0 + k] * sv[k];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          double sacc = 0.0;
+#pragma unroll
+          for (int k = 0; k <= jj; ++k) sacc = fma(x[k], ui[k][jj], sacc);
+          l[jj] = sacc;
+        }
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) A[tid][j0 + jj] = l[jj];
+      } else if (tid < j0) {                           // rows above the block: their U entries of these columns take the signs
+#pragma unroll
+        for (int k = 0; k < 8; ++k) A[tid][j0 + k] *= sv[k];
+      }
+    } else if (tid < 2 * PB) {
+      const int k = tid - PB;
+      if (k >= j0 + 8) {                               // row panel: U[blk][k] = Lkk^-1 A[blk][k]
+        double y[8], u[8];
+#pragma unroll
+        for (int ii = 0; ii < 8; ++ii) y[ii] = A[j0 + ii][k];
+#pragma unroll
+        for (int ii = 0; ii < 8; ++ii) {
+          double sacc = 0.0;
+#pragma unroll
+          for (int k2 = 0; k2 <= ii; ++k2) sacc = fma(li[ii][k2], y[k2], sacc);
+          u[ii] = sacc;
+        }
+#pragma unroll
+        for (int ii = 0; ii < 8; ++ii) A[j0 + ii][k] = u[ii];
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {                                    // (after the barrier: every thread has read the original block)
+#pragma unroll
+      for (int ii = 0; ii < 8; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) A[j0 + ii][j0 + jj] = a[ii][jj];
+    }
+    if (cb < NB8 - 1) {                                // trailing: A[i][k] -= sum_jj L[i][j0 + jj] U[j0 + jj][k]
+      double lr[4][8], uc[4][8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) { lr[q][jj] = A[ti + 16 * q][j0 + jj]; uc[q][jj] = A[j0 + jj][tk + 16 * q]; }
+#pragma unroll
+      for (int qa = 0; qa < 4; ++qa)
+#pragma unroll
+        for (int qb = 0; qb < 4; ++qb) {
+          const int i = ti + 16 * qa, k = tk + 16 * qb;
+          if (i >= j0 + 8 && k >= j0 + 8) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) sacc = fma(lr[qa][jj], uc[qb][jj], sacc);
+            A[i][k] -= sacc;
+          }
+        }
+    }
+    __syncthreads();
   }
 }
 
@@ -91,7 +365,7 @@ sbr_gram_kernel(const double* X, int64_t ldx, int m, const double* __restrict__ 
   extern __shared__ double smem[];
   double (*Xs)[PLD] = reinterpret_cast<double (*)[PLD]>(smem);
   double (*Ls)[PLD] = reinterpret_cast<double (*)[PLD]>(smem + PB * PLD);
-  __shared__ double rdiag[PB];
+  __shared__ double s_dinv[512];
   const int tid = threadIdx.x;
   if ((int)blockIdx.x == nch) {                       // lower x lower product (accumulated R^T of the passes)
     if (!Ma) return;
@@ -113,17 +387,9 @@ sbr_gram_kernel(const double* X, int64_t ldx, int m, const double* __restrict__ 
   }
   if (Lf) {
     load64(Ls, Lf, tid, PT);
+    for (int e = tid; e < 512; e += PT) s_dinv[e] = Lf[PB * PB + e];
     __syncthreads();
-    if (tid < PB) rdiag[tid] = 1.0 / Ls[tid][tid];
-    __syncthreads();
-    if (tid < PB) {
-      double x[PB];
-#pragma unroll
-      for (int c = 0; c < PB; ++c) x[c] = Xs[tid][c];
-      solve_lt(x, Ls, rdiag);
-#pragma unroll
-      for (int c = 0; c < PB; ++c) Xs[tid][c] = x[c];
-    }
+    rows_trsm_lt(Xs, Ls, s_dinv, tid);
     __syncthreads();
     for (int e = tid; e < PB * PB; e += PT) {
       const int r = e >> 6, c = e & 63;
@@ -160,26 +426,27 @@ __global__ void __launch_bounds__(PT) sbr_reduce_kernel(RedParams P) {
   extern __shared__ double smem[];
   double (*Ls)[PLD] = reinterpret_cast<double (*)[PLD]>(smem);
   double (*Ts)[PLD] = reinterpret_cast<double (*)[PLD]>(smem + PB * PLD);
-  __shared__ double colbuf[PB], rdiag[PB];
-  __shared__ double s_b0, s_b1;
+  __shared__ double s_dinv[512], s_linv[512], s_uinv[512], s_sg[PB];
   __shared__ int s_last;
   const int tid = threadIdx.x;
   {
-    // 64 elements per CTA, 4 threads per element (each a quarter of the partials, fixed order -> deterministic)
-    const int e = blockIdx.x * (PT / 4) + (tid >> 2), part = tid & 3;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int p = part;
-    for (; p + 12 < P.npart; p += 16) {
-      const double a0 = __ldcg(P.part + (int64_t)p * PB * PB + e);
-      const double a1 = __ldcg(P.part + (int64_t)(p + 4) * PB * PB + e);
-      const double a2 = __ldcg(P.part + (int64_t)(p + 8) * PB * PB + e);
-      const double a3 = __ldcg(P.part + (int64_t)(p + 12) * PB * PB + e);
-      s0 += a0; s1 += a1; s2 += a2; s3 += a3;
+    // 16 elements per CTA, 16 threads per element: each thread loads its partials in batches of 8 independent loads
+    // (fixed order -> deterministic), then a shuffle tree
+    const int e = blockIdx.x * (PT / 16) + (tid >> 4), part = tid & 15;
+    double s = 0.0;
+    for (int p0 = part; p0 < P.npart; p0 += 16 * 8) {
+      double v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int p = p0 + 16 * q;
+        v[q] = p < P.npart ? __ldcg(P.part + (int64_t)p * PB * PB + e) : 0.0;
+      }
+      s += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
     }
-    for (; p < P.npart; p += 4) s0 += __ldcg(P.part + (int64_t)p * PB * PB + e);
-    double s = (s0 + s1) + (s2 + s3);
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 8);
     if (part == 0) P.G[e] = s;
   }
   __threadfence();
@@ -205,88 +472,37 @@ __global__ void __launch_bounds__(PT) sbr_reduce_kernel(RedParams P) {
     for (int q = 0; q < 16; ++q) P.C1[i * PB + jq + 4 * q] = acc[q];
     return;
   }
-  if (tid >= PB) return;                              // the factorisations run on two warps (named barrier)
-  double row[PB];
-#pragma unroll
-  for (int k = 0; k < PB; ++k) row[k] = __ldcg(P.G + tid * PB + k);
+  // ---- modes 0-2: Cholesky of the (shifted) Gram matrix
+  for (int e = tid; e < PB * PB; e += PT) Ls[e >> 6][e & 63] = __ldcg(P.G + e);
+  __syncthreads();
   if (P.mode == 0) {                                  // shift = 11 (m b + b (b + 1)) u trace(G)
-    double dg = 0.0;                                  // (static indices only: `row` must stay in registers)
-#pragma unroll
-    for (int k = 0; k < PB; ++k) dg = k == tid ? row[k] : dg;
-    colbuf[tid] = dg;
-    bar64();
     double tr = 0.0;
-    for (int k = 0; k < PB; ++k) tr += colbuf[k];
-    double nd = dg + 11.0 * ((double)P.m * PB + PB * (PB + 1)) * 1.1102230246251565e-16 * tr;
-    if (!(tr > 0.0) || !isfinite(tr)) { nd = 1.0; if (tid == 0) atomicExch(P.fail, 1); }
-#pragma unroll
-    for (int k = 0; k < PB; ++k) row[k] = k == tid ? nd : row[k];
-    bar64();
+    for (int k = 0; k < PB; ++k) tr += Ls[k][k];
+    const bool bad = !(tr > 0.0) || !isfinite(tr);
+    if (bad && tid == 0) atomicExch(P.fail, 1);
+    __syncthreads();
+    if (tid < PB)
+      Ls[tid][tid] = bad ? 1.0 : Ls[tid][tid] + 11.0 * ((double)P.m * PB + PB * (PB + 1)) * 1.1102230246251565e-16 * tr;
+    __syncthreads();
   }
-  // right-looking Cholesky, thread = row (lower part kept)
-#pragma unroll
-  for (int j = 0; j < PB; ++j) {
-    if (tid == j) {
-      double d = row[j];
-      if (!(d > 0.0) || !isfinite(d)) { d = 1.0; atomicExch(P.fail, 2); }
-      const double rinv = fast_rsqrt(d);              // (~1e-15; sqrt + divide would sit on the critical path 64 times)
-      row[j] = d * rinv;
-      s_b0 = rinv;
-    }
-    bar64();
-    if (tid > j) { row[j] *= s_b0; colbuf[tid] = row[j]; }
-    bar64();
-    if (tid > j) {
-      const double lij = row[j];
-#pragma unroll
-      for (int k = j + 1; k < PB; ++k)
-        if (k <= tid) row[k] = fma(-lij, colbuf[k], row[k]);
-    }
+  chol64_blocked(Ls, s_dinv, tid, P.fail);
+  for (int e = tid; e < PB * PB; e += PT) {
+    const int r = e >> 6, c = e & 63;
+    P.Lout[e] = c <= r ? Ls[r][c] : 0.0;
   }
-#pragma unroll
-  for (int k = 0; k < PB; ++k) {
-    const double v = k <= tid ? row[k] : 0.0;
-    Ls[tid][k] = v;
-    P.Lout[tid * PB + k] = v;
-  }
+  for (int e = tid; e < 512; e += PT) P.Lout[PB * PB + e] = s_dinv[e];
   if (P.mode != 2) return;
   // ---- Householder reconstruction on the top block: A = -(Qtop L^-T), LU without pivoting of A diag(s) + I
-  {
-    double dg = 1.0;
-#pragma unroll
-    for (int k = 0; k < PB; ++k) dg = k == tid ? row[k] : dg;
-    rdiag[tid] = 1.0 / dg;
-  }
-  bar64();
-#pragma unroll
-  for (int k = 0; k < PB; ++k) row[k] = P.Qtop[tid * PB + k];
-  solve_lt(row, Ls, rdiag);
-#pragma unroll
-  for (int k = 0; k < PB; ++k) row[k] = -row[k];
-#pragma unroll
-  for (int j = 0; j < PB; ++j) {
-    if (tid == j) {
-      const double a = row[j];
-      const double s = a >= 0.0 ? 1.0 : -1.0;
-      s_b0 = s;
-      s_b1 = fast_rcp(s * a + 1.0);
-      P.sign[j] = s;
-#pragma unroll
-      for (int k = j + 1; k < PB; ++k) colbuf[k] = row[k];
-    }
-    bar64();
-    row[j] *= s_b0;
-    if (tid == j) row[j] += 1.0;
-    if (tid > j) {
-      const double l = row[j] * s_b1;
-      row[j] = l;
-#pragma unroll
-      for (int k = j + 1; k < PB; ++k) row[k] = fma(-l, colbuf[k], row[k]);
-    }
-    bar64();
-  }
-#pragma unroll
-  for (int k = 0; k < PB; ++k) P.LU[tid * PB + k] = row[k];
+  for (int e = tid; e < PB * PB; e += PT) Ts[e >> 6][e & 63] = P.Qtop[e];
+  __syncthreads();
+  rows_trsm_lt(Ts, Ls, s_dinv, tid);
+  __syncthreads();
+  for (int e = tid; e < PB * PB; e += PT) Ts[e >> 6][e & 63] = -Ts[e >> 6][e & 63];
+  __syncthreads();
+  lu64_sign_blocked(Ts, s_linv, s_uinv, s_sg, tid);
+  for (int e = tid; e < PB * PB; e += PT) P.LU[e] = Ts[e >> 6][e & 63];
+  for (int e = tid; e < 512; e += PT) { P.LU[PB * PB + e] = s_linv[e]; P.LU[PB * PB + 512 + e] = s_uinv[e]; }
+  if (tid < PB) P.sign[tid] = s_sg[tid];
 }
 
 // ------------------------------------------------------------------ (3) Y = reconstruction applied to all rows
@@ -302,24 +518,19 @@ sbr_applyfinal_kernel(const double* __restrict__ Q, int m, const double* __restr
   double (*Ls)[PLD] = reinterpret_cast<double (*)[PLD]>(smem);
   double (*Us)[PLD] = reinterpret_cast<double (*)[PLD]>(smem + PB * PLD);
   double (*Xs)[PLD] = reinterpret_cast<double (*)[PLD]>(smem + 2 * PB * PLD);
-  __shared__ double rdiag[PB], ru[PB], sg[PB];
+  __shared__ double s_inv[512], s_uinv[512], sg[PB];
   const int tid = threadIdx.x;
-  if ((int)blockIdx.x == nch) {                       // T: T Y1^T = U  (forward in c, thread = row of T)
-    load64(Us, LU, tid, PT);
-    __syncthreads();
-    if (tid < PB) {
-      double t[PB];
-#pragma unroll
-      for (int c = 0; c < PB; ++c) t[c] = c >= tid ? Us[tid][c] : 0.0;
-#pragma unroll
-      for (int c = 0; c < PB; ++c) {                   // t[c] final; later entries: t[c2] -= t[c] Y1[c2][c]
-        const double tc = t[c];
-#pragma unroll
-        for (int c2 = c + 1; c2 < PB; ++c2) t[c2] = fma(-tc, Us[c2][c], t[c2]);
-      }
-#pragma unroll
-      for (int c = 0; c < PB; ++c) Tout[tid * PB + c] = t[c];
+  if ((int)blockIdx.x == nch) {                       // T: T Y1^T = U  (row solves with the unit lower Y1)
+    load64(Ls, LU, tid, PT);
+    for (int e = tid; e < PB * PB; e += PT) {
+      const int r = e >> 6, c = e & 63;
+      Xs[r][c] = c >= r ? LU[e] : 0.0;
     }
+    for (int e = tid; e < 512; e += PT) s_inv[e] = LU[PB * PB + e];      // inverses of the unit lower diagonal blocks
+    __syncthreads();
+    rows_trsm_lt(Xs, Ls, s_inv, tid);
+    __syncthreads();
+    for (int e = tid; e < PB * PB; e += PT) Tout[e] = Xs[e >> 6][e & 63];
     return;
   }
   if ((int)blockIdx.x == nch + 1) {                   // R = diag(s) (M12 L3)^T, written into the band
@@ -354,20 +565,15 @@ sbr_applyfinal_kernel(const double* __restrict__ Q, int m, const double* __restr
     Xs[r][c] = r < rows ? Q[(int64_t)(r0 + r) * PB + c] : 0.0;
   }
   if (tid < PB) sg[tid] = sign[tid];
+  for (int e = tid; e < 512; e += PT) { s_inv[e] = L3[PB * PB + e]; s_uinv[e] = LU[PB * PB + 512 + e]; }
   __syncthreads();
-  if (tid < PB) { rdiag[tid] = 1.0 / Ls[tid][tid]; ru[tid] = 1.0 / Us[tid][tid]; }
-  __syncthreads();
-  if (tid < PB) {
-    double x[PB];
-#pragma unroll
-    for (int c = 0; c < PB; ++c) x[c] = Xs[tid][c];
-    solve_lt(x, Ls, rdiag);
-#pragma unroll
-    for (int c = 0; c < PB; ++c) x[c] *= -sg[c];
-    solve_u(x, Us, ru);
-#pragma unroll
-    for (int c = 0; c < PB; ++c) Xs[tid][c] = x[c];
+  rows_trsm_lt(Xs, Ls, s_inv, tid);
+  {
+    const int r = tid >> 2, kq = tid & 3;
+    for (int k = kq; k < PB; k += 4) Xs[r][k] *= -sg[k];
+    __syncwarp();
   }
+  rows_trsm_u(Xs, Us, s_uinv, tid);
   __syncthreads();
   for (int e = tid; e < PB * PB; e += PT) {
     const int r = e >> 6, c = e & 63;
@@ -810,6 +1016,61 @@ static SbrPlan sbr_plan(int64_t n) {
   return p;
 }
 
+// internal high-priority stream + two events per device (created once, kept for the life of the process)
+struct SbrStreams { cudaStream_t panel = nullptr; cudaEvent_t ev_qr = nullptr, ev_x = nullptr; };
+static SbrStreams* sbr_streams() {
+  static SbrStreams per_dev[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SbrStreams& s = per_dev[dev];
+  if (!s.panel) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&s.panel, cudaStreamNonBlocking, hi) != cudaSuccess) { s.panel = nullptr; return nullptr; }
+    cudaEventCreateWithFlags(&s.ev_qr, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&s.ev_x, cudaEventDisableTiming);
+  }
+  return &s;
+}
+
+// XMCA_SYTRD2_PROF=1: CUDA events between the launches of xmca_sytrd2, summed per kernel class and printed to stderr
+// (diagnostics: ncu's per-launch times are cold-cache and overstate the small straight-line kernels)
+struct SbrProf {
+  bool on = false;
+  cudaStream_t st = nullptr;
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> cls;
+  void init(cudaStream_t s) {
+    const char* e = getenv("XMCA_SYTRD2_PROF");
+    on = e && e[0] == '1';
+    st = s;
+    if (on) mark(-1);
+  }
+  void mark(int c) {
+    if (!on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    ev.push_back(e);
+    cls.push_back(c);
+  }
+  void report(int64_t n) {
+    if (!on) return;
+    static const char* names[] = {"gram", "reduce", "applyfinal", "symm", "yz", "xbuild", "syr2k", "tail", "extract", "chase"};
+    double sum[10] = {0}; int cnt[10] = {0};
+    cudaEventSynchronize(ev.back());
+    for (size_t i = 1; i < ev.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+      sum[cls[i]] += ms; cnt[cls[i]]++;
+    }
+    fprintf(stderr, "xmca_sytrd2 n=%lld:", (long long)n);
+    for (int c = 0; c < 10; ++c) if (cnt[c]) fprintf(stderr, " %s %.2f ms/%d", names[c], sum[c], cnt[c]);
+    fprintf(stderr, "\n");
+    for (auto e : ev) cudaEventDestroy(e);
+  }
+};
+
 }  // namespace xmca
 
 using namespace xmca;
@@ -838,8 +1099,9 @@ extern "C" int xmca_sytrd2(int64_t n, double* d_A, int64_t lda, double* d_d, dou
   double* Zp = reinterpret_cast<double*>(ws + pl.off_zp);
   double* Gpart = reinterpret_cast<double*>(ws + pl.off_gpart);
   double* small = reinterpret_cast<double*>(ws + pl.off_small);
-  double* G = small, *L1 = small + 4096, *L2 = small + 2 * 4096, *L3 = small + 3 * 4096, *LU = small + 4 * 4096,
-        *M12 = small + 5 * 4096, *C1 = small + 6 * 4096, *sign = small + 7 * 4096;
+  const int SL = PB * PB + 1024;                      // slot: 64 x 64 matrix + two sets of 8 x 8 diagonal-block inverses
+  double* G = small, *L1 = small + SL, *L2 = small + 2 * SL, *L3 = small + 3 * SL, *LU = small + 4 * SL,
+        *M12 = small + 5 * SL, *C1 = small + 6 * SL, *sign = small + 7 * SL;
   int* ints = reinterpret_cast<int*>(ws + pl.off_ints);
   int* ticket = ints, *fail = ints + 1, *counters = ints + 8;
 
@@ -854,13 +1116,32 @@ extern "C" int xmca_sytrd2(int64_t n, double* d_A, int64_t lda, double* d_d, dou
   XMCA_CUDA(cudaFuncSetAttribute(sbr_xbuild_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
   XMCA_CUDA(cudaFuncSetAttribute(sbr_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4));
   const int nsm = sm_count();
+  SbrProf prof;
+  prof.init(st);
+  // Look-ahead: the factorisation of panel p + 1 (latency bound: three Gram / Cholesky rounds and the reconstruction)
+  // runs on an internal high-priority stream `sp` next to the rank-128 update of the trailing matrix by panel p on the
+  // caller's stream.  For that the update is split: the first block column of A22 (= the next panel and the next
+  // diagonal block) is updated by a skinny product on `sp`, the rest A22[64:, 64:] by the big one on `st`.
+  SbrStreams* ss = prof.on ? nullptr : sbr_streams();
+  cudaStream_t sp = ss ? ss->panel : st;
+  if (ss) {
+    XMCA_CUDA(cudaEventRecord(ss->ev_x, st));
+    XMCA_CUDA(cudaStreamWaitEvent(sp, ss->ev_x, 0));
+  }
 
   for (int p = 0; p < np; ++p) {
     const int kb = p * PB, r0 = kb + PB, m = (int)n - r0;
     double* Tp = d_tfac + (int64_t)p * PB * PB;
     if (m < PB) {
+      if (ss) {                                       // join: the tail runs on the caller's stream
+        XMCA_CUDA(cudaEventRecord(ss->ev_qr, sp));
+        XMCA_CUDA(cudaStreamWaitEvent(st, ss->ev_qr, 0));
+        sp = st;
+        ss = nullptr;
+      }
       sbr_tail_kernel<<<1, PT, sm4, st>>>(d_A, lda, (int)n, kb, AB, Tp);
       XMCA_LAUNCHED();
+      prof.mark(7);
       continue;
     }
     const int nch = (m + PB - 1) / PB;
@@ -868,60 +1149,101 @@ extern "C" int xmca_sytrd2(int64_t n, double* d_A, int64_t lda, double* d_d, dou
     RedParams R;
     R.part = Gpart; R.npart = nch; R.G = G; R.ticket = ticket; R.m = m; R.Qtop = Qb; R.LU = LU; R.sign = sign;
     R.Tm = Tp; R.C1 = C1; R.fail = fail;
-    // pass 1 (shifted), 2, 3
-    sbr_gram_kernel<<<nch, PT, sm2, st>>>(Pp, lda, m, nullptr, nullptr, Gpart, nch, nullptr, nullptr, nullptr);
+    // ---- panel stream: pass 1 (shifted), 2, 3, reconstruction
+    sbr_gram_kernel<<<nch, PT, sm2, sp>>>(Pp, lda, m, nullptr, nullptr, Gpart, nch, nullptr, nullptr, nullptr);
     XMCA_LAUNCHED();
+    prof.mark(0);
     R.mode = 0; R.Lout = L1;
-    sbr_reduce_kernel<<<NRED, PT, sm2, st>>>(R);
+    sbr_reduce_kernel<<<NRED, PT, sm2, sp>>>(R);
     XMCA_LAUNCHED();
-    sbr_gram_kernel<<<nch, PT, sm2, st>>>(Pp, lda, m, L1, Qb, Gpart, nch, nullptr, nullptr, nullptr);
+    prof.mark(1);
+    sbr_gram_kernel<<<nch, PT, sm2, sp>>>(Pp, lda, m, L1, Qb, Gpart, nch, nullptr, nullptr, nullptr);
     XMCA_LAUNCHED();
+    prof.mark(0);
     R.mode = 1; R.Lout = L2;
-    sbr_reduce_kernel<<<NRED, PT, sm2, st>>>(R);
+    sbr_reduce_kernel<<<NRED, PT, sm2, sp>>>(R);
     XMCA_LAUNCHED();
-    sbr_gram_kernel<<<nch + 1, PT, sm2, st>>>(Qb, PB, m, L2, Qb, Gpart, nch, L1, L2, M12);
+    prof.mark(1);
+    sbr_gram_kernel<<<nch + 1, PT, sm2, sp>>>(Qb, PB, m, L2, Qb, Gpart, nch, L1, L2, M12);
     XMCA_LAUNCHED();
+    prof.mark(0);
     R.mode = 2; R.Lout = L3;
-    sbr_reduce_kernel<<<NRED, PT, sm2, st>>>(R);
+    sbr_reduce_kernel<<<NRED, PT, sm2, sp>>>(R);
     XMCA_LAUNCHED();
-    sbr_applyfinal_kernel<<<nch + 2, PT, sm3, st>>>(Qb, m, L3, LU, sign, Yb, Pp, lda, nch, Tp, M12, AB, kb);
+    prof.mark(1);
+    sbr_applyfinal_kernel<<<nch + 2, PT, sm3, sp>>>(Qb, m, L3, LU, sign, Yb, Pp, lda, nch, Tp, M12, AB, kb);
     XMCA_LAUNCHED();
-    // Z = A22 Y
+    prof.mark(2);
+    if (ss) {
+      XMCA_CUDA(cudaEventRecord(ss->ev_qr, sp));
+      XMCA_CUDA(cudaStreamWaitEvent(st, ss->ev_qr, 0));
+    }
+    // ---- caller's stream: Z = A22 Y (A22 complete: the previous big update is ordered before it on `st`)
     const int tiles = (m + SY_BM - 1) / SY_BM;
-    int split = (2 * nsm + tiles - 1) / tiles;
-    if (split > pl.max_split) split = pl.max_split;
-    if (split > (m + 127) / 128) split = (m + 127) / 128;
-    if (split < 1) split = 1;
+    // split-K factor: the one that fills whole waves of 2 CTAs per SM best (a nearly empty last wave costs a full one)
+    int split = 1;
+    {
+      const int slots = 2 * nsm, smax = min(pl.max_split, (m + 127) / 128);
+      double best = -1.0;
+      for (int sq = 1; sq <= smax; ++sq) {
+        const int ctas = tiles * sq, waves = (ctas + slots - 1) / slots;
+        const double eff = (double)ctas / ((double)waves * slots) - 0.004 * sq;       // (mild preference for fewer partials)
+        if (eff > best) { best = eff; split = sq; }
+      }
+    }
     int kchunk = ((m + split - 1) / split + SY_BK - 1) / SY_BK * SY_BK;
     split = (m + kchunk - 1) / kchunk;
     double* A22 = d_A + (int64_t)r0 * lda + r0;
     sbr_symm_kernel<<<dim3(tiles, split), SY_T, 0, st>>>(A22, lda, m, Yb, Zp, kchunk);
     XMCA_LAUNCHED();
+    prof.mark(3);
     sbr_yz_kernel<<<nch, PT, sm2, st>>>(Zp, split, m, Yb, Zb, Gpart);
     XMCA_LAUNCHED();
+    prof.mark(4);
     R.mode = 3;
     sbr_reduce_kernel<<<NRED, PT, sm2, st>>>(R);
     XMCA_LAUNCHED();
+    prof.mark(1);
     sbr_xbuild_kernel<<<nch, PT, sm3, st>>>(Zb, Yb, m, C1, Tp, XY, YX);
     XMCA_LAUNCHED();
-    // A22 -= XY YX^T  (symmetric result: lower tiles computed, upper mirrored)
-    int rc = xmca_gemm_ex(1, 1, m, m, 2 * PB, -1.0, XY, XMCA_F64, 2 * PB, YX, XMCA_F64, 2 * PB, A22, XMCA_F64, lda, 1,
-                          XMCA_F64, 1, nullptr, 0, XMCA_GEMM_SYMMETRIC, stream);
+    prof.mark(5);
+    if (ss) {
+      XMCA_CUDA(cudaEventRecord(ss->ev_x, st));
+      XMCA_CUDA(cudaStreamWaitEvent(sp, ss->ev_x, 0));
+    }
+    // ---- A22 -= XY YX^T in two pieces: first block column (next panel + next diagonal block) on the panel stream,
+    //      A22[64:, 64:] on the caller's stream (symmetric: lower tiles computed, upper mirrored)
+    int rc = xmca_gemm_ex(1, 1, m, PB, 2 * PB, -1.0, XY, XMCA_F64, 2 * PB, YX, XMCA_F64, 2 * PB, A22, XMCA_F64, lda, 1,
+                          XMCA_F64, 1, nullptr, 0, 0, sp);
     if (rc != XMCA_OK) return rc;
+    if (m > PB) {
+      rc = xmca_gemm_ex(1, 1, m - PB, m - PB, 2 * PB, -1.0, XY + (int64_t)PB * 2 * PB, XMCA_F64, 2 * PB,
+                        YX + (int64_t)PB * 2 * PB, XMCA_F64, 2 * PB, A22 + (int64_t)PB * lda + PB, XMCA_F64, lda, 1,
+                        XMCA_F64, 1, nullptr, 0, XMCA_GEMM_SYMMETRIC, st);
+      if (rc != XMCA_OK) return rc;
+    }
+    prof.mark(6);
+  }
+  if (ss) {                                           // join
+    XMCA_CUDA(cudaEventRecord(ss->ev_qr, sp));
+    XMCA_CUDA(cudaStreamWaitEvent(st, ss->ev_qr, 0));
   }
   {
     const int64_t tot = n * (PB + 1);
     sbr_band_extract_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(d_A, lda, (int)n, np, AB);
     XMCA_LAUNCHED();
+    prof.mark(8);
   }
   // stage 2; the reflectors go to the strict upper triangle of A (row j, columns > j), free after stage 1
   if (!(want_vectors & 4)) {                         // (bit 2: stop after stage 1 -- diagnostics, scripts/check_sytrd2.py)
     int rc = sb_chase(AB, (int)n, counters, (want_vectors & 1) ? d_A : nullptr, lda, d_d, d_e, st);
     if (rc != XMCA_OK) return rc;
+    prof.mark(9);
   }
   int h_fail = 0;
   XMCA_CUDA(cudaMemcpyAsync(&h_fail, fail, sizeof(int), cudaMemcpyDeviceToHost, st));
   XMCA_CUDA(cudaStreamSynchronize(st));
+  prof.report(n);
   if (h_fail)
     return ::xmca::fail(XMCA_NUMERIC, "xmca_sytrd2: panel factorisation broke down (matrix not finite or panel rank deficient)",
                         __FILE__, __LINE__);
