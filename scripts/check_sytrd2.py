@@ -14,7 +14,13 @@ from xmca_b200 import _lib as L, device as D
 lib = L.load()
 raw = lib._raw
 raw.xmca_dbg_band_chase.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
-                                    C.c_void_p, C.c_void_p]
+                                    C.c_void_p, C.c_void_p, C.c_void_p]
+raw.xmca_dbg_band_chase_ll_bytes.restype = C.c_size_t
+raw.xmca_dbg_band_chase_ll_bytes.argtypes = [C.c_int64]
+
+
+def ll_buffer(n):
+    return torch.zeros(int(raw.xmca_dbg_band_chase_ll_bytes(n)), dtype=torch.uint8, device="cuda")
 B = 64
 
 
@@ -67,7 +73,7 @@ def check_stage2(n, seed=0, vectors=True):
     V2 = D.zeros((n, n), D.f64())
     cnt = torch.zeros(n + 8, dtype=torch.int32, device="cuda")
     rc = raw.xmca_dbg_band_chase(n, L.ptr(AB), L.ptr(d), L.ptr(e), L.ptr(V2) if vectors else None, n, L.ptr(cnt),
-                                 None, L.stream_ptr())
+                                 None, L.ptr(ll_buffer(n)), L.stream_ptr())
     torch.cuda.synchronize()
     dh, eh = D.to_host(d), D.to_host(e)
     lam = tri_eigs(dh, eh)
@@ -209,7 +215,10 @@ def chase_profile(n):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
-        raw.xmca_dbg_band_chase(n, L.ptr(AB), L.ptr(d), L.ptr(e), L.ptr(V2), n, L.ptr(cnt), L.ptr(prof), L.stream_ptr())
+        llb = ll_buffer(n)
+        torch.cuda.synchronize()
+        e0.record()
+        raw.xmca_dbg_band_chase(n, L.ptr(AB), L.ptr(d), L.ptr(e), L.ptr(V2), n, L.ptr(cnt), L.ptr(prof), L.ptr(llb), L.stream_ptr())
         e1.record()
         torch.cuda.synchronize()
         p = prof.cpu().numpy()

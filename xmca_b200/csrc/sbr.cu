@@ -31,7 +31,8 @@ constexpr int PT = 256;             // threads of the chunk kernels
 constexpr int NRED = 256;           // CTAs of the reduction kernels (16 elements each, 16 threads per element)
 
 int sb_chase(double* AB, int n, int* counters, double* V2, int64_t ldv, double* d, double* e, cudaStream_t st,
-             long long* prof = nullptr);
+             long long* prof = nullptr, void* ll = nullptr);
+size_t sb_chase_ll_bytes(int n);
 int sb_apply_q2(const double* V2, int64_t ldv, int n, double* Z, int64_t ldz, int kvec, cudaStream_t st);
 
 __device__ __forceinline__ void bar64() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
@@ -656,6 +657,98 @@ sbr_symm_kernel(const double* __restrict__ A, int64_t lda, int m, const double* 
   }
 }
 
+// ------------------------------------------------------------------ (8) A22 -= XY YX^T, symmetric rank-128 update on the DMMA pipe
+// XY = [X | Y], YX = [Y | X] (m x 128, k contiguous).  CTA tile 128 rows x 64 columns, 256 threads, two CTAs per SM so
+// that the read-modify-write of one tile overlaps the MMAs of the other (the general kernel runs one 512-thread CTA
+// per SM and spent more time in the prologue / epilogue of these K = 128 tiles than in their MMAs).  Only tiles that
+// touch the lower triangle are launched (1-D grid over row tile bm, column tile bn <= 2 bm + 1); entries with
+// col <= row are written and mirrored, so the matrix stays exactly symmetric.
+__global__ void __launch_bounds__(SY_T, 2)
+sbr_syr2k_kernel(const double* __restrict__ XY, const double* __restrict__ YX, int m, double* __restrict__ D, int64_t ldd) {
+  __shared__ double As[SY_BK][SY_LDA];
+  __shared__ double Bs[SY_BK][SY_LDB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
+  // blockIdx.x -> (bm, bn): tiles of row bm start at bm (bm + 1)
+  int bm = (int)((sqrtf(4.0f * (float)blockIdx.x + 1.0f) - 1.0f) * 0.5f);
+  while ((bm + 1) * (bm + 2) <= (int)blockIdx.x) ++bm;
+  while (bm * (bm + 1) > (int)blockIdx.x) --bm;
+  const int bn = (int)blockIdx.x - bm * (bm + 1);
+  const int m0 = bm * SY_BM, n0 = bn * PB;
+  double c[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { c[i][j][0] = 0.0; c[i][j][1] = 0.0; }
+  const int akk = tid & 15, ar = tid >> 4;
+  double ra[8], rb[4];
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = m0 + ar + 16 * i;
+      ra[i] = r < m ? XY[(int64_t)r * (2 * PB) + k0 + akk] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = n0 + ar + 16 * i;
+      rb[i] = r < m ? YX[(int64_t)r * (2 * PB) + k0 + akk] : 0.0;
+    }
+  };
+  gload(0);
+  for (int k0 = 0; k0 < 2 * PB; k0 += SY_BK) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) As[akk][(ar + 16 * i) ^ ((akk >> 2) & 3)] = ra[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) Bs[akk][(ar + 16 * i) ^ ((akk >> 2) & 3)] = rb[i];
+    __syncthreads();
+    if (k0 + SY_BK < 2 * PB) gload(k0 + SY_BK);
+#pragma unroll
+    for (int ks = 0; ks < SY_BK; ks += 4) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        a[i] = As[ks + tig][(wm + 8 * i + gid) ^ ((ks >> 2) & 3)];
+        b[i] = Bs[ks + tig][(wn + 8 * i + gid) ^ ((ks >> 2) & 3)];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(c[i][j][0]), "+d"(c[i][j][1]) : "d"(a[i]), "d"(b[j]));
+    }
+    __syncthreads();
+  }
+  // epilogue: all old values first (independent loads), then the stores
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = m0 + wm + 8 * i + gid;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int cc = n0 + wn + 8 * j + 2 * tig + e;
+        const double old = (r < m && cc <= r) ? D[(int64_t)r * ldd + cc] : 0.0;
+        c[i][j][e] = old - c[i][j][e];
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = m0 + wm + 8 * i + gid;
+    if (r >= m) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int cc = n0 + wn + 8 * j + 2 * tig + e;
+        if (cc > r) continue;
+        D[(int64_t)r * ldd + cc] = c[i][j][e];
+        if (cc < r) D[(int64_t)cc * ldd + r] = c[i][j][e];
+      }
+  }
+}
+
 // ------------------------------------------------------------------ (5) Z = sum of the split-K partials, partial Y^T Z
 __global__ void __launch_bounds__(PT)
 sbr_yz_kernel(const double* __restrict__ Zp, int split, int m, const double* __restrict__ Ybuf,
@@ -993,7 +1086,7 @@ static int sbr_npanels(int64_t n) {                  // panels with m = n - (k +
 }
 
 struct SbrPlan {
-  size_t off_ab, off_q, off_y, off_z, off_xy, off_yx, off_zp, off_gpart, off_small, off_ints, total;
+  size_t off_ab, off_q, off_y, off_z, off_xy, off_yx, off_zp, off_gpart, off_small, off_ints, off_ll, total;
   int max_split;
 };
 
@@ -1012,6 +1105,7 @@ static SbrPlan sbr_plan(int64_t n) {
   p.off_gpart = o; o += al256(((nn + PB - 1) / PB + 1) * PB * PB * 8);
   p.off_small = o; o += al256(16 * PB * PB * 8);
   p.off_ints = o;  o += al256((nn + 64) * 4);
+  p.off_ll = o;    o += al256(sb_chase_ll_bytes((int)n) + 256);
   p.total = o;
   return p;
 }
@@ -1217,10 +1311,10 @@ extern "C" int xmca_sytrd2(int64_t n, double* d_A, int64_t lda, double* d_d, dou
                           XMCA_F64, 1, nullptr, 0, 0, sp);
     if (rc != XMCA_OK) return rc;
     if (m > PB) {
-      rc = xmca_gemm_ex(1, 1, m - PB, m - PB, 2 * PB, -1.0, XY + (int64_t)PB * 2 * PB, XMCA_F64, 2 * PB,
-                        YX + (int64_t)PB * 2 * PB, XMCA_F64, 2 * PB, A22 + (int64_t)PB * lda + PB, XMCA_F64, lda, 1,
-                        XMCA_F64, 1, nullptr, 0, XMCA_GEMM_SYMMETRIC, st);
-      if (rc != XMCA_OK) return rc;
+      const int mm = m - PB, tm = (mm + SY_BM - 1) / SY_BM;
+      sbr_syr2k_kernel<<<tm * (tm + 1), SY_T, 0, st>>>(XY + (int64_t)PB * 2 * PB, YX + (int64_t)PB * 2 * PB, mm,
+                                                       A22 + (int64_t)PB * lda + PB, lda);
+      XMCA_LAUNCHED();
     }
     prof.mark(6);
   }
@@ -1236,7 +1330,7 @@ extern "C" int xmca_sytrd2(int64_t n, double* d_A, int64_t lda, double* d_d, dou
   }
   // stage 2; the reflectors go to the strict upper triangle of A (row j, columns > j), free after stage 1
   if (!(want_vectors & 4)) {                         // (bit 2: stop after stage 1 -- diagnostics, scripts/check_sytrd2.py)
-    int rc = sb_chase(AB, (int)n, counters, (want_vectors & 1) ? d_A : nullptr, lda, d_d, d_e, st);
+    int rc = sb_chase(AB, (int)n, counters, (want_vectors & 1) ? d_A : nullptr, lda, d_d, d_e, st, nullptr, ws + pl.off_ll);
     if (rc != XMCA_OK) return rc;
     prof.mark(9);
   }
@@ -1276,7 +1370,8 @@ extern "C" int xmca_ormtr2(int64_t n, const double* d_A, int64_t lda, const doub
 }
 
 // diagnostics (scripts/check_sytrd2.py): stage 2 alone on a caller-built band array (n x 128 doubles, see sbtrd.cu)
+extern "C" size_t xmca_dbg_band_chase_ll_bytes(int64_t n) { return sb_chase_ll_bytes((int)n); }
 extern "C" int xmca_dbg_band_chase(int64_t n, double* d_AB, double* d_d, double* d_e, double* d_V2, int64_t ldv,
-                                   int* d_counters, long long* d_prof, void* stream) {
-  return sb_chase(d_AB, (int)n, d_counters, d_V2, ldv, d_d, d_e, reinterpret_cast<cudaStream_t>(stream), d_prof);
+                                   int* d_counters, long long* d_prof, void* d_ll, void* stream) {
+  return sb_chase(d_AB, (int)n, d_counters, d_V2, ldv, d_d, d_e, reinterpret_cast<cudaStream_t>(stream), d_prof, d_ll);
 }
