@@ -1,9 +1,11 @@
-"""Import the UNMODIFIED reference (``/root/reference/xmca``) in the build
-container so the oracle can be pinned against it and golden vectors generated.
+"""Import the UNMODIFIED reference (``xmca`` package of nicrie/xmca) so the oracle can be pinned against it,
+golden vectors generated, and -- in ``bench.py --impl reference`` / ``cpu_baseline`` -- the reference's own CPU
+path timed on the GPU box's host cores.
 
-TEST INFRASTRUCTURE ONLY.  ``/root/reference`` does not exist on the GPU box:
-nothing that runs there imports this module (the tests that use it are skipped
-when the reference tree is absent).
+TEST / BASELINE INFRASTRUCTURE ONLY; the product never imports it.  Two locations are tried:
+``/root/reference`` (the build container) and ``oracle/_ref`` -- a verbatim, git-ignored copy of the reference's
+``xmca/`` package directory that ``__graft_entry__.build()`` makes when ``/root/reference`` exists, so that it
+travels to the GPU box with the snapshot like the built ``.so`` (it is never committed).
 
 The three shims are the ones recorded in SURVEY.md Appendix A; they live here,
 never in the reference tree.
@@ -16,12 +18,18 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("XMCA_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CANDIDATES = [os.environ.get("XMCA_REFERENCE_ROOT", "/root/reference"), os.path.join(_HERE, "_ref")]
+REFERENCE_ROOT = next((c for c in _CANDIDATES if os.path.isdir(os.path.join(c, "xmca"))), _CANDIDATES[0])
 FIXTURES = os.path.join(REFERENCE_ROOT, "tests", "integration", "fixtures")
 
 
 def reference_available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "xmca"))
+
+
+def reference_location() -> str:
+    return REFERENCE_ROOT
 
 
 def import_reference_mca():

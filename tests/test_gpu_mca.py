@@ -219,6 +219,66 @@ def test_rule_n_distribution_matches_oracle(MCA):
     np.testing.assert_array_equal(got, again)              # counter-based RNG: reproducible
 
 
+def _replay_reference_stream(m, n_runs, n_modes, complexify=False, rotated=False):
+    """rule_n with the surrogate fields drawn on the HOST exactly as the reference draws them (global numpy stream,
+    float64, full grid: array.py:1756) and pushed through the device run body."""
+    from xmca_b200 import device as D
+    from xmca_b200 import rule_n as RN
+
+    def fn(T, n_vars, run, seed, cplx, rot, n_rot, power):
+        fields = []
+        for S in n_vars:
+            X = D.to_device(np.random.standard_normal([T, S]))
+            D.center_columns(X)
+            fields.append(X)
+        return RN.variance_of_fields(fields, cplx, rot, n_rot, power)
+    return RN.rule_n(m, n_runs, n_modes, seed=0, _surrogate_fn=fn, pair_runs=False)
+
+
+def test_rule_n_run_body_matches_live_reference(MCA, live):
+    """EXACT parity of the Monte-Carlo run body: the reference's own rule_n(4, 10) on case A (NaN columns: the
+    surrogates live on the full grid) with np.random.seed(123), committed in tests/golden/live_cases.npz."""
+    m = MCA(live["A/left"].copy(), live["A/right"].copy())
+    m.solve()
+    np.random.seed(123)
+    got = _replay_reference_stream(m, 4, 10)
+    assert got.shape == live["A/rule_n"].shape
+    np.testing.assert_allclose(got, live["A/rule_n"], rtol=1e-6)
+
+
+@pytest.mark.parametrize("complexify,rotated", [(False, True), (True, False), (True, True)])
+def test_rule_n_run_body_matches_oracle_on_the_same_stream(MCA, live, complexify, rotated):
+    """rotated / complex models have no golden rule_n in the reference: the oracle (pinned to the live reference by
+    tests/test_oracle.py) replays the same numpy stream."""
+    A, B = live["A/left"].copy(), live["A/right"].copy()
+    m = MCA(A.copy(), B.copy())
+    m.solve(complexify=complexify)
+    ref = orc.solve(orc.make_model(A.copy(), B.copy()), complexify=complexify)
+    if rotated:
+        m.rotate(6, 1)
+        orc.rotate(ref, 6, 1)
+    np.random.seed(321)
+    got = _replay_reference_stream(m, 3, 5, complexify, rotated)
+    np.random.seed(321)
+    want = orc.rule_n(ref, 3, 5)
+    assert got.shape == want.shape
+    np.testing.assert_allclose(got, want, rtol=2e-5 if rotated else 1e-6)
+
+
+def test_rule_n_default_surrogates_are_float64_and_nan_columns_work(MCA, live):
+    """Reference-faithful defaults: float64 surrogates on the FULL grid (NaN columns included) -- case A has
+    57 valid columns on the left, 60 grid points; the spectra are sliced by the model's rank."""
+    m = MCA(live["A/left"].copy(), live["A/right"].copy())
+    m.solve()
+    full = m.rule_n(3, seed=5)
+    assert full.shape == (m._analysis["rank"], 3) and full.dtype == np.float64
+    fast = m.rule_n(3, seed=5, surrogate_dtype="float32")
+    assert fast.shape == full.shape
+    np.testing.assert_allclose(fast, full, rtol=5e-2)           # other Philox draws (fp32), same statistics
+    with pytest.raises(ValueError):
+        m.rule_n(2, surrogate_dtype="float16")
+
+
 @pytest.mark.parametrize("complexify", [False, True])
 @pytest.mark.parametrize("rotated", [False, True])
 def test_rule_n_paired_runs_equal_single_runs(MCA, monkeypatch, rotated, complexify):
@@ -581,3 +641,32 @@ def test_default_route_at_moderate_size(MCA, shape):
     m.rotate(8, 1)
     orc.rotate(ref, 8, 1)
     np.testing.assert_allclose(m.variance(8), orc.get_variance(ref, 8), rtol=1e-4)
+
+
+@pytest.mark.parametrize("complexify,n_rot,power", [(False, 100, 1), (False, 72, 2), (True, 40, 1)])
+def test_wide_rotation_beyond_the_fused_kernel(MCA, complexify, n_rot, power):
+    """The reference accepts any n_rot >= 2 (array.py:810-813); beyond the fused kernels' shared-memory limit (64 real /
+    32 complex) the same fixed point runs as device products + host p x p SVD (engine.varimax_wide).  The planted
+    modes keep the criterion well conditioned; compared with the numpy restatement of rotation.py."""
+    A, B = orc.synthetic_fields(400, 260, 220, seed=61, k=120, dtype=np.float64)
+    m = MCA(A.copy(), B.copy())
+    m.solve(complexify=complexify)
+    ref = orc.solve(orc.make_model(A.copy(), B.copy()), complexify=complexify)
+    try:
+        orc.rotate(ref, n_rot, power)
+    except orc.NotConverged:
+        with pytest.raises(RuntimeError):
+            m.rotate(n_rot, power)
+        return
+    m.rotate(n_rot, power)
+    assert m._analysis["n_rot"] == n_rot
+    np.testing.assert_allclose(m.variance(n_rot), orc.get_variance(ref, n_rot), rtol=1e-5)
+    for k in ("left", "right"):
+        np.testing.assert_allclose(m.norm(n_rot)[k], orc.get_norm(ref, n_rot)[k], rtol=1e-5)
+    R = m.rotation_matrix()
+    assert R.shape == (n_rot, n_rot)
+    if power == 1:
+        np.testing.assert_allclose(R.conj().T @ R, np.eye(n_rot), atol=1e-9)
+    e, er = m.eofs(10), orc.eofs(ref, 10)
+    al, ar = orc.align_modes(er["left"].reshape(-1, 10), e["left"].reshape(-1, 10), e["right"].reshape(-1, 10))
+    assert np.abs(al - er["left"].reshape(-1, 10)).max() < 1e-3 * np.abs(er["left"]).max()

@@ -158,6 +158,30 @@ def _rule_n_worker(rank, world, port, out_dir):
     np.testing.assert_array_equal(paired, got)
     mine = list(__import__("xmca_b200.rule_n", fromlist=["partition"]).partition(11, world, rank))
     assert calls == [(mine[k], mine[k + 1]) for k in range(0, len(mine) - 1, 2)]
+
+    # seed=None: ONE seed, drawn on rank 0 and broadcast -- every rank must use the same Philox key whatever its own
+    # numpy state is (the ranks are given different states on purpose)
+    seen = []
+
+    def seed_stub(T, n_vars, run, seed, cplx, rot, n_rot, power):
+        seen.append(seed)
+        return stub(T, n_vars, run, seed % 1000, cplx, rot, n_rot, power)
+
+    np.random.seed(5 if rank == 0 else 999)
+    none_seed = rule_n(m, 7, n_modes=4, seed=None, _surrogate_fn=seed_stub)
+    assert len(set(seen)) == 1
+    np.save(os.path.join(out_dir, "seed%d.npy" % rank), np.array(seen[:1]))
+    np.save(os.path.join(out_dir, "none%d.npy" % rank), none_seed)
+
+    # NaN columns: the model's rank (7 here) is smaller than the length of the surrogates' spectra (9): the
+    # reference stacks the full spectra, rescales by their FULL sum and slices by the model's rank (array.py:1767-1771)
+    m2 = MCA(rng.standard_normal((40, 12)), rng.standard_normal((40, 9)))
+    m2._analysis["rank"] = 7
+    m2._norm = {"left": np.sqrt(np.linspace(7, 1, 7)), "right": np.sqrt(np.linspace(7, 1, 7))}
+    m2._var_idx = np.arange(7)
+    m2._singular_values = np.linspace(7, 1, 7)
+    nan_case = rule_n(m2, 4, seed=3, _surrogate_fn=stub)
+    np.save(os.path.join(out_dir, "nan%d.npy" % rank), nan_case)
     dist.destroy_process_group()
 
 
@@ -177,6 +201,20 @@ def test_rule_n_two_rank_gloo_matches_single_process(tmp_path):
         s = np.sort(np.random.default_rng(1000 * 17 + run).random(9))[::-1] + run
         cols.append(s * ref_sum / s.sum())
     np.testing.assert_allclose(r0, np.array(cols).T[:4], rtol=1e-14)
+    # seed=None: both ranks used rank 0's draw; the result equals a single-process run with the same numpy state
+    s0, s1 = np.load(tmp_path / "seed0.npy"), np.load(tmp_path / "seed1.npy")
+    assert s0[0] == s1[0]
+    np.random.seed(5)
+    assert s0[0] == np.random.randint(0, 2 ** 31 - 1)
+    np.testing.assert_array_equal(np.load(tmp_path / "none0.npy"), np.load(tmp_path / "none1.npy"))
+    # NaN-column case: (rank 7 rows) x 4 runs, columns rescaled by the full 9-entry sum
+    nan0 = np.load(tmp_path / "nan0.npy")
+    assert nan0.shape == (7, 4)
+    want = []
+    for run in range(4):
+        sp = np.sort(np.random.default_rng(1000 * 3 + run).random(9))[::-1] + run
+        want.append(sp * np.linspace(7, 1, 7).sum() / sp.sum())
+    np.testing.assert_allclose(nan0, np.array(want).T[:7], rtol=1e-14)
 
 
 def test_xmca_facade_constructor_and_metadata():

@@ -507,8 +507,6 @@ class MCA:
         if power < 1:
             raise ValueError("`power` must be >=1")
         self._require_solved("singular values")
-        if n_rot > (32 if self._analysis["is_complex"] else 64):
-            raise ValueError("the fused rotation kernel supports n_rot <= 64 (<= 32 for complex models)")
         sv = self._get_svals(n_rot)
         n_rot = sv.size
         if self._analysis["is_complex"]:
@@ -535,9 +533,10 @@ class MCA:
         self._analysis["n_rot"] = n_rot
         self._analysis["power"] = power
         self._solve_info["varimax_iterations"] = iters
-        st = D.to_host(D.last_varimax_stats)
-        self._solve_info["varimax_svd_sweeps"] = int(st[3])
-        self._solve_info["varimax_phase_clocks"] = [float(x) for x in st[4:10]]
+        if n_rot <= E.VARIMAX_FUSED_MAX_P and D.last_varimax_stats is not None:
+            st = D.to_host(D.last_varimax_stats)
+            self._solve_info["varimax_svd_sweeps"] = int(st[3])
+            self._solve_info["varimax_phase_clocks"] = [float(x) for x in st[4:10]]
         # rotated EOFs = L_rot / norm (array.py:640): one scaled copy per field, kept on the host
         self._rot_eofs = {}
         bounds = {"left": (0, s_left), "right": (s_left, n_all)}

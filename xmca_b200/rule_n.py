@@ -173,42 +173,66 @@ def gather_spectra(local: np.ndarray, valid: np.ndarray, n_runs: int, group=None
     return np.concatenate(cols, axis=1) if cols else np.zeros((modes, 0))
 
 
+def _broadcast_seed(seed, group):
+    """One seed for all ranks: rank 0's value (drawn from ITS global numpy stream when seed is None, the analogue of
+    the reference consuming `np.random`, array.py:1756) is broadcast, so the Philox keys -- and therefore the result --
+    do not depend on the number of GPUs."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed)
+    rank = dist.get_rank(group)
+    val = int(np.random.randint(0, 2 ** 31 - 1)) if (seed is None and rank == 0) else int(seed or 0)
+    backend = dist.get_backend(group)
+    devc = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    t = torch.tensor([val], dtype=torch.int64, device=devc)
+    dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    return int(t.item())
+
+
 def rule_n(model, n_runs, n_modes=None, seed=None, group=None, _surrogate_fn=None, surrogate_dtype=None,
            pair_runs=True, _pair_fn=None):
     """Sharded Rule N for an ``xmca_b200.MCA`` model (array.py:1716-1771).
 
-    surrogate_dtype: the reference draws float64 surrogates whatever the model's dtype
-    (array.py:1756); a conscious deviation here: the surrogates follow the MODEL's field dtype
-    (fp32 model -> fp32 Gaussian fields, Gram matrices on the tensor cores), which changes nothing
-    statistically; pass "float64" for the reference's behaviour.  The returned spectra are fp64.
-    pair_runs: the runs are processed two at a time through one batched tridiagonalisation
-    (same surrogates, same spectra to rounding; see `device_surrogate_variance_pair`)."""
+    surrogate_dtype: "float64" (default: the reference draws float64 surrogates whatever the model's dtype,
+    array.py:1756) or "float32" -- an opt-in fast mode for fp32 models (fp32 Gaussian fields, Gram matrices on the
+    tensor cores), statistically equivalent.  The returned spectra are fp64.
+    seed: Philox key; None draws one from rank 0's global numpy stream and broadcasts it.
+    pair_runs: the runs are processed two at a time (`device_surrogate_variance_pair`; same surrogates, same
+    spectra to rounding)."""
     import torch.distributed as dist
     T = model._n_observations["left"]
     n_vars = [model._n_variables[k] for k in model._keys]
     complexify = model._analysis["is_complex"]
     rotated = model._analysis["is_rotated"]
     n_rot, power = model._analysis["n_rot"], model._analysis["power"]
-    if seed is None:
-        seed = int(np.random.randint(0, 2 ** 31 - 1))          # consume the global numpy stream once
+    seed = _broadcast_seed(seed, group)
     if dist.is_available() and dist.is_initialized():
         world, rank = dist.get_world_size(group), dist.get_rank(group)
     else:
         world, rank = 1, 0
     fn = _surrogate_fn or device_surrogate_variance
     if surrogate_dtype is None:
-        surrogate_dtype = "float32" if model._field_means[model._keys[0]].dtype == np.float32 else "float64"
+        surrogate_dtype = "float64"
+    if surrogate_dtype not in ("float32", "float64"):
+        raise ValueError("surrogate_dtype must be 'float32' or 'float64'")
     extra = {} if _surrogate_fn is not None else {"dtype": surrogate_dtype}
     ref = model._get_variance()
     mine = partition(n_runs, world, rank)
-    modes = ref.size
+    # The surrogates live on the FULL grid (NaN columns included, array.py:1745), so their spectra have
+    # min(T, *n_vars) entries (n_rot when rotated) -- possibly more than the model's own rank when NaN columns were
+    # dropped.  The reference stacks the full spectra and slices afterwards (array.py:1767-1771).
+    modes = int(min(n_rot, T, *n_vars)) if rotated else int(min(T, *n_vars))
     local = np.full((modes, len(mine)), np.nan)
     valid = np.zeros(len(mine), dtype=bool)
+
     def store(j, spec):
         if spec is None:
             return
         spec = np.asarray(spec, dtype=np.float64)
-        local[:spec.size, j] = spec * (ref.sum() / spec.sum())   # column-wise rescale, array.py:1768-1769
+        k = min(spec.size, modes)
+        local[:, j] = 0.0
+        local[:k, j] = spec[:k] * (ref.sum() / spec.sum())      # column-wise rescale, array.py:1768-1769
         valid[j] = True
 
     runs = list(mine)
@@ -226,4 +250,4 @@ def rule_n(model, n_runs, n_modes=None, seed=None, group=None, _surrogate_fn=Non
             store(j, fn(T, n_vars, runs[j], seed, complexify, rotated, n_rot, power, **extra))
             j += 1
     sv = gather_spectra(local, valid, n_runs, group)
-    return sv[model._get_slice(n_modes)]
+    return sv[model._get_slice(n_modes)]                    # array.py:1771 (bounded by the MODEL's rank, as there)

@@ -156,9 +156,9 @@ class xMCA(MCA):
     def rule_north(self, n=None):
         return self._mode_array(super().rule_north(n), n, "error singular values")
 
-    def rule_n(self, n_runs, n_modes=None, seed=None, group=None):
+    def rule_n(self, n_runs, n_modes=None, seed=None, group=None, surrogate_dtype=None):
         """xarray.py:1447-1488: (mode, run) DataArray of the surrogate spectra."""
-        sv = super().rule_n(n_runs, n_modes, seed=seed, group=group)
+        sv = super().rule_n(n_runs, n_modes, seed=seed, group=group, surrogate_dtype=surrogate_dtype)
         return _xr().DataArray(sv, dims=["mode", "run"],
                                coords={"mode": self._modes(n_modes, sv.shape[0]),
                                        "run": np.arange(1, sv.shape[1] + 1)},
