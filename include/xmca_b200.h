@@ -192,13 +192,16 @@ int xmca_ormtr(int64_t n, const double* d_A, int64_t lda, const double* d_tau, i
  *   Returns XMCA_NUMERIC if a panel factorisation broke down (non-finite input / exactly rank-deficient
  *   panel): the caller falls back to xmca_sytrd.  Synchronises `stream` once at the end to read that flag.
  * xmca_ormtr2: rows of d_Z (k x n) <- Q row with Q = Q1 Q2 from xmca_sytrd2 (eigenvectors of the tridiagonal ->
- *   eigenvectors of the original matrix; array.py:584 for the modes that are asked for). */
+ *   eigenvectors of the original matrix; array.py:584 for the modes that are asked for).  Stage 2: one CTA per
+ *   vector (kept in shared memory), reflector data prefetched one sweep ahead; stage 1: three products per panel
+ *   over all vectors (workspace xmca_ormtr2_workspace_bytes; without it a per-vector kernel is used). */
 size_t xmca_sytrd2_workspace_bytes(int64_t n);
 size_t xmca_sytrd2_tfac_bytes(int64_t n);
 int xmca_sytrd2(int64_t n, double* d_A, int64_t lda, double* d_d, double* d_e, double* d_tfac,
                 int want_vectors, void* d_workspace, size_t workspace_bytes, void* stream);
+size_t xmca_ormtr2_workspace_bytes(int64_t n, int64_t k);
 int xmca_ormtr2(int64_t n, const double* d_A, int64_t lda, const double* d_tfac, int64_t k,
-                double* d_Z, int64_t ldz, void* stream);
+                double* d_Z, int64_t ldz, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* ---- analytic signal (Hilbert transform along time) ----------------------
  * Replaces scipy.signal.hilbert(field, axis=0) of array.py:464 by two linear operators that

@@ -262,7 +262,8 @@ def test_rule_n_run_body_matches_oracle_on_the_same_stream(MCA, live, complexify
     np.random.seed(321)
     want = orc.rule_n(ref, 3, 5)
     assert got.shape == want.shape
-    np.testing.assert_allclose(got, want, rtol=2e-5 if rotated else 1e-6)
+    # (case A is fp32: the model's own variance sum -- the rescale target -- carries fp32 rounding)
+    np.testing.assert_allclose(got, want, rtol=2e-5 if rotated else 5e-6)
 
 
 def test_rule_n_default_surrogates_are_float64_and_nan_columns_work(MCA, live):
@@ -545,7 +546,7 @@ def test_full_size_config2_invariants(MCA):
         np.testing.assert_allclose(V[side].T.astype(np.float64) @ V[side], np.eye(k), atol=2e-5)
     VL, VR = torch.from_numpy(V["left"]).cuda(), torch.from_numpy(V["right"]).cuda()
     small = D.to_host(D.matmul(D.matmul(VL, C, trans_a=True), VR))                  # k x k, = diag(sigma)
-    np.testing.assert_allclose(np.diag(small), sv[:k], rtol=2e-5)
+    np.testing.assert_allclose(np.diag(small), sv[:k], rtol=1e-5)
     off = small - np.diag(np.diag(small))
     assert np.abs(off).max() < 2e-5 * sv[0]
     U = m.pcs(k, rotated=False)
@@ -670,3 +671,135 @@ def test_wide_rotation_beyond_the_fused_kernel(MCA, complexify, n_rot, power):
     e, er = m.eofs(10), orc.eofs(ref, 10)
     al, ar = orc.align_modes(er["left"].reshape(-1, 10), e["left"].reshape(-1, 10), e["right"].reshape(-1, 10))
     assert np.abs(al - er["left"].reshape(-1, 10)).max() < 1e-3 * np.abs(er["left"]).max()
+
+
+def _leading_separated(sigma, k, gap=1e-3):
+    """indices < k whose singular value is separated from both neighbours by a relative gap"""
+    s = np.asarray(sigma[:k + 1], dtype=np.float64)
+    rel = np.abs(np.diff(s)) / s[:-1]
+    ok = np.ones(k, dtype=bool)
+    ok[1:] &= rel[:k - 1] > gap
+    ok &= rel[:k] > gap
+    return np.nonzero(ok)[0]
+
+
+def test_c3_shaped_complex_varimax_default_routing(MCA):
+    """BASELINE config 3 in shape (complex MCA + Varimax n_rot = 20, fp32, T < S) at a size the oracle finishes in
+    seconds, through the DEFAULT routing (two-stage tridiagonal route, frequency-domain embedding):
+    sigma rtol 1e-5 (fp32 bar of north_star), principal-subspace angle < 1e-4, rotated variances."""
+    T, S1, S2, k = 1024, 3000, 2600, 20
+    A, B = orc.synthetic_fields(T, S1, S2, seed=71, k=32, dtype=np.float32)
+    m = MCA(A.copy(), B.copy())
+    m.solve(complexify=True)
+    assert m._solve_info["route"] == "tridiag"
+    ref = orc.solve(orc.make_model(A.copy(), B.copy()), complexify=True)
+    np.testing.assert_allclose(m.singular_values(k), ref.sigma[:k], rtol=1e-5)
+    V = m._get_V(k, rotated=False)
+    for side in ("left", "right"):
+        assert orc.subspace_angle(V[side].astype(np.complex128), ref.V[side][:, :k].astype(np.complex128)) < 1e-4
+    try:
+        orc.rotate(ref, k, 1)
+    except orc.NotConverged:
+        with pytest.raises(RuntimeError):
+            m.rotate(k, 1)
+        return
+    m.rotate(k, 1)
+    np.testing.assert_allclose(m.variance(k), orc.get_variance(ref, k), rtol=2e-4)
+    p, pr = m.pcs(k), orc.pcs(ref, k)
+    al, ar = orc.align_modes(pr["left"], p["left"], p["right"])
+    assert max(np.abs(al - pr["left"]).max(), np.abs(ar - pr["right"]).max()) < 5e-3 * np.abs(pr["left"]).max()
+
+
+def test_c5_shaped_fp64_promax4_default_routing(MCA):
+    """BASELINE config 5 in shape (fp64, Promax power 4, n_rot = 50, S1 = 2 S2 > T) through the default routing:
+    sigma rtol 1e-12 on the separated leading modes (fp64 bar of north_star), subspace angle < 1e-4, Promax results."""
+    T, S1, S2, k = 1536, 4000, 2000, 50
+    A, B = orc.synthetic_fields(T, S1, S2, seed=72, k=64, dtype=np.float64)
+    m = MCA(A.copy(), B.copy())
+    m.solve()
+    assert m._solve_info["route"] == "tridiag"
+    ref = orc.solve(orc.make_model(A.copy(), B.copy()))
+    sep = _leading_separated(ref.sigma, k)
+    assert sep.size >= 30
+    np.testing.assert_allclose(m.singular_values(k)[sep], ref.sigma[:k][sep], rtol=1e-12)
+    np.testing.assert_allclose(m.singular_values(), ref.sigma, rtol=1e-9, atol=1e-12 * ref.sigma[0])
+    V = m._get_V(k, rotated=False)
+    for side in ("left", "right"):
+        assert orc.subspace_angle(V[side], ref.V[side][:, :k]) < 1e-4
+    try:
+        orc.rotate(ref, k, 4)
+    except orc.NotConverged:                          # the reference raises too (rotation.py:66-71): same behaviour required
+        with pytest.raises(RuntimeError):
+            m.rotate(k, 4)
+        return
+    m.rotate(k, 4)
+    np.testing.assert_allclose(m.variance(k), orc.get_variance(ref, k), rtol=1e-6)
+    idx = ref.var_idx
+    np.testing.assert_allclose(np.abs(m.correlation_matrix()), np.abs(ref.Phi[idx, :][:, idx]), atol=1e-6)
+    p, pr = m.pcs(k), orc.pcs(ref, k)
+    al, ar = orc.align_modes(pr["left"], p["left"], p["right"])
+    assert max(np.abs(al - pr["left"]).max(), np.abs(ar - pr["right"]).max()) < 1e-6 * np.abs(pr["left"]).max()
+
+
+def test_full_size_config3_invariants(MCA):
+    """BASELINE config 3 at FULL size (complex MCA, T 8192, S1 = S2 32768, fp32, rotate(20, 1)): unrotated V^H V = I
+    (test_orthogonality), U_L^H U_R / dof = I for unrotated AND Varimax-rotated PCs (test_correlation), rotated EOFs not
+    orthogonal, sum of rotated variances = sum of the first 20 singular values' variance (orthogonal rotation)."""
+    from bench import synthetic_fields
+    T, S, k = 8192, 32768, 20
+    A, B = synthetic_fields(T, S, S, seed=2025)
+    m = MCA(A, B)
+    del A, B
+    m.solve(complexify=True)
+    assert m._solve_info["route"] == "tridiag" and m._analysis["rank"] == T
+    sv = m.singular_values().astype(np.float64)
+    assert np.all(np.diff(sv) <= 1e-6 * sv[0])
+    V = m._get_V(k, rotated=False)
+    for side in ("left", "right"):
+        np.testing.assert_allclose(V[side].conj().T.astype(np.complex128) @ V[side], np.eye(k), atol=5e-5)
+    U = m.pcs(k, rotated=False)
+    np.testing.assert_allclose(U["left"].conj().T.astype(np.complex128) @ U["right"] / (T - 1), np.eye(k), atol=2e-3)
+    m.rotate(k, 1)
+    np.testing.assert_allclose(m.variance(k).sum(), sv[:k].sum(), rtol=1e-5)
+    Ur = m.pcs(k)
+    np.testing.assert_allclose(Ur["left"].conj().T @ Ur["right"] / (T - 1), np.eye(k), atol=2e-3)
+    E = m.eofs(k)["left"].reshape(-1, k)
+    gram = E.conj().T @ E
+    assert np.abs(gram - np.diag(np.diag(gram))).max() > 1e-3
+    import torch
+    torch.cuda.empty_cache()
+
+
+def test_full_size_config5_invariants(MCA):
+    """BASELINE config 5 at FULL size (fp64, T 16384, S1 65536, S2 32768, rotate(50, 4)): sum(sigma^2) = ||C||_F^2 from
+    the independent identity ||A^T B||_F^2 = trace(G_A G_B) (Gram matrices on the fp64 DMMA product), V^T V = I,
+    U_L^T U_R / dof = I unrotated; Promax(4): correlated PCs (test_correlation expects != I), unit diagonal of Phi."""
+    import torch
+    from bench import synthetic_fields
+    from xmca_b200 import device as D
+    T, S1, S2, k = 16384, 65536, 32768, 50
+    A, B = synthetic_fields(T, S1, S2, seed=2026, dtype=np.float64)
+    m = MCA(A, B)
+    del A, B
+    m.solve()
+    assert m._solve_info["route"] == "tridiag" and m._analysis["rank"] == T
+    sv = m.singular_values()
+    dA, dB = m._device_fields()["left"], m._device_fields()["right"]
+    GA = D.matmul(dA, dA, trans_b=True, symmetric=True)
+    GB = D.matmul(dB, dB, trans_b=True, symmetric=True)
+    frob2 = float((GA * GB).sum().item()) / (T - 1) ** 2
+    del GA, GB
+    torch.cuda.empty_cache()
+    np.testing.assert_allclose((sv ** 2).sum(), frob2, rtol=1e-10)
+    V = m._get_V(k, rotated=False)
+    for side in ("left", "right"):
+        np.testing.assert_allclose(V[side].T @ V[side], np.eye(k), atol=1e-9)
+    U = m.pcs(k, rotated=False)
+    np.testing.assert_allclose(U["left"].T @ U["right"] / (T - 1), np.eye(k), atol=1e-8)
+    m.rotate(k, 4)
+    Phi = m.correlation_matrix()
+    np.testing.assert_allclose(np.diag(Phi), 1.0, atol=1e-10)
+    Ur = m.pcs(k)
+    cor = Ur["left"].T @ Ur["right"] / (T - 1)
+    assert np.abs(cor - np.eye(k)).max() > 1e-4
+    torch.cuda.empty_cache()

@@ -1344,8 +1344,18 @@ extern "C" int xmca_sytrd2(int64_t n, double* d_A, int64_t lda, double* d_d, dou
   return XMCA_OK;
 }
 
+// workspace of xmca_ormtr2: U, U2 (k x 64 each) and the split-K partials of U = Z Y
+static int ormtr2_split(int64_t m) {                  // the product has ONE 128 x 128 output tile: K chunks of 64 spread it
+  int64_t s = m / 64;                                  // over the SMs (a CTA's time is its number of k steps)
+  return (int)(s < 1 ? 1 : (s > 128 ? 128 : s));
+}
+extern "C" size_t xmca_ormtr2_workspace_bytes(int64_t n, int64_t k) {
+  if (n <= 0 || k <= 0) return 0;
+  return al256((size_t)k * PB * 8) * 2 + al256(xmca_gemm_workspace_bytes(k, PB, ormtr2_split(n), XMCA_F64)) + 256;
+}
+
 extern "C" int xmca_ormtr2(int64_t n, const double* d_A, int64_t lda, const double* d_tfac, int64_t k,
-                           double* d_Z, int64_t ldz, void* stream) {
+                           double* d_Z, int64_t ldz, void* d_workspace, size_t workspace_bytes, void* stream) {
   XMCA_REQUIRE(n >= 1 && k >= 0 && d_A && d_tfac && d_Z && ldz >= n, "xmca_ormtr2: bad argument");
   if (k == 0) return XMCA_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1353,6 +1363,31 @@ extern "C" int xmca_ormtr2(int64_t n, const double* d_A, int64_t lda, const doub
   if (rc != XMCA_OK) return rc;
   const int np = sbr_npanels(n);
   if (np == 0) return XMCA_OK;
+  if (d_workspace && workspace_bytes >= xmca_ormtr2_workspace_bytes(n, k)) {
+    // stage 1 as products over ALL vectors at once (Y is read twice per panel in total, not twice per vector):
+    //   U = Z[:, r0:] Y (split-K), U2 = U T^T, Z[:, r0:] -= U2 Y^T        (rows of Z: z <- z (I - Y T^T Y^T))
+    char* ws = reinterpret_cast<char*>(d_workspace);
+    double* U = reinterpret_cast<double*>(ws);
+    double* U2 = reinterpret_cast<double*>(ws + al256((size_t)k * PB * 8));
+    void* gws = ws + 2 * al256((size_t)k * PB * 8);
+    for (int p = np - 1; p >= 0; --p) {
+      const int64_t r0 = (int64_t)(p + 1) * PB, m = n - r0;
+      const double* Y = d_A + r0 * lda + (int64_t)p * PB;
+      const double* T = d_tfac + (int64_t)p * PB * PB;
+      double* Zs = d_Z + r0;
+      const int split = ormtr2_split(m);
+      rc = xmca_gemm_ex(1, 0, k, PB, m, 1.0, Zs, XMCA_F64, ldz, Y, XMCA_F64, lda, U, XMCA_F64, PB, 0, XMCA_F64, split,
+                        gws, xmca_gemm_workspace_bytes(k, PB, split, XMCA_F64), 0, stream);
+      if (rc != XMCA_OK) return rc;
+      rc = xmca_gemm_ex(1, 1, k, PB, PB, 1.0, U, XMCA_F64, PB, T, XMCA_F64, PB, U2, XMCA_F64, PB, 0, XMCA_F64, 1, nullptr, 0,
+                        0, stream);
+      if (rc != XMCA_OK) return rc;
+      rc = xmca_gemm_ex(1, 1, k, m, PB, -1.0, U2, XMCA_F64, PB, Y, XMCA_F64, lda, Zs, XMCA_F64, ldz, 1, XMCA_F64, 1, nullptr,
+                        0, 0, stream);
+      if (rc != XMCA_OK) return rc;
+    }
+    return XMCA_OK;
+  }
   const size_t extra = (PB * PLD + 2 * 8 * PB + 2 * PB) * sizeof(double);
   const size_t one = sizeof(double) * (size_t)n;
   if (2 * one + extra <= 200 * 1024 && k > sm_count()) {

@@ -283,8 +283,10 @@ def ormtr2(S_reflectors, tfac, Z):
     """Rows of Z <- Q row (in place), Q = Q1 Q2 from `sytrd2`."""
     lib = L.load()
     n = S_reflectors.shape[0]
+    ws_bytes = lib.xmca_ormtr2_workspace_bytes(n, Z.shape[0])
+    ws = empty((ws_bytes,), torch().uint8)
     rc = lib.xmca_ormtr2(n, L.ptr(S_reflectors), _ld(S_reflectors), L.ptr(tfac), Z.shape[0], L.ptr(Z), _ld(Z),
-                         L.stream_ptr())
+                         L.ptr(ws), ws_bytes, L.stream_ptr())
     L.check(rc, "xmca_ormtr2")
     return Z
 
