@@ -224,13 +224,15 @@ def chase_profile(n):
         p = prof.cpu().numpy()
         nt = max(int(p[6]), 1)
         names = ["wait", "load", "matvec", "update+larfg", "store", "publish"]
-        print("chase n=%d vectors=%s: %.2f ms, %d tasks; clocks/task: %s" % (
-            n, vec, e0.elapsed_time(e1), nt, ", ".join("%s %.0f" % (a, p[i] / nt) for i, a in enumerate(names))), flush=True)
+        print("chase n=%d vectors=%s: %.2f ms, %d tasks; clocks/task: %s; LL mismatches %d" % (
+            n, vec, e0.elapsed_time(e1), nt, ", ".join("%s %.0f" % (a, p[i] / nt) for i, a in enumerate(names)), int(p[7])),
+            flush=True)
 
 
 if __name__ == "__main__":
     if "prof" in sys.argv:
-        chase_profile(8192)
+        for nn in ([int(a) for a in sys.argv if a.isdigit()] or [8192]):
+            chase_profile(nn)
         sys.exit(0)
     quick = "quick" in sys.argv
     if "tiny" in sys.argv:             # for compute-sanitizer
