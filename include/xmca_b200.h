@@ -190,13 +190,17 @@ int xmca_ormtr(int64_t n, const double* d_A, int64_t lda, const double* d_tau, i
  *   (row j: sweep j, leading entry of every reflector replaced by its tau); d_tfac (xmca_sytrd2_tfac_bytes)
  *   receives the 64 x 64 triangular factors T_p of  W_p = I - Y_p T_p Y_p^T.
  *   Returns XMCA_NUMERIC if a panel factorisation broke down (non-finite input / exactly rank-deficient
- *   panel): the caller falls back to xmca_sytrd.  Synchronises `stream` once at the end to read that flag.
+ *   panel): the caller falls back to xmca_sytrd.  Synchronises `stream` once at the end to read that flag -- unless
+ *   bit 3 (value 8) of want_vectors is set: then the call only enqueues, and the caller reads the int32 flag at byte
+ *   offset xmca_sytrd2_info_offset(n) of d_workspace after its own synchronisation (non-zero = breakdown).  Two such
+ *   calls on two streams overlap on the device (the paired surrogate runs of rule_n, array.py:1753-1765).
  * xmca_ormtr2: rows of d_Z (k x n) <- Q row with Q = Q1 Q2 from xmca_sytrd2 (eigenvectors of the tridiagonal ->
  *   eigenvectors of the original matrix; array.py:584 for the modes that are asked for).  Stage 2: one CTA per
  *   vector (kept in shared memory), reflector data prefetched one sweep ahead; stage 1: three products per panel
  *   over all vectors (workspace xmca_ormtr2_workspace_bytes; without it a per-vector kernel is used). */
 size_t xmca_sytrd2_workspace_bytes(int64_t n);
 size_t xmca_sytrd2_tfac_bytes(int64_t n);
+size_t xmca_sytrd2_info_offset(int64_t n);
 int xmca_sytrd2(int64_t n, double* d_A, int64_t lda, double* d_d, double* d_e, double* d_tfac,
                 int want_vectors, void* d_workspace, size_t workspace_bytes, void* stream);
 size_t xmca_ormtr2_workspace_bytes(int64_t n, int64_t k);

@@ -94,6 +94,8 @@ def load():
     lib.xmca_sytrd2_workspace_bytes.argtypes = [i64]
     lib.xmca_sytrd2_tfac_bytes.restype = sz
     lib.xmca_sytrd2_tfac_bytes.argtypes = [i64]
+    lib.xmca_sytrd2_info_offset.restype = sz
+    lib.xmca_sytrd2_info_offset.argtypes = [i64]
     lib.xmca_sytrd2.argtypes = [i64, vp, i64, vp, vp, vp, i32, vp, sz, vp]
     lib.xmca_ormtr2_workspace_bytes.restype = sz
     lib.xmca_ormtr2_workspace_bytes.argtypes = [i64, i64]
@@ -140,7 +142,7 @@ def load():
 _NO_TIMING = ("xmca_last_error", "xmca_version", "xmca_launch_count", "xmca_gemm_workspace_bytes",
               "xmca_jacobi_padded_cols", "xmca_jacobi_workspace_bytes", "xmca_varimax_workspace_bytes",
               "xmca_cholesky_workspace_bytes", "xmca_cholesky_invdiag_bytes", "xmca_trsm_workspace_bytes",
-              "xmca_sytrd_max_n", "xmca_sytrd_workspace_bytes", "xmca_sytrd2_workspace_bytes", "xmca_sytrd2_tfac_bytes", "xmca_ormtr2_workspace_bytes", "xmca_stein_workspace_bytes", "xmca_dft_rows",
+              "xmca_sytrd_max_n", "xmca_sytrd_workspace_bytes", "xmca_sytrd2_workspace_bytes", "xmca_sytrd2_tfac_bytes", "xmca_sytrd2_info_offset", "xmca_ormtr2_workspace_bytes", "xmca_stein_workspace_bytes", "xmca_dft_rows",
               "xmca_varimax_complex_workspace_bytes")
 _profile = None
 

@@ -1110,21 +1110,33 @@ static SbrPlan sbr_plan(int64_t n) {
   return p;
 }
 
-// internal high-priority stream + two events per device (created once, kept for the life of the process)
-struct SbrStreams { cudaStream_t panel = nullptr; cudaEvent_t ev_qr = nullptr, ev_x = nullptr; };
-static SbrStreams* sbr_streams() {
-  static SbrStreams per_dev[64];
+// internal high-priority panel stream + two events, one set per (device, caller stream) so that two reductions
+// enqueued on two streams (the paired surrogate runs of rule_n) do not serialise on one panel stream.  Created once,
+// kept for the life of the process (a handful per device).
+struct SbrStreams { cudaStream_t owner = nullptr; bool used = false; cudaStream_t panel = nullptr; cudaEvent_t ev_qr = nullptr, ev_x = nullptr; };
+static SbrStreams* sbr_streams(cudaStream_t caller) {
+  constexpr int SLOTS = 4;
+  static SbrStreams pool[64][SLOTS];
+  static int next_slot[64];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  SbrStreams& s = per_dev[dev];
-  if (!s.panel) {
+  SbrStreams* s = nullptr;
+  for (int i = 0; i < SLOTS; ++i)
+    if (pool[dev][i].used && pool[dev][i].owner == caller) s = &pool[dev][i];
+  if (!s) {
+    s = &pool[dev][next_slot[dev]];
+    next_slot[dev] = (next_slot[dev] + 1) % SLOTS;
+    s->owner = caller;
+    s->used = true;
+  }
+  if (!s->panel) {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    if (cudaStreamCreateWithPriority(&s.panel, cudaStreamNonBlocking, hi) != cudaSuccess) { s.panel = nullptr; return nullptr; }
-    cudaEventCreateWithFlags(&s.ev_qr, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&s.ev_x, cudaEventDisableTiming);
+    if (cudaStreamCreateWithPriority(&s->panel, cudaStreamNonBlocking, hi) != cudaSuccess) { s->panel = nullptr; return nullptr; }
+    cudaEventCreateWithFlags(&s->ev_qr, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&s->ev_x, cudaEventDisableTiming);
   }
-  return &s;
+  return s;
 }
 
 // XMCA_SYTRD2_PROF=1: CUDA events between the launches of xmca_sytrd2, summed per kernel class and printed to stderr
@@ -1170,6 +1182,7 @@ struct SbrProf {
 using namespace xmca;
 
 extern "C" size_t xmca_sytrd2_workspace_bytes(int64_t n) { return n > 0 ? sbr_plan(n).total : 0; }
+extern "C" size_t xmca_sytrd2_info_offset(int64_t n) { return n > 0 ? sbr_plan(n).off_ints + sizeof(int) : 0; }
 extern "C" size_t xmca_sytrd2_tfac_bytes(int64_t n) {
   const int np = n > 0 ? sbr_npanels(n) : 0;
   return (size_t)(np > 0 ? np : 1) * PB * PB * sizeof(double);
@@ -1216,7 +1229,7 @@ extern "C" int xmca_sytrd2(int64_t n, double* d_A, int64_t lda, double* d_d, dou
   // runs on an internal high-priority stream `sp` next to the rank-128 update of the trailing matrix by panel p on the
   // caller's stream.  For that the update is split: the first block column of A22 (= the next panel and the next
   // diagonal block) is updated by a skinny product on `sp`, the rest A22[64:, 64:] by the big one on `st`.
-  SbrStreams* ss = prof.on ? nullptr : sbr_streams();
+  SbrStreams* ss = prof.on ? nullptr : sbr_streams(st);
   cudaStream_t sp = ss ? ss->panel : st;
   if (ss) {
     XMCA_CUDA(cudaEventRecord(ss->ev_x, st));
@@ -1334,6 +1347,7 @@ extern "C" int xmca_sytrd2(int64_t n, double* d_A, int64_t lda, double* d_d, dou
     if (rc != XMCA_OK) return rc;
     prof.mark(9);
   }
+  if (want_vectors & 8) return XMCA_OK;                // asynchronous: the caller reads the flag at xmca_sytrd2_info_offset
   int h_fail = 0;
   XMCA_CUDA(cudaMemcpyAsync(&h_fail, fail, sizeof(int), cudaMemcpyDeviceToHost, st));
   XMCA_CUDA(cudaStreamSynchronize(st));

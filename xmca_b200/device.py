@@ -261,10 +261,12 @@ def sytrd_pair(S2):
     return d, e, tau
 
 
-def sytrd2(S, want_vectors=True):
+def sytrd2(S, want_vectors=True, sync=True):
     """Two-stage tridiagonalisation (dense -> band 64 on the DMMA pipe -> tridiagonal by bulge chasing) of the
     symmetric fp64 matrix S (n x n, both triangles, DESTROYED: it then holds both reflector sets).
-    Returns (d, e, tfac).  Raises LinAlgError if a panel factorisation broke down."""
+    Returns (d, e, tfac).  Raises LinAlgError if a panel factorisation broke down.
+    sync=False: only enqueues on the current stream and returns (d, e, tfac, pending); call `sytrd2_check(pending)`
+    after the stream has been synchronised (it raises LinAlgError on a breakdown)."""
     lib = L.load()
     t = torch()
     n = S.shape[0]
@@ -273,10 +275,20 @@ def sytrd2(S, want_vectors=True):
     tfac = empty((lib.xmca_sytrd2_tfac_bytes(n) // 8,), t.float64)
     ws_bytes = lib.xmca_sytrd2_workspace_bytes(n)
     ws = empty((ws_bytes,), t.uint8)
-    rc = lib.xmca_sytrd2(n, L.ptr(S), _ld(S), L.ptr(d), L.ptr(e), L.ptr(tfac), 1 if want_vectors else 0,
+    flags = (1 if want_vectors else 0) | (0 if sync else 8)
+    rc = lib.xmca_sytrd2(n, L.ptr(S), _ld(S), L.ptr(d), L.ptr(e), L.ptr(tfac), flags,
                          L.ptr(ws), ws_bytes, L.stream_ptr())
     L.check(rc, "xmca_sytrd2")
-    return d, e, tfac
+    if sync:
+        return d, e, tfac
+    off = int(lib.xmca_sytrd2_info_offset(n))
+    return d, e, tfac, ws[off:off + 4]
+
+
+def sytrd2_check(pending):
+    """Breakdown flag of an asynchronous `sytrd2` (reads 4 bytes from the device: synchronises)."""
+    if int(pending.view(torch().int32).item()) != 0:
+        raise np.linalg.LinAlgError("xmca_sytrd2: panel factorisation broke down")
 
 
 def ormtr2(S_reflectors, tfac, Z):

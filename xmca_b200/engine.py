@@ -292,6 +292,22 @@ class TridiagResult:
                 S = self._S = self._build_S()
         self._finish(*D.sytrd(S), S)
 
+    def reduce_begin(self):
+        """Enqueue the two-stage reduction on the CURRENT stream without synchronising (`reduce_end` finishes)."""
+        S = self._S
+        d, e, tfac, pending = D.sytrd2(S, sync=False)
+        self._pending = (d, e, tfac, pending, S)
+
+    def reduce_end(self):
+        d, e, tfac, pending, S = self._pending
+        self._pending = None
+        try:
+            D.sytrd2_check(pending)
+            return self._finish(d, e, None, S, tfac)
+        except np.linalg.LinAlgError:
+            S = self._S = self._build_S()
+        self._finish(*D.sytrd(S), S)
+
     def _finish(self, d, e, tau, Q, tfac=None):
         """Spectrum from the tridiagonal form (d, e) of S; Q: the matrix that holds the reflectors (one-stage: rows +
         tau; two-stage: panel reflectors below the band, sweep reflectors above the diagonal, + tfac)."""
@@ -473,11 +489,23 @@ def spectrum_embedding(X, F=None):
     return D.embed_complex(ZZ)
 
 
+_PAIR_STREAMS = {}
+
+
+def _pair_streams():
+    """Two side streams per device for the paired surrogate runs (created once)."""
+    t = D.torch()
+    dev = t.cuda.current_device()
+    if dev not in _PAIR_STREAMS:
+        _PAIR_STREAMS[dev] = (t.cuda.Stream(), t.cuda.Stream())
+    return _PAIR_STREAMS[dev]
+
+
 def solve_real_pair(A0, B0, A1, B1, null_basis=None, dof=None, want_vectors=True):
     """Two independent real solves of the same shape (the surrogate runs of rule_n, array.py:1753-1765).
-    On the tridiagonal route both symmetric matrices are reduced by ONE batched call (xmca_sytrd_batched:
-    half of the SMs each, so one streams while the other is in its latency-bound phases); otherwise two
-    plain `solve_real` calls.  Returns the two results."""
+    On the tridiagonal route the two models are processed on two streams with asynchronous reductions (two-stage
+    mode), or -- one-stage mode -- their matrices are reduced by ONE batched call (xmca_sytrd_batched: half of the SMs
+    each); otherwise two plain `solve_real` calls.  Returns the two results."""
     T, S1 = A0.shape
     pca = B0 is None
     S2 = S1 if pca else B0.shape[1]
@@ -486,15 +514,43 @@ def solve_real_pair(A0, B0, A1, B1, null_basis=None, dof=None, want_vectors=True
     single = lambda A, B: solve_real(A, B, want_vectors=want_vectors, null_basis=null_basis, dof=dof)
     if not (same and TRIDIAG_MIN_N <= rank <= D.sytrd_max_n()):
         return single(A0, B0), single(A1, B1)
+    if SYTRD_MODE == "two_stage":
+        # Two streams: the reduction of the first model is only ENQUEUED (xmca_sytrd2 with the no-sync flag), so its
+        # latency-bound parts (panel factorisations, bulge chasing: a third of the SMs at most) run under the
+        # GEMM-bound construction of the second model's matrix, and the two reductions under each other.
+        t = D.torch()
+        cur = t.cuda.current_stream()
+        s0, s1 = _pair_streams()
+        for x in (A0, B0, A1, B1, null_basis):
+            if x is not None and hasattr(x, "record_stream"):
+                x.record_stream(s0)
+                x.record_stream(s1)
+        s0.wait_stream(cur)
+        s1.wait_stream(cur)
+        try:
+            with t.cuda.stream(s0):
+                r0 = TridiagResult(A0, B0, null_basis, dof, defer=True)
+                r0.reduce_begin()
+            with t.cuda.stream(s1):
+                r1 = TridiagResult(A1, B1, null_basis, dof, defer=True)
+                r1.reduce_begin()
+            with t.cuda.stream(s0):
+                r0.reduce_end()
+            with t.cuda.stream(s1):
+                r1.reduce_end()
+        except np.linalg.LinAlgError:
+            s0.synchronize()
+            s1.synchronize()
+            return single(A0, B0), single(A1, B1)
+        finally:
+            cur.wait_stream(s0)
+            cur.wait_stream(s1)
+        return r0, r1
     try:
         r0 = TridiagResult(A0, B0, null_basis, dof, defer=True)
         r1 = TridiagResult(A1, B1, null_basis, dof, defer=True)
     except np.linalg.LinAlgError:
         return single(A0, B0), single(A1, B1)
-    if SYTRD_MODE == "two_stage":
-        r0.reduce()
-        r1.reduce()
-        return r0, r1
     n = r0.n
     Sp = D.empty((2, n, n), D.f64())
     Sp[0].copy_(r0._S)
