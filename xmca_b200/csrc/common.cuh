@@ -81,15 +81,16 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
   return y;
 }
 
-inline int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
+inline int sm_count() {                 // of the CURRENT device (cached per device id)
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cache[dev] == 0) {
+    int n = 0;
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+    cache[dev] = n > 0 ? n : 148;
   }
-  return n;
+  return cache[dev];
 }
 
 }  // namespace xmca

@@ -519,12 +519,9 @@ static int launch_tc(int64_t M, int64_t N, int64_t K, float alpha, const float* 
   if ((rc = make_map(&mAl, Alo, M, K, lda, TC_BM)) != XMCA_OK) return rc;
   if ((rc = make_map(&mBh, Bhi, N, K, ldb, BN)) != XMCA_OK) return rc;
   if ((rc = make_map(&mBl, Blo, N, K, ldb, BN)) != XMCA_OK) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    XMCA_CUDA(cudaFuncSetAttribute(tc_gemm_nt_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  // (function attributes are per DEVICE: set on every call -- a process-wide one-time flag breaks a second GPU)
+  XMCA_CUDA(cudaFuncSetAttribute(tc_gemm_nt_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Cfg::kSmemBytes));
   const int tiles_m = (int)((M + TC_BM - 1) / TC_BM), tiles_n = (int)((N + BN - 1) / BN);
   tc_gemm_nt_kernel<BN><<<tiles_m * tiles_n, TC_THREADS, Cfg::kSmemBytes, st>>>(
       mAh, mAl, mBh, mBl, (int)M, (int)N, (int)K, alpha, D, ldd, frob2, tiles_m, tiles_n);
@@ -575,11 +572,7 @@ extern "C" int xmca_tc_gemm_nt_f64(int64_t M, int64_t N, int64_t K, double alpha
   if ((rc = make_map(&mAl, d_Alo, M, K, lda, TC_BM)) != XMCA_OK) return rc;
   if ((rc = make_map(&mBh, d_Bhi, N, K, ldb, TG_BN)) != XMCA_OK) return rc;
   if ((rc = make_map(&mBl, d_Blo, N, K, ldb, TG_BN)) != XMCA_OK) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    XMCA_CUDA(cudaFuncSetAttribute(tc_gemm_nt_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  XMCA_CUDA(cudaFuncSetAttribute(tc_gemm_nt_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   const int tiles_m = (int)((M + TC_BM - 1) / TC_BM), tiles_n = (int)((N + TG_BN - 1) / TG_BN);
   tc_gemm_nt_f64_kernel<<<tiles_m * tiles_n, TC_THREADS, Cfg::kSmemBytes, st>>>(
       mAh, mAl, mBh, mBl, (int)M, (int)N, (int)K, alpha, d_D, ldd, symmetric, tiles_m, tiles_n);

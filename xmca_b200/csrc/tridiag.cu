@@ -1151,11 +1151,7 @@ extern "C" int xmca_ormtr(int64_t n, const double* d_A, int64_t lda, const doubl
                           double* d_Z, int64_t ldz, void* stream) {
   XMCA_REQUIRE(n >= 1 && k >= 1 && d_A && d_tau && d_Z && lda >= n && ldz >= n, "xmca_ormtr: bad argument");
   XMCA_REQUIRE(n <= xmca_sytrd_max_n(), "xmca_ormtr: n too large");
-  static bool attr = false;
-  if (!attr) {
-    XMCA_CUDA(cudaFuncSetAttribute(ormtr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 26000 * 8));
-    attr = true;
-  }
+  XMCA_CUDA(cudaFuncSetAttribute(ormtr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 26000 * 8));
   ormtr_kernel<<<(unsigned)k, OR_THREADS, (size_t)n * 8, (cudaStream_t)stream>>>((int)n, d_A, lda, d_tau, d_Z, ldz);
   XMCA_LAUNCHED();
   return XMCA_OK;

@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace cg = cooperative_groups;
 
@@ -34,6 +35,7 @@ struct VarimaxParams {
   double* partial;     // [2*grid][VSLOT]
   double* reduced;     // [VSLOT]
   double* B; int64_t ldb; double* R; double* out;   // out: [0]=iterations [1]=converged [2]=d [3]=svd sweeps total
+  int jacobi_oe;       // in-loop sweeps in the odd-even ordering with register-resident columns (default)
 };
 
 // Z[i][j] = sum_k X(i,k) Y(k,j) for i, j, k < p (padded entries -> 0), 64 x 64 output by the first 256 threads
@@ -250,6 +252,112 @@ __device__ int polar_jacobi(double* X, double* V, int pe, const unsigned char* r
     if (m <= stop2) break;              // largest squared cosine seen BEFORE this sweep's rotations
   }
   return sweeps;
+}
+
+// One sweep of the same one-sided Jacobi in the ODD-EVEN TRANSPOSITION ordering with the odd-position columns held
+// in REGISTERS: slot s (warp w serves slots w and w + 16) keeps position 2 s + 1 ("co") for the whole sweep and works
+// on it together with the even-position column to its left (even steps, position 2 s) or to its right (odd steps,
+// position 2 s + 2), which lives in shared memory ("ce": one column read and one written per slot and step).  After
+// every rotation the two columns trade places, so each column meets every other exactly once in pe steps and the
+// order ends up reversed (undone at the end).  Per step a slot moves 8 column halves through shared memory; the
+// round-robin version above moves 32 (both columns of X and V read and written) and was bound by exactly that
+// traffic (~1000 clocks per step for 16 warps; measured 98 k clocks per sweep at p = 50).
+// Same rotation, same skip / convergence bookkeeping, fp32 reductions for the rotation angle (in-loop use only).
+__device__ int polar_jacobi_oe(double* X, double* V, int pe, double* s_max, double skip2) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int nslots = pe >> 1;
+  double cmax2 = 0.0;
+  double xo0[2], xo1[2], vo0[2], vo1[2];                 // co of the two slots: rows lane, lane + 32 of X and V
+  bool on[2];
+  int slot[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    slot[u] = warp + u * nwarps;
+    on[u] = slot[u] < nslots;
+    const int co = on[u] ? 2 * slot[u] + 1 : 0;
+    xo0[u] = on[u] ? X[co * VPP + lane] : 0.0; xo1[u] = on[u] ? X[co * VPP + lane + 32] : 0.0;
+    vo0[u] = on[u] ? V[co * VPP + lane] : 0.0; vo1[u] = on[u] ? V[co * VPP + lane + 32] : 0.0;
+  }
+  for (int step = 0; step < pe; ++step) {
+    const int odd = step & 1;
+    int ce[2];
+    bool act[2];
+    double xe0[2], xe1[2], al[2], be[2], ga[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      ce[u] = 2 * slot[u] + 2 * odd;                     // even step: position 2 s, odd step: position 2 s + 2
+      act[u] = on[u] && ce[u] < pe;
+      xe0[u] = act[u] ? X[ce[u] * VPP + lane] : 0.0; xe1[u] = act[u] ? X[ce[u] * VPP + lane + 32] : 0.0;
+      al[u] = xo0[u] * xo0[u] + xo1[u] * xo1[u];
+      be[u] = xe0[u] * xe0[u] + xe1[u] * xe1[u];
+      ga[u] = xo0[u] * xe0[u] + xo1[u] * xe1[u];
+    }
+    {
+      float x8[8] = {(float)al[0], (float)be[0], (float)ga[0], 0.0f, (float)al[1], (float)be[1], (float)ga[1], 0.0f};
+      float y4[4], z2[2];
+      const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float keep = b4 ? x8[k + 4] : x8[k], send = b4 ? x8[k] : x8[k + 4];
+        y4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float keep = b3 ? y4[k + 2] : y4[k], send = b3 ? y4[k] : y4[k + 2];
+        z2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+      float r1 = (b2 ? z2[1] : z2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? z2[0] : z2[1], 4);
+      r1 += __shfl_xor_sync(0xffffffffu, r1, 2);
+      r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
+      al[0] = (double)__shfl_sync(0xffffffffu, r1, 0);  be[0] = (double)__shfl_sync(0xffffffffu, r1, 4);
+      ga[0] = (double)__shfl_sync(0xffffffffu, r1, 8);
+      al[1] = (double)__shfl_sync(0xffffffffu, r1, 16); be[1] = (double)__shfl_sync(0xffffffffu, r1, 20);
+      ga[1] = (double)__shfl_sync(0xffffffffu, r1, 24);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!act[u]) continue;
+      double c = 1.0, sn = 0.0;
+      const double ab = al[u] * be[u], g2 = ga[u] * ga[u];
+      if (g2 > skip2 * ab && fabs(ga[u]) > 1e-300) {
+        cmax2 = fmax(cmax2, g2 * fast_rcp(ab));
+        const float zf = (float)((be[u] - al[u]) * fast_rcp(2.0 * ga[u]));
+        const float tf = copysignf(1.0f, zf) / (fabsf(zf) + sqrtf(fmaf(zf, zf, 1.0f)));
+        const double t = (double)tf;
+        c = fast_rsqrt(fma(t, t, 1.0));
+        sn = c * t;
+      }
+      // rotate (p, q) = (co, ce) and trade places: the "q" result stays in the registers, the "p" result goes to ce
+      const double ve0 = V[ce[u] * VPP + lane], ve1 = V[ce[u] * VPP + lane + 32];
+      const double np0 = c * xo0[u] - sn * xe0[u], np1 = c * xo1[u] - sn * xe1[u];
+      const double nq0 = sn * xo0[u] + c * xe0[u], nq1 = sn * xo1[u] + c * xe1[u];
+      const double wp0 = c * vo0[u] - sn * ve0, wp1 = c * vo1[u] - sn * ve1;
+      const double wq0 = sn * vo0[u] + c * ve0, wq1 = sn * vo1[u] + c * ve1;
+      xo0[u] = nq0; xo1[u] = nq1; vo0[u] = wq0; vo1[u] = wq1;
+      X[ce[u] * VPP + lane] = np0; X[ce[u] * VPP + lane + 32] = np1;
+      V[ce[u] * VPP + lane] = wp0; V[ce[u] * VPP + lane + 32] = wp1;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    if (!on[u]) continue;
+    const int co = 2 * slot[u] + 1;
+    X[co * VPP + lane] = xo0[u]; X[co * VPP + lane + 32] = xo1[u];
+    V[co * VPP + lane] = vo0[u]; V[co * VPP + lane + 32] = vo1[u];
+  }
+  __syncthreads();
+  // the sweep reversed the order of the columns: put them back (column q <-> column pe - 1 - q, X and V alike)
+  for (int e = threadIdx.x; e < (pe >> 1) * VP; e += blockDim.x) {
+    const int q = e >> 6, r = e & 63, q2 = pe - 1 - q;
+    const double a = X[q * VPP + r], b = X[q2 * VPP + r];
+    X[q * VPP + r] = b; X[q2 * VPP + r] = a;
+    const double va = V[q * VPP + r], vb = V[q2 * VPP + r];
+    V[q * VPP + r] = vb; V[q2 * VPP + r] = va;
+  }
+  if (lane == 0) s_max[warp] = cmax2;
+  __syncthreads();
+  return 1;
 }
 
 // Two-stage deterministic reduction of the per-CTA partials: every CTA owns a slice of the
@@ -491,7 +599,7 @@ __global__ void __launch_bounds__(VTHREADS, 1) varimax_kernel(VarimaxParams P) {
       }
       m2 = block_max(m2, s_max);
       if (m2 <= 1e-6) break;
-      svd_sweeps += polar_jacobi(Xs, Vs, pe, rr, s_max, 1e-6, 1, 1e-8);
+      svd_sweeps += P.jacobi_oe ? polar_jacobi_oe(Xs, Vs, pe, s_max, 1e-8) : polar_jacobi(Xs, Vs, pe, rr, s_max, 1e-6, 1, 1e-8);
       __syncthreads();
     }
     for (int e = tid; e < VP * VP; e += VTHREADS) {                  // G -> Et in place
@@ -631,6 +739,10 @@ extern "C" int xmca_varimax(const void* d_L, int l_dtype, int64_t n, int p, int6
   P.partial = reinterpret_cast<double*>(ws + o); o += ((size_t)4 * 148 + 64) * 2 * VSLOT * 8;
   P.reduced = reinterpret_cast<double*>(ws + o);
   P.B = d_B; P.ldb = ldb; P.R = d_R; P.out = d_out;
+  {
+    const char* e = getenv("XMCA_VARIMAX_JACOBI");       // "rr": the round-robin sweep (A/B runs)
+    P.jacobi_oe = !(e && e[0] == 'r');
+  }
 
   void* args[] = {&P};
   if (l_dtype == XMCA_F64)
