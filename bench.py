@@ -67,7 +67,14 @@ def workload_string(workload):
 
 
 # one `ncu --set full` capture of the two DMMA kernels of xmca_sytrd2 (profiles/r2_ncu_summary.md), per launch
-SYTRD2_NCU = {"traffic": None}
+SYTRD2_NCU = {"traffic": 323.1e6, "traffic_algorithmic_same_launch": 315.0e6,
+              "traffic_note": "ONE launch of sbr_symm_kernel (ncu --set full, n = 8192, panel ~29, m = 6272, 184 us): 312 MB read + "
+                              "11 MB written for m^2 * 8 = 315 MB of algorithmic bytes, 79 % DMMA-pipe active (27.5 TFLOP/s); "
+                              "sbr_syr2k_kernel: 412 MB for 453 MB algorithmic, 63 % (profiles/r2_ncu_summary.md); `achieved` "
+                              "averages the WHOLE call (panel factorisations and the latency-bound bulge chasing included)",
+              "kernels_ncu": {"sbr_symm_kernel": {"tflops": 27.5, "dmma_pipe_active_pct": 79.3},
+                              "sbr_syr2k_kernel": {"tflops": 21.5, "dmma_pipe_active_pct": 63.5},
+                              "sb_chase_kernel": {"ms": 68.0, "bound": "latency (L2 round trips; 8 MB band, L2 resident)"}}}
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of sytrd_panel_kernel<true> (ncu --set full, n = 8192,
 # panel 9 of 128) next to the algorithmic bytes of that launch (64 columns x n'^2 x 4 B)
