@@ -122,7 +122,10 @@ __device__ __forceinline__ void chol64_blocked(double (*A)[PLD], double* Dinv, i
 #pragma unroll
       for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) { lr[q][jj] = A[ti + 16 * q][j0 + jj]; lc[q][jj] = A[tk + 16 * q][j0 + jj]; }
+        for (int jj = 0; jj < 8; ++jj) {            // (rows of the diagonal block are being written back by thread 0: not read)
+          lr[q][jj] = ti + 16 * q >= j0 + 8 ? A[ti + 16 * q][j0 + jj] : 0.0;
+          lc[q][jj] = tk + 16 * q >= j0 + 8 ? A[tk + 16 * q][j0 + jj] : 0.0;
+        }
 #pragma unroll
       for (int qa = 0; qa < 4; ++qa)
 #pragma unroll
@@ -319,7 +322,10 @@ __device__ __forceinline__ void lu64_sign_blocked(double (*A)[PLD], double* Linv
 #pragma unroll
       for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) { lr[q][jj] = A[ti + 16 * q][j0 + jj]; uc[q][jj] = A[j0 + jj][tk + 16 * q]; }
+        for (int jj = 0; jj < 8; ++jj) {            // (the diagonal block is being written back by thread 0: not read)
+          lr[q][jj] = ti + 16 * q >= j0 + 8 ? A[ti + 16 * q][j0 + jj] : 0.0;
+          uc[q][jj] = tk + 16 * q >= j0 + 8 ? A[j0 + jj][tk + 16 * q] : 0.0;
+        }
 #pragma unroll
       for (int qa = 0; qa < 4; ++qa)
 #pragma unroll
