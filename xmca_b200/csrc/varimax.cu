@@ -26,6 +26,8 @@ constexpr int VT = 32;          // rows per tile
 constexpr int VTHREADS = 512;
 constexpr int VSLOT = VP * VP + VP;   // doubles per partial: T1 (64x64) + c (64)
 constexpr int VPP = VP + 1;           // padded stride of the column-major p x p work matrices (bank-conflict free)
+constexpr int RS = VP + 4;            // row stride of the rotation R and of the streamed tiles: DMMA fragment loads
+                                      // (address tig * RS + gid) are then bank-conflict free
 
 struct VarimaxParams {
   const void* L; int ldt; int64_t n; int p; int64_t ldl;
@@ -104,7 +106,7 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 // The error is third order in the cosines: <= ~1e-8 here, where one more Jacobi sweep would cost 5x as much.
 // In: Et (row-major 64 x 64, zero diagonal / padding), s[64].  Out: Z (row-major 64 x 64); returns
 // sum_ij Z_ij G_ij = trace(polar(X)^T X) = the sum of the singular values.
-__device__ __noinline__ double gram_inv_sqrt2(const double* Et, const double* s, double* Z, int p, double* red) {
+__device__ __noinline__ double gram_inv_sqrt2(const double* Et, const double* s, double* Z, int zs, int p, double* red) {
   double dd = 0.0;
   if (threadIdx.x < 256) {
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -139,7 +141,7 @@ __device__ __noinline__ double gram_inv_sqrt2(const double* Et, const double* s,
           z = ((i == j) ? 1.0 / si : 0.0) - et * rij + (ssum * f[r][c] + h[r][c]) * rij / ssum;
           dd = fma(z, (i == j) ? si * si : et * ssum, dd);
         }
-        Z[i * VP + j] = z;
+        Z[i * zs + j] = z;
       }
   }
   return block_sum(dd, red);
@@ -390,8 +392,8 @@ template <typename TS>
 __global__ void __launch_bounds__(VTHREADS, 1) varimax_kernel(VarimaxParams P) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ double sm[];
-  double* Rs = sm;                    // rotation (64x64, row-major)
-  double* Gs = Rs + VP * VP;          // A^T A
+  double* Rs = sm;                    // rotation (64x64, row-major, row stride RS)
+  double* Gs = Rs + VP * RS;          // A^T A
   double* Ws = Gs + VP * VP;          // scratch (G R)
   double* Vs = Ws + VP * VP;          // right singular vectors, warm start   (column-major, stride VPP)
   double* Xs = Vs + VP * VPP;         // SVD work matrix, then U              (column-major, stride VPP)
@@ -422,7 +424,7 @@ __global__ void __launch_bounds__(VTHREADS, 1) varimax_kernel(VarimaxParams P) {
   for (int e = tid; e < VP * VP; e += VTHREADS) {
     int i = e >> 6, j = e & 63;
     double id = (i == j && i < p) ? 1.0 : 0.0;
-    Rs[e] = id; Vs[i * VPP + j] = (i == j) ? 1.0 : 0.0;
+    Rs[i * RS + j] = id; Vs[i * VPP + j] = (i == j) ? 1.0 : 0.0;
   }
 
   // T1-phase thread mapping: 4x4 register block of the 64x64 accumulator, two row-halves
@@ -431,7 +433,6 @@ __global__ void __launch_bounds__(VTHREADS, 1) varimax_kernel(VarimaxParams P) {
   const int jcol = tid & 63, rg = tid >> 6;
 
   double acc[4][4];
-  double csq;
 
   // ---------------- phase 0: h, An = L / h, G = An^T An ----------------
 #pragma unroll
@@ -505,71 +506,118 @@ __global__ void __launch_bounds__(VTHREADS, 1) varimax_kernel(VarimaxParams P) {
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-    csq = 0.0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int64_t r0 = tile * VT;
-      __syncthreads();
-      for (int e = tid; e < VT * VP; e += VTHREADS) {
-        int r = e >> 6, c = e & 63;
-        int64_t row = r0 + r;
-        As[e] = (row < n && c < p) ? (double)An[row * p + c] : 0.0;
-      }
-      __syncthreads();
-      {   // b = a R for 4 rows x 1 column
-        double b4[4] = {0.0, 0.0, 0.0, 0.0};
-        if (jcol < p) {
-          for (int k = 0; k < p; ++k) {
-            const double rk = Rs[k * VP + jcol];
+    // Streaming pass on the fp64 tensor-core path (mma.sync.m8n8k4): per 32-row tile  b = a R  (warp: 8 rows x 16
+    // columns), then T1 += a^T (b^3) (warp: a 16 x 16 block of T1, accumulators kept over all tiles of the CTA) and
+    // the column sums of b^2.  Tiles live in shared memory with row stride RS (conflict-free fragment loads); the
+    // next tile's elements are fetched into registers while the current one is processed.
+    {
+      double* At = As;                 // [VT][RS] tile of An            (aliases Ts: free during the pass)
+      double* Bt = Ws;                 // [VT][RS] tile of (a R)^3       (Ws: scratch of the polar phase)
+      const int lane = tid & 31, w = tid >> 5, gid = lane >> 2, tig = lane & 3;
+      const int rb = w & 3, cg = w >> 2;             // b = a R: rows 8 rb .., columns 16 cg ..
+      const int ksteps = (p + 3) >> 2;
+      double t1[2][2][2], cq[2][2];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) b4[q] = fma(As[(rg * 4 + q) * VP + k], rk, b4[q]);
-          }
-        }
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) { t1[a][b][0] = 0.0; t1[a][b][1] = 0.0; cq[a][b] = 0.0; }
+      const int lr = tid >> 6, lc = tid & 63;        // loader: rows lr + 8 q, column lc
+      double pre[4];
+      auto fetch = [&](int64_t tile) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          csq = fma(b4[q], b4[q], csq);
-          Bs[(rg * 4 + q) * VP + jcol] = b4[q] * b4[q] * b4[q];
+          const int64_t row = tile * VT + lr + 8 * q;
+          pre[q] = (row < n && lc < p) ? (double)An[row * p + lc] : 0.0;
+        }
+      };
+      if ((int64_t)blockIdx.x < ntiles) fetch(blockIdx.x);
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) At[(lr + 8 * q) * RS + lc] = pre[q];
+        __syncthreads();
+        if (tile + gridDim.x < ntiles) fetch(tile + gridDim.x);
+        {
+          double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+          const double* ap = At + (8 * rb + gid) * RS + tig;
+          const double* rp = Rs + tig * RS + 16 * cg + gid;
+#pragma unroll 4
+          for (int kk = 0; kk < ksteps; ++kk) {
+            const double a = ap[4 * kk], b0 = rp[4 * kk * RS], b1 = rp[4 * kk * RS + 8];
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[0][0]), "+d"(c[0][1]) : "d"(a), "d"(b0));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[1][0]), "+d"(c[1][1]) : "d"(a), "d"(b1));
+          }
+#pragma unroll
+          for (int nb = 0; nb < 2; ++nb) {
+            double2 v;
+            cq[nb][0] = fma(c[nb][0], c[nb][0], cq[nb][0]);
+            cq[nb][1] = fma(c[nb][1], c[nb][1], cq[nb][1]);
+            v.x = c[nb][0] * c[nb][0] * c[nb][0];
+            v.y = c[nb][1] * c[nb][1] * c[nb][1];
+            *reinterpret_cast<double2*>(Bt + (8 * rb + gid) * RS + 16 * cg + 8 * nb + 2 * tig) = v;
+          }
+        }
+        __syncthreads();
+        {
+          const double* ap = At + tig * RS + 16 * rb + gid;      // A fragment: a[row 4 ks + tig][column i0 + gid]
+          const double* bp = Bt + tig * RS + 16 * cg + gid;      // B fragment: b3[row 4 ks + tig][column j0 + gid]
+#pragma unroll
+          for (int ks = 0; ks < VT / 4; ++ks) {
+            const double a0 = ap[4 * ks * RS], a1 = ap[4 * ks * RS + 8];
+            const double b0 = bp[4 * ks * RS], b1 = bp[4 * ks * RS + 8];
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(t1[0][0][0]), "+d"(t1[0][0][1]) : "d"(a0), "d"(b0));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(t1[0][1][0]), "+d"(t1[0][1][1]) : "d"(a0), "d"(b1));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(t1[1][0][0]), "+d"(t1[1][0][1]) : "d"(a1), "d"(b0));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(t1[1][1][0]), "+d"(t1[1][1][1]) : "d"(a1), "d"(b1));
+          }
         }
       }
+      // per-CTA partial (ONE slot per CTA in the iteration): T1 block of this warp, column sums of b^2
       __syncthreads();
-#pragma unroll 4
-      for (int r = half * 16; r < half * 16 + 16; ++r) {
-        double a[4], b[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { a[i] = As[r * VP + bi + 16 * i]; b[i] = Bs[r * VP + bj + 16 * i]; }
+      for (int nb = 0; nb < 2; ++nb)
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int u = 0; u < 2; ++u) {
+          double v = cq[nb][u];
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          if (gid == 0) At[w * 16 + 8 * nb + 2 * tig + u] = v;
+        }
+      __syncthreads();
+      double* slot = P.partial + (int64_t)blockIdx.x * VSLOT;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
-      }
-    }
-    // per-CTA partials: T1 blocks (two halves) and column sums of b^2
-    __syncthreads();
-    As[rg * VP + jcol] = csq;           // 8 row-groups x 64 columns
-    __syncthreads();
-    {
-      double* slot = P.partial + ((int64_t)blockIdx.x * 2 + half) * VSLOT;
+      for (int ib = 0; ib < 2; ++ib)
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) slot[(bi + 16 * i) * VP + bj + 16 * j] = acc[i][j];
-      if ((tid & 255) < VP) {
-        double s = 0.0;
-        if (half == 0) for (int g = 0; g < VTHREADS / 64; ++g) s += As[g * VP + (tid & 255)];
-        slot[VP * VP + (tid & 255)] = s;
+        for (int jb = 0; jb < 2; ++jb) {
+          double2 v;
+          v.x = t1[ib][jb][0];
+          v.y = t1[ib][jb][1];
+          *reinterpret_cast<double2*>(slot + (16 * rb + 8 * ib + gid) * VP + 16 * cg + 8 * jb + 2 * tig) = v;
+        }
+      if (tid < VP) {
+        const int g4 = (tid >> 4) * 4, wi = tid & 15;
+        slot[VP * VP + tid] = (At[g4 * 16 + wi] + At[(g4 + 1) * 16 + wi]) + (At[(g4 + 2) * 16 + wi] + At[(g4 + 3) * 16 + wi]);
       }
     }
     __threadfence();
     { long long c1 = clock64(); tk[0] += c1 - c0; c0 = c1; }
     grid.sync();
     { long long c1 = clock64(); tk[1] += c1 - c0; c0 = c1; }
-    reduce_partials(P.partial, P.reduced, 2 * (int)gridDim.x);
+    reduce_partials(P.partial, P.reduced, (int)gridDim.x);
     __threadfence();
     grid.sync();
     { long long c1 = clock64(); tk[2] += c1 - c0; c0 = c1; }
 
     // ---- phase 2 (redundant on every CTA): T, polar factor, convergence ----
     if (tid < VP) cs[tid] = P.reduced[VP * VP + tid];
-    small_matmul(Gs, VP, 1, Rs, VP, 1, Ws, VP, 1, p);      // Ws = G R
+    small_matmul(Gs, VP, 1, Rs, RS, 1, Ws, VP, 1, p);      // Ws = G R
     __syncthreads();
     const double gn = P.gamma / (double)n;
     for (int e = tid; e < VP * VP; e += VTHREADS) {
@@ -608,11 +656,11 @@ __global__ void __launch_bounds__(VTHREADS, 1) varimax_kernel(VarimaxParams P) {
       Ws[e] = (i != j && i < p && j < p && ssum > 0.0) ? Ws[e] / ssum : 0.0;
     }
     __syncthreads();
-    d_new = gram_inv_sqrt2(Ws, cs, Rs, p, s_max);                    // Rs = Z
+    d_new = gram_inv_sqrt2(Ws, cs, Rs, RS, p, s_max);                // Rs = Z
     __syncthreads();
-    small_matmul(Rs, VP, 1, Vs, VPP, 1, Ws, VP, 1, p);               // Y = Z V^T:  Y(i,l) = sum_j Z(i,j) V(l,j)
+    small_matmul(Rs, RS, 1, Vs, VPP, 1, Ws, VP, 1, p);               // Y = Z V^T:  Y(i,l) = sum_j Z(i,j) V(l,j)
     __syncthreads();
-    small_matmul(Xs, 1, VPP, Ws, VP, 1, Rs, VP, 1, p);               // R = X Y
+    small_matmul(Xs, 1, VPP, Ws, VP, 1, Rs, RS, 1, p);               // R = X Y
     __syncthreads();
     { long long c1 = clock64(); tk[4] += c1 - c0; c0 = c1; }
     auto finish_polar = [&]() {
@@ -628,7 +676,7 @@ __global__ void __launch_bounds__(VTHREADS, 1) varimax_kernel(VarimaxParams P) {
       }
       __syncthreads();
       // R(i,l) = sum_j U(i,j) V(l,j); U(i,j) = Xs[j*VPP+i], V(l,j) = Vs[j*VPP+l]
-      small_matmul(Xs, 1, VPP, Vs, VPP, 1, Rs, VP, 1, p);
+      small_matmul(Xs, 1, VPP, Vs, VPP, 1, Rs, RS, 1, p);
       double dd = 0.0;
       for (int j = 0; j < p; ++j) dd += cs[j];
       __syncthreads();
@@ -663,7 +711,7 @@ __global__ void __launch_bounds__(VTHREADS, 1) varimax_kernel(VarimaxParams P) {
     if (jcol < p) {
       double b4[4] = {0.0, 0.0, 0.0, 0.0};
       for (int k = 0; k < p; ++k) {
-        const double rk = Rs[k * VP + jcol];
+        const double rk = Rs[k * RS + jcol];
 #pragma unroll
         for (int q = 0; q < 4; ++q) b4[q] = fma(As[(rg * 4 + q) * VP + k], rk, b4[q]);
       }
@@ -675,14 +723,14 @@ __global__ void __launch_bounds__(VTHREADS, 1) varimax_kernel(VarimaxParams P) {
     }
   }
   if (blockIdx.x == 0) {
-    for (int e = tid; e < p * p; e += VTHREADS) P.R[e] = Rs[(e / p) * VP + (e % p)];
+    for (int e = tid; e < p * p; e += VTHREADS) P.R[e] = Rs[(e / p) * RS + (e % p)];
     if (tid == 0) { P.out[0] = (double)it; P.out[1] = (double)converged; P.out[2] = d; P.out[3] = (double)svd_sweeps;
       for (int q = 0; q < 6; ++q) P.out[4 + q] = (double)tk[q]; }
   }
 }
 
 static size_t varimax_smem_bytes() {
-  return (size_t)(3 * VP * VP + 3 * VP * VPP + VP) * sizeof(double) + (size_t)VP * VP;
+  return (size_t)(VP * RS + 2 * VP * VP + 3 * VP * VPP + VP) * sizeof(double) + (size_t)VP * VP;
 }
 
 template <typename TS>
