@@ -288,6 +288,8 @@ int xmca_promax_target_complex(const double* d_Xr, const double* d_Xi, int64_t l
  * |d - d_old| / d < tol (rotation.py:62).  All p x p state is fp64.
  * Outputs: d_R (p x p row-major fp64), d_B (n x p row-major fp64: rotated
  * loadings, de-normalised, rotation.py:74-77), iterations.
+ * d_out: 16 doubles of statistics: [0] iterations, [1] converged, [2] sum of singular values, [3] Jacobi sweeps,
+ * [4..9] phase clocks of CTA 0, [10] rotations applied, [11] / [12] pairs seen with a cosine above 1e-4 / 1e-3.
  * Returns XMCA_NOT_CONVERGED after max_iter (rotation.py:66-71). */
 size_t xmca_varimax_workspace_bytes(int64_t n, int p);
 int xmca_varimax(const void* d_L, int l_dtype, int64_t n, int p, int64_t ldl,

@@ -37,7 +37,8 @@ struct VarimaxParams {
   double* partial;     // [2*grid][VSLOT]
   double* reduced;     // [VSLOT]
   double* B; int64_t ldb; double* R; double* out;   // out: [0]=iterations [1]=converged [2]=d [3]=svd sweeps total
-  int jacobi_oe;       // in-loop sweeps in the odd-even ordering with register-resident columns (default)
+  int jacobi_oe;       // in-loop sweeps: 0 round-robin, 1 odd-even ordering with register-resident columns (a warp per
+                       // slot), 2 the same with half a warp per slot (default)
 };
 
 // Z[i][j] = sum_k X(i,k) Y(k,j) for i, j, k < p (padded entries -> 0), 64 x 64 output by the first 256 threads
@@ -265,7 +266,7 @@ __device__ int polar_jacobi(double* X, double* V, int pe, const unsigned char* r
 // round-robin version above moves 32 (both columns of X and V read and written) and was bound by exactly that
 // traffic (~1000 clocks per step for 16 warps; measured 98 k clocks per sweep at p = 50).
 // Same rotation, same skip / convergence bookkeeping, fp32 reductions for the rotation angle (in-loop use only).
-__device__ int polar_jacobi_oe(double* X, double* V, int pe, double* s_max, double skip2) {
+__device__ int polar_jacobi_oe(double* X, double* V, int pe, double* s_max, double skip2, int* nrot = nullptr) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int nslots = pe >> 1;
   double cmax2 = 0.0;
@@ -323,6 +324,7 @@ __device__ int polar_jacobi_oe(double* X, double* V, int pe, double* s_max, doub
       const double ab = al[u] * be[u], g2 = ga[u] * ga[u];
       if (g2 > skip2 * ab && fabs(ga[u]) > 1e-300) {
         cmax2 = fmax(cmax2, g2 * fast_rcp(ab));
+        if (nrot && lane == 0) atomicAdd(nrot, 1);
         const float zf = (float)((be[u] - al[u]) * fast_rcp(2.0 * ga[u]));
         const float tf = copysignf(1.0f, zf) / (fabsf(zf) + sqrtf(fmaf(zf, zf, 1.0f)));
         const double t = (double)tf;
@@ -358,6 +360,100 @@ __device__ int polar_jacobi_oe(double* X, double* V, int pe, double* s_max, doub
     V[q * VPP + r] = vb; V[q2 * VPP + r] = va;
   }
   if (lane == 0) s_max[warp] = cmax2;
+  __syncthreads();
+  return 1;
+}
+
+// The odd-even sweep with a FRACTION of a warp per slot (LPS = 16 or 8 lanes, 64 / LPS rows per lane): the step is
+// bound by the number of warp instructions issued (two slots per warp used to run as two interleaved instruction
+// streams), so serving 32 / LPS slots with ONE stream divides it.  Slot s = (32 / LPS) warp + lane / LPS; same
+// rotations, same bookkeeping as polar_jacobi_oe.  Measured on the config-2 rotation (clocks per iteration of the
+// whole polar phase): a warp per slot 144 k, half a warp 118 k (ships), a quarter 132 k (too few warps left).
+template <int LPS>
+__device__ int polar_jacobi_oe_part(double* X, double* V, int pe, double* s_max, double skip2, int* nrot = nullptr) {
+  constexpr int RPL = VP / LPS, H1 = LPS / 2, H2 = LPS / 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hl = lane & (LPS - 1), base = lane & ~(LPS - 1);
+  const int nslots = pe >> 1, slot = (32 / LPS) * warp + lane / LPS;
+  const bool on = slot < nslots;
+  double cmax2 = 0.0;
+  double xo[RPL], vo[RPL];
+  {
+    const int co = on ? 2 * slot + 1 : 0;
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+      xo[r] = on ? X[co * VPP + hl + LPS * r] : 0.0;
+      vo[r] = on ? V[co * VPP + hl + LPS * r] : 0.0;
+    }
+  }
+  const bool bh = lane & H1, bq = lane & H2;
+  for (int step = 0; step < pe; ++step) {
+    const int ce = 2 * slot + 2 * (step & 1);            // even step: position 2 s, odd step: position 2 s + 2
+    const bool act = on && ce < pe;
+    double xe[RPL], al = 0.0, be = 0.0, ga = 0.0;
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+      xe[r] = act ? X[ce * VPP + hl + LPS * r] : 0.0;
+      al = fma(xo[r], xo[r], al);
+      be = fma(xe[r], xe[r], be);
+      ga = fma(xo[r], xe[r], ga);
+    }
+    {
+      // three sums over the LPS lanes of the slot in fp32 (they only steer the angle): transposed butterfly
+      const float x0 = (float)al, x1 = (float)be, x2 = (float)ga;
+      const float y0 = (bh ? x2 : x0) + __shfl_xor_sync(0xffffffffu, bh ? x0 : x2, H1);
+      const float y1 = (bh ? 0.0f : x1) + __shfl_xor_sync(0xffffffffu, bh ? x1 : 0.0f, H1);
+      float z = (bq ? y1 : y0) + __shfl_xor_sync(0xffffffffu, bq ? y0 : y1, H2);
+#pragma unroll
+      for (int o = H2 / 2; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+      // lanes [0, H2): al, [H2, 2 H2): be, [2 H2, 3 H2): ga (of this slot's lane group)
+      al = (double)__shfl_sync(0xffffffffu, z, base);
+      be = (double)__shfl_sync(0xffffffffu, z, base + H2);
+      ga = (double)__shfl_sync(0xffffffffu, z, base + 2 * H2);
+    }
+    double c = 1.0, sn = 0.0;
+    {
+      const double ab = al * be, g2 = ga * ga;
+      if (act && g2 > skip2 * ab && fabs(ga) > 1e-300) {
+        cmax2 = fmax(cmax2, g2 * fast_rcp(ab));
+        if (nrot && hl == 0) atomicAdd(nrot, 1);
+        const float zf = (float)((be - al) * fast_rcp(2.0 * ga));
+        const float tf = copysignf(1.0f, zf) / (fabsf(zf) + sqrtf(fmaf(zf, zf, 1.0f)));
+        const double t = (double)tf;
+        c = fast_rsqrt(fma(t, t, 1.0));
+        sn = c * t;
+      }
+    }
+    if (act) {
+      // rotate (p, q) = (co, ce) and trade places: the "q" result stays in the registers, the "p" result goes to ce
+      double ve[RPL];
+#pragma unroll
+      for (int r = 0; r < RPL; ++r) ve[r] = V[ce * VPP + hl + LPS * r];
+#pragma unroll
+      for (int r = 0; r < RPL; ++r) {
+        const double np = c * xo[r] - sn * xe[r], nq = sn * xo[r] + c * xe[r];
+        const double wp = c * vo[r] - sn * ve[r], wq = sn * vo[r] + c * ve[r];
+        xo[r] = nq; vo[r] = wq;
+        X[ce * VPP + hl + LPS * r] = np;
+        V[ce * VPP + hl + LPS * r] = wp;
+      }
+    }
+    __syncthreads();
+  }
+  if (on) {
+    const int co = 2 * slot + 1;
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) { X[co * VPP + hl + LPS * r] = xo[r]; V[co * VPP + hl + LPS * r] = vo[r]; }
+  }
+  __syncthreads();
+  // the sweep reversed the order of the columns: put them back (column q <-> column pe - 1 - q, X and V alike)
+  for (int e = threadIdx.x; e < (pe >> 1) * VP; e += blockDim.x) {
+    const int q = e >> 6, r = e & 63, q2 = pe - 1 - q;
+    const double a = X[q * VPP + r], b = X[q2 * VPP + r];
+    X[q * VPP + r] = b; X[q2 * VPP + r] = a;
+    const double va = V[q * VPP + r], vb = V[q2 * VPP + r];
+    V[q * VPP + r] = vb; V[q2 * VPP + r] = va;
+  }
+  if (hl == 0) s_max[(32 / LPS) * warp + lane / LPS] = cmax2;
   __syncthreads();
   return 1;
 }
@@ -403,8 +499,12 @@ __global__ void __launch_bounds__(VTHREADS, 1) varimax_kernel(VarimaxParams P) {
   double* cs = As + VP * VPP;         // [64] column sums / sigma
   unsigned char* rr = reinterpret_cast<unsigned char*>(cs + VP);   // [(pe-1)*pe]
   __shared__ double s_max[VTHREADS / 32];
+  __shared__ double s_max2[4 * (VTHREADS / 32)];   // (per slot of the part-warp sweeps)
+  __shared__ int s_cnt[4];            // diagnostics (out[10..12]): rotations applied by the in-loop sweeps, pairs whose
+                                      // cosine exceeded 1e-4 / 1e-3 when a Gram matrix was inspected
 
   const int tid = threadIdx.x, p = P.p, pe = (p + 1) & ~1;
+  if (tid < 4) s_cnt[tid] = 0;
   const int64_t n = P.n;
   const TS* L = reinterpret_cast<const TS*>(P.L);
   TS* An = reinterpret_cast<TS*>(P.An);
@@ -643,11 +743,17 @@ __global__ void __launch_bounds__(VTHREADS, 1) varimax_kernel(VarimaxParams P) {
       for (int e = tid; e < VP * VP; e += VTHREADS) {
         const int i = e >> 6, j = e & 63;
         const double den = cs[i] * cs[j];
-        if (i != j && i < p && j < p && den > 0.0) { const double c = Ws[e] / den; m2 = fmax(m2, c * c); }
+        if (i != j && i < p && j < p && den > 0.0) {
+          const double c = Ws[e] / den;
+          m2 = fmax(m2, c * c);
+          if (i < j && c * c > 1e-8) atomicAdd(&s_cnt[1], 1);
+          if (i < j && c * c > 1e-6) atomicAdd(&s_cnt[2], 1);
+        }
       }
       m2 = block_max(m2, s_max);
       if (m2 <= 1e-6) break;
-      svd_sweeps += P.jacobi_oe ? polar_jacobi_oe(Xs, Vs, pe, s_max, 1e-8) : polar_jacobi(Xs, Vs, pe, rr, s_max, 1e-6, 1, 1e-8);
+      svd_sweeps += P.jacobi_oe == 2 ? polar_jacobi_oe_part<16>(Xs, Vs, pe, s_max2, 1e-8, &s_cnt[0]) :
+                    P.jacobi_oe == 1 ? polar_jacobi_oe(Xs, Vs, pe, s_max, 1e-8, &s_cnt[0]) : polar_jacobi(Xs, Vs, pe, rr, s_max, 1e-6, 1, 1e-8);
       __syncthreads();
     }
     for (int e = tid; e < VP * VP; e += VTHREADS) {                  // G -> Et in place
@@ -725,7 +831,8 @@ __global__ void __launch_bounds__(VTHREADS, 1) varimax_kernel(VarimaxParams P) {
   if (blockIdx.x == 0) {
     for (int e = tid; e < p * p; e += VTHREADS) P.R[e] = Rs[(e / p) * RS + (e % p)];
     if (tid == 0) { P.out[0] = (double)it; P.out[1] = (double)converged; P.out[2] = d; P.out[3] = (double)svd_sweeps;
-      for (int q = 0; q < 6; ++q) P.out[4 + q] = (double)tk[q]; }
+      for (int q = 0; q < 6; ++q) P.out[4 + q] = (double)tk[q];
+      for (int q = 0; q < 3; ++q) P.out[10 + q] = (double)s_cnt[q]; }
   }
 }
 
@@ -788,8 +895,8 @@ extern "C" int xmca_varimax(const void* d_L, int l_dtype, int64_t n, int p, int6
   P.reduced = reinterpret_cast<double*>(ws + o);
   P.B = d_B; P.ldb = ldb; P.R = d_R; P.out = d_out;
   {
-    const char* e = getenv("XMCA_VARIMAX_JACOBI");       // "rr": the round-robin sweep (A/B runs)
-    P.jacobi_oe = !(e && e[0] == 'r');
+    const char* e = getenv("XMCA_VARIMAX_JACOBI");       // A/B runs: "rr" round-robin, "oe" odd-even with a warp per slot
+    P.jacobi_oe = (e && e[0] == 'r') ? 0 : (e && e[0] == 'o') ? 1 : 2;
   }
 
   void* args[] = {&P};
