@@ -25,9 +25,9 @@ constexpr int VP = 64;          // padded number of rotated modes (p <= 64)
 constexpr int VT = 32;          // rows per tile
 constexpr int VTHREADS = 512;
 constexpr int VSLOT = VP * VP + VP;   // doubles per partial: T1 (64x64) + c (64)
-constexpr int VPP = VP + 1;           // padded stride of the column-major p x p work matrices (bank-conflict free)
-constexpr int RS = VP + 4;            // row stride of the rotation R and of the streamed tiles: DMMA fragment loads
-                                      // (address tig * RS + gid) are then bank-conflict free
+constexpr int VPP = VP + 4;           // stride of EVERY p x p work matrix: fp64 MMA fragment loads (address
+                                      // gid * VPP + tig or tig * VPP + gid) are bank-conflict free for stride = 4 mod 8
+constexpr int RS = VPP;               // row stride of the rotation R and of the streamed tiles
 
 struct VarimaxParams {
   const void* L; int ldt; int64_t n; int p; int64_t ldl;
@@ -41,38 +41,46 @@ struct VarimaxParams {
                        // slot), 2 the same with half a warp per slot (default)
 };
 
-// Z[i][j] = sum_k X(i,k) Y(k,j) for i, j, k < p (padded entries -> 0), 64 x 64 output by the first 256 threads
-// of the CTA: a 4 x 4 register block per thread (rows 4 ty + r, columns tx + 16 c), so that one k step of a warp
-// costs 8 shared-memory wavefronts for 512 FMAs -- the products are bound by the shared-memory crossbar, not by
-// the fp64 pipe.  Element access: X(i,k) = X[i * xs_i + k * xs_k], Y(k,j) = Y[k * ys_k + j * ys_j] (transposed /
-// padded operands are expressed through strides); Z is written at Z[i * zs_i + j * zs_j].
+// Z[i][j] = sum_k X(i,k) Y(k,j) for i, j, k < p (padded entries -> 0), 64 x 64 output on the fp64 tensor-core path
+// (mma.sync.m8n8k4): 16 warps, warp w owns the 16 x 16 block (w & 3, w >> 2): per k step of 4 two A and two B
+// fragments (one double per lane each) feed four MMAs.  Element access: X(i,k) = X[i * xs_i + k * xs_k],
+// Y(k,j) = Y[k * ys_k + j * ys_j] (transposed operands are expressed through strides; every matrix has the leading
+// stride VPP, so the fragment loads are conflict free either way); Z is written at Z[i * zs_i + j * zs_j].
+// At least one operand must be zero for k in [p, 4 ceil(p / 4)) -- all work matrices are zero padded.
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
 __device__ __forceinline__ void small_matmul(const double* X, int xs_i, int xs_k, const double* Y, int ys_k, int ys_j,
                                              double* Z, int zs_i, int zs_j, int p) {
-  if (threadIdx.x >= 256) return;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  double acc[4][4];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, gid = lane >> 2, tig = lane & 3;
+  const int i0 = 16 * (w & 3), j0 = 16 * (w >> 2);
+  double acc[2][2][2];
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
+  for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
-  for (int k = 0; k < p; ++k) {
-    double a[4], b[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) a[r] = X[(4 * ty + r) * xs_i + k * xs_k];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) b[c] = Y[k * ys_k + (tx + 16 * c) * ys_j];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) acc[r][c] = fma(a[r], b[c], acc[r][c]);
+    for (int b = 0; b < 2; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+  const double* xp = X + (i0 + gid) * xs_i + tig * xs_k;
+  const double* yp = Y + tig * ys_k + (j0 + gid) * ys_j;
+  const int ksteps = (p + 3) >> 2;
+#pragma unroll 4
+  for (int kk = 0; kk < ksteps; ++kk) {
+    const double a0 = xp[4 * kk * xs_k], a1 = xp[4 * kk * xs_k + 8 * xs_i];
+    const double b0 = yp[4 * kk * ys_k], b1 = yp[4 * kk * ys_k + 8 * ys_j];
+    dmma(acc[0][0], a0, b0);
+    dmma(acc[0][1], a0, b1);
+    dmma(acc[1][0], a1, b0);
+    dmma(acc[1][1], a1, b1);
   }
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
+  for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int i = 4 * ty + r, j = tx + 16 * c;
-      Z[i * zs_i + j * zs_j] = (i < p && j < p) ? acc[r][c] : 0.0;
-    }
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int i = i0 + 8 * a + gid, j = j0 + 8 * b + 2 * tig + e;
+        Z[i * zs_i + j * zs_j] = (i < p && j < p) ? acc[a][b][e] : 0.0;
+      }
 }
 
 // max over the CTA (every thread gets it); red: one double per warp
@@ -105,46 +113,47 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 //   Et_ij = E_ij / (s_i + s_j)
 // (f[a, b] = -1 / (ra rb (ra + rb)),  f[a, b, c] = (ra + rb + rc) / (ra rb rc (ra + rb)(rb + rc)(ra + rc)), r = sqrt).
 // The error is third order in the cosines: <= ~1e-8 here, where one more Jacobi sweep would cost 5x as much.
-// In: Et (row-major 64 x 64, zero diagonal / padding), s[64].  Out: Z (row-major 64 x 64); returns
+// In: Et (row-major, stride VPP, zero diagonal / padding), s[64].  Out: Z (row-major, stride VPP); returns
 // sum_ij Z_ij G_ij = trace(polar(X)^T X) = the sum of the singular values.
-__device__ __noinline__ double gram_inv_sqrt2(const double* Et, const double* s, double* Z, int zs, int p, double* red) {
+__device__ __noinline__ double gram_inv_sqrt2(const double* Et, const double* s, double* Z, int p, double* red) {
+  // f = Et diag(1 / s) Et and h = Et Et on the fp64 tensor-core path (same warp tiling as small_matmul)
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, gid = lane >> 2, tig = lane & 3;
+  const int i0 = 16 * (w & 3), j0 = 16 * (w >> 2);
+  double f[2][2][2], h[2][2][2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) { f[a][b][0] = f[a][b][1] = 0.0; h[a][b][0] = h[a][b][1] = 0.0; }
+  const double* xp = Et + (i0 + gid) * VPP + tig;
+  const double* yp = Et + tig * VPP + j0 + gid;
+  const int ksteps = (p + 3) >> 2;
+#pragma unroll 2
+  for (int kk = 0; kk < ksteps; ++kk) {
+    const double sk = s[4 * kk + tig];
+    const double rk = sk > 0.0 ? 1.0 / sk : 0.0;
+    const double a0 = xp[4 * kk], a1 = xp[4 * kk + 8 * VPP];
+    const double b0 = yp[4 * kk * VPP], b1 = yp[4 * kk * VPP + 8];
+    const double a0r = a0 * rk, a1r = a1 * rk;
+    dmma(h[0][0], a0, b0); dmma(h[0][1], a0, b1); dmma(h[1][0], a1, b0); dmma(h[1][1], a1, b1);
+    dmma(f[0][0], a0r, b0); dmma(f[0][1], a0r, b1); dmma(f[1][0], a1r, b0); dmma(f[1][1], a1r, b1);
+  }
   double dd = 0.0;
-  if (threadIdx.x < 256) {
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    double f[4][4], h[4][4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+  for (int a = 0; a < 2; ++a)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) { f[r][c] = 0.0; h[r][c] = 0.0; }
-    for (int k = 0; k < p; ++k) {
-      const double rk = s[k] > 0.0 ? 1.0 / s[k] : 0.0;
-      double a[4], b[4];
+    for (int b = 0; b < 2; ++b)
 #pragma unroll
-      for (int r = 0; r < 4; ++r) a[r] = Et[(4 * ty + r) * VP + k];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) b[c] = Et[k * VP + tx + 16 * c];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const double ak = a[r] * rk;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) { f[r][c] = fma(ak, b[c], f[r][c]); h[r][c] = fma(a[r], b[c], h[r][c]); }
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int i = 4 * ty + r, j = tx + 16 * c;
+      for (int e = 0; e < 2; ++e) {
+        const int i = i0 + 8 * a + gid, j = j0 + 8 * b + 2 * tig + e;
         const double si = s[i], sj = s[j];
         double z = 0.0;
         if (i < p && j < p && si > 0.0 && sj > 0.0) {
-          const double et = Et[i * VP + j], ssum = si + sj, rij = 1.0 / (si * sj);
-          z = ((i == j) ? 1.0 / si : 0.0) - et * rij + (ssum * f[r][c] + h[r][c]) * rij / ssum;
+          const double et = Et[i * VPP + j], ssum = si + sj, rij = 1.0 / (si * sj);
+          z = ((i == j) ? 1.0 / si : 0.0) - et * rij + (ssum * f[a][b][e] + h[a][b][e]) * rij / ssum;
           dd = fma(z, (i == j) ? si * si : et * ssum, dd);
         }
-        Z[i * zs + j] = z;
+        Z[i * VPP + j] = z;
       }
-  }
   return block_sum(dd, red);
 }
 
@@ -488,10 +497,10 @@ template <typename TS>
 __global__ void __launch_bounds__(VTHREADS, 1) varimax_kernel(VarimaxParams P) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ double sm[];
-  double* Rs = sm;                    // rotation (64x64, row-major, row stride RS)
-  double* Gs = Rs + VP * RS;          // A^T A
-  double* Ws = Gs + VP * VP;          // scratch (G R)
-  double* Vs = Ws + VP * VP;          // right singular vectors, warm start   (column-major, stride VPP)
+  double* Rs = sm;                    // rotation (row-major; all p x p matrices: 64 x VPP)
+  double* Gs = Rs + VP * VPP;         // A^T A
+  double* Ws = Gs + VP * VPP;         // scratch (G R)
+  double* Vs = Ws + VP * VPP;         // right singular vectors, warm start   (column-major, stride VPP)
   double* Xs = Vs + VP * VPP;         // SVD work matrix, then U              (column-major, stride VPP)
   double* As = Xs + VP * VPP;         // tile [32][64]
   double* Bs = As + VT * VP;          // tile [32][64]
@@ -592,7 +601,7 @@ __global__ void __launch_bounds__(VTHREADS, 1) varimax_kernel(VarimaxParams P) {
   reduce_partials(P.partial, P.reduced, 2 * (int)gridDim.x);
   __threadfence();
   grid.sync();
-  for (int e = tid; e < VP * VP; e += VTHREADS) Gs[e] = P.reduced[e];
+  for (int e = tid; e < VP * VP; e += VTHREADS) Gs[(e >> 6) * VPP + (e & 63)] = P.reduced[e];
   __syncthreads();
 
   // ---------------- fixed-point iteration ----------------
@@ -717,12 +726,12 @@ __global__ void __launch_bounds__(VTHREADS, 1) varimax_kernel(VarimaxParams P) {
 
     // ---- phase 2 (redundant on every CTA): T, polar factor, convergence ----
     if (tid < VP) cs[tid] = P.reduced[VP * VP + tid];
-    small_matmul(Gs, VP, 1, Rs, RS, 1, Ws, VP, 1, p);      // Ws = G R
+    small_matmul(Gs, VPP, 1, Rs, RS, 1, Ws, VPP, 1, p);    // Ws = G R
     __syncthreads();
     const double gn = P.gamma / (double)n;
     for (int e = tid; e < VP * VP; e += VTHREADS) {
       int i = e >> 6, k = e & 63;                        // T^T[k][i] = T[i][k]
-      Ts[k * VPP + i] = (i < p && k < p) ? P.reduced[e] - gn * Ws[e] * cs[k] : 0.0;
+      Ts[k * VPP + i] = (i < p && k < p) ? P.reduced[e] - gn * Ws[i * VPP + k] * cs[k] : 0.0;
     }
     __syncthreads();
     // X = T V (warm start): X(i,j) = sum_k T(i,k) V(k,j); T(i,k) = Ts[k*VPP+i], V(k,j) = Vs[j*VPP+k]; lanes <-> i
@@ -735,16 +744,16 @@ __global__ void __launch_bounds__(VTHREADS, 1) varimax_kernel(VarimaxParams P) {
     // and R = polar(X) V^T.  The converged rotation is polished to full accuracy by Jacobi sweeps below.
     double d_new = 0.0;
     for (int guard = 0; guard < 40; ++guard) {
-      small_matmul(Xs, VPP, 1, Xs, 1, VPP, Ws, VP, 1, p);            // G(i,j) = x_i . x_j
+      small_matmul(Xs, VPP, 1, Xs, 1, VPP, Ws, VPP, 1, p);           // G(i,j) = x_i . x_j
       __syncthreads();
-      if (tid < VP) cs[tid] = (tid < p) ? sqrt(Ws[tid * VP + tid]) : 0.0;
+      if (tid < VP) cs[tid] = (tid < p) ? sqrt(Ws[tid * VPP + tid]) : 0.0;
       __syncthreads();
       double m2 = 0.0;
       for (int e = tid; e < VP * VP; e += VTHREADS) {
         const int i = e >> 6, j = e & 63;
         const double den = cs[i] * cs[j];
         if (i != j && i < p && j < p && den > 0.0) {
-          const double c = Ws[e] / den;
+          const double c = Ws[i * VPP + j] / den;
           m2 = fmax(m2, c * c);
           if (i < j && c * c > 1e-8) atomicAdd(&s_cnt[1], 1);
           if (i < j && c * c > 1e-6) atomicAdd(&s_cnt[2], 1);
@@ -759,14 +768,14 @@ __global__ void __launch_bounds__(VTHREADS, 1) varimax_kernel(VarimaxParams P) {
     for (int e = tid; e < VP * VP; e += VTHREADS) {                  // G -> Et in place
       const int i = e >> 6, j = e & 63;
       const double ssum = cs[i] + cs[j];
-      Ws[e] = (i != j && i < p && j < p && ssum > 0.0) ? Ws[e] / ssum : 0.0;
+      Ws[i * VPP + j] = (i != j && i < p && j < p && ssum > 0.0) ? Ws[i * VPP + j] / ssum : 0.0;
     }
     __syncthreads();
-    d_new = gram_inv_sqrt2(Ws, cs, Rs, RS, p, s_max);                // Rs = Z
+    d_new = gram_inv_sqrt2(Ws, cs, Rs, p, s_max);                    // Rs = Z
     __syncthreads();
-    small_matmul(Rs, RS, 1, Vs, VPP, 1, Ws, VP, 1, p);               // Y = Z V^T:  Y(i,l) = sum_j Z(i,j) V(l,j)
+    small_matmul(Rs, RS, 1, Vs, VPP, 1, Ws, VPP, 1, p);              // Y = Z V^T:  Y(i,l) = sum_j Z(i,j) V(l,j)
     __syncthreads();
-    small_matmul(Xs, 1, VPP, Ws, VP, 1, Rs, RS, 1, p);               // R = X Y
+    small_matmul(Xs, 1, VPP, Ws, VPP, 1, Rs, RS, 1, p);              // R = X Y
     __syncthreads();
     { long long c1 = clock64(); tk[4] += c1 - c0; c0 = c1; }
     auto finish_polar = [&]() {
@@ -837,7 +846,7 @@ __global__ void __launch_bounds__(VTHREADS, 1) varimax_kernel(VarimaxParams P) {
 }
 
 static size_t varimax_smem_bytes() {
-  return (size_t)(VP * RS + 2 * VP * VP + 3 * VP * VPP + VP) * sizeof(double) + (size_t)VP * VP;
+  return (size_t)(6 * VP * VPP + VP) * sizeof(double) + (size_t)VP * VP;
 }
 
 template <typename TS>
