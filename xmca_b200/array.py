@@ -386,8 +386,16 @@ class MCA:
 
     def _rotated_loadings_host(self, k):
         """V sqrt(sigma) R / norm for field k (array.py:634-640), from the device
-        product L_rot computed in rotate()."""
+        product L_rot computed in rotate() (downloaded on first use)."""
+        if k not in self._rot_eofs:
+            self._rot_eofs[k] = D.to_host(self._rot_eofs_dev[k])
         return self._rot_eofs[k]
+
+    def _no_nan_index_dev(self, k):
+        cache = self.__dict__.setdefault("_no_nan_dev", {})
+        if k not in cache:
+            cache[k] = D.to_device(np.ascontiguousarray(self._no_nan_index[k]))
+        return cache[k]
 
     def _get_U(self, n=None, rotated=True):
         self._require_solved("principal components")
@@ -474,6 +482,9 @@ class MCA:
                          "following: None, eigen, std, max".format(scaling))
 
     def _get_eofs(self, n=None, scaling="None", phase_shift=0, rotated=True):
+        if rotated and self._analysis["is_rotated"] and not self._analysis["is_complex"] \
+                and all(k in getattr(self, "_rot_eofs_dev", {}) for k in self._keys):
+            return self._get_eofs_rotated_dev(n, scaling)
         V = self._get_V(n, rotated=rotated)
         out = {}
         for k in self._keys:
@@ -485,6 +496,28 @@ class MCA:
                 full = full * cmath.rect(1, phase_shift)
             norm_k = self._get_norm(V["left"].shape[1], sorted=True)[k] if scaling == "eigen" else None
             out[k] = self._apply_scaling(full, scaling, norm_k, tuple(range(full.ndim - 1)))
+        return out
+
+    def _get_eofs_rotated_dev(self, n, scaling):
+        """Rotated real model: the same result as the general path (`_get_V` -> mode order -> full grid with NaN at
+        the removed points, array.py:634-642 / 1245-1262), with the reordering and the scatter done on the device and
+        ONE download per field instead of three host-side copies of the S x n_rot array."""
+        t = D.torch()
+        cols = np.ascontiguousarray(self._var_idx[self._get_slice(n)])
+        idx = D.to_device(cols.astype(np.int64))
+        out = {}
+        for k in self._keys:
+            v = self._rot_eofs_dev[k].index_select(1, idx)
+            nm = int(v.shape[1])
+            mask = self._no_nan_index[k]
+            if bool(np.all(mask)):
+                full = v
+            else:
+                full = t.full((self._n_variables[k], nm), float("nan"), dtype=v.dtype, device=v.device)
+                full[self._no_nan_index_dev(k)] = v
+            arr = D.to_host(full).reshape(self._fields_spatial_shape[k] + (nm,))
+            norm_k = self._get_norm(nm, sorted=True)[k] if scaling == "eigen" else None
+            out[k] = self._apply_scaling(arr, scaling, norm_k, tuple(range(arr.ndim - 1)))
         return out
 
     def _get_pcs(self, n=None, scaling="None", phase_shift=0, rotated=True):
@@ -537,13 +570,15 @@ class MCA:
             st = D.to_host(D.last_varimax_stats)
             self._solve_info["varimax_svd_sweeps"] = int(st[3])
             self._solve_info["varimax_phase_clocks"] = [float(x) for x in st[4:10]]
-        # rotated EOFs = L_rot / norm (array.py:640): one scaled copy per field, kept on the host
+        # rotated EOFs = L_rot / norm (array.py:640): one scaled copy per field; it stays on the device (`eofs` reorders
+        # it, re-inserts the NaN grid points there and downloads once), a host copy is made only when asked for
         self._rot_eofs = {}
+        self._rot_eofs_dev = {}
         bounds = {"left": (0, s_left), "right": (s_left, n_all)}
         for k in self._keys:
             lo, hi = bounds[k]
             inv = D.to_device(1.0 / self._norm[k])
-            self._rot_eofs[k] = D.to_host(D.scale_copy(Lrot[lo:hi], col_scale=inv))
+            self._rot_eofs_dev[k] = D.scale_copy(Lrot[lo:hi], col_scale=inv)
 
     def _rotate_complex(self, sv, n_rot, power, tol):
         """Complex model: fused complex Varimax kernel on the planar loadings."""
@@ -568,6 +603,7 @@ class MCA:
         self._analysis["power"] = power
         self._solve_info["varimax_iterations"] = iters
         self._rot_eofs = {}
+        self._rot_eofs_dev = {}
         bounds = {"left": (0, s_left), "right": (s_left, n_all)}
         for k in self._keys:
             lo, hi = bounds[k]
