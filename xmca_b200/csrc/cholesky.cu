@@ -14,7 +14,9 @@
 // update are products on the general fp64 kernel (xmca_gemm), which is where
 // all the n^3/3 work is.
 #include "common.cuh"
+#include "small64.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace xmca {
 
@@ -92,6 +94,82 @@ chol_diag_kernel(double* __restrict__ A, int64_t lda, int64_t k0, int nb, double
   for (int i = 0; i < CB; ++i) inv[i * CB + tid] = (i >= tid) ? sv[i] : 0.0;
   for (int e = tid; e < CB * CB; e += CB) {
     const int i = e >> 6, j = e & 63;
+    if (i < nb && j < nb) A[(k0 + i) * lda + k0 + j] = Ls[i][j];
+  }
+}
+
+// The same diagonal-block step with 256 threads and the blocked-by-8 factorisation of small64.cuh (the 64-thread
+// kernel above keeps a row per thread in registers and runs its 64-step recurrences fully unrolled: ~40 us warm, bound
+// by instruction fetch).  inv(L_kk) follows from the 8 x 8 diagonal-block inverses by block forward substitution,
+// one warp per block column J:  Inv_JJ = Dinv_J,  Inv_IJ = -Dinv_I sum_{K = J}^{I - 1} L_IK Inv_KJ.
+constexpr int CD_T = 256;
+
+__global__ void __launch_bounds__(CD_T)
+chol_diag_blocked_kernel(double* __restrict__ A, int64_t lda, int64_t k0, int nb, double* __restrict__ inv,
+                         int* __restrict__ flag, double min_pivot) {
+  extern __shared__ double cd_smem[];
+  double (*Ls)[PLD] = reinterpret_cast<double (*)[PLD]>(cd_smem);
+  double (*Is)[PLD] = reinterpret_cast<double (*)[PLD]>(cd_smem + PB * PLD);
+  __shared__ double s_dinv[512];
+  __shared__ int s_fail, s_bad;
+  const int tid = threadIdx.x;
+  if (tid == 0) { s_fail = 0; s_bad = 0; }
+  for (int e = tid; e < PB * PB; e += CD_T) {
+    const int i = e >> 6, j = e & 63;
+    Ls[i][j] = (i < nb && j < nb) ? (j <= i ? A[(k0 + i) * lda + k0 + j] : 0.0) : ((i == j) ? 1.0 : 0.0);
+    Is[i][j] = 0.0;
+  }
+  __syncthreads();
+  chol64_blocked(Ls, s_dinv, tid, &s_fail, min_pivot, &s_bad);
+  __syncthreads();
+  if (s_bad) {
+    if (tid == 0) atomicCAS(flag, 0, (int)(k0 + s_bad));
+    return;
+  }
+  {
+    const int J = tid >> 5, lane = tid & 31;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int e = lane + 32 * q, r = e >> 3, c = e & 7;
+      Is[8 * J + r][8 * J + c] = s_dinv[J * 64 + r * 8 + c];
+    }
+    __syncwarp();
+    for (int I = J + 1; I < 8; ++I) {
+      double sv[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int e = lane + 32 * q, r = e >> 3, c = e & 7;
+        double acc = 0.0;
+        for (int k = 8 * J; k < 8 * I; ++k) acc = fma(Ls[8 * I + r][k], Is[k][8 * J + c], acc);
+        sv[q] = acc;
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int e = lane + 32 * q;
+        Is[8 * I + (e >> 3)][8 * J + (e & 7)] = sv[q];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int e = lane + 32 * q, r = e >> 3, c = e & 7;
+        double acc = 0.0;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc = fma(s_dinv[I * 64 + r * 8 + t], Is[8 * I + t][8 * J + c], acc);
+        sv[q] = -acc;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int e = lane + 32 * q;
+        Is[8 * I + (e >> 3)][8 * J + (e & 7)] = sv[q];
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < PB * PB; e += CD_T) {
+    const int i = e >> 6, j = e & 63;
+    inv[e] = Is[i][j];
     if (i < nb && j < nb) A[(k0 + i) * lda + k0 + j] = Ls[i][j];
   }
 }
@@ -176,6 +254,11 @@ extern "C" int xmca_cholesky(int64_t n, double* d_A, int64_t lda, double* d_invd
     cudaEventDestroy(ev_panel); cudaEventDestroy(ev_bulk); cudaStreamDestroy(chain);
   };
   int rc = XMCA_OK;
+  const size_t cd_smem_bytes = 2 * PB * PLD * sizeof(double);
+  const char* cd_mode = getenv("XMCA_CHOL_DIAG");                 // "rows": the 64-thread row-per-thread kernel (A/B runs)
+  const bool blocked_diag = !(cd_mode && cd_mode[0] == 'r');
+  if (blocked_diag && cudaFuncSetAttribute(chol_diag_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)cd_smem_bytes) != cudaSuccess) rc = XMCA_CUDA_ERROR;
   // the chain starts after everything already queued on the caller's stream (the matrix, the flag reset)
   if (cudaEventRecord(ev_bulk, st) != cudaSuccess || cudaStreamWaitEvent(chain, ev_bulk, 0) != cudaSuccess) rc = XMCA_CUDA_ERROR;
   bool bulk_pending = false;
@@ -184,7 +267,10 @@ extern "C" int xmca_cholesky(int64_t n, double* d_A, int64_t lda, double* d_invd
     const int nb = (int)((n - k0) < CB ? (n - k0) : CB);
     double* inv = d_invdiag + (size_t)b * CB * CB;
     double* panel = panels[b & 1];
-    chol_diag_kernel<<<1, CB, 0, chain>>>(d_A, lda, k0, nb, inv, flag, min_pivot > 0.0 ? min_pivot : 0.0);
+    if (blocked_diag)
+      chol_diag_blocked_kernel<<<1, CD_T, cd_smem_bytes, chain>>>(d_A, lda, k0, nb, inv, flag, min_pivot > 0.0 ? min_pivot : 0.0);
+    else
+      chol_diag_kernel<<<1, CB, 0, chain>>>(d_A, lda, k0, nb, inv, flag, min_pivot > 0.0 ? min_pivot : 0.0);
     if (cudaGetLastError() != cudaSuccess) { rc = XMCA_CUDA_ERROR; break; }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     const int64_t rem = n - k0 - nb;
