@@ -28,6 +28,11 @@ for (n0, _, a1, _), (n1, b0, _, _) in zip(rec[:-1], rec[1:]):
 gaps.append((rec[-1][0] + " -> <end>", rec[-1][2].elapsed_time(e_end)))
 for name, g in sorted(gaps, key=lambda x: -x[1])[:16]:
     print("  %7.2f ms  %s" % (g, name))
+print("ordered calls (ms in call / gap before it):")
+prev = e_begin
+for name, a0, a1, nl in rec:
+    print("   %-22s %8.2f   gap %6.2f" % (name, a0.elapsed_time(a1), prev.elapsed_time(a0)))
+    prev = a1
 
 # host-side view of the tail: wall time of each public call of the step, then a cProfile of the accessors
 import time, cProfile, pstats
@@ -43,3 +48,10 @@ pr = cProfile.Profile()
 m.solve()
 pr.enable(); m.rotate(50, 1); m.singular_values(50); m.pcs(50); m.eofs(50); torch.cuda.synchronize(); pr.disable()
 pstats.Stats(pr).sort_stats("tottime").print_stats(14)
+
+# per-call device time of three more steps
+for rep in range(3):
+    _lib.profile_begin()
+    bench.hot_path_step(m, 50, 50)
+    pr2 = _lib.profile_end()
+    print("  step calls:", {k: round(v["ms"], 1) for k, v in pr2.items() if v["ms"] > 0.5})

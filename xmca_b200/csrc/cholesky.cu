@@ -205,6 +205,33 @@ static int copy_block(const double* X, int64_t ldx, double* Y, int64_t ldy, int6
   return XMCA_OK;
 }
 
+// internal high-priority stream + events of the look-ahead, one set per (device, caller's stream), created on first use
+struct CholStreams { cudaStream_t owner = nullptr; bool used = false; cudaStream_t chain = nullptr; cudaEvent_t ev_panel = nullptr, ev_bulk = nullptr; };
+static CholStreams* chol_streams(cudaStream_t caller) {
+  constexpr int SLOTS = 4;
+  static CholStreams pool[64][SLOTS];
+  static int next_slot[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  CholStreams* s = nullptr;
+  for (int i = 0; i < SLOTS; ++i)
+    if (pool[dev][i].used && pool[dev][i].owner == caller) s = &pool[dev][i];
+  if (!s) {
+    s = &pool[dev][next_slot[dev]];
+    next_slot[dev] = (next_slot[dev] + 1) % SLOTS;
+    s->owner = caller;
+    s->used = true;
+  }
+  if (!s->chain) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&s->chain, cudaStreamNonBlocking, hi) != cudaSuccess) { s->chain = nullptr; return nullptr; }
+    cudaEventCreateWithFlags(&s->ev_panel, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&s->ev_bulk, cudaEventDisableTiming);
+  }
+  return s;
+}
+
 struct CholPlan { int64_t nblk; size_t off_inv, off_panel, off_flag, total; };
 
 static CholPlan chol_plan(int64_t n, int64_t nrhs) {
@@ -241,18 +268,13 @@ extern "C" int xmca_cholesky(int64_t n, double* d_A, int64_t lda, double* d_invd
   XMCA_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
   // Look-ahead: the critical chain (diagonal block -> panel -> update of the NEXT block column) runs on an
   // internal HIGH-priority stream; the rest of each trailing update (block columns >= b + 2) stays on the caller's
-  // stream, one step behind, under the next step's chain.  The stream / event objects live for the call only.
-  cudaStream_t chain = nullptr;
-  cudaEvent_t ev_panel = nullptr, ev_bulk = nullptr;
-  int prio_lo = 0, prio_hi = 0;
-  XMCA_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-  XMCA_CUDA(cudaStreamCreateWithPriority(&chain, cudaStreamNonBlocking, prio_hi));
-  XMCA_CUDA(cudaEventCreateWithFlags(&ev_panel, cudaEventDisableTiming));
-  XMCA_CUDA(cudaEventCreateWithFlags(&ev_bulk, cudaEventDisableTiming));
-  auto cleanup = [&]() {
-    cudaStreamSynchronize(chain);
-    cudaEventDestroy(ev_panel); cudaEventDestroy(ev_bulk); cudaStreamDestroy(chain);
-  };
+  // stream, one step behind, under the next step's chain.  The stream / event objects are kept per (device, caller's
+  // stream): creating and destroying them per call costs more than a block step and synchronises the device.
+  CholStreams* cs = chol_streams(st);
+  XMCA_REQUIRE(cs != nullptr, "xmca_cholesky: cannot create the internal stream");
+  cudaStream_t chain = cs->chain;
+  cudaEvent_t ev_panel = cs->ev_panel, ev_bulk = cs->ev_bulk;
+  auto cleanup = [&]() { cudaStreamSynchronize(chain); };     // (the stream / events are kept for the next call)
   int rc = XMCA_OK;
   const size_t cd_smem_bytes = 2 * PB * PLD * sizeof(double);
   const char* cd_mode = getenv("XMCA_CHOL_DIAG");                 // "rows": the 64-thread row-per-thread kernel (A/B runs)
