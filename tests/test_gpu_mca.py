@@ -803,3 +803,33 @@ def test_full_size_config5_invariants(MCA):
     cor = Ur["left"].T @ Ur["right"] / (T - 1)
     assert np.abs(cor - np.eye(k)).max() > 1e-4
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("scaling", ["None", "eigen", "max", "std"])
+def test_rotated_eofs_device_path_equals_general_path(MCA, scaling):
+    """`eofs()` of a rotated real model reorders the modes and re-inserts the NaN grid points on the device
+    (`_get_eofs_rotated_dev`); the result must be IDENTICAL to the general host path (`_get_V` -> full grid,
+    array.py:634-642 / :1245-1262), for every mode selection and scaling."""
+    rng = np.random.default_rng(11)
+    A = rng.standard_normal((120, 9, 7)).astype(np.float32)
+    B = rng.standard_normal((120, 6, 8)).astype(np.float32)
+    A[:, 2, 3] = np.nan
+    A[5, 0, 1] = np.nan
+    B[:, 5, 7] = np.nan
+    m = MCA(A, B)
+    m.solve()
+    m.rotate(8, 1)
+    for n in (None, 3, slice(2, 6), 8):
+        got = m.eofs(n, scaling=scaling)
+        V = m._get_V(n, rotated=True)                          # host path: download + reorder on the host
+        for k in ("left", "right"):
+            nm = V[k].shape[1]
+            full = np.full((m._n_variables[k], nm), np.nan, dtype=V[k].dtype)
+            full[m._no_nan_index[k], :] = V[k]
+            full = full.reshape(m._fields_spatial_shape[k] + (nm,))
+            norm_k = m._get_norm(nm, sorted=True)[k] if scaling == "eigen" else None
+            want = m._apply_scaling(full, scaling, norm_k, tuple(range(full.ndim - 1)))
+            assert got[k].shape == want.shape and got[k].dtype == want.dtype
+            np.testing.assert_array_equal(np.isnan(got[k]), np.isnan(want))
+            np.testing.assert_array_equal(np.nan_to_num(got[k]), np.nan_to_num(want))
+    assert np.isnan(m.eofs(2)["left"][2, 3]).all() and np.isnan(m.eofs(2)["right"][5, 7]).all()
