@@ -42,6 +42,26 @@ def test_gemm_split_k_and_accumulate(D):
     np.testing.assert_allclose(got32, A @ B, rtol=2e-3, atol=2e-2)
 
 
+@pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_gemm_skinny_n_tile(D, ta, tb, dt):
+    """Projections onto a few modes (N <= 64, long K, M >= 512) run on the 256 x 64 tile of the fp64 DMMA path: every
+    operand layout, ragged M / N / K, mixed dtypes, split-K (chosen by `matmul`) and accumulation."""
+    r = _rng(5)
+    M, N, K = 1111, 50, 2600
+    A = r.standard_normal((K, M) if ta else (M, K)).astype(dt)
+    B = r.standard_normal((N, K) if tb else (K, N))                        # fp64 vectors against fp32 / fp64 fields
+    want = (A.T if ta else A).astype(np.float64) @ (B.T if tb else B)
+    got = D.to_host(D.matmul(D.to_device(A), D.to_device(B), trans_a=ta, trans_b=tb, alpha=-0.25))
+    np.testing.assert_allclose(got, -0.25 * want, rtol=1e-12, atol=1e-12 * np.abs(want).max())
+    out = D.to_device(np.full((M, N), 2.0))
+    got = D.to_host(D.matmul(D.to_device(A), D.to_device(B), trans_a=ta, trans_b=tb, out=out, accumulate=True))
+    np.testing.assert_allclose(got, want + 2.0, rtol=1e-12, atol=1e-12 * np.abs(want).max())
+    got32 = D.to_host(D.matmul(D.to_device(A), D.to_device(B), trans_a=ta, trans_b=tb, out_dtype=D.f32()))
+    assert got32.dtype == np.float32
+    np.testing.assert_allclose(got32, want, rtol=1e-5, atol=1e-5 * np.abs(want).max())
+
+
 @pytest.mark.parametrize("shape", [(128, 256, 64), (300, 200, 100), (512, 640, 1000), (96, 40, 37)])
 def test_tc_gemm_matches_fp64(D, shape):
     """3xTF32 tcgen05 product vs fp64 numpy: error at the fp32 level."""

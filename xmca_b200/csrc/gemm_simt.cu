@@ -272,6 +272,156 @@ gemm_dmma_kernel(int64_t M, int64_t N, int64_t K, double alpha,
   }
 }
 
+// ------------------------------------------------------------------ fp64 DMMA, skinny N (projections onto a few modes)
+// N <= 64 (array.py:640 / :667: fields times 20-50 vectors): on the 128 x 128 tile half of the warps compute columns that do
+// not exist.  Same inner product with a 256 x 64 block tile: 16 warps as 8 x 2, warp tile 32 x 32, operand slabs [k][mn]
+// with pitches 260 / 68 (the same XOR swizzle).  No structure flags.
+constexpr int SK_BM = 256, SK_BN = 64, SK_LDA = SK_BM + 4, SK_LDB = SK_BN + 4;
+
+template <bool KMAJOR>
+__device__ __forceinline__ void sk_load_a(double (&r)[8], const void* p, int dt, int64_t ld,
+                                          int64_t m0, int64_t M, int64_t k0, int64_t k_end, int tid) {
+  if (KMAJOR) {
+    const int kk = tid & 15, m = tid >> 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t mm = m0 + m + 32 * i, k = k0 + kk;
+      r[i] = (mm < M && k < k_end) ? ld_elem<double>(p, dt, mm * ld + k) : 0.0;
+    }
+  } else {
+    const int m = tid & 255, kk = tid >> 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t mm = m0 + m, k = k0 + kk + 2 * i;
+      r[i] = (mm < M && k < k_end) ? ld_elem<double>(p, dt, k * ld + mm) : 0.0;
+    }
+  }
+}
+template <bool KMAJOR>
+__device__ __forceinline__ void sk_store_a(const double (&r)[8], double (*s)[SK_LDA], int tid) {
+  if (KMAJOR) {
+    const int kk = tid & 15, m = tid >> 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[kk][(m + 32 * i) ^ ((kk >> 2) & 3)] = r[i];
+  } else {
+    const int m = tid & 255, kk = tid >> 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[kk + 2 * i][m ^ (((kk + 2 * i) >> 2) & 3)] = r[i];
+  }
+}
+template <bool KMAJOR>
+__device__ __forceinline__ void sk_load_b(double (&r)[2], const void* p, int dt, int64_t ld,
+                                          int64_t n0, int64_t N, int64_t k0, int64_t k_end, int tid) {
+  if (KMAJOR) {
+    const int kk = tid & 15, n = tid >> 4;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int64_t nn = n0 + n + 32 * i, k = k0 + kk;
+      r[i] = (nn < N && k < k_end) ? ld_elem<double>(p, dt, nn * ld + k) : 0.0;
+    }
+  } else {
+    const int n = tid & 63, kk = tid >> 6;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int64_t nn = n0 + n, k = k0 + kk + 8 * i;
+      r[i] = (nn < N && k < k_end) ? ld_elem<double>(p, dt, k * ld + nn) : 0.0;
+    }
+  }
+}
+template <bool KMAJOR>
+__device__ __forceinline__ void sk_store_b(const double (&r)[2], double (*s)[SK_LDB], int tid) {
+  if (KMAJOR) {
+    const int kk = tid & 15, n = tid >> 4;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) s[kk][(n + 32 * i) ^ ((kk >> 2) & 3)] = r[i];
+  } else {
+    const int n = tid & 63, kk = tid >> 6;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) s[kk + 8 * i][n ^ (((kk + 8 * i) >> 2) & 3)] = r[i];
+  }
+}
+
+template <bool AK, bool BKM>
+__global__ void __launch_bounds__(DT)
+gemm_dmma_skinny_kernel(int64_t M, int64_t N, int64_t K, double alpha,
+                        const void* __restrict__ A, int adt, int64_t lda,
+                        const void* __restrict__ B, int bdt, int64_t ldb,
+                        void* __restrict__ D, int ddt, int64_t ldd, int accumulate,
+                        double* __restrict__ partial, int64_t k_chunk) {
+  __shared__ double As[BK][SK_LDA];
+  __shared__ double Bs[BK][SK_LDB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int wm = (warp & 7) * 32, wn = (warp >> 3) * 32;
+  const int64_t m0 = (int64_t)blockIdx.y * SK_BM, n0 = (int64_t)blockIdx.x * SK_BN;
+  const int64_t kb = (int64_t)blockIdx.z * k_chunk;
+  const int64_t ke = min(K, kb + k_chunk);
+
+  double c[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { c[i][j][0] = 0.0; c[i][j][1] = 0.0; }
+  double ra[8], rb[2];
+  if (kb < ke) {
+    sk_load_a<AK>(ra, A, adt, lda, m0, M, kb, ke, tid);
+    sk_load_b<BKM>(rb, B, bdt, ldb, n0, N, kb, ke, tid);
+  }
+  for (int64_t k0 = kb; k0 < ke; k0 += BK) {
+    sk_store_a<AK>(ra, As, tid);
+    sk_store_b<BKM>(rb, Bs, tid);
+    __syncthreads();
+    if (k0 + BK < ke) {
+      sk_load_a<AK>(ra, A, adt, lda, m0, M, k0 + BK, ke, tid);
+      sk_load_b<BKM>(rb, B, bdt, ldb, n0, N, k0 + BK, ke, tid);
+    }
+#pragma unroll
+    for (int ks = 0; ks < BK; ks += 4) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        a[i] = As[ks + tig][(wm + 8 * i + gid) ^ ((ks >> 2) & 3)];
+        b[i] = Bs[ks + tig][(wn + 8 * i + gid) ^ ((ks >> 2) & 3)];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(c[i][j][0]), "+d"(c[i][j][1]) : "d"(a[i]), "d"(b[j]));
+    }
+    __syncthreads();
+  }
+  if (!partial && accumulate) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t m = m0 + wm + 8 * i + gid;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int64_t n = n0 + wn + 8 * j + 2 * tig + e;
+          const double old = (m < M && n < N) ? load_as_double(D, ddt, m * ldd + n) : 0.0;
+          c[i][j][e] = fma(alpha, c[i][j][e], old);
+        }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + wm + 8 * i + gid;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int64_t n = n0 + wn + 8 * j + 2 * tig + e;
+        if (n >= N) continue;
+        if (partial) partial[((int64_t)blockIdx.z * M + m) * N + n] = c[i][j][e];
+        else store_from_double(D, ddt, m * ldd + n, accumulate ? c[i][j][e] : alpha * c[i][j][e]);
+      }
+  }
+}
+
 template <typename T>
 __global__ void splitk_reduce_kernel(int64_t M, int64_t N, int split, double alpha,
                                      const T* __restrict__ partial,
@@ -295,6 +445,26 @@ static int launch_gemm(int ak, int bk, int64_t M, int64_t N, int64_t K, double a
   if (k_chunk < BK) k_chunk = BK;
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)split);
   T* partial = split > 1 ? reinterpret_cast<T*>(ws) : nullptr;
+  if (sizeof(T) == 8 && N <= SK_BN && M >= 2 * SK_BM && K >= 1024 && flags == 0) {     // skinny N, long K: 256 x 64 tiles
+    double* dpart = reinterpret_cast<double*>(partial);
+    dim3 sgrid(1, (unsigned)((M + SK_BM - 1) / SK_BM), (unsigned)split);
+#define GOS(AKF, BKF)                                                                            \
+  gemm_dmma_skinny_kernel<AKF, BKF><<<sgrid, DT, 0, st>>>(M, N, K, alpha, A, adt, lda, B, bdt, ldb, \
+                                                          D, ddt, ldd, accumulate, dpart, k_chunk)
+    if (ak && bk) GOS(true, true);
+    else if (ak && !bk) GOS(true, false);
+    else if (!ak && bk) GOS(false, true);
+    else GOS(false, false);
+#undef GOS
+    XMCA_LAUNCHED();
+    if (split > 1) {
+      int64_t tot = M * N;
+      splitk_reduce_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
+          M, N, split, alpha, partial, D, ddt, ldd, accumulate);
+      XMCA_LAUNCHED();
+    }
+    return XMCA_OK;
+  }
   if (sizeof(T) == 8) {                 // fp64 accumulation: DMMA kernel
     double* dpart = reinterpret_cast<double*>(partial);
 #define GOD(AKF, BKF)                                                                    \
