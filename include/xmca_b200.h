@@ -153,7 +153,7 @@ int xmca_trsm_lt(int64_t n, int64_t nrhs, const double* d_L, int64_t ldl, const 
  *   latency-bound phases (column update, reflector, reductions).  This is what the independent surrogate
  *   runs of rule_n (array.py:1753-1765) use.  Problem 1 lives stride_a doubles behind d_A and stride_v
  *   doubles behind d_d / d_e / d_tau; d_workspace: batch * xmca_sytrd_workspace_bytes(n).
- * xmca_stebz: all n eigenvalues, DESCENDING, into d_w (d_scratch: n + 8 doubles).
+ * xmca_stebz: all n eigenvalues, DESCENDING, into d_w (d_scratch: 2 n + 8 doubles, 16-byte aligned).
  *   Synchronises `stream` once (Gershgorin bounds come back to the host).
  * xmca_stein: eigenvectors of the tridiagonal for the k eigenvalues d_lambda
  *   (descending), written as ROWS of d_Z (k x n, ldz).  d_cluster_start

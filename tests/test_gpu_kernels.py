@@ -194,6 +194,48 @@ def test_cholesky_rejects_indefinite(D):
         D.cholesky(D.to_device(G))
 
 
+@pytest.mark.parametrize("case", ["diagonal", "toeplitz", "decoupled", "graded", "clustered", "wilkinson", "n1", "n2", "n9",
+                                  "negative", "tiny_scale", "huge_scale"])
+def test_bisection_on_special_tridiagonals(D, case, monkeypatch):
+    """`xmca_stebz` (Sturm sequence in product form with renormalisation, pivmin rule applied on redo) against LAPACK on
+    tridiagonals that exercise exact zeros in the sequence, decoupled blocks, 300 orders of magnitude of grading,
+    clusters, every remainder length of the 8-step chunks, and extreme scalings; both recurrence forms."""
+    r = _rng(17)
+    n = 257
+    if case == "diagonal":
+        d, e = r.standard_normal(n), np.zeros(n - 1)
+    elif case == "toeplitz":                         # zero diagonal: p_j vanishes exactly at x = 0 for odd j
+        d, e = np.zeros(n), np.ones(n - 1)
+    elif case == "decoupled":
+        d, e = r.standard_normal(n), r.standard_normal(n - 1)
+        e[::7] = 0.0
+    elif case == "graded":
+        d = np.logspace(0, -150, n)
+        e = 0.1 * np.sqrt(d[:-1] * d[1:])
+    elif case == "clustered":
+        d = np.concatenate([np.full(100, 1.0), np.full(100, 1.0 + 1e-13), r.uniform(0, 2, 57)])
+        e = np.full(n - 1, 1e-14)
+    elif case == "wilkinson":
+        d, e = np.abs(np.arange(n) - n // 2).astype(float), np.ones(n - 1)
+    elif case in ("n1", "n2", "n9"):
+        n = int(case[1:])
+        d, e = r.standard_normal(n), r.standard_normal(max(n - 1, 1))[:n - 1]
+    elif case == "negative":
+        d, e = -np.abs(r.standard_normal(n)) - 3.0, 0.3 * r.standard_normal(n - 1)
+    else:
+        sc = 1e-140 if case == "tiny_scale" else 1e140
+        d, e = sc * r.standard_normal(n), sc * r.standard_normal(n - 1)
+    Tm = np.diag(d) + (np.diag(e, 1) + np.diag(e, -1) if n > 1 else 0.0)
+    ref = np.linalg.eigvalsh(Tm)[::-1]
+    tol = 4e-15 * n * max(np.abs(ref).max(), 1e-300)
+    epad = np.concatenate([e, [0.0]])                # device arrays: d (n), e (n - 1, one spare entry)
+    for mode in ("prod", "quot"):
+        monkeypatch.setenv("XMCA_STEBZ", mode)
+        w = D.to_host(D.stebz(D.to_device(d.copy()), D.to_device(epad.copy())))
+        assert w.shape == (n,) and np.all(np.diff(w) <= 0.0)
+        np.testing.assert_allclose(w, ref, atol=tol, rtol=0, err_msg=mode)
+
+
 @pytest.mark.parametrize("n", [5, 64, 200, 777, 1500, 4700])
 def test_tridiagonal_eigensolver(D, n):
     """sytrd + stebz give all eigenvalues; stein + ormtr the leading eigenvectors (also inside

@@ -647,6 +647,113 @@ stebz_kernel(int n, const double* __restrict__ d, const double* __restrict__ e2,
   if (live && sub == 0) w[k] = 0.5 * (lo + hi);
 }
 
+// The same search with the Sturm sequence in its PRODUCT form  p_j = (d_j - x) p_{j-1} - e_{j-1}^2 p_{j-2}  (count =
+// sign changes): the dependent chain per step is one DFMA instead of a Newton-refined reciprocal plus two more
+// operations (~85 clocks), and the recurrence is all there is to this kernel.  The matrix is scaled by s = 1 / ||T||
+// (es = e^2 s^2 precomputed, d s - x s folded into one FMA), so a step grows the pair by at most 3x; every 8 steps both
+// values are renormalised by the larger binary exponent (overflow impossible, underflow only for a value ~1e-300 below
+// its partner, which then no longer matters).  A value below 1e-290 of its predecessor is replaced by -1e-290 p_{j-1}
+// (LAPACK's pivmin rule in product form).  Brackets / tolerances are the scaled ones; the result is scaled back.
+__global__ void __launch_bounds__(128)
+stebz_prod_kernel(int n, const double2* __restrict__ pk, double d0s, double tn,
+                  double gl, double gu, double abstol, double* __restrict__ w) {
+  // pk[j] = (d_j s, e_{j-1}^2 s^2) for j = 1 .. n - 1 (one 16-byte warp-uniform load per step); d0s = d_0 s
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = gid / SB_LANES, sub = gid % SB_LANES;
+  const bool live = k < n;
+  const int want = n - 1 - (live ? k : n - 1);          // index in ascending order
+  const unsigned lane = threadIdx.x & 31, grp = lane & ~(SB_LANES - 1);
+  constexpr double TINY = 1e-290;
+  double lo = gl, hi = gu;                              // scaled units
+  for (int it = 0; it < 80; ++it) {
+    const double h = (hi - lo) * (1.0 / (SB_LANES + 1));
+    const double x = lo + h * (double)(sub + 1);
+    unsigned cnt = 0;
+    double p0 = 1.0, p1 = d0s - x;
+    cnt += (unsigned)__double2hiint(p1) >> 31;
+    // one step: three fp64 operations (the kernel is bound by fp64 issue, not by the chain).  The pivmin rule is
+    // only DETECTED here, on the exponent fields with integer instructions; a chunk in which it fired (rare) is
+    // redone from its saved state with the rule applied (`careful`).
+    unsigned bad = 0;
+    auto step = [&](const double2 v) {
+      const double t = v.x - x;
+      const double pn = fma(t, p1, -v.y * p0);
+      const unsigned hn = (unsigned)__double2hiint(pn), h1 = (unsigned)__double2hiint(p1);
+      bad |= (unsigned)((hn & 0x7ff00000u) + (963u << 20) < (h1 & 0x7ff00000u));      // |pn| < ~1e-290 |p1|
+      cnt += (hn ^ h1) >> 31;
+      p0 = p1;
+      p1 = pn;
+    };
+    auto careful = [&](const double2 v) {
+      const double t = v.x - x;
+      double pn = fma(t, p1, -v.y * p0);
+      if (fabs(pn) < TINY * fabs(p1)) pn = -TINY * p1;
+      cnt += ((unsigned)__double2hiint(pn) ^ (unsigned)__double2hiint(p1)) >> 31;
+      p0 = p1;
+      p1 = pn;
+    };
+    auto renorm = [&]() {                                 // by the larger binary exponent of the pair
+      const int e1 = (__double2hiint(p1) >> 20) & 0x7ff, e0 = (__double2hiint(p0) >> 20) & 0x7ff;
+      const int em = max(max(e1, e0), 1);
+      const double sc = __hiloint2double((2046 - em) << 20, 0);        // 2^(1023 - em): em in [1, 2045]
+      p1 *= sc;
+      p0 *= sc;
+    };
+    // chunks of 8 steps in two register buffers (A, B): the operands of the next chunk are loaded before the 8
+    // dependent steps of the current one
+    int j = 1;
+    double2 va[8], vb[8];
+    auto load = [&](double2 (&v)[8], int j0) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(pk + j0 + u);
+    };
+    auto run = [&](const double2 (&v)[8]) {
+      const double s0 = p0, s1 = p1;
+      const unsigned c0 = cnt;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) step(v[u]);
+      if (bad) {
+        p0 = s0; p1 = s1; cnt = c0; bad = 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) careful(v[u]);       // (static indices: the buffers must stay in registers)
+      }
+      renorm();
+    };
+    if (j + 8 <= n) load(va, j);
+    while (j + 8 <= n) {
+      if (j + 16 <= n) load(vb, j + 8);
+      run(va);
+      j += 8;
+      if (j + 8 > n) break;
+      if (j + 16 <= n) load(va, j + 8);
+      run(vb);
+      j += 8;
+    }
+    if (j < n) {
+      for (; j < n; ++j) careful(__ldg(pk + j));
+      renorm();
+    }
+    // first sub-point whose count exceeds `want` bounds the eigenvalue from above
+    const unsigned above = __ballot_sync(0xffffffffu, (int)cnt > want);
+    const unsigned mine = (above >> grp) & ((1u << SB_LANES) - 1u);
+    const int first = mine ? (__ffs(mine) - 1) : SB_LANES;       // SB_LANES: above every sub-point
+    const double nlo = (first == 0) ? lo : lo + h * (double)first;
+    const double nhi = (first == SB_LANES) ? hi : lo + h * (double)(first + 1);
+    const bool stalled = !(nlo > lo || nhi < hi) || !(nhi - nlo > 0.0);
+    lo = nlo; hi = nhi;
+    const bool done = stalled || (hi - lo) <= fmax(abstol, 2.220446049250313e-16 * fmax(fabs(lo), fabs(hi)));
+    if (__all_sync(0xffffffffu, done)) break;
+  }
+  if (live && sub == 0) w[k] = 0.5 * (lo + hi) * tn;
+}
+
+// pk[j] = (d_j s, e_{j-1}^2 s^2), j = 1 .. n - 1 (pk[0] unused)
+__global__ void stebz_pack_kernel(int n, const double* __restrict__ d, const double* __restrict__ e, double s,
+                                  double2* __restrict__ pk) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= 1 && j < n) pk[j] = make_double2(d[j] * s, e[j - 1] * e[j - 1] * s * s);
+}
+
 __global__ void square_kernel(int n, const double* __restrict__ e, double* __restrict__ e2) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < n) e2[j] = e[j] * e[j];
@@ -654,7 +761,7 @@ __global__ void square_kernel(int n, const double* __restrict__ e, double* __res
 
 __global__ void tridiag_bounds_kernel(int n, const double* __restrict__ d, const double* __restrict__ e,
                                       double* __restrict__ out) {
-  // out[0] = Gershgorin lower, out[1] = upper, out[2] = max e^2   (single CTA)
+  // out[0] = Gershgorin lower, out[1] = upper, out[2] = max e^2, out[3] = d[0]   (single CTA)
   __shared__ double red[3][32];
   double lo = INFINITY, hi = -INFINITY, e2 = 0.0;
   for (int j = threadIdx.x; j < n; j += blockDim.x) {
@@ -674,7 +781,7 @@ __global__ void tridiag_bounds_kernel(int n, const double* __restrict__ d, const
     for (int i = 1; i < (int)(blockDim.x >> 5); ++i) {
       lo = fmin(lo, red[0][i]); hi = fmax(hi, red[1][i]); e2 = fmax(e2, red[2][i]);
     }
-    out[0] = lo; out[1] = hi; out[2] = e2;
+    out[0] = lo; out[1] = hi; out[2] = e2; out[3] = d[0];
   }
 }
 
@@ -1105,11 +1212,11 @@ extern "C" int xmca_sytrd_batched(int64_t n, int batch, double* d_A, int64_t lda
 
 extern "C" int xmca_stebz(int64_t n, const double* d_d, const double* d_e, double* d_w, double* d_scratch,
                           void* stream) {
-  XMCA_REQUIRE(n >= 1 && d_d && d_e && d_w && d_scratch, "xmca_stebz: bad argument");   // d_scratch: n + 8 doubles
+  XMCA_REQUIRE(n >= 1 && d_d && d_e && d_w && d_scratch, "xmca_stebz: bad argument");   // d_scratch: 2 n + 8 doubles
   cudaStream_t st = (cudaStream_t)stream;
   tridiag_bounds_kernel<<<1, 1024, 0, st>>>((int)n, d_d, d_e, d_scratch);
   XMCA_LAUNCHED();
-  double h[3];
+  double h[4];
   XMCA_CUDA(cudaMemcpyAsync(h, d_scratch, sizeof h, cudaMemcpyDeviceToHost, st));
   XMCA_CUDA(cudaStreamSynchronize(st));
   if (!isfinite(h[0]) || !isfinite(h[1]))
@@ -1120,10 +1227,21 @@ extern "C" int xmca_stebz(int64_t n, const double* d_d, const double* d_e, doubl
   const double gu = h[1] + 2.0 * 2.220446049250313e-16 * tn * (double)n + 1e-300;
   const double pivmin = 2.2250738585072014e-308 * fmax(1.0, h[2]);
   double* d_e2 = d_scratch + 8;
-  square_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((int)n - 1, d_e, d_e2);
-  XMCA_LAUNCHED();
   const int64_t threads = n * SB_LANES;
-  stebz_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>((int)n, d_d, d_e2, gl, gu, pivmin, 1e-18 * tn, d_w);
+  const char* mode = getenv("XMCA_STEBZ");               // "quot": the quotient-form recurrence (A/B runs)
+  if (mode && mode[0] == 'q' || !(tn > 0.0)) {
+    square_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((int)n - 1, d_e, d_e2);
+    XMCA_LAUNCHED();
+    stebz_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>((int)n, d_d, d_e2, gl, gu, pivmin, 1e-18 * tn, d_w);
+    XMCA_LAUNCHED();
+    return XMCA_OK;
+  }
+  const double s = 1.0 / tn;
+  double2* d_pk = reinterpret_cast<double2*>(d_scratch + 8);          // 16-byte aligned: d_scratch comes from an allocator
+  XMCA_REQUIRE(((uintptr_t)d_pk & 15) == 0, "xmca_stebz: d_scratch must be 16-byte aligned");
+  stebz_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((int)n, d_d, d_e, s, d_pk);
+  XMCA_LAUNCHED();
+  stebz_prod_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>((int)n, d_pk, h[3] * s, tn, gl * s, gu * s, 1e-18, d_w);
   XMCA_LAUNCHED();
   return XMCA_OK;
 }

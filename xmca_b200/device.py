@@ -308,7 +308,7 @@ def stebz(d, e):
     lib = L.load()
     n = d.shape[0]
     w = empty((n,), f64())
-    scratch = empty((n + 8,), f64())
+    scratch = empty((2 * n + 8,), f64())
     rc = lib.xmca_stebz(n, L.ptr(d), L.ptr(e), L.ptr(w), L.ptr(scratch), L.stream_ptr())
     L.check(rc, "xmca_stebz")
     return w
