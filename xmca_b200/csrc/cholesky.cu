@@ -106,7 +106,7 @@ constexpr int CD_T = 256;
 
 __global__ void __launch_bounds__(CD_T)
 chol_diag_blocked_kernel(double* __restrict__ A, int64_t lda, int64_t k0, int nb, double* __restrict__ inv,
-                         int* __restrict__ flag, double min_pivot) {
+                         int* __restrict__ flag, double min_pivot, double* __restrict__ first_out, int first_rows) {
   extern __shared__ double cd_smem[];
   double (*Ls)[PLD] = reinterpret_cast<double (*)[PLD]>(cd_smem);
   double (*Is)[PLD] = reinterpret_cast<double (*)[PLD]>(cd_smem + PB * PLD);
@@ -118,6 +118,9 @@ chol_diag_blocked_kernel(double* __restrict__ A, int64_t lda, int64_t k0, int nb
     const int i = e >> 6, j = e & 63;
     Ls[i][j] = (i < nb && j < nb) ? (j <= i ? A[(k0 + i) * lda + k0 + j] : 0.0) : ((i == j) ? 1.0 : 0.0);
     Is[i][j] = 0.0;
+    // copy of the first tile of the panel below (block (b + 1, b), still unsolved): every CTA of chol_panel_step_kernel
+    // needs it while CTA 0 of that kernel overwrites the original in place
+    if (first_out) first_out[e] = i < first_rows ? A[(k0 + PB + i) * lda + k0 + j] : 0.0;
   }
   __syncthreads();
   chol64_blocked(Ls, s_dinv, tid, &s_fail, min_pivot, &s_bad);
@@ -172,6 +175,98 @@ chol_diag_blocked_kernel(double* __restrict__ A, int64_t lda, int64_t k0, int nb
     inv[e] = Is[i][j];
     if (i < nb && j < nb) A[(k0 + i) * lda + k0 + j] = Ls[i][j];
   }
+}
+
+// One block step below the diagonal block in ONE launch (chain of the factorisation: diagonal block -> this kernel):
+//   L_i = A_i inv(L_kk)^T            for the 64-row tile i of the panel (written in place and to the panel buffer),
+//   A[i, next block column] -= L_i L_f^T,   L_f = the FIRST tile of the panel (rows k0 + 64 ..), which every CTA recomputes
+// instead of waiting for the CTA that owns it (from a copy of the unsolved tile that the diagonal-block kernel made: the
+// original is overwritten in place by CTA 0).  Three 64 x 64 x 64 products per CTA on the fp64 DMMA path (8 warps, warp
+// tile 16 x 32), operands in shared memory at pitch 68.  Replaces three launches (panel product, copy back, update of the
+// next block column) of the generic kernels.
+constexpr int CF_T = 256, CF_LD = 68;
+
+// acc[a][b][e]: C[i0 + 8 a + gid][j0 + 8 b + 2 tig + e], i0 = 16 (warp & 3), j0 = 32 (warp >> 2);
+// C = sum_k X(i, k) Y(k, j), X(i, k) = X[i * xs_i + k * xs_k], Y(k, j) = Y[k * ys_k + j * ys_j], k < 64
+__device__ __forceinline__ void cf_mm64(const double* X, int xs_i, int xs_k, const double* Y, int ys_k, int ys_j,
+                                        double (&acc)[2][4][2]) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, gid = lane >> 2, tig = lane & 3;
+  const int i0 = 16 * (w & 3), j0 = 32 * (w >> 2);
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+  const double* xp = X + (i0 + gid) * xs_i + tig * xs_k;
+  const double* yp = Y + tig * ys_k + (j0 + gid) * ys_j;
+#pragma unroll 4
+  for (int kk = 0; kk < 16; ++kk) {
+    double af[2], bf[4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) af[a] = xp[4 * kk * xs_k + 8 * a * xs_i];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) bf[b] = yp[4 * kk * ys_k + 8 * b * ys_j];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(acc[a][b][0]), "+d"(acc[a][b][1]) : "d"(af[a]), "d"(bf[b]));
+  }
+}
+
+__global__ void __launch_bounds__(CF_T)
+chol_panel_step_kernel(double* __restrict__ A, int64_t lda, int64_t k0, int64_t rem, const double* __restrict__ inv,
+                       const double* __restrict__ first, double* __restrict__ panel) {
+  extern __shared__ double cf_smem[];
+  double* Xs = cf_smem;                       // tile i of the panel, then L_i      [64][68]
+  double* Fs = Xs + 64 * CF_LD;               // first tile of the panel, then L_f  [64][68]
+  double* Is = Fs + 64 * CF_LD;               // inv(L_kk), lower                   [64][68]
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, gid = lane >> 2, tig = lane & 3;
+  const int i0w = 16 * (w & 3), j0w = 32 * (w >> 2);
+  const int64_t r0 = (int64_t)blockIdx.x * 64;                       // first panel row of this tile
+  const int rows = (int)min((int64_t)64, rem - r0);
+  const int rows_f = (int)min((int64_t)64, rem);
+  const double* Ap = A + (k0 + 64) * lda + k0;                       // the panel: rem x 64, pitch lda
+  for (int e = tid; e < 64 * 64; e += CF_T) {
+    const int r = e >> 6, c = e & 63;
+    Xs[r * CF_LD + c] = r < rows ? Ap[(r0 + r) * lda + c] : 0.0;
+    Fs[r * CF_LD + c] = first[e];                 // (copy made by the diagonal-block kernel; rows >= rows_f are zero)
+    Is[r * CF_LD + c] = inv[e];
+  }
+  __syncthreads();
+  double li[2][4][2], lf[2][4][2];
+  cf_mm64(Xs, CF_LD, 1, Is, 1, CF_LD, li);                           // L_i[r][c] = sum_k X[r][k] inv[c][k]
+  cf_mm64(Fs, CF_LD, 1, Is, 1, CF_LD, lf);
+  __syncthreads();
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int r = i0w + 8 * a + gid, c = j0w + 8 * b + 2 * tig;
+      Xs[r * CF_LD + c] = li[a][b][0]; Xs[r * CF_LD + c + 1] = li[a][b][1];
+      Fs[r * CF_LD + c] = lf[a][b][0]; Fs[r * CF_LD + c + 1] = lf[a][b][1];
+      if (r < rows) {
+        double* ai = A + (k0 + 64 + r0 + r) * lda + k0 + c;
+        ai[0] = li[a][b][0]; ai[1] = li[a][b][1];
+        double* pp = panel + (r0 + r) * 64 + c;
+        pp[0] = li[a][b][0]; pp[1] = li[a][b][1];
+      }
+    }
+  __syncthreads();
+  // update of the next block column: A[k0 + 64 + r0 + r][k0 + 64 + c] -= sum_k L_i[r][k] L_f[c][k],  c < min(64, rem)
+  double u[2][4][2];
+  cf_mm64(Xs, CF_LD, 1, Fs, 1, CF_LD, u);
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int r = i0w + 8 * a + gid, c = j0w + 8 * b + 2 * tig;
+      if (r < rows) {
+        double* an = A + (k0 + 64 + r0 + r) * lda + k0 + 64 + c;
+        if (c < rows_f) an[0] -= u[a][b][0];
+        if (c + 1 < rows_f) an[1] -= u[a][b][1];
+      }
+    }
 }
 
 // zero the strict upper triangle of an n x n row-major matrix
@@ -241,7 +336,7 @@ static CholPlan chol_plan(int64_t n, int64_t nrhs) {
   p.off_inv = o;   o += (size_t)p.nblk * CB * CB * sizeof(double);
   int64_t w = nrhs > CB ? nrhs : CB;
   p.off_panel = o; o += (2 * (size_t)n * CB + (size_t)CB * w) * sizeof(double);   // two panel buffers (look-ahead)
-  p.off_flag = o;  o += 256;
+  p.off_flag = o;  o += 256 + (size_t)CB * CB * sizeof(double);          // flag + copy of the first panel tile (fused step)
   p.total = o;
   return p;
 }
@@ -279,6 +374,12 @@ extern "C" int xmca_cholesky(int64_t n, double* d_A, int64_t lda, double* d_invd
   const size_t cd_smem_bytes = 2 * PB * PLD * sizeof(double);
   const char* cd_mode = getenv("XMCA_CHOL_DIAG");                 // "rows": the 64-thread row-per-thread kernel (A/B runs)
   const bool blocked_diag = !(cd_mode && cd_mode[0] == 'r');
+  const char* cs_mode = getenv("XMCA_CHOL_STEP");                 // "generic": panel product / copy / update as three launches
+  const bool fused_step = blocked_diag && !(cs_mode && cs_mode[0] == 'g');
+  double* first_tile = reinterpret_cast<double*>(ws + pl.off_flag) + 16;      // 64 x 64 behind the flag
+  const size_t cf_smem_bytes = 3 * 64 * CF_LD * sizeof(double);
+  if (fused_step && cudaFuncSetAttribute(chol_panel_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)cf_smem_bytes) != cudaSuccess) rc = XMCA_CUDA_ERROR;
   if (blocked_diag && cudaFuncSetAttribute(chol_diag_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)cd_smem_bytes) != cudaSuccess) rc = XMCA_CUDA_ERROR;
   // the chain starts after everything already queued on the caller's stream (the matrix, the flag reset)
@@ -289,29 +390,41 @@ extern "C" int xmca_cholesky(int64_t n, double* d_A, int64_t lda, double* d_invd
     const int nb = (int)((n - k0) < CB ? (n - k0) : CB);
     double* inv = d_invdiag + (size_t)b * CB * CB;
     double* panel = panels[b & 1];
+    const int64_t rem_b = n - k0 - nb;
+    const bool fuse = fused_step && nb == CB && rem_b > 0;
     if (blocked_diag)
-      chol_diag_blocked_kernel<<<1, CD_T, cd_smem_bytes, chain>>>(d_A, lda, k0, nb, inv, flag, min_pivot > 0.0 ? min_pivot : 0.0);
+      chol_diag_blocked_kernel<<<1, CD_T, cd_smem_bytes, chain>>>(d_A, lda, k0, nb, inv, flag, min_pivot > 0.0 ? min_pivot : 0.0,
+                                                                  fuse ? first_tile : nullptr, (int)(rem_b < CB ? rem_b : CB));
     else
       chol_diag_kernel<<<1, CB, 0, chain>>>(d_A, lda, k0, nb, inv, flag, min_pivot > 0.0 ? min_pivot : 0.0);
     if (cudaGetLastError() != cudaSuccess) { rc = XMCA_CUDA_ERROR; break; }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     const int64_t rem = n - k0 - nb;
     if (rem <= 0) break;
-    // panel: L_ik = A_ik inv(L_kk)^T   (rem x nb) -> workspace, then back in place
     double* Aik = d_A + (k0 + nb) * lda + k0;
-    rc = xmca_gemm(1, 1, rem, nb, nb, 1.0, Aik, XMCA_F64, lda, inv, XMCA_F64, CB, panel, XMCA_F64, CB, 0,
-                   XMCA_F64, 1, nullptr, 0, (void*)chain);
-    if (rc != XMCA_OK) break;
-    if ((rc = copy_block(panel, CB, Aik, lda, rem, nb, chain)) != XMCA_OK) break;
-    if (cudaEventRecord(ev_panel, chain) != cudaSuccess) { rc = XMCA_CUDA_ERROR; break; }
-    // the previous step's bulk update also touched block column b + 1: it has to land first
-    if (bulk_pending && cudaStreamWaitEvent(chain, ev_bulk, 0) != cudaSuccess) { rc = XMCA_CUDA_ERROR; break; }
-    // trailing update  A_ij -= L_ik L_jk^T  (tiles on or below the diagonal): the next block column on the chain ...
     double* Att = d_A + (k0 + nb) * lda + (k0 + nb);
     const int64_t c1 = rem < CB ? rem : CB;
-    rc = xmca_gemm_ex(1, 1, rem, c1, nb, -1.0, panel, XMCA_F64, CB, panel, XMCA_F64, CB, Att, XMCA_F64, lda, 1,
-                      XMCA_F64, 1, nullptr, 0, 0, (void*)chain);       // (the strict upper part is zeroed at the end)
-    if (rc != XMCA_OK) break;
+    if (fuse) {
+      // the previous step's bulk update also touched block column b + 1: it has to land first
+      if (bulk_pending && cudaStreamWaitEvent(chain, ev_bulk, 0) != cudaSuccess) { rc = XMCA_CUDA_ERROR; break; }
+      chol_panel_step_kernel<<<(unsigned)((rem + 63) / 64), CF_T, cf_smem_bytes, chain>>>(d_A, lda, k0, rem, inv, first_tile, panel);
+      if (cudaGetLastError() != cudaSuccess) { rc = XMCA_CUDA_ERROR; break; }
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      if (cudaEventRecord(ev_panel, chain) != cudaSuccess) { rc = XMCA_CUDA_ERROR; break; }
+    } else {
+      // panel: L_ik = A_ik inv(L_kk)^T   (rem x nb) -> workspace, then back in place
+      rc = xmca_gemm(1, 1, rem, nb, nb, 1.0, Aik, XMCA_F64, lda, inv, XMCA_F64, CB, panel, XMCA_F64, CB, 0,
+                     XMCA_F64, 1, nullptr, 0, (void*)chain);
+      if (rc != XMCA_OK) break;
+      if ((rc = copy_block(panel, CB, Aik, lda, rem, nb, chain)) != XMCA_OK) break;
+      if (cudaEventRecord(ev_panel, chain) != cudaSuccess) { rc = XMCA_CUDA_ERROR; break; }
+      // the previous step's bulk update also touched block column b + 1: it has to land first
+      if (bulk_pending && cudaStreamWaitEvent(chain, ev_bulk, 0) != cudaSuccess) { rc = XMCA_CUDA_ERROR; break; }
+      // trailing update  A_ij -= L_ik L_jk^T  (tiles on or below the diagonal): the next block column on the chain ...
+      rc = xmca_gemm_ex(1, 1, rem, c1, nb, -1.0, panel, XMCA_F64, CB, panel, XMCA_F64, CB, Att, XMCA_F64, lda, 1,
+                        XMCA_F64, 1, nullptr, 0, 0, (void*)chain);       // (the strict upper part is zeroed at the end)
+      if (rc != XMCA_OK) break;
+    }
     // ... and the remaining block columns on the caller's stream
     const int64_t rem2 = rem - c1;
     if (rem2 > 0) {
