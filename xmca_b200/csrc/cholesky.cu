@@ -107,6 +107,7 @@ constexpr int CD_T = 256;
 __global__ void __launch_bounds__(CD_T)
 chol_diag_blocked_kernel(double* __restrict__ A, int64_t lda, int64_t k0, int nb, double* __restrict__ inv,
                          int* __restrict__ flag, double min_pivot, double* __restrict__ first_out, int first_rows) {
+  pdl_enter();
   extern __shared__ double cd_smem[];
   double (*Ls)[PLD] = reinterpret_cast<double (*)[PLD]>(cd_smem);
   double (*Is)[PLD] = reinterpret_cast<double (*)[PLD]>(cd_smem + PB * PLD);
@@ -217,6 +218,7 @@ __device__ __forceinline__ void cf_mm64(const double* X, int xs_i, int xs_k, con
 __global__ void __launch_bounds__(CF_T)
 chol_panel_step_kernel(double* __restrict__ A, int64_t lda, int64_t k0, int64_t rem, const double* __restrict__ inv,
                        const double* __restrict__ first, double* __restrict__ panel) {
+  pdl_enter();
   extern __shared__ double cf_smem[];
   double* Xs = cf_smem;                       // tile i of the panel, then L_i      [64][68]
   double* Fs = Xs + 64 * CF_LD;               // first tile of the panel, then L_f  [64][68]
@@ -393,8 +395,8 @@ extern "C" int xmca_cholesky(int64_t n, double* d_A, int64_t lda, double* d_invd
     const int64_t rem_b = n - k0 - nb;
     const bool fuse = fused_step && nb == CB && rem_b > 0;
     if (blocked_diag)
-      chol_diag_blocked_kernel<<<1, CD_T, cd_smem_bytes, chain>>>(d_A, lda, k0, nb, inv, flag, min_pivot > 0.0 ? min_pivot : 0.0,
-                                                                  fuse ? first_tile : nullptr, (int)(rem_b < CB ? rem_b : CB));
+      launch_pdl(true, chol_diag_blocked_kernel, dim3(1), dim3(CD_T), cd_smem_bytes, chain, d_A, lda, k0, nb, inv, flag,
+                 min_pivot > 0.0 ? min_pivot : 0.0, fuse ? first_tile : nullptr, (int)(rem_b < CB ? rem_b : CB));
     else
       chol_diag_kernel<<<1, CB, 0, chain>>>(d_A, lda, k0, nb, inv, flag, min_pivot > 0.0 ? min_pivot : 0.0);
     if (cudaGetLastError() != cudaSuccess) { rc = XMCA_CUDA_ERROR; break; }
@@ -407,7 +409,8 @@ extern "C" int xmca_cholesky(int64_t n, double* d_A, int64_t lda, double* d_invd
     if (fuse) {
       // the previous step's bulk update also touched block column b + 1: it has to land first
       if (bulk_pending && cudaStreamWaitEvent(chain, ev_bulk, 0) != cudaSuccess) { rc = XMCA_CUDA_ERROR; break; }
-      chol_panel_step_kernel<<<(unsigned)((rem + 63) / 64), CF_T, cf_smem_bytes, chain>>>(d_A, lda, k0, rem, inv, first_tile, panel);
+      launch_pdl(true, chol_panel_step_kernel, dim3((unsigned)((rem + 63) / 64)), dim3(CF_T), cf_smem_bytes, chain, d_A, lda, k0, rem,
+                 inv, first_tile, panel);
       if (cudaGetLastError() != cudaSuccess) { rc = XMCA_CUDA_ERROR; break; }
       g_launches.fetch_add(1, std::memory_order_relaxed);
       if (cudaEventRecord(ev_panel, chain) != cudaSuccess) { rc = XMCA_CUDA_ERROR; break; }

@@ -65,6 +65,7 @@ gemm_simt_kernel(int64_t M, int64_t N, int64_t K, double alpha,
                  const void* __restrict__ B, int bdt, int64_t ldb,
                  void* __restrict__ D, int ddt, int64_t ldd, int accumulate,
                  T* __restrict__ partial, int64_t k_chunk, int flags) {
+  pdl_enter();
   __shared__ T As[BK][BM + PAD];
   __shared__ T Bs[BK][BN + PAD];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -185,6 +186,7 @@ gemm_dmma_kernel(int64_t M, int64_t N, int64_t K, double alpha,
                  const void* __restrict__ B, int bdt, int64_t ldb,
                  void* __restrict__ D, int ddt, int64_t ldd, int accumulate,
                  double* __restrict__ partial, int64_t k_chunk, int flags) {
+  pdl_enter();
   __shared__ double As[BK][DLD];
   __shared__ double Bs[BK][DLD];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -348,6 +350,7 @@ gemm_dmma_skinny_kernel(int64_t M, int64_t N, int64_t K, double alpha,
                         const void* __restrict__ B, int bdt, int64_t ldb,
                         void* __restrict__ D, int ddt, int64_t ldd, int accumulate,
                         double* __restrict__ partial, int64_t k_chunk) {
+  pdl_enter();
   __shared__ double As[BK][SK_LDA];
   __shared__ double Bs[BK][SK_LDB];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -426,6 +429,7 @@ template <typename T>
 __global__ void splitk_reduce_kernel(int64_t M, int64_t N, int split, double alpha,
                                      const T* __restrict__ partial,
                                      void* __restrict__ D, int ddt, int64_t ldd, int accumulate) {
+  pdl_enter();
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= M * N) return;
   double s = 0.0;
@@ -449,8 +453,8 @@ static int launch_gemm(int ak, int bk, int64_t M, int64_t N, int64_t K, double a
     double* dpart = reinterpret_cast<double*>(partial);
     dim3 sgrid(1, (unsigned)((M + SK_BM - 1) / SK_BM), (unsigned)split);
 #define GOS(AKF, BKF)                                                                            \
-  gemm_dmma_skinny_kernel<AKF, BKF><<<sgrid, DT, 0, st>>>(M, N, K, alpha, A, adt, lda, B, bdt, ldb, \
-                                                          D, ddt, ldd, accumulate, dpart, k_chunk)
+  launch_pdl(true, gemm_dmma_skinny_kernel<AKF, BKF>, sgrid, dim3(DT), 0, st, M, N, K, alpha, A, adt, lda, B, bdt, ldb, \
+             D, ddt, ldd, accumulate, dpart, k_chunk)
     if (ak && bk) GOS(true, true);
     else if (ak && !bk) GOS(true, false);
     else if (!ak && bk) GOS(false, true);
@@ -459,8 +463,8 @@ static int launch_gemm(int ak, int bk, int64_t M, int64_t N, int64_t K, double a
     XMCA_LAUNCHED();
     if (split > 1) {
       int64_t tot = M * N;
-      splitk_reduce_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
-          M, N, split, alpha, partial, D, ddt, ldd, accumulate);
+      launch_pdl(true, splitk_reduce_kernel<T>, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st,
+                 M, N, split, alpha, (const T*)partial, D, ddt, ldd, accumulate);
       XMCA_LAUNCHED();
     }
     return XMCA_OK;
@@ -468,8 +472,8 @@ static int launch_gemm(int ak, int bk, int64_t M, int64_t N, int64_t K, double a
   if (sizeof(T) == 8) {                 // fp64 accumulation: DMMA kernel
     double* dpart = reinterpret_cast<double*>(partial);
 #define GOD(AKF, BKF)                                                                    \
-  gemm_dmma_kernel<AKF, BKF><<<grid, DT, 0, st>>>(M, N, K, alpha, A, adt, lda, B, bdt, ldb, \
-                                                  D, ddt, ldd, accumulate, dpart, k_chunk, flags)
+  launch_pdl(true, gemm_dmma_kernel<AKF, BKF>, grid, dim3(DT), 0, st, M, N, K, alpha, A, adt, lda, B, bdt, ldb, \
+             D, ddt, ldd, accumulate, dpart, k_chunk, flags)
     if (ak && bk) GOD(true, true);
     else if (ak && !bk) GOD(true, false);
     else if (!ak && bk) GOD(false, true);
@@ -478,15 +482,15 @@ static int launch_gemm(int ak, int bk, int64_t M, int64_t N, int64_t K, double a
     XMCA_LAUNCHED();
     if (split > 1) {
       int64_t tot = M * N;
-      splitk_reduce_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
-          M, N, split, alpha, partial, D, ddt, ldd, accumulate);
+      launch_pdl(true, splitk_reduce_kernel<T>, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st,
+                 M, N, split, alpha, (const T*)partial, D, ddt, ldd, accumulate);
       XMCA_LAUNCHED();
     }
     return XMCA_OK;
   }
 #define GO(AKF, BKF)                                                                     \
-  gemm_simt_kernel<T, AKF, BKF><<<grid, NT, 0, st>>>(M, N, K, alpha, A, adt, lda, B, bdt, \
-                                                     ldb, D, ddt, ldd, accumulate, partial, k_chunk, flags)
+  launch_pdl(true, gemm_simt_kernel<T, AKF, BKF>, grid, dim3(NT), 0, st, M, N, K, alpha, A, adt, lda, B, bdt, \
+             ldb, D, ddt, ldd, accumulate, partial, k_chunk, flags)
   if (ak && bk) GO(true, true);
   else if (ak && !bk) GO(true, false);
   else if (!ak && bk) GO(false, true);

@@ -37,6 +37,7 @@ int sb_apply_q2(const double* V2, int64_t ldv, int n, double* Z, int64_t ldz, in
 
 __device__ __forceinline__ void bar64() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
 
+
 // ------------------------------------------------------------------ small dense helpers (one CTA)
 // 64 x 64 (pitch PLD) from / to global (pitch 64), all threads of the CTA
 __device__ __forceinline__ void load64(double (*s)[PLD], const double* __restrict__ g, int tid, int nthreads) {
@@ -269,6 +270,7 @@ __global__ void __launch_bounds__(PT)
 sbr_gram_kernel(const double* X, int64_t ldx, int m, const double* __restrict__ Lf,
                 double* Qout, double* __restrict__ Gpart, int nch,
                 const double* __restrict__ Ma, const double* __restrict__ Mb, double* __restrict__ Mout) {
+  pdl_enter();
   extern __shared__ double smem[];
   double (*Xs)[PLD] = reinterpret_cast<double (*)[PLD]>(smem);
   double (*Ls)[PLD] = reinterpret_cast<double (*)[PLD]>(smem + PB * PLD);
@@ -330,6 +332,7 @@ struct RedParams {
 };
 
 __global__ void __launch_bounds__(PT) sbr_reduce_kernel(RedParams P) {
+  pdl_enter();
   extern __shared__ double smem[];
   double (*Ls)[PLD] = reinterpret_cast<double (*)[PLD]>(smem);
   double (*Ts)[PLD] = reinterpret_cast<double (*)[PLD]>(smem + PB * PLD);
@@ -421,6 +424,7 @@ sbr_applyfinal_kernel(const double* __restrict__ Q, int m, const double* __restr
                       const double* __restrict__ sign, double* __restrict__ Ybuf, double* __restrict__ Sp, int64_t lda,
                       int nch, double* __restrict__ Tout, const double* __restrict__ M12, double* __restrict__ AB,
                       int kb) {
+  pdl_enter();
   extern __shared__ double smem[];
   double (*Ls)[PLD] = reinterpret_cast<double (*)[PLD]>(smem);
   double (*Us)[PLD] = reinterpret_cast<double (*)[PLD]>(smem + PB * PLD);
@@ -498,6 +502,7 @@ constexpr int SY_BM = 128, SY_BK = 16, SY_T = 256, SY_LDA = SY_BM + 4, SY_LDB = 
 __global__ void __launch_bounds__(SY_T, 2)
 sbr_symm_kernel(const double* __restrict__ A, int64_t lda, int m, const double* __restrict__ Y,
                 double* __restrict__ Zp, int kchunk) {
+  pdl_enter();
   __shared__ double As[SY_BK][SY_LDA];
   __shared__ double Bs[SY_BK][SY_LDB];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -571,6 +576,7 @@ sbr_symm_kernel(const double* __restrict__ A, int64_t lda, int m, const double* 
 // col <= row are written and mirrored, so the matrix stays exactly symmetric.
 __global__ void __launch_bounds__(SY_T, 2)
 sbr_syr2k_kernel(const double* __restrict__ XY, const double* __restrict__ YX, int m, double* __restrict__ D, int64_t ldd) {
+  pdl_enter();
   __shared__ double As[SY_BK][SY_LDA];
   __shared__ double Bs[SY_BK][SY_LDB];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -659,6 +665,7 @@ sbr_syr2k_kernel(const double* __restrict__ XY, const double* __restrict__ YX, i
 __global__ void __launch_bounds__(PT)
 sbr_yz_kernel(const double* __restrict__ Zp, int split, int m, const double* __restrict__ Ybuf,
               double* __restrict__ Zbuf, double* __restrict__ Gpart) {
+  pdl_enter();
   extern __shared__ double smem[];
   double (*Ys)[PLD] = reinterpret_cast<double (*)[PLD]>(smem);
   double (*Zs)[PLD] = reinterpret_cast<double (*)[PLD]>(smem + PB * PLD);
@@ -706,6 +713,7 @@ __global__ void __launch_bounds__(PT)
 sbr_xbuild_kernel(const double* __restrict__ Zbuf, const double* __restrict__ Ybuf, int m,
                   const double* __restrict__ C1, const double* __restrict__ Tm,
                   double* __restrict__ XY, double* __restrict__ YX) {
+  pdl_enter();
   extern __shared__ double smem[];
   double (*Ys)[PLD] = reinterpret_cast<double (*)[PLD]>(smem);
   double (*Zs)[PLD] = reinterpret_cast<double (*)[PLD]>(smem + PB * PLD);
@@ -1129,6 +1137,8 @@ extern "C" int xmca_sytrd2(int64_t n, double* d_A, int64_t lda, double* d_d, dou
   XMCA_CUDA(cudaFuncSetAttribute(sbr_xbuild_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
   XMCA_CUDA(cudaFuncSetAttribute(sbr_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4));
   const int nsm = sm_count();
+  const char* pdl_env = getenv("XMCA_SYTRD2_PDL");       // "0": ordinary launches (A/B runs)
+  const bool pdl = !(pdl_env && pdl_env[0] == '0');
   SbrProf prof;
   prof.init(st);
   // Look-ahead: the factorisation of panel p + 1 (latency bound: three Gram / Cholesky rounds and the reconstruction)
@@ -1163,28 +1173,28 @@ extern "C" int xmca_sytrd2(int64_t n, double* d_A, int64_t lda, double* d_d, dou
     R.part = Gpart; R.npart = nch; R.G = G; R.ticket = ticket; R.m = m; R.Qtop = Qb; R.LU = LU; R.sign = sign;
     R.Tm = Tp; R.C1 = C1; R.fail = fail;
     // ---- panel stream: pass 1 (shifted), 2, 3, reconstruction
-    sbr_gram_kernel<<<nch, PT, sm2, sp>>>(Pp, lda, m, nullptr, nullptr, Gpart, nch, nullptr, nullptr, nullptr);
+    XMCA_CUDA(launch_pdl(pdl, sbr_gram_kernel, dim3(nch), dim3(PT), sm2, sp, Pp, lda, m, nullptr, nullptr, Gpart, nch, nullptr, nullptr, nullptr));
     XMCA_LAUNCHED();
     prof.mark(0);
     R.mode = 0; R.Lout = L1;
-    sbr_reduce_kernel<<<NRED, PT, sm2, sp>>>(R);
+    XMCA_CUDA(launch_pdl(pdl, sbr_reduce_kernel, dim3(NRED), dim3(PT), sm2, sp, R));
     XMCA_LAUNCHED();
     prof.mark(1);
-    sbr_gram_kernel<<<nch, PT, sm2, sp>>>(Pp, lda, m, L1, Qb, Gpart, nch, nullptr, nullptr, nullptr);
+    XMCA_CUDA(launch_pdl(pdl, sbr_gram_kernel, dim3(nch), dim3(PT), sm2, sp, Pp, lda, m, L1, Qb, Gpart, nch, nullptr, nullptr, nullptr));
     XMCA_LAUNCHED();
     prof.mark(0);
     R.mode = 1; R.Lout = L2;
-    sbr_reduce_kernel<<<NRED, PT, sm2, sp>>>(R);
+    XMCA_CUDA(launch_pdl(pdl, sbr_reduce_kernel, dim3(NRED), dim3(PT), sm2, sp, R));
     XMCA_LAUNCHED();
     prof.mark(1);
-    sbr_gram_kernel<<<nch + 1, PT, sm2, sp>>>(Qb, PB, m, L2, Qb, Gpart, nch, L1, L2, M12);
+    XMCA_CUDA(launch_pdl(pdl, sbr_gram_kernel, dim3(nch + 1), dim3(PT), sm2, sp, Qb, PB, m, L2, Qb, Gpart, nch, L1, L2, M12));
     XMCA_LAUNCHED();
     prof.mark(0);
     R.mode = 2; R.Lout = L3;
-    sbr_reduce_kernel<<<NRED, PT, sm2, sp>>>(R);
+    XMCA_CUDA(launch_pdl(pdl, sbr_reduce_kernel, dim3(NRED), dim3(PT), sm2, sp, R));
     XMCA_LAUNCHED();
     prof.mark(1);
-    sbr_applyfinal_kernel<<<nch + 2, PT, sm3, sp>>>(Qb, m, L3, LU, sign, Yb, Pp, lda, nch, Tp, M12, AB, kb);
+    XMCA_CUDA(launch_pdl(pdl, sbr_applyfinal_kernel, dim3(nch + 2), dim3(PT), sm3, sp, Qb, m, L3, LU, sign, Yb, Pp, lda, nch, Tp, M12, AB, kb));
     XMCA_LAUNCHED();
     prof.mark(2);
     if (ss) {
@@ -1207,17 +1217,17 @@ extern "C" int xmca_sytrd2(int64_t n, double* d_A, int64_t lda, double* d_d, dou
     int kchunk = ((m + split - 1) / split + SY_BK - 1) / SY_BK * SY_BK;
     split = (m + kchunk - 1) / kchunk;
     double* A22 = d_A + (int64_t)r0 * lda + r0;
-    sbr_symm_kernel<<<dim3(tiles, split), SY_T, 0, st>>>(A22, lda, m, Yb, Zp, kchunk);
+    XMCA_CUDA(launch_pdl(pdl, sbr_symm_kernel, dim3(tiles, split), dim3(SY_T), 0, st, A22, lda, m, Yb, Zp, kchunk));
     XMCA_LAUNCHED();
     prof.mark(3);
-    sbr_yz_kernel<<<nch, PT, sm2, st>>>(Zp, split, m, Yb, Zb, Gpart);
+    XMCA_CUDA(launch_pdl(pdl, sbr_yz_kernel, dim3(nch), dim3(PT), sm2, st, Zp, split, m, Yb, Zb, Gpart));
     XMCA_LAUNCHED();
     prof.mark(4);
     R.mode = 3;
-    sbr_reduce_kernel<<<NRED, PT, sm2, st>>>(R);
+    XMCA_CUDA(launch_pdl(pdl, sbr_reduce_kernel, dim3(NRED), dim3(PT), sm2, st, R));
     XMCA_LAUNCHED();
     prof.mark(1);
-    sbr_xbuild_kernel<<<nch, PT, sm3, st>>>(Zb, Yb, m, C1, Tp, XY, YX);
+    XMCA_CUDA(launch_pdl(pdl, sbr_xbuild_kernel, dim3(nch), dim3(PT), sm3, st, Zb, Yb, m, C1, Tp, XY, YX));
     XMCA_LAUNCHED();
     prof.mark(5);
     if (ss) {
@@ -1231,8 +1241,7 @@ extern "C" int xmca_sytrd2(int64_t n, double* d_A, int64_t lda, double* d_d, dou
     if (rc != XMCA_OK) return rc;
     if (m > PB) {
       const int mm = m - PB, tm = (mm + SY_BM - 1) / SY_BM;
-      sbr_syr2k_kernel<<<tm * (tm + 1), SY_T, 0, st>>>(XY + (int64_t)PB * 2 * PB, YX + (int64_t)PB * 2 * PB, mm,
-                                                       A22 + (int64_t)PB * lda + PB, lda);
+      XMCA_CUDA(launch_pdl(pdl, sbr_syr2k_kernel, dim3(tm * (tm + 1)), dim3(SY_T), 0, st, XY + (int64_t)PB * 2 * PB, YX + (int64_t)PB * 2 * PB, mm, A22 + (int64_t)PB * lda + PB, lda));
       XMCA_LAUNCHED();
     }
     prof.mark(6);
