@@ -21,6 +21,7 @@ constexpr int CPP = CP + 1;            // stride of the column-major work matric
 constexpr int CT = 32;                 // rows per tile
 constexpr int CTHREADS = 512;
 constexpr int CSLOT = 2 * CP * CP + CP;   // doubles per partial: T1 re, T1 im, c
+constexpr int CQ = 2 * CP + 4;            // pitch of the real images used by the MMA streaming pass (conflict-free fragments)
 
 struct VarimaxCParams {
   const void* Lr; const void* Li; int64_t ldl; int64_t n; int p;
@@ -130,6 +131,10 @@ __global__ void __launch_bounds__(CTHREADS, 1) varimax_complex_kernel(VarimaxCPa
   double* Tr = Ar;                      double* Ti = Ar + CP * CPP;     // T^T (stride CPP), aliases the tiles
   double* cs = Ar + 4 * CT * CP;        // [32]
   unsigned char* rr = reinterpret_cast<unsigned char*>(cs + CP);
+  // streaming pass on the fp64 tensor-core path (iteration phase): real 64 x 64 image of the rotation, tiles at pitch CQ
+  double* Rq = reinterpret_cast<double*>(rr + CP * CP);     // [64][CQ]: rows k < 32: [Rr | Ri], rows 32 + k: [-Ri | Rr]
+  double* At = Rq + 2 * CP * CQ;                            // [CT][CQ]: [a_re (32) | a_im (32)]
+  double* Bt = At + CT * CQ;                                // [CT][CQ]: [g_re | g_im],  g = b |b|^2
   __shared__ double s_max[CTHREADS / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -225,66 +230,108 @@ __global__ void __launch_bounds__(CTHREADS, 1) varimax_complex_kernel(VarimaxCPa
   int it = 0, converged = 0, svd_sweeps = 0;
   for (it = 1; it <= P.max_iter; ++it) {
     const double d_old = d;
-    t1r[0] = t1r[1] = t1i[0] = t1i[1] = 0.0;
-    csq = 0.0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int64_t r0 = tile * CT;
-      __syncthreads();
-      for (int e = tid; e < CT * CP; e += CTHREADS) {
-        const int r = e >> 5, c = e & 31;
-        const int64_t row = r0 + r;
-        const bool ok = row < n && c < p;
-        Ar[e] = ok ? (double)Anr[row * p + c] : 0.0;
-        Ai[e] = ok ? (double)Ani[row * p + c] : 0.0;
+    // ---- streaming pass on mma.sync.m8n8k4.f64 through the REAL image of the complex products:
+    //   [b_re | b_im] = [a_re | a_im] [[Rr, Ri], [-Ri, Rr]]          (32 x 64 tile, K = 2 x 32 with the zero k-steps skipped)
+    //   T1_re += a_re^T g_re + a_im^T g_im,   T1_im += a_re^T g_im - a_im^T g_re      (contraction over the tile's rows)
+    // warp w: rows 8 (w & 3) and the real + imaginary 8-column block (w >> 2) of b (so that |b|^2 is thread local),
+    // then the 8 x 8 block (i-block w & 3, j-block w >> 2) of T1.  The next tile is fetched into registers meanwhile.
+    {
+      const int gid = lane >> 2, tig = lane & 3;
+      const int rb = warp & 3, cb = warp >> 2;
+      const int kq = (p + 3) >> 2;
+      for (int e = tid; e < 2 * CP * 2 * CP; e += CTHREADS) {          // real image of R (R changes every iteration)
+        const int k = e >> 6, c = e & 63;
+        const int kr = k & 31, cr = c & 31;
+        double v;
+        if (k < CP) v = c < CP ? Rr[kr * CP + cr] : Ri[kr * CP + cr];
+        else v = c < CP ? -Ri[kr * CP + cr] : Rr[kr * CP + cr];
+        Rq[k * CQ + c] = v;
       }
-      __syncthreads();
-      {   // b = a R for 2 rows x 1 column, then g = b |b|^2
-        double br[2] = {0.0, 0.0}, bi[2] = {0.0, 0.0};
-        if (jcol < p) {
-          for (int k = 0; k < p; ++k) {
-            const double rkr = Rr[k * CP + jcol], rki = Ri[k * CP + jcol];
+      double tr[2] = {0.0, 0.0}, tp[2] = {0.0, 0.0}, tn[2] = {0.0, 0.0}, cq[2] = {0.0, 0.0};
+      const int lr = tid >> 5, lc = tid & 31;                           // loader: rows lr, lr + 16; column lc; re and im
+      double pre[4];
+      auto fetch = [&](int64_t tile) {
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              const double ar = Ar[(rg * 2 + q) * CP + k], ai = Ai[(rg * 2 + q) * CP + k];
-              br[q] = fma(ar, rkr, fma(-ai, rki, br[q]));
-              bi[q] = fma(ar, rki, fma(ai, rkr, bi[q]));
+        for (int q = 0; q < 2; ++q) {
+          const int64_t row = tile * CT + lr + 16 * q;
+          const bool ok = row < n && lc < p;
+          pre[2 * q] = ok ? (double)Anr[row * p + lc] : 0.0;
+          pre[2 * q + 1] = ok ? (double)Ani[row * p + lc] : 0.0;
+        }
+      };
+      if ((int64_t)blockIdx.x < ntiles) fetch(blockIdx.x);
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          At[(lr + 16 * q) * CQ + lc] = pre[2 * q];
+          At[(lr + 16 * q) * CQ + CP + lc] = pre[2 * q + 1];
+        }
+        __syncthreads();
+        if (tile + gridDim.x < ntiles) fetch(tile + gridDim.x);
+        {
+          double cr[2] = {0.0, 0.0}, ci[2] = {0.0, 0.0};
+          const double* ap = At + (8 * rb + gid) * CQ + tig;
+          const double* rp = Rq + tig * CQ + 8 * cb + gid;
+#pragma unroll
+          for (int half = 0; half < 2; ++half)
+            for (int kk = 0; kk < kq; ++kk) {
+              const int k0 = CP * half + 4 * kk;
+              const double a = ap[k0], b_r = rp[k0 * CQ], b_i = rp[k0 * CQ + CP];
+              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                           : "+d"(cr[0]), "+d"(cr[1]) : "d"(a), "d"(b_r));
+              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                           : "+d"(ci[0]), "+d"(ci[1]) : "d"(a), "d"(b_i));
             }
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const double m2 = cr[e] * cr[e] + ci[e] * ci[e];
+            cq[e] += m2;
+            double* g = Bt + (8 * rb + gid) * CQ + 8 * cb + 2 * tig + e;
+            g[0] = cr[e] * m2;
+            g[CP] = ci[e] * m2;
           }
         }
+        __syncthreads();
+        {
+          const double* ap = At + tig * CQ + 8 * rb + gid;              // a[row 4 ks + tig][column i0 + gid] (re; + CP: im)
+          const double* gp = Bt + tig * CQ + 8 * cb + gid;              // g[row 4 ks + tig][column j0 + gid]
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const double m2 = br[q] * br[q] + bi[q] * bi[q];
-          csq += m2;
-          Br[(rg * 2 + q) * CP + jcol] = br[q] * m2;
-          Bi[(rg * 2 + q) * CP + jcol] = bi[q] * m2;
+          for (int ks = 0; ks < CT / 4; ++ks) {
+            const double a_r = ap[4 * ks * CQ], a_i = ap[4 * ks * CQ + CP];
+            const double g_r = gp[4 * ks * CQ], g_i = gp[4 * ks * CQ + CP];
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(tr[0]), "+d"(tr[1]) : "d"(a_r), "d"(g_r));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(tr[0]), "+d"(tr[1]) : "d"(a_i), "d"(g_i));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(tp[0]), "+d"(tp[1]) : "d"(a_r), "d"(g_i));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(tn[0]), "+d"(tn[1]) : "d"(a_i), "d"(g_r));
+          }
         }
+      }
+      // per-CTA partial: T1 block of this warp, column sums of |b|^2 (summed over the four row-block warps)
+      __syncthreads();
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        double v = cq[e];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (gid == 0) At[warp * 8 + 2 * tig + e] = v;
       }
       __syncthreads();
-#pragma unroll 4
-      for (int r = 0; r < CT; ++r) {
-        const double gr = Br[r * CP + lane], gi = Bi[r * CP + lane];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const double ar = Ar[r * CP + warp + 16 * q], ai = Ai[r * CP + warp + 16 * q];   // conj(a_i) g_j
-          t1r[q] = fma(ar, gr, fma(ai, gi, t1r[q]));
-          t1i[q] = fma(ar, gi, fma(-ai, gr, t1i[q]));
-        }
-      }
-    }
-    __syncthreads();
-    Ar[rg * CP + jcol] = csq;            // 16 row groups x 32 columns
-    __syncthreads();
-    {
       double* slot = P.partial + (int64_t)blockIdx.x * CSLOT;
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        slot[(warp + 16 * q) * CP + lane] = t1r[q];
-        slot[CP * CP + (warp + 16 * q) * CP + lane] = t1i[q];
+      for (int e = 0; e < 2; ++e) {
+        const int i = 8 * rb + gid, j = 8 * cb + 2 * tig + e;
+        slot[i * CP + j] = tr[e];
+        slot[CP * CP + i * CP + j] = tp[e] - tn[e];
       }
       if (tid < CP) {
-        double s = 0.0;
-        for (int g = 0; g < CTHREADS / 32; ++g) s += Ar[g * CP + tid];
-        slot[2 * CP * CP + tid] = s;
+        const int g4 = (tid >> 3) * 4, wi = tid & 7;                    // column tid = 8 cb + wi: warps 4 cb .. 4 cb + 3
+        slot[2 * CP * CP + tid] = (At[g4 * 8 + wi] + At[(g4 + 1) * 8 + wi]) + (At[(g4 + 2) * 8 + wi] + At[(g4 + 3) * 8 + wi]);
       }
     }
     __threadfence();
@@ -390,7 +437,8 @@ __global__ void __launch_bounds__(CTHREADS, 1) varimax_complex_kernel(VarimaxCPa
 }
 
 static size_t varimaxc_smem_bytes() {
-  return (size_t)(6 * CP * CP + 4 * CP * CPP + 4 * CT * CP + CP) * sizeof(double) + (size_t)CP * CP;
+  return (size_t)(6 * CP * CP + 4 * CP * CPP + 4 * CT * CP + CP) * sizeof(double) + (size_t)CP * CP +
+         (size_t)(2 * CP + 2 * CT) * CQ * sizeof(double);
 }
 
 constexpr size_t VC_MAX_GRID = 4 * 148 + 64;
