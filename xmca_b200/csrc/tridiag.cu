@@ -604,11 +604,12 @@ syr2k_tiles_kernel(const double* __restrict__ VW, const double* __restrict__ WV,
 }
 
 // ------------------------------------------------------------------ bisection
-// (fast_rcp: the Sturm recurrence is one long dependent chain, its latency is what is being paid for)
-// Eight lanes per eigenvalue index k (0 = LARGEST, descending output): every level evaluates the
-// Sturm count at 8 interior points of the current bracket (9-section, ~3.2 bits per level), so
-// the dependent chain is ~17 levels * n steps instead of ~55 * n for plain bisection.
-constexpr int SB_LANES = 8;
+// SB_LANES lanes per eigenvalue index k (0 = LARGEST, descending output): every level evaluates the Sturm count at
+// SB_LANES interior points of the current bracket.  Multi-section shortens the dependent chain (levels) at the price
+// of more evaluations in total (9-section: 20 levels x 8 = 160 per eigenvalue, 5-section: 27 x 4 = 108, bisection: 63):
+// with the product-form recurrence the kernel is bound by fp64 issue, so FOUR lanes win (n = 8192: 8 lanes 5.9 ms,
+// 4 lanes 4.5 ms); the quotient form (latency bound) was tuned with eight.
+constexpr int SB_LANES = 4;
 
 __global__ void __launch_bounds__(128)
 stebz_kernel(int n, const double* __restrict__ d, const double* __restrict__ e2,
