@@ -37,6 +37,7 @@ struct VarimaxParams {
   double* partial;     // [2*grid][VSLOT]
   double* reduced;     // [VSLOT]
   double* B; int64_t ldb; double* R; double* out;   // out: [0]=iterations [1]=converged [2]=d [3]=svd sweeps total
+  unsigned int* bar;   // arrival counter of the lightweight grid barrier (zeroed before the launch)
   int jacobi_oe;       // in-loop sweeps: 0 round-robin, 1 odd-even ordering with register-resident columns (a warp per
                        // slot), 2 the same with half a warp per slot (default)
 };
@@ -493,6 +494,22 @@ __device__ __forceinline__ void reduce_partials(const double* partial, double* r
   }
 }
 
+// Grid-wide barrier of the co-resident CTAs (cooperative launch): one monotonically increasing arrival counter,
+// red.release / ld.acquire by thread 0 between two CTA barriers (the same barrier as in tridiag.cu; about half the
+// latency of cooperative_groups' grid.sync(), which the iteration pays twice).
+__device__ __forceinline__ void vm_grid_barrier(unsigned int* counter, unsigned int& epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    epoch += gridDim.x;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < epoch);
+  }
+  __syncthreads();
+}
+
 template <typename TS>
 __global__ void __launch_bounds__(VTHREADS, 1) varimax_kernel(VarimaxParams P) {
   cg::grid_group grid = cg::this_grid();
@@ -607,6 +624,7 @@ __global__ void __launch_bounds__(VTHREADS, 1) varimax_kernel(VarimaxParams P) {
   // ---------------- fixed-point iteration ----------------
   double d = 0.0;
   int it = 0, converged = 0, svd_sweeps = 0;
+  unsigned int bar_epoch = 0;
   long long tk[6] = {0, 0, 0, 0, 0, 0};   // per-phase clock64 totals (block 0), returned in out[4..9]
   for (it = 1; it <= P.max_iter; ++it) {
     const double d_old = d;
@@ -715,13 +733,11 @@ __global__ void __launch_bounds__(VTHREADS, 1) varimax_kernel(VarimaxParams P) {
         slot[VP * VP + tid] = (At[g4 * 16 + wi] + At[(g4 + 1) * 16 + wi]) + (At[(g4 + 2) * 16 + wi] + At[(g4 + 3) * 16 + wi]);
       }
     }
-    __threadfence();
     { long long c1 = clock64(); tk[0] += c1 - c0; c0 = c1; }
-    grid.sync();
+    vm_grid_barrier(P.bar, bar_epoch);
     { long long c1 = clock64(); tk[1] += c1 - c0; c0 = c1; }
     reduce_partials(P.partial, P.reduced, (int)gridDim.x);
-    __threadfence();
-    grid.sync();
+    vm_grid_barrier(P.bar, bar_epoch);
     { long long c1 = clock64(); tk[2] += c1 - c0; c0 = c1; }
 
     // ---- phase 2 (redundant on every CTA): T, polar factor, convergence ----
@@ -902,6 +918,8 @@ extern "C" int xmca_varimax(const void* d_L, int l_dtype, int64_t n, int p, int6
   P.h = reinterpret_cast<double*>(ws + o); o += ((size_t)n * 8 + 255) / 256 * 256;
   P.partial = reinterpret_cast<double*>(ws + o); o += ((size_t)4 * 148 + 64) * 2 * VSLOT * 8;
   P.reduced = reinterpret_cast<double*>(ws + o);
+  P.bar = reinterpret_cast<unsigned int*>(P.reduced + VSLOT);        // (inside the 256-byte pad of the plan)
+  XMCA_CUDA(cudaMemsetAsync(P.bar, 0, sizeof(unsigned int), st));
   P.B = d_B; P.ldb = ldb; P.R = d_R; P.out = d_out;
   {
     const char* e = getenv("XMCA_VARIMAX_JACOBI");       // A/B runs: "rr" round-robin, "oe" odd-even with a warp per slot
